@@ -1,0 +1,119 @@
+// C ABI: check_patterns() and the compiled-database introspection entry points of include/gpugrep.h.
+// Host only: nothing here touches CUDA, so it is safe to call before fork().
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "../../include/gpugrep.h"
+#include "database.hpp"
+
+namespace gpugrep {
+thread_local std::string g_last_error;
+void set_last_error(const std::string& e) { g_last_error = e; }
+}  // namespace gpugrep
+
+struct gpugrep_db {
+    std::shared_ptr<gpugrep::Database> db;
+};
+
+extern "C" {
+
+// Replaces reference hyperscanner.c:154-167.
+int check_patterns(const char* const* patterns, const unsigned int* pattern_flags, const unsigned int* pattern_ids,
+                   const unsigned int elements) {
+    int rc = 0;
+    std::string err;
+    auto db = gpugrep::cached_database(patterns, pattern_flags, pattern_ids, elements, rc, err);
+    if (!db) {
+        gpugrep::set_last_error(err);
+        return GPUGREP_DB;
+    }
+    gpugrep::set_last_error("");
+    return 0;
+}
+
+const char* gpugrep_last_error(void) { return gpugrep::g_last_error.c_str(); }
+const char* gpugrep_version(void) { return "gpugrep 0.1.0 (sm_100a)"; }
+
+gpugrep_db* gpugrep_db_compile(const char* const* patterns, const unsigned int* pattern_flags,
+                               const unsigned int* pattern_ids, unsigned int elements, int* rc) {
+    std::string err;
+    std::shared_ptr<gpugrep::Database> db;
+    int r = gpugrep::compile_database(patterns, pattern_flags, pattern_ids, elements, db, err);
+    if (rc) *rc = r;
+    gpugrep::set_last_error(err);
+    if (r != 0) return nullptr;
+    return new gpugrep_db{db};
+}
+
+void gpugrep_db_free(gpugrep_db* db) { delete db; }
+
+int gpugrep_db_get_info(const gpugrep_db* h, gpugrep_db_info* out) {
+    if (!h || !out) return -1;
+    const gpugrep::Database& db = *h->db;
+    std::memset(out, 0, sizeof(*out));
+    out->patterns = (unsigned)db.patterns.size();
+    out->groups = (unsigned)db.groups.size();
+    out->simple = db.simple;
+    out->simple_id = db.simple_id;
+    out->prefilter = db.prefilter.enabled;
+    out->prefilter_stride = (unsigned)db.prefilter.stride;
+    out->prefilter_fold = db.prefilter.fold_case;
+    out->prefilter_log2_bits = (unsigned)db.prefilter.log2_bits;
+    out->prefilter_grams = (unsigned)db.prefilter.num_grams;
+    out->prefilter_min_factor = (unsigned)db.prefilter.min_factor_len;
+    for (auto& g : db.groups) out->total_states += (unsigned)g.dfa.num_states;
+    return 0;
+}
+
+int gpugrep_db_get_group(const gpugrep_db* h, unsigned int group, gpugrep_group_info* out) {
+    if (!h || !out || group >= h->db->groups.size()) return -1;
+    const gpugrep::Dfa& d = h->db->groups[group].dfa;
+    out->states = (unsigned)d.num_states;
+    out->classes = (unsigned)d.num_classes;
+    out->stride = (unsigned)d.stride;
+    out->first_accept = (unsigned)d.first_accept;
+    out->sink_match = d.sink_match;
+    out->dead = d.dead;
+    out->accept_sets = (unsigned)d.accept_sets.size();
+    out->members = (unsigned)h->db->groups[group].members.size();
+    return 0;
+}
+
+int gpugrep_db_copy_group(const gpugrep_db* h, unsigned int group, uint8_t* byte_class, uint32_t* trans, uint32_t* accept_of) {
+    if (!h || group >= h->db->groups.size()) return -1;
+    const gpugrep::Dfa& d = h->db->groups[group].dfa;
+    if (byte_class) std::memcpy(byte_class, d.byte_class, 256);
+    if (trans) std::memcpy(trans, d.trans.data(), d.trans.size() * sizeof(uint32_t));
+    if (accept_of) std::memcpy(accept_of, d.accept_of.data(), d.accept_of.size() * sizeof(uint32_t));
+    return 0;
+}
+
+int gpugrep_db_accept_reports(const gpugrep_db* h, unsigned int group, unsigned int accept, unsigned int* ids,
+                              unsigned int* singlematch, unsigned int cap) {
+    if (!h || group >= h->db->groups.size()) return -1;
+    const auto& rb = h->db->report_begin[group];
+    if (accept + 1 >= rb.size()) return -1;
+    unsigned n = 0;
+    for (uint32_t k = rb[accept]; k < rb[accept + 1]; k++, n++) {
+        if (n < cap) {
+            if (ids) ids[n] = h->db->reports[k].id;
+            if (singlematch) singlematch[n] = h->db->reports[k].singlematch;
+        }
+    }
+    return (int)n;
+}
+
+size_t gpugrep_db_copy_prefilter(const gpugrep_db* h, uint32_t* words, size_t cap_words, uint32_t* hash_mul) {
+    if (!h || !h->db->prefilter.enabled) return 0;
+    const auto& pf = h->db->prefilter;
+    size_t n = std::min(cap_words, pf.bitmap.size());
+    if (words) std::memcpy(words, pf.bitmap.data(), n * sizeof(uint32_t));
+    if (hash_mul) *hash_mul = pf.hash_mul;
+    return n;
+}
+
+const char* gpugrep_db_prefilter_note(const gpugrep_db* h) { return h ? h->db->prefilter.note.c_str() : ""; }
+
+}  // extern "C"

@@ -1,0 +1,165 @@
+/*
+ * libgpugrep.so — C ABI of the B200-native multi-pattern log scanner.
+ *
+ * Section 1 is the drop-in boundary: exactly the two symbols the reference's Python layer binds with ctypes
+ * (reference hypergrep/utils.py:116-121 and :339-349), with the signatures, record layout, return codes and
+ * callback discipline of the reference's C shim (reference hypergrep/lib/c/hyperscanner.c:25-56, 154-159,
+ * 248-258).  Section 2 holds extensions used by this repo's bench, tests and tools; the reference has no
+ * equivalent for them.
+ *
+ * No symbol in this header takes or returns a torch / CUDA runtime type: plain pointers, sizes and PODs only.
+ */
+#ifndef GPUGREP_H
+#define GPUGREP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 1. Drop-in boundary
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Return codes: reference hyperscanner.c:25-33 (enum hyperscanner_ret). 0 = success. */
+enum gpugrep_ret {
+    GPUGREP_OK = 0,
+    GPUGREP_COMPILE_MEM = 1, /* HYPERSCANNER_COMPILE_MEM: result slots could not be allocated            */
+    GPUGREP_COMPILE = 2,     /* HYPERSCANNER_COMPILE                                                       */
+    GPUGREP_SCRATCH = 3,     /* HYPERSCANNER_SCRATCH: device / pinned scratch could not be allocated       */
+    GPUGREP_DB = 4,          /* HYPERSCANNER_DB: a pattern was rejected (unsupported construct, empty ...) */
+    GPUGREP_STATE_MEM = 5,   /* HYPERSCANNER_STATE_MEM                                                     */
+    GPUGREP_GZ_OPEN = 6,     /* HYPERSCANNER_GZ_OPEN: the input file could not be opened                   */
+    GPUGREP_SCAN = 7         /* HYPERSCANNER_SCAN: a CUDA error during the scan (no GPU, launch failure)   */
+};
+
+/* hyperscanner_result_t, reference hyperscanner.c:42-46 == ctypes `Result`, reference utils.py:25-40.
+ * sizeof == 24 on x86-64: id @0, line_number @8, line @16. */
+typedef struct hyperscanner_result {
+    unsigned int id;                /* the user's match id of the pattern group that matched            */
+    unsigned long long line_number; /* 0-based pseudo-line index (one per gzgets() of buffer_size)      */
+    char* line;                     /* NUL-terminated line bytes incl. trailing '\n'; valid during the callback only */
+} hyperscanner_result_t;
+
+/* hs_event, reference hyperscanner.c:54.  Invoked synchronously on the calling thread, in file order, with
+ * 1 <= result_count <= buffer_count: full batches first, then the remainder (hyperscanner.c:94-98, 311-313). */
+typedef void (*hs_event)(hyperscanner_result_t* results, int result_count);
+
+/* Replaces reference hyperscanner.c:248-326 `hyperscan()`.
+ * file_name: plain, gzip or zstd file.  patterns/pattern_flags/pattern_ids: `elements` entries; flags are
+ * HS_FLAG_CASELESS=1 | DOTALL=2 | MULTILINE=4 | SINGLEMATCH=8 (other bits -> 4).  buffer_size: a pseudo-line is
+ * at most buffer_size-1 bytes (the reference's gzgets buffer).  buffer_count: callback batch size (clamped to
+ * max_match_count when that is smaller, hyperscanner.c:259-262).  max_match_count: stop after the line on which
+ * the total reaches it; 0 = unlimited. */
+int hyperscan(char* file_name, const char* const* patterns, const unsigned int* pattern_flags,
+              const unsigned int* pattern_ids, const unsigned int elements, hs_event on_event,
+              const int buffer_size, int buffer_count, unsigned long long max_match_count);
+
+/* Replaces reference hyperscanner.c:154-167 `check_patterns()`: 0 if the set compiles, else 4.
+ * Never touches CUDA (safe before fork()). */
+int check_patterns(const char* const* patterns, const unsigned int* pattern_flags,
+                   const unsigned int* pattern_ids, const unsigned int elements);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * 2. Extensions (bench / tests / tools)
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Per-call statistics of the scan entry points below (all fields are outputs). */
+typedef struct gpugrep_stats {
+    unsigned long long bytes_scanned;  /* uncompressed bytes handed to the kernels                        */
+    unsigned long long lines;          /* pseudo-lines seen                                                */
+    unsigned long long matches;        /* results delivered (or counted when on_event is NULL)             */
+    unsigned long long candidates;     /* 16-byte chunks flagged by the prefilter (0 when it is off)       */
+    unsigned long long h2d_bytes;      /* host->device bytes copied inside the call                        */
+    unsigned long long d2h_bytes;      /* device->host bytes copied inside the call                        */
+    double gpu_ms;                     /* CUDA-event time of all kernels of the call, summed over segments */
+    double stream_kernel_ms;           /* of which: the streaming prefilter/newline kernel                 */
+    double wall_ms;                    /* host wall-clock of the call                                      */
+    unsigned int launches;             /* kernels launched by this library inside the call                 */
+    unsigned int stream_launches;      /* of which: launches of the streaming kernel                       */
+    unsigned int segments;             /* device segments processed                                        */
+    unsigned int path;                 /* bit 0: prefilter fast path used; bit 1: general line-table path used */
+} gpugrep_stats;
+
+#define GPUGREP_LOC_HOST 0   /* data is host memory (pinned memory is copied directly, pageable is staged) */
+#define GPUGREP_LOC_DEVICE 1 /* data is a device pointer on the current device                            */
+
+/* Scan a memory buffer holding the (decompressed) file contents; same pattern, batching and callback
+ * semantics as hyperscan().  on_event may be NULL: matches are then only counted (no line bytes are copied).
+ * `stream` is an optional cudaStream_t (as void*) to enqueue on, NULL = the library's own stream. */
+int gpugrep_scan_buffer(const void* data, size_t size, int location, const char* const* patterns,
+                        const unsigned int* pattern_flags, const unsigned int* pattern_ids, unsigned int elements,
+                        hs_event on_event, int buffer_size, int buffer_count, unsigned long long max_match_count,
+                        void* stream, gpugrep_stats* stats);
+
+/* hyperscan() plus statistics. */
+int gpugrep_scan_file(const char* file_name, const char* const* patterns, const unsigned int* pattern_flags,
+                      const unsigned int* pattern_ids, unsigned int elements, hs_event on_event, int buffer_size,
+                      int buffer_count, unsigned long long max_match_count, gpugrep_stats* stats);
+
+/* Byte-range sharding helper for multi-GPU runs: rank r of `world` scans
+ * [gpugrep_shard_begin(r), gpugrep_shard_begin(r+1)) where each boundary is advanced to just past the next '\n'.
+ * `data` is host memory. */
+size_t gpugrep_shard_begin(const void* data, size_t size, unsigned int rank, unsigned int world);
+
+/* Select the CUDA device used by subsequent calls from this thread's process (default: $GPUGREP_DEVICE,
+ * else $LOCAL_RANK, else 0). */
+void gpugrep_set_device(int device);
+
+/* Path of the libzstd shared object used for .zst ingest (default "libzstd.so.1"). */
+void gpugrep_set_zstd_path(const char* path);
+
+/* Human-readable reason of the last failure on this thread ("" if none). */
+const char* gpugrep_last_error(void);
+const char* gpugrep_version(void);
+
+/* ---- compiled-database introspection (pattern compiler tests) ---- */
+typedef struct gpugrep_db gpugrep_db;
+
+typedef struct gpugrep_db_info {
+    unsigned int patterns;
+    unsigned int groups;          /* DFA groups                                                     */
+    unsigned int simple;          /* 1: every pattern SINGLEMATCH with one shared id                */
+    unsigned int simple_id;
+    unsigned int prefilter;       /* 1: literal prefilter enabled                                   */
+    unsigned int prefilter_stride;
+    unsigned int prefilter_fold;
+    unsigned int prefilter_log2_bits;
+    unsigned int prefilter_grams;
+    unsigned int prefilter_min_factor;
+    unsigned int total_states;
+    unsigned int reserved;
+} gpugrep_db_info;
+
+typedef struct gpugrep_group_info {
+    unsigned int states;
+    unsigned int classes;        /* byte classes; column `classes` is the end-of-data symbol */
+    unsigned int stride;         /* classes + 1                                              */
+    unsigned int first_accept;   /* states >= first_accept report                            */
+    int sink_match;              /* simple mode: absorbing "matched" state, else -1          */
+    int dead;                    /* absorbing non-reporting state, else -1                   */
+    unsigned int accept_sets;
+    unsigned int members;
+} gpugrep_group_info;
+
+gpugrep_db* gpugrep_db_compile(const char* const* patterns, const unsigned int* pattern_flags,
+                               const unsigned int* pattern_ids, unsigned int elements, int* rc);
+void gpugrep_db_free(gpugrep_db* db);
+int gpugrep_db_get_info(const gpugrep_db* db, gpugrep_db_info* out);
+int gpugrep_db_get_group(const gpugrep_db* db, unsigned int group, gpugrep_group_info* out);
+/* Copies the tables of one group: byte_class[256], trans[states*stride], accept_of[states]. */
+int gpugrep_db_copy_group(const gpugrep_db* db, unsigned int group, uint8_t* byte_class, uint32_t* trans,
+                          uint32_t* accept_of);
+/* Reports of accept set `accept` of `group`: writes up to cap (id, singlematch) pairs, returns the count. */
+int gpugrep_db_accept_reports(const gpugrep_db* db, unsigned int group, unsigned int accept, unsigned int* ids,
+                              unsigned int* singlematch, unsigned int cap);
+/* Copies the prefilter bitmap ((1 << log2_bits) / 32 words); returns words copied, 0 if disabled. */
+size_t gpugrep_db_copy_prefilter(const gpugrep_db* db, uint32_t* words, size_t cap_words, uint32_t* hash_mul);
+const char* gpugrep_db_prefilter_note(const gpugrep_db* db);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPUGREP_H */
