@@ -1,0 +1,1118 @@
+// CUDA engine for sm_100a: streaming newline/prefilter kernel, scans, candidate verification (DFA), compaction.
+//
+// Replaces, for one device-resident segment of file bytes, the reference's per-line loop
+//   gzgets (line split)  -> hs_scan (match)          -> hs_callback (record)
+//   hyperscanner.c:199      hyperscanner.c:217           hyperscanner.c:83-102
+// Two paths produce identical results:
+//   FAST    (simple mode + literal prefilter + no over-long lines):
+//           k_stream -> scan -> k_list_candidates -> k_verify_simple -> scan -> k_emit_simple
+//   GENERAL (everything else, and the fallback when a fast-path capacity bound is hit):
+//           k_stream(no filter) -> scan -> k_newline_positions -> pseudo-line table -> k_match_pl_* -> scan -> emit
+// All byte offsets inside a segment are 32-bit (segments are < 4 GiB); line numbers are rebased on the host.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "engine.hpp"
+
+namespace gpugrep {
+
+// ------------------------------------------------------------------------------------------------------------
+// device-side views
+// ------------------------------------------------------------------------------------------------------------
+struct GroupDev {
+    const uint16_t* trans;      // [states][stride]
+    const uint8_t* cls;         // [256] byte -> class
+    const uint32_t* accept_of;  // [states] (general mode)
+    uint32_t stride, eod, first_accept, dead, accept_base, pad;
+};
+
+struct DbView {
+    const GroupDev* groups;
+    int ngroups;
+};
+
+struct CandRes {
+    uint32_t first_line;    // pseudo-line number (inside the segment) of the line containing the chunk's first byte
+    uint32_t first_start;   // its start offset
+    uint32_t mask;          // bit j: the j-th line intersecting the chunk matched (and is owned by this chunk)
+};
+
+struct Totals {
+    unsigned long long meta_total;   // candidates << 32 | newlines
+    unsigned long long rec_total;    // records to emit (fast path) / generic scan totals
+    unsigned long long aux_total;
+    unsigned int flags;              // bit0: a 64 KiB super-block without newline; bit1: candidate overflow; bit2: record overflow
+    unsigned int last_byte;
+    unsigned int max_line;           // general path: longest line
+    unsigned int pad;
+};
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t e_ = (expr);                                                            \
+        if (e_ != cudaSuccess) {                                                            \
+            error = std::string(#expr) + ": " + cudaGetErrorString(e_);                     \
+            return 7;                                                                       \
+        }                                                                                   \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------------------
+// SWAR helpers
+// ------------------------------------------------------------------------------------------------------------
+// 0x80 in every byte of w equal to the byte replicated in `rep`.  Exact (no borrow between bytes):
+// u = (w ^ rep) | 0x80 never borrows when 1 is subtracted per byte; bit 7 of the result is clear iff the low 7 bits
+// matched, and ~w / rep bit 7 handling below makes the top bit exact for rep < 0x80.
+__device__ __forceinline__ uint32_t eq_mask4(uint32_t w, uint32_t rep) {
+    uint32_t u = (w ^ rep) | 0x80808080u;
+    uint32_t t = u - 0x01010101u;
+    return ~(t | w) & 0x80808080u;   // valid for rep bytes < 0x80 ('\n' = 0x0a, NUL = 0x00)
+}
+// 4 flag bits (0x80 per byte) -> 4 contiguous bits
+__device__ __forceinline__ uint32_t movemask4(uint32_t z) { return ((z >> 7) * 0x01020408u) >> 24 & 0xFu; }
+
+__device__ __forceinline__ uint32_t newline_mask16(const uint4& v) {
+    return movemask4(eq_mask4(v.x, 0x0a0a0a0au)) | (movemask4(eq_mask4(v.y, 0x0a0a0a0au)) << 4) |
+           (movemask4(eq_mask4(v.z, 0x0a0a0a0au)) << 8) | (movemask4(eq_mask4(v.w, 0x0a0a0a0au)) << 12);
+}
+__device__ __forceinline__ uint32_t newline_count16(const uint4& v) {
+    uint32_t a = eq_mask4(v.x, 0x0a0a0a0au), b = eq_mask4(v.y, 0x0a0a0a0au), c = eq_mask4(v.z, 0x0a0a0a0au), d = eq_mask4(v.w, 0x0a0a0a0au);
+    return __popc((a >> 7) | (b >> 6) | (c >> 5) | (d >> 4));
+}
+
+// streaming 16-byte load that does not pollute L1
+__device__ __forceinline__ uint4 ld_stream16(const uint8_t* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+// cached 16-byte load of the aligned chunk at `off`; bytes at or beyond n read as zero
+__device__ __forceinline__ uint4 ld_chunk(const uint8_t* data, size_t off, size_t n) {
+    uint4 v = *reinterpret_cast<const uint4*>(data + off);   // within the same 16-byte granule as byte n-1 at worst
+    if (off + 16 > n) {
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            size_t b = off + 4 * i;
+            if (b >= n) w[i] = 0;
+            else if (b + 4 > n) w[i] &= (1u << (8 * (n - b))) - 1u;
+        }
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    return v;
+}
+
+// index just past the last '\n' strictly before `pos` (0 if none): start of the line containing byte `pos`
+__device__ size_t line_start_of(const uint8_t* data, size_t pos) {
+    while (pos > 0) {
+        size_t base = (pos - 1) & ~(size_t)15;
+        uint4 v = *reinterpret_cast<const uint4*>(data + base);
+        uint32_t m = newline_mask16(v);
+        uint32_t span = (uint32_t)(pos - base);   // bytes [base, pos) are candidates, 1..16
+        if (span < 16) m &= (1u << span) - 1u;
+        if (m) return base + (32 - __clz(m));
+        pos = base;
+    }
+    return 0;
+}
+
+// index just past the first '\n' at or after `pos`, or n if there is none
+__device__ size_t line_end_of(const uint8_t* data, size_t pos, size_t n) {
+    size_t base = pos & ~(size_t)15;
+    uint32_t skip = (uint32_t)(pos - base);
+    while (base < n) {
+        uint4 v = ld_chunk(data, base, n);
+        uint32_t m = newline_mask16(v) & ~((1u << skip) - 1u);
+        if (m) return base + __ffs(m);
+        skip = 0;
+        base += 16;
+    }
+    return n;
+}
+
+// newlines in [from, to), from 16-byte aligned
+__device__ uint32_t count_newlines(const uint8_t* data, size_t from, size_t to) {
+    uint32_t c = 0;
+    for (size_t b = from; b < to; b += 16) {
+        uint4 v = *reinterpret_cast<const uint4*>(data + b);
+        uint32_t m = newline_mask16(v);
+        if (b + 16 > to) m &= (1u << (to - b)) - 1u;
+        c += __popc(m);
+    }
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K1: streaming kernel.  One warp owns a 512-byte block per step: 32 x 16-byte coalesced loads, newline count
+// (SWAR + popc + warp reduce) and, when the prefilter is on, one hashed-bitmap probe per sampled 4-byte gram.
+// Output: meta[block] = newline_count << 32 | ballot(lanes whose 16-byte chunk has a gram hit).
+// STRIDE: 0 = no prefilter, else sample every STRIDE-th byte position (4, 2, 1).  Algorithmic traffic: 1 byte
+// read per input byte + 8 bytes written per 512.
+// ------------------------------------------------------------------------------------------------------------
+template <int STRIDE, bool FOLD>
+__device__ __forceinline__ uint32_t probe_chunk(const uint4& v, uint32_t next, const uint32_t* __restrict__ bm, uint32_t mul, int shift) {
+    uint32_t w[5] = {v.x, v.y, v.z, v.w, next};
+    if (FOLD) {
+#pragma unroll
+        for (int i = 0; i < 5; i++) w[i] |= 0x20202020u;
+    }
+    uint32_t hit = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+#pragma unroll
+        for (int s = 0; s < 4; s += STRIDE) {
+            uint32_t gram = s == 0 ? w[i] : __funnelshift_r(w[i], w[i + 1], 8 * s);
+            uint32_t h = (gram * mul) >> shift;
+            hit |= bm[h >> 5] >> (h & 31);
+        }
+    }
+    return hit & 1u;
+}
+
+template <int STRIDE, bool FOLD>
+__global__ void __launch_bounds__(256) k_stream(const uint8_t* __restrict__ data, size_t n, size_t nblk, unsigned long long* __restrict__ meta,
+                                                const uint32_t* __restrict__ bitmap, int log2_bits, uint32_t mul) {
+    extern __shared__ uint32_t s_bitmap[];
+    if (STRIDE > 0) {
+        const int words = 1 << (log2_bits - 5);
+        for (int i = threadIdx.x; i < words; i += blockDim.x) s_bitmap[i] = bitmap[i];
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    const int shift = 32 - log2_bits;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    constexpr int U = 4;   // 512-byte blocks in flight per warp
+    for (size_t g0 = warp * U; g0 < nblk; g0 += nwarps * U) {
+        uint4 v[U];
+        uint32_t nx[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            size_t off = (g0 + u) * 512 + (size_t)lane * 16;
+            if (off + 16 <= n) v[u] = ld_stream16(data + off);
+            else if (off < n) v[u] = ld_chunk(data, off, n);
+            else v[u] = make_uint4(0, 0, 0, 0);
+            nx[u] = 0;
+        }
+        if (STRIDE > 0 && STRIDE < 4) {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                // first word of the following chunk: the next lane's, or (lane 31) the next block's first word
+                uint32_t down = __shfl_down_sync(0xffffffffu, v[u].x, 1);
+                if (lane == 31) {
+                    size_t off = (g0 + u + 1) * 512;
+                    down = 0;
+                    if (off < n) down = ld_chunk(data, off, n).x;
+                }
+                nx[u] = down;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (g0 + u >= nblk) break;
+            uint32_t cnt = newline_count16(v[u]);
+            uint32_t hit = 0;
+            if (STRIDE > 0) hit = probe_chunk<(STRIDE > 0 ? STRIDE : 4), FOLD>(v[u], nx[u], s_bitmap, mul, shift);
+            // chunks that start at or beyond n can never be candidates
+            if ((g0 + u) * 512 + (size_t)lane * 16 >= n) hit = 0;
+            uint32_t mask = __ballot_sync(0xffffffffu, hit != 0);
+            uint32_t total = __reduce_add_sync(0xffffffffu, cnt);
+            if (lane == 0) meta[g0 + u] = ((unsigned long long)total << 32) | mask;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Exclusive scan over u64 values produced by a loader functor: three kernels (block sums, scan of sums, write).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long long v, unsigned long long* s_warp, unsigned long long* s_total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    unsigned long long incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned long long w = lane < nw ? s_warp[lane] : 0ull;
+        unsigned long long wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += t;
+        }
+        if (lane < nw) s_warp[lane] = wi - w;
+        if (lane == 31) *s_total = wi;
+    }
+    __syncthreads();
+    return s_warp[wid] + incl - v;
+}
+
+struct LoadMeta {   // meta word -> candidates << 32 | newlines
+    const unsigned long long* meta;
+    __device__ unsigned long long operator()(size_t i) const {
+        unsigned long long m = meta[i];
+        return ((unsigned long long)__popc((uint32_t)m) << 32) | (m >> 32);
+    }
+};
+struct LoadResMask {   // records per candidate; *count (device) bounds the valid prefix
+    const CandRes* res;
+    const unsigned long long* meta_total;
+    size_t cap;
+    __device__ unsigned long long operator()(size_t i) const {
+        size_t cnt = (size_t)(*meta_total >> 32);
+        if (cnt > cap) cnt = cap;
+        return i < cnt ? (unsigned long long)__popc(res[i].mask) : 0ull;
+    }
+};
+struct LoadU8 {
+    const uint8_t* p;
+    __device__ unsigned long long operator()(size_t i) const { return p[i]; }
+};
+struct LoadU32 {
+    const uint32_t* p;
+    __device__ unsigned long long operator()(size_t i) const { return p[i]; }
+};
+
+template <class Load>
+__global__ void __launch_bounds__(kScanThreads) k_scan_sums(Load load, size_t n, unsigned long long* __restrict__ sums) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_total;
+    size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+    unsigned long long acc = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) if (base + k < n) acc += load(base + k);
+    block_exclusive_scan(acc, s_warp, &s_total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = s_total;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_top(unsigned long long* __restrict__ sums, size_t nb, unsigned long long* __restrict__ total) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_total;
+    size_t per = (nb + blockDim.x - 1) / blockDim.x;
+    size_t lo = (size_t)threadIdx.x * per, hi = lo + per < nb ? lo + per : nb;
+    unsigned long long acc = 0;
+    for (size_t i = lo; i < hi; i++) acc += sums[i];
+    unsigned long long run = block_exclusive_scan(acc, s_warp, &s_total);
+    for (size_t i = lo; i < hi; i++) {
+        unsigned long long v = sums[i];
+        sums[i] = run;
+        run += v;
+    }
+    if (threadIdx.x == 0) *total = s_total;
+}
+
+template <class Load>
+__global__ void __launch_bounds__(kScanThreads) k_scan_write(Load load, size_t n, const unsigned long long* __restrict__ sums,
+                                                             unsigned long long* __restrict__ out) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_total;
+    size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
+    unsigned long long vals[kScanItems];
+    unsigned long long acc = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        vals[k] = base + k < n ? load(base + k) : 0ull;
+        acc += vals[k];
+    }
+    unsigned long long run = block_exclusive_scan(acc, s_warp, &s_total) + sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        if (base + k < n) out[base + k] = run;
+        run += vals[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// DFA walk over one scanned block [start, lim): leading NULs are skipped and the block ends at the first later
+// NUL (reference hyperscanner.c:205-217: strip loop + strlen), at '\n' (inclusive) or at lim.
+// ------------------------------------------------------------------------------------------------------------
+struct ByteCursor {
+    const uint8_t* data;
+    size_t pos, lim;
+    uint32_t word;
+    __device__ __forceinline__ ByteCursor(const uint8_t* d, size_t p, size_t l) : data(d), pos(p), lim(l), word(0) {
+        if (p < l) word = *reinterpret_cast<const uint32_t*>(data + (p & ~(size_t)3));
+    }
+    __device__ __forceinline__ uint32_t get() const { return (word >> (8 * (pos & 3))) & 0xffu; }
+    __device__ __forceinline__ void next() {
+        pos++;
+        if ((pos & 3) == 0 && pos < lim) word = *reinterpret_cast<const uint32_t*>(data + pos);
+    }
+};
+
+__device__ __forceinline__ size_t skip_leading_nuls(const uint8_t* data, size_t start, size_t lim) {
+    ByteCursor c(data, start, lim);
+    while (c.pos < lim && c.get() == 0) c.next();
+    return c.pos;
+}
+
+// simple mode: does any pattern match the block?
+__device__ bool block_matches(const DbView& db, const uint8_t* data, size_t start, size_t lim) {
+    size_t p0 = skip_leading_nuls(data, start, lim);
+    for (int g = 0; g < db.ngroups; g++) {
+        const GroupDev G = db.groups[g];
+        uint32_t s = 0;
+        bool dead = false;
+        ByteCursor c(data, p0, lim);
+        while (c.pos < lim) {
+            uint32_t b = c.get();
+            if (b == 0) break;
+            s = G.trans[s * G.stride + G.cls[b]];
+            if (s >= G.first_accept) return true;
+            if (s == G.dead) { dead = true; break; }
+            if (b == '\n') break;
+            c.next();
+        }
+        if (!dead) {
+            s = G.trans[s * G.stride + G.eod];
+            if (s >= G.first_accept) return true;
+        }
+    }
+    return false;
+}
+
+// general mode: count (out == nullptr) or write the reports of the block
+__device__ uint32_t block_events(const DbView& db, const uint8_t* data, size_t start, size_t lim, uint32_t line, uint32_t pl_start,
+                                 uint32_t pl_len, EventRec* out) {
+    size_t p0 = skip_leading_nuls(data, start, lim);
+    uint32_t k = 0;
+    for (int g = 0; g < db.ngroups; g++) {
+        const GroupDev G = db.groups[g];
+        uint32_t s = 0;
+        bool dead = false;
+        ByteCursor c(data, p0, lim);
+        while (c.pos < lim) {
+            uint32_t b = c.get();
+            if (b == 0) break;
+            s = G.trans[s * G.stride + G.cls[b]];
+            if (s >= G.first_accept) {
+                if (out) out[k] = EventRec{line, pl_start, pl_len, (uint32_t)(c.pos - p0), G.accept_base + G.accept_of[s]};
+                k++;
+            }
+            if (s == G.dead) { dead = true; break; }
+            c.next();
+            if (b == '\n') break;
+        }
+        if (!dead) {
+            s = G.trans[s * G.stride + G.eod];
+            if (s >= G.first_accept) {
+                if (out) out[k] = EventRec{line, pl_start, pl_len, (uint32_t)(c.pos - p0), G.accept_base + G.accept_of[s]};
+                k++;
+            }
+        }
+    }
+    return k;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// FAST PATH kernels
+// ------------------------------------------------------------------------------------------------------------
+// Flags segments that may contain a line too long for the fast path: an aligned super-block of `blocks_per_super`
+// 512-byte blocks without any newline.
+__global__ void k_check_long(const unsigned long long* __restrict__ prefix, size_t nblk, size_t blocks_per_super, const unsigned long long* meta_total,
+                             Totals* totals) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t lo = j * blocks_per_super, hi = lo + blocks_per_super;
+    if (hi > nblk) return;   // partial trailing super-block cannot hide a full one
+    uint32_t a = (uint32_t)prefix[lo];
+    uint32_t b = hi < nblk ? (uint32_t)prefix[hi] : (uint32_t)*meta_total;
+    if (a == b) atomicOr(&totals->flags, 1u);
+}
+
+// meta/prefix -> ordered list of candidate chunk indices
+__global__ void k_list_candidates(const unsigned long long* __restrict__ meta, const unsigned long long* __restrict__ prefix, size_t nblk,
+                                  uint32_t* __restrict__ cand, size_t cap, Totals* totals) {
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nblk) return;
+    uint32_t mask = (uint32_t)meta[g];
+    if (!mask) return;
+    size_t at = (size_t)(prefix[g] >> 32);
+    while (mask) {
+        int b = __ffs(mask) - 1;
+        mask &= mask - 1;
+        if (at < cap) cand[at] = (uint32_t)(g * 32 + b);
+        else { atomicOr(&totals->flags, 2u); return; }
+        at++;
+    }
+}
+
+// One thread per candidate chunk: verify every line that intersects the chunk; the line that starts before the
+// chunk is owned by the FIRST flagged chunk it intersects (exact de-duplication without sorting).
+__global__ void __launch_bounds__(128) k_verify_simple(DbView db, const uint8_t* __restrict__ data, size_t n, const unsigned long long* __restrict__ meta,
+                                                       const unsigned long long* __restrict__ prefix, const uint32_t* __restrict__ cand,
+                                                       const unsigned long long* meta_total, size_t cap, CandRes* __restrict__ res) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t ncand = (size_t)(*meta_total >> 32);
+    if (ncand > cap) ncand = cap;
+    if (i >= ncand) return;
+    const uint32_t c = cand[i];
+    const size_t o = (size_t)c * 16;
+    uint4 v = ld_chunk(data, o, n);
+    uint32_t nlm = newline_mask16(v);
+    if (o + 16 > n) nlm &= (1u << (n - o)) - 1u;
+    const size_t ls = line_start_of(data, o);
+    // ownership of the first line: no flagged chunk in [ls/16, c)
+    bool owned = true;
+    {
+        size_t c0 = ls >> 4;
+        if (c0 < c) {
+            for (size_t gb = c0 >> 5; gb <= ((size_t)c >> 5) && owned; gb++) {
+                uint32_t m = (uint32_t)meta[gb];
+                if (gb == (c0 >> 5)) m &= ~((1u << (c0 & 31)) - 1u);
+                if (gb == ((size_t)c >> 5)) m &= (1u << (c & 31)) - 1u;
+                if (m) owned = false;
+            }
+        }
+    }
+    const size_t lb = ls >> 9;
+    const uint32_t line_no = (uint32_t)prefix[lb] + count_newlines(data, lb << 9, ls);
+    uint32_t mask = 0;
+    if (owned && block_matches(db, data, ls, n)) mask |= 1u;
+    int j = 1;
+    uint32_t m = nlm;
+    while (m) {
+        int b = __ffs(m) - 1;
+        m &= m - 1;
+        size_t st = o + b + 1;
+        if (st >= n || st >= o + 16) break;
+        if (block_matches(db, data, st, n)) mask |= 1u << j;
+        j++;
+    }
+    res[i] = CandRes{line_no, (uint32_t)ls, mask};
+}
+
+__global__ void __launch_bounds__(128) k_emit_simple(const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
+                                                     const CandRes* __restrict__ res, const unsigned long long* __restrict__ recoff,
+                                                     const unsigned long long* meta_total, size_t cap, LineRec* __restrict__ recs, size_t rec_cap,
+                                                     Totals* totals) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t ncand = (size_t)(*meta_total >> 32);
+    if (ncand > cap) ncand = cap;
+    if (i >= ncand) return;
+    CandRes r = res[i];
+    if (!r.mask) return;
+    size_t at = (size_t)recoff[i];
+    const size_t o = (size_t)cand[i] * 16;
+    uint4 v = ld_chunk(data, o, n);
+    uint32_t nlm = newline_mask16(v);
+    if (o + 16 > n) nlm &= (1u << (n - o)) - 1u;
+    uint32_t mask = r.mask;
+    int j = 0;
+    size_t st = r.first_start;
+    while (true) {
+        if (mask & (1u << j)) {
+            size_t en = line_end_of(data, st, n);
+            if (at < rec_cap) recs[at] = LineRec{r.first_line + (uint32_t)j, (uint32_t)st, (uint32_t)(en - st)};
+            else atomicOr(&totals->flags, 4u);
+            at++;
+        }
+        if (!nlm) break;
+        int b = __ffs(nlm) - 1;
+        nlm &= nlm - 1;
+        st = o + b + 1;
+        j++;
+        if ((mask >> j) == 0) break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// GENERAL PATH kernels
+// ------------------------------------------------------------------------------------------------------------
+// warp per 512-byte block: write the offset of every '\n' at its global rank
+__global__ void __launch_bounds__(256) k_newline_positions(const uint8_t* __restrict__ data, size_t n, size_t nblk,
+                                                           const unsigned long long* __restrict__ prefix, uint32_t* __restrict__ nlpos) {
+    const int lane = threadIdx.x & 31;
+    size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= nblk) return;
+    size_t off = g * 512 + (size_t)lane * 16;
+    uint32_t m = 0;
+    if (off < n) {
+        uint4 v = ld_chunk(data, off, n);
+        m = newline_mask16(v);
+        if (off + 16 > n) m &= (1u << (n - off)) - 1u;
+    }
+    uint32_t cnt = __popc(m), incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    size_t at = (size_t)(uint32_t)prefix[g] + (incl - cnt);
+    while (m) {
+        int b = __ffs(m) - 1;
+        m &= m - 1;
+        nlpos[at++] = (uint32_t)(off + b);
+    }
+}
+
+__device__ __forceinline__ void line_extent(const uint32_t* nlpos, size_t nl_total, size_t n, size_t i, uint32_t& start, uint32_t& len) {
+    start = i ? nlpos[i - 1] + 1 : 0;
+    uint32_t end = i < nl_total ? nlpos[i] + 1 : (uint32_t)n;
+    len = end - start;
+}
+
+// pseudo-lines per line for a gzgets buffer of buffer_size (limit = buffer_size - 1 bytes per read)
+__global__ void k_count_pseudo_lines(const uint32_t* __restrict__ nlpos, size_t nl_total, size_t n, size_t nlines, uint32_t limit,
+                                     uint32_t* __restrict__ npl, Totals* totals) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlines) return;
+    uint32_t st, len;
+    line_extent(nlpos, nl_total, n, i, st, len);
+    npl[i] = (len + limit - 1) / limit;
+    if (len > limit) atomicMax(&totals->max_line, len);
+}
+
+__global__ void k_build_pseudo_lines(const uint32_t* __restrict__ nlpos, size_t nl_total, size_t n, size_t nlines, uint32_t limit,
+                                     const unsigned long long* __restrict__ ploff, uint32_t* __restrict__ pl_start, uint32_t* __restrict__ pl_len) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nlines) return;
+    uint32_t st, len;
+    line_extent(nlpos, nl_total, n, i, st, len);
+    size_t at = ploff ? (size_t)ploff[i] : i;
+    while (len > 0) {
+        uint32_t take = len < limit ? len : limit;
+        pl_start[at] = st;
+        pl_len[at] = take;
+        at++;
+        st += take;
+        len -= take;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_match_pl_simple(DbView db, const uint8_t* __restrict__ data, const uint32_t* __restrict__ pl_start,
+                                                         const uint32_t* __restrict__ pl_len, size_t npl, uint8_t* __restrict__ flags) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npl) return;
+    size_t st = pl_start[i];
+    flags[i] = block_matches(db, data, st, st + pl_len[i]) ? 1 : 0;
+}
+
+__global__ void k_emit_pl_simple(const uint32_t* __restrict__ pl_start, const uint32_t* __restrict__ pl_len, size_t npl, const uint8_t* __restrict__ flags,
+                                 const unsigned long long* __restrict__ off, LineRec* __restrict__ recs) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npl || !flags[i]) return;
+    recs[off[i]] = LineRec{(uint32_t)i, pl_start[i], pl_len[i]};
+}
+
+__global__ void __launch_bounds__(128) k_match_pl_events(DbView db, const uint8_t* __restrict__ data, const uint32_t* __restrict__ pl_start,
+                                                         const uint32_t* __restrict__ pl_len, size_t npl, uint32_t* __restrict__ counts,
+                                                         const unsigned long long* __restrict__ off, EventRec* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npl) return;
+    size_t st = pl_start[i];
+    uint32_t len = pl_len[i];
+    if (out) {
+        if (counts[i]) block_events(db, data, st, st + len, (uint32_t)i, (uint32_t)st, len, out + off[i]);
+    } else {
+        counts[i] = block_events(db, data, st, st + len, (uint32_t)i, (uint32_t)st, len, nullptr);
+    }
+}
+
+// warp per record: copy matched line bytes into a packed buffer (device-resident scans with a callback)
+__global__ void k_gather_lines(const uint8_t* __restrict__ data, const uint32_t* __restrict__ starts, const uint32_t* __restrict__ lens,
+                               const unsigned long long* __restrict__ outoff, size_t count, uint8_t* __restrict__ out) {
+    size_t r = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= count) return;
+    const uint8_t* src = data + starts[r];
+    uint8_t* dst = out + outoff[r];
+    uint32_t len = lens[r];
+    for (uint32_t k = lane; k < len; k += 32) dst[k] = src[k];
+    if (lane == 0) dst[len] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+};
+
+int g_device = -1;
+int g_num_sms = 148;
+std::mutex g_mu;
+
+}  // namespace
+
+struct DeviceDb {
+    std::shared_ptr<Database> db;
+    int device = 0;
+    std::vector<void*> allocs;
+    GroupDev* d_groups = nullptr;
+    int ngroups = 0;
+    uint32_t* d_bitmap = nullptr;
+    bool simple = false;
+    ~DeviceDb() { for (void* p : allocs) cudaFree(p); }
+};
+
+class ScanSlot {
+public:
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // 0/1: whole segment, 2/3: streaming kernel
+    DevBuf d_input, d_meta, d_prefix, d_sums, d_cand, d_res, d_recoff, d_recs, d_totals;
+    DevBuf d_nlpos, d_npl, d_ploff, d_plstart, d_pllen, d_flags, d_counts, d_events, d_gather, d_gidx;
+    PinBuf h_totals, h_recs, h_stage, h_gather;
+    // state of the in-flight segment
+    const DeviceDb* ddb = nullptr;
+    const uint8_t* data = nullptr;   // device pointer of the segment
+    size_t n = 0, nblk = 0, cand_cap = 0, rec_cap = 0;
+    int buffer_size = 0;
+    bool fast = false;
+    SegmentStats stats;
+    bool in_use = false;
+
+    int run_general(SegmentResult& out, std::string& error);
+};
+
+int engine_select_device(int device, std::string& error) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        error = std::string("no CUDA device available: ") + cudaGetErrorString(e) + " (libgpugrep has no CPU fallback)";
+        return 7;
+    }
+    if (device < 0 || device >= count) device = 0;
+    CUDA_TRY(cudaSetDevice(device));
+    if (g_device != device) {
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        g_num_sms = prop.multiProcessorCount;
+        g_device = device;
+    }
+    return 0;
+}
+
+int engine_current_device() { return g_device; }
+
+std::shared_ptr<DeviceDb> engine_upload(const std::shared_ptr<Database>& db, std::string& error) {
+    static std::mutex mu;
+    static std::vector<std::pair<std::weak_ptr<Database>, std::shared_ptr<DeviceDb>>> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (auto it = cache.begin(); it != cache.end();) {
+        auto sp = it->first.lock();
+        if (!sp) { it = cache.erase(it); continue; }
+        if (sp == db && it->second->device == dev) return it->second;
+        ++it;
+    }
+    auto out = std::make_shared<DeviceDb>();
+    out->db = db;
+    out->device = dev;
+    out->simple = db->simple;
+    auto upload = [&](const void* src, size_t bytes) -> void* {
+        void* p = nullptr;
+        if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) return nullptr;
+        out->allocs.push_back(p);
+        if (bytes && cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+        return p;
+    };
+    std::vector<GroupDev> groups;
+    for (size_t g = 0; g < db->groups.size(); g++) {
+        const Dfa& d = db->groups[g].dfa;
+        if (d.num_states > 65536) { error = "DFA group exceeds 65536 states"; return nullptr; }
+        std::vector<uint16_t> t16(d.trans.size());
+        for (size_t k = 0; k < d.trans.size(); k++) t16[k] = (uint16_t)d.trans[k];
+        GroupDev G{};
+        G.trans = (const uint16_t*)upload(t16.data(), t16.size() * sizeof(uint16_t));
+        G.cls = (const uint8_t*)upload(d.byte_class, 256);
+        G.accept_of = (const uint32_t*)upload(d.accept_of.data(), d.accept_of.size() * sizeof(uint32_t));
+        if (!G.trans || !G.cls || !G.accept_of) { error = "cudaMalloc/cudaMemcpy failed while uploading DFA tables"; return nullptr; }
+        G.stride = (uint32_t)d.stride;
+        G.eod = (uint32_t)d.num_classes;
+        G.first_accept = (uint32_t)d.first_accept;
+        G.dead = d.dead >= 0 ? (uint32_t)d.dead : 0xffffffffu;
+        G.accept_base = db->report_begin.empty() ? 0u : 0u;
+        groups.push_back(G);
+    }
+    // accept_base: flattened index of (group, accept set) = sum of accept-set counts of earlier groups
+    uint32_t base = 0;
+    for (size_t g = 0; g < groups.size(); g++) {
+        groups[g].accept_base = base;
+        base += (uint32_t)db->groups[g].dfa.accept_sets.size();
+    }
+    out->d_groups = (GroupDev*)upload(groups.data(), groups.size() * sizeof(GroupDev));
+    out->ngroups = (int)groups.size();
+    if (!out->d_groups) { error = "cudaMalloc failed for group table"; return nullptr; }
+    if (db->prefilter.enabled) {
+        out->d_bitmap = (uint32_t*)upload(db->prefilter.bitmap.data(), db->prefilter.bitmap.size() * sizeof(uint32_t));
+        if (!out->d_bitmap) { error = "cudaMalloc failed for prefilter bitmap"; return nullptr; }
+    }
+    cache.emplace_back(db, out);
+    if (cache.size() > 8) cache.erase(cache.begin());
+    return out;
+}
+
+namespace {
+std::vector<ScanSlot*> g_free_slots;
+}
+
+ScanSlot* engine_acquire_slot(std::string& error) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { error = "cudaGetDevice failed"; return nullptr; }
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        for (size_t i = 0; i < g_free_slots.size(); i++) {
+            if (g_free_slots[i]->device == dev) {
+                ScanSlot* s = g_free_slots[i];
+                g_free_slots.erase(g_free_slots.begin() + i);
+                s->in_use = true;
+                return s;
+            }
+        }
+    }
+    ScanSlot* s = new ScanSlot();
+    s->device = dev;
+    if (cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess) { error = "cudaStreamCreate failed"; delete s; return nullptr; }
+    for (auto& e : s->ev) if (cudaEventCreate(&e) != cudaSuccess) { error = "cudaEventCreate failed"; delete s; return nullptr; }
+    if (s->d_totals.reserve(sizeof(Totals)) != cudaSuccess || s->h_totals.reserve(sizeof(Totals)) != cudaSuccess) {
+        error = "scratch allocation failed"; delete s; return nullptr;
+    }
+    s->in_use = true;
+    return s;
+}
+
+void engine_release_slot(ScanSlot* slot) {
+    if (!slot) return;
+    slot->in_use = false;
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_free_slots.push_back(slot);
+}
+
+uint8_t* slot_host_buffer(ScanSlot* slot, size_t capacity, std::string& error) {
+    if (slot->h_stage.reserve(capacity + 64) != cudaSuccess) { error = "cudaHostAlloc failed for the staging buffer"; return nullptr; }
+    return slot->h_stage.as<uint8_t>();
+}
+
+template <class Load>
+static void launch_scan(cudaStream_t st, Load load, size_t n, unsigned long long* out, unsigned long long* sums, unsigned long long* total,
+                        SegmentStats& stats) {
+    size_t nb = (n + kScanTile - 1) / kScanTile;
+    if (nb == 0) nb = 1;
+    k_scan_sums<Load><<<(unsigned)nb, kScanThreads, 0, st>>>(load, n, sums);
+    k_scan_top<<<1, 1024, 0, st>>>(sums, nb, total);
+    k_scan_write<Load><<<(unsigned)nb, kScanThreads, 0, st>>>(load, n, sums, out);
+    stats.launches += 3;
+}
+
+template <int STRIDE, bool FOLD>
+static cudaError_t launch_stream(cudaStream_t st, int grid, size_t smem, const uint8_t* data, size_t n, size_t nblk, unsigned long long* meta,
+                                 const uint32_t* bitmap, int log2_bits, uint32_t mul) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_stream<STRIDE, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    k_stream<STRIDE, FOLD><<<grid, 256, smem, st>>>(data, n, nblk, meta, bitmap, log2_bits, mul);
+    return cudaGetLastError();
+}
+
+int slot_submit(ScanSlot* s, const DeviceDb& ddb, const uint8_t* host_data, const uint8_t* dev_data, size_t n, int buffer_size,
+                void* user_stream, std::string& error) {
+    if (n >= ((size_t)1 << 32) - 1024) { error = "segment too large"; return 7; }
+    s->stream = user_stream ? (cudaStream_t)user_stream : s->own_stream;
+    cudaStream_t st = s->stream;
+    s->ddb = &ddb;
+    s->n = n;
+    s->buffer_size = buffer_size;
+    s->stats = SegmentStats();
+    s->nblk = (n + 511) / 512;
+    const Prefilter& pf = ddb.db->prefilter;
+    // fast path: simple mode + prefilter + buffer large enough that "a super-block without newline" is a cheap
+    // sufficient test for "no line needs gzgets splitting"
+    size_t super_bytes = 0;
+    if (buffer_size >= 1024) {
+        super_bytes = 512;
+        while (super_bytes * 4 <= (size_t)buffer_size && super_bytes < 65536) super_bytes *= 2;   // 2*super-1 <= buffer_size-1
+    }
+    s->fast = ddb.simple && pf.enabled && super_bytes >= 512 && std::getenv("GPUGREP_FORCE_GENERAL") == nullptr;
+
+    if (host_data) {
+        if (s->d_input.reserve(n + 1024) != cudaSuccess) { error = "cudaMalloc failed for the input segment"; return 3; }
+        CUDA_TRY(cudaMemcpyAsync(s->d_input.p, host_data, n, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemsetAsync(s->d_input.as<uint8_t>() + n, 0, 1024, st));
+        s->data = s->d_input.as<uint8_t>();
+        s->stats.h2d_bytes += n;
+    } else {
+        if (((uintptr_t)dev_data & 15) != 0) { error = "device buffers must be 16-byte aligned"; return 7; }
+        s->data = dev_data;
+    }
+    s->cand_cap = n / 64 + 4096;
+    s->rec_cap = n / 48 + 4096;
+    size_t nb_scan = (std::max(s->nblk, s->cand_cap) + kScanTile - 1) / kScanTile + 1;
+    if (s->d_meta.reserve((s->nblk + 8) * 8) != cudaSuccess || s->d_prefix.reserve((s->nblk + 8) * 8) != cudaSuccess ||
+        s->d_sums.reserve(nb_scan * 8) != cudaSuccess) { error = "cudaMalloc failed for scan scratch"; return 3; }
+    if (s->fast) {
+        if (s->d_cand.reserve(s->cand_cap * 4) != cudaSuccess || s->d_res.reserve(s->cand_cap * sizeof(CandRes)) != cudaSuccess ||
+            s->d_recoff.reserve(s->cand_cap * 8) != cudaSuccess || s->d_recs.reserve(s->rec_cap * sizeof(LineRec)) != cudaSuccess) {
+            error = "cudaMalloc failed for candidate scratch"; return 3;
+        }
+    }
+    Totals* dT = s->d_totals.as<Totals>();
+    CUDA_TRY(cudaMemsetAsync(dT, 0, sizeof(Totals), st));
+    CUDA_TRY(cudaEventRecord(s->ev[0], st));
+    if (n == 0) {
+        CUDA_TRY(cudaEventRecord(s->ev[1], st));
+        return 0;
+    }
+    // ---- K1 ----
+    int grid = g_num_sms * 8;
+    size_t max_grid = (s->nblk + 31) / 32;   // 8 warps x 4 blocks per CTA step
+    if ((size_t)grid > max_grid) grid = (int)std::max<size_t>(1, max_grid);
+    unsigned long long* meta = s->d_meta.as<unsigned long long>();
+    CUDA_TRY(cudaEventRecord(s->ev[2], st));
+    cudaError_t le;
+    if (s->fast) {
+        size_t smem = ((size_t)1 << pf.log2_bits) / 8;
+        if (smem > 64 * 1024) grid = g_num_sms * (smem > 100 * 1024 ? 1 : 2);
+        if ((size_t)grid > max_grid) grid = (int)std::max<size_t>(1, max_grid);
+        int key = pf.stride * 2 + (pf.fold_case ? 1 : 0);
+        switch (key) {
+            case 8: le = launch_stream<4, false>(st, grid, smem, s->data, n, s->nblk, meta, ddb.d_bitmap, pf.log2_bits, pf.hash_mul); break;
+            case 9: le = launch_stream<4, true>(st, grid, smem, s->data, n, s->nblk, meta, ddb.d_bitmap, pf.log2_bits, pf.hash_mul); break;
+            case 4: le = launch_stream<2, false>(st, grid, smem, s->data, n, s->nblk, meta, ddb.d_bitmap, pf.log2_bits, pf.hash_mul); break;
+            case 5: le = launch_stream<2, true>(st, grid, smem, s->data, n, s->nblk, meta, ddb.d_bitmap, pf.log2_bits, pf.hash_mul); break;
+            case 2: le = launch_stream<1, false>(st, grid, smem, s->data, n, s->nblk, meta, ddb.d_bitmap, pf.log2_bits, pf.hash_mul); break;
+            default: le = launch_stream<1, true>(st, grid, smem, s->data, n, s->nblk, meta, ddb.d_bitmap, pf.log2_bits, pf.hash_mul); break;
+        }
+    } else {
+        le = launch_stream<0, false>(st, grid, 0, s->data, n, s->nblk, meta, nullptr, 13, 0);
+    }
+    if (le != cudaSuccess) { error = std::string("k_stream launch: ") + cudaGetErrorString(le); return 7; }
+    CUDA_TRY(cudaEventRecord(s->ev[3], st));
+    s->stats.launches++;
+    s->stats.stream_launches++;
+    // ---- scan of (candidates, newlines) ----
+    unsigned long long* prefix = s->d_prefix.as<unsigned long long>();
+    launch_scan(st, LoadMeta{meta}, s->nblk, prefix, s->d_sums.as<unsigned long long>(), &dT->meta_total, s->stats);
+    if (s->fast) {
+        size_t bps = super_bytes / 512;
+        size_t nsuper = s->nblk / bps;
+        if (nsuper) {
+            k_check_long<<<(unsigned)((nsuper + 255) / 256), 256, 0, st>>>(prefix, s->nblk, bps, &dT->meta_total, dT);
+            s->stats.launches++;
+        }
+        k_list_candidates<<<(unsigned)((s->nblk + 255) / 256), 256, 0, st>>>(meta, prefix, s->nblk, s->d_cand.as<uint32_t>(), s->cand_cap, dT);
+        DbView view{ddb.d_groups, ddb.ngroups};
+        unsigned vgrid = (unsigned)((s->cand_cap + 127) / 128);
+        k_verify_simple<<<vgrid, 128, 0, st>>>(view, s->data, n, meta, prefix, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap,
+                                               s->d_res.as<CandRes>());
+        launch_scan(st, LoadResMask{s->d_res.as<CandRes>(), &dT->meta_total, s->cand_cap}, s->cand_cap, s->d_recoff.as<unsigned long long>(),
+                    s->d_sums.as<unsigned long long>(), &dT->rec_total, s->stats);
+        k_emit_simple<<<vgrid, 128, 0, st>>>(s->data, n, s->d_cand.as<uint32_t>(), s->d_res.as<CandRes>(), s->d_recoff.as<unsigned long long>(),
+                                             &dT->meta_total, s->cand_cap, s->d_recs.as<LineRec>(), s->rec_cap, dT);
+        s->stats.launches += 3;
+        CUDA_TRY(cudaEventRecord(s->ev[1], st));
+    }
+    CUDA_TRY(cudaMemcpyAsync(&dT->last_byte, s->data + n - 1, 1, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s->h_totals.p, dT, sizeof(Totals), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int ScanSlot::run_general(SegmentResult& out, std::string& error) {
+    cudaStream_t st = stream;
+    Totals* dT = d_totals.as<Totals>();
+    Totals* hT = h_totals.as<Totals>();
+    stats.path |= 2;
+    const size_t nl_total = (size_t)(uint32_t)hT->meta_total;
+    const bool trailing = n > 0 && (hT->last_byte & 0xff) != '\n';
+    const size_t nlines = nl_total + (trailing ? 1 : 0);
+    unsigned long long* prefix = d_prefix.as<unsigned long long>();
+    if (d_nlpos.reserve((nl_total + 1) * 4) != cudaSuccess) { error = "cudaMalloc failed for newline index"; return 3; }
+    if (nblk) {
+        k_newline_positions<<<(unsigned)((nblk * 32 + 255) / 256), 256, 0, st>>>(data, n, nblk, prefix, d_nlpos.as<uint32_t>());
+        stats.launches++;
+    }
+    const uint32_t limit = (uint32_t)std::max(1, buffer_size - 1);
+    size_t npl_total = nlines;
+    bool split = false;
+    if (nlines) {
+        if (d_npl.reserve(nlines * 4) != cudaSuccess) { error = "cudaMalloc failed"; return 3; }
+        k_count_pseudo_lines<<<(unsigned)((nlines + 255) / 256), 256, 0, st>>>(d_nlpos.as<uint32_t>(), nl_total, n, nlines, limit, d_npl.as<uint32_t>(), dT);
+        stats.launches++;
+        CUDA_TRY(cudaMemcpyAsync(hT, dT, sizeof(Totals), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        split = hT->max_line > limit;
+        if (split) {
+            size_t nb_scan = (nlines + kScanTile - 1) / kScanTile + 1;
+            if (d_ploff.reserve(nlines * 8) != cudaSuccess || d_sums.reserve(nb_scan * 8) != cudaSuccess) { error = "cudaMalloc failed"; return 3; }
+            launch_scan(st, LoadU32{d_npl.as<uint32_t>()}, nlines, d_ploff.as<unsigned long long>(), d_sums.as<unsigned long long>(), &dT->aux_total, stats);
+            CUDA_TRY(cudaMemcpyAsync(hT, dT, sizeof(Totals), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            npl_total = (size_t)hT->aux_total;
+        }
+        if (d_plstart.reserve(npl_total * 4) != cudaSuccess || d_pllen.reserve(npl_total * 4) != cudaSuccess) { error = "cudaMalloc failed"; return 3; }
+        k_build_pseudo_lines<<<(unsigned)((nlines + 255) / 256), 256, 0, st>>>(d_nlpos.as<uint32_t>(), nl_total, n, nlines, limit,
+                                                                                 split ? d_ploff.as<unsigned long long>() : nullptr,
+                                                                                 d_plstart.as<uint32_t>(), d_pllen.as<uint32_t>());
+        stats.launches++;
+    }
+    out.num_lines = npl_total;
+    out.lines = nullptr; out.num_line_recs = 0; out.events = nullptr; out.num_events = 0;
+    if (npl_total == 0) {
+        CUDA_TRY(cudaEventRecord(ev[1], st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return 0;
+    }
+    DbView view{ddb->d_groups, ddb->ngroups};
+    size_t nb_scan = (npl_total + kScanTile - 1) / kScanTile + 1;
+    if (d_sums.reserve(nb_scan * 8) != cudaSuccess || d_recoff.reserve(npl_total * 8) != cudaSuccess) { error = "cudaMalloc failed"; return 3; }
+    unsigned mgrid = (unsigned)((npl_total + 127) / 128);
+    if (ddb->simple) {
+        if (d_flags.reserve(npl_total) != cudaSuccess) { error = "cudaMalloc failed"; return 3; }
+        k_match_pl_simple<<<mgrid, 128, 0, st>>>(view, data, d_plstart.as<uint32_t>(), d_pllen.as<uint32_t>(), npl_total, d_flags.as<uint8_t>());
+        stats.launches++;
+        launch_scan(st, LoadU8{d_flags.as<uint8_t>()}, npl_total, d_recoff.as<unsigned long long>(), d_sums.as<unsigned long long>(), &dT->rec_total, stats);
+        CUDA_TRY(cudaMemcpyAsync(hT, dT, sizeof(Totals), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        size_t nrec = (size_t)hT->rec_total;
+        if (nrec) {
+            if (d_recs.reserve(nrec * sizeof(LineRec)) != cudaSuccess) { error = "cudaMalloc failed"; return 3; }
+            if (h_recs.reserve(nrec * sizeof(LineRec)) != cudaSuccess) { error = "cudaHostAlloc failed"; return 3; }
+            k_emit_pl_simple<<<(unsigned)((npl_total + 255) / 256), 256, 0, st>>>(d_plstart.as<uint32_t>(), d_pllen.as<uint32_t>(), npl_total,
+                                                                                    d_flags.as<uint8_t>(), d_recoff.as<unsigned long long>(), d_recs.as<LineRec>());
+            stats.launches++;
+            CUDA_TRY(cudaEventRecord(ev[1], st));
+            CUDA_TRY(cudaMemcpyAsync(h_recs.p, d_recs.p, nrec * sizeof(LineRec), cudaMemcpyDeviceToHost, st));
+            stats.d2h_bytes += nrec * sizeof(LineRec);
+        } else {
+            CUDA_TRY(cudaEventRecord(ev[1], st));
+        }
+        CUDA_TRY(cudaStreamSynchronize(st));
+        out.lines = h_recs.as<LineRec>();
+        out.num_line_recs = nrec;
+    } else {
+        if (d_counts.reserve(npl_total * 4) != cudaSuccess) { error = "cudaMalloc failed"; return 3; }
+        k_match_pl_events<<<mgrid, 128, 0, st>>>(view, data, d_plstart.as<uint32_t>(), d_pllen.as<uint32_t>(), npl_total, d_counts.as<uint32_t>(), nullptr, nullptr);
+        stats.launches++;
+        launch_scan(st, LoadU32{d_counts.as<uint32_t>()}, npl_total, d_recoff.as<unsigned long long>(), d_sums.as<unsigned long long>(), &dT->rec_total, stats);
+        CUDA_TRY(cudaMemcpyAsync(hT, dT, sizeof(Totals), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        size_t nev = (size_t)hT->rec_total;
+        if (nev > ((size_t)1 << 27)) { error = "too many match events in one segment (non-SINGLEMATCH pattern matching nearly every byte?)"; return 7; }
+        if (nev) {
+            if (d_events.reserve(nev * sizeof(EventRec)) != cudaSuccess) { error = "cudaMalloc failed"; return 3; }
+            if (h_recs.reserve(nev * sizeof(EventRec)) != cudaSuccess) { error = "cudaHostAlloc failed"; return 3; }
+            k_match_pl_events<<<mgrid, 128, 0, st>>>(view, data, d_plstart.as<uint32_t>(), d_pllen.as<uint32_t>(), npl_total, d_counts.as<uint32_t>(),
+                                                     d_recoff.as<unsigned long long>(), d_events.as<EventRec>());
+            stats.launches++;
+            CUDA_TRY(cudaEventRecord(ev[1], st));
+            CUDA_TRY(cudaMemcpyAsync(h_recs.p, d_events.p, nev * sizeof(EventRec), cudaMemcpyDeviceToHost, st));
+            stats.d2h_bytes += nev * sizeof(EventRec);
+        } else {
+            CUDA_TRY(cudaEventRecord(ev[1], st));
+        }
+        CUDA_TRY(cudaStreamSynchronize(st));
+        out.events = h_recs.as<EventRec>();
+        out.num_events = nev;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int slot_collect(ScanSlot* s, SegmentResult& out, std::string& error) {
+    cudaStream_t st = s->stream;
+    out = SegmentResult();
+    CUDA_TRY(cudaStreamSynchronize(st));
+    s->stats.d2h_bytes += sizeof(Totals);
+    if (s->n == 0) { out.stats = s->stats; return 0; }
+    Totals* hT = s->h_totals.as<Totals>();
+    bool done = false;
+    if (s->fast) {
+        s->stats.candidates = hT->meta_total >> 32;
+        if (hT->flags == 0) {
+            s->stats.path |= 1;
+            size_t nrec = (size_t)hT->rec_total;
+            const size_t nl_total = (size_t)(uint32_t)hT->meta_total;
+            out.num_lines = nl_total + ((hT->last_byte & 0xff) != '\n' ? 1 : 0);
+            if (nrec) {
+                if (s->h_recs.reserve(nrec * sizeof(LineRec)) != cudaSuccess) { error = "cudaHostAlloc failed"; return 3; }
+                CUDA_TRY(cudaMemcpyAsync(s->h_recs.p, s->d_recs.p, nrec * sizeof(LineRec), cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                s->stats.d2h_bytes += nrec * sizeof(LineRec);
+            }
+            out.lines = s->h_recs.as<LineRec>();
+            out.num_line_recs = nrec;
+            done = true;
+        }
+    }
+    if (!done) {
+        int rc = s->run_general(out, error);
+        if (rc) return rc;
+    }
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]) == cudaSuccess) s->stats.gpu_ms = ms;
+    if (cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]) == cudaSuccess) s->stats.stream_ms = ms;
+    out.stats = s->stats;
+    return 0;
+}
+
+int slot_gather_lines(ScanSlot* s, const uint32_t* starts, const uint32_t* lens, size_t count, uint8_t* out, std::string& error) {
+    if (count == 0) return 0;
+    cudaStream_t st = s->stream;
+    // offsets on the host (small), then one gather kernel and one D2H
+    std::vector<unsigned long long> off(count);
+    unsigned long long total = 0;
+    for (size_t i = 0; i < count; i++) { off[i] = total; total += (unsigned long long)lens[i] + 1; }
+    if (s->d_gidx.reserve(count * 16) != cudaSuccess || s->d_gather.reserve(total) != cudaSuccess || s->h_gather.reserve(total) != cudaSuccess) {
+        error = "allocation failed in gather"; return 3;
+    }
+    uint32_t* d_starts = s->d_gidx.as<uint32_t>();
+    uint32_t* d_lens = d_starts + count;
+    unsigned long long* d_off = reinterpret_cast<unsigned long long*>(d_starts + 2 * count);
+    CUDA_TRY(cudaMemcpyAsync(d_starts, starts, count * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_lens, lens, count * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_off, off.data(), count * 8, cudaMemcpyHostToDevice, st));
+    k_gather_lines<<<(unsigned)((count * 32 + 255) / 256), 256, 0, st>>>(s->data, d_starts, d_lens, d_off, count, s->d_gather.as<uint8_t>());
+    CUDA_TRY(cudaMemcpyAsync(s->h_gather.p, s->d_gather.p, total, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    std::memcpy(out, s->h_gather.p, total);
+    s->stats.launches++;
+    s->stats.d2h_bytes += total;
+    return 0;
+}
+
+}  // namespace gpugrep

@@ -1,0 +1,76 @@
+// CUDA engine interface (host side).  The kernels replace the reference's per-line loop
+// gzgets -> hs_scan -> hs_callback (reference hyperscanner.c:198-226, 83-102) for one device-resident segment
+// of (decompressed) file bytes that starts at a pseudo-line start and ends at a pseudo-line end.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <memory>
+#include <string>
+
+#include "database.hpp"
+
+namespace gpugrep {
+
+// One matched pseudo-line (simple mode: every pattern SINGLEMATCH, one shared id).
+struct LineRec {
+    uint32_t line;    // pseudo-line index inside the segment
+    uint32_t start;   // byte offset of the pseudo-line inside the segment
+    uint32_t len;     // bytes, trailing '\n' included when present
+};
+
+// One automaton report (general mode): some accept set fired at `end` inside pseudo-line `line`.
+struct EventRec {
+    uint32_t line, start, len;
+    uint32_t end;      // match end offset relative to the scanned block (after leading-NUL stripping)
+    uint32_t report;   // index into Database::report_begin flattened over groups (DeviceDb::accept_base)
+};
+
+struct SegmentStats {
+    double gpu_ms = 0, stream_ms = 0;
+    unsigned launches = 0, stream_launches = 0;
+    unsigned long long candidates = 0;
+    unsigned long long h2d_bytes = 0, d2h_bytes = 0;
+    unsigned path = 0;   // bit0 fast path, bit1 general path
+};
+
+struct SegmentResult {
+    uint64_t num_lines = 0;        // pseudo-lines in the segment
+    const LineRec* lines = nullptr;   // simple mode, file order (pinned host memory owned by the slot)
+    size_t num_line_recs = 0;
+    const EventRec* events = nullptr; // general mode, grouped by line in file order
+    size_t num_events = 0;
+    SegmentStats stats;
+};
+
+struct DeviceDb;   // device-resident tables of one Database on one device
+class ScanSlot;    // stream + scratch + pinned result buffers for one in-flight segment
+
+// All functions return 0 or a reference return code (3 = scratch allocation, 7 = CUDA failure) and set `error`.
+int engine_select_device(int device, std::string& error);
+int engine_current_device();
+
+std::shared_ptr<DeviceDb> engine_upload(const std::shared_ptr<Database>& db, std::string& error);
+
+ScanSlot* engine_acquire_slot(std::string& error);   // pooled per device; never returns a slot in use
+void engine_release_slot(ScanSlot* slot);
+
+// Pinned staging buffer of the slot (grow-only); used by host ingest to read file bytes into.
+uint8_t* slot_host_buffer(ScanSlot* slot, size_t capacity, std::string& error);
+
+// Enqueue the scan of one segment.  Exactly one of host_data / dev_data is non-null.
+//  host_data: host memory (pinned => direct H2D; pageable => cudaMemcpyAsync stages it), n bytes.
+//  dev_data : device pointer, 16-byte aligned, n bytes, stays valid until slot_collect returns.
+//  user_stream: optional cudaStream_t to run on instead of the slot's own stream.
+int slot_submit(ScanSlot* slot, const DeviceDb& ddb, const uint8_t* host_data, const uint8_t* dev_data, size_t n,
+                int buffer_size, void* user_stream, std::string& error);
+// Wait for the segment and expose its results (valid until the next slot_submit on this slot).
+int slot_collect(ScanSlot* slot, SegmentResult& out, std::string& error);
+
+// Copy the bytes of matched lines to the host when the input lives only on the device (device-resident scans
+// with a callback).  `recs` are LineRec-like (start,len) pairs already on the host; out must hold sum(len)+count.
+int slot_gather_lines(ScanSlot* slot, const uint32_t* starts, const uint32_t* lens, size_t count, uint8_t* out,
+                      std::string& error);
+
+constexpr size_t kMaxSegmentBytes = (size_t)1 << 30;
+
+}  // namespace gpugrep

@@ -1,0 +1,219 @@
+// Host ingest implementations.  See ingest.hpp.
+#include "ingest.hpp"
+
+#include <dlfcn.h>
+#include <fcntl.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <cerrno>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace gpugrep {
+namespace {
+
+std::mutex g_zstd_mu;
+std::string g_zstd_path = "libzstd.so.1";
+
+// raw file with a small look-ahead buffer
+class RawFile {
+public:
+    explicit RawFile(int fd) : fd_(fd) {}
+    ~RawFile() { if (fd_ >= 0) ::close(fd_); }
+    size_t read(uint8_t* dst, size_t cap) {
+        size_t got = 0;
+        while (got < cap) {
+            ssize_t r = ::read(fd_, dst + got, cap - got);
+            if (r < 0) { if (errno == EINTR) continue; break; }   // EISDIR etc: end of data (zlib's gzgets returns NULL)
+            if (r == 0) break;
+            got += (size_t)r;
+        }
+        return got;
+    }
+private:
+    int fd_;
+};
+
+class PlainSource : public ByteSource {
+public:
+    PlainSource(std::unique_ptr<RawFile> f, const uint8_t* head, size_t head_len) : f_(std::move(f)), head_(head, head + head_len) {}
+    size_t read(uint8_t* dst, size_t cap) override {
+        size_t got = 0;
+        if (head_pos_ < head_.size()) {
+            got = std::min(cap, head_.size() - head_pos_);
+            std::memcpy(dst, head_.data() + head_pos_, got);
+            head_pos_ += got;
+        }
+        if (got < cap) got += f_->read(dst + got, cap - got);
+        return got;
+    }
+    const char* kind() const override { return "plain"; }
+private:
+    std::unique_ptr<RawFile> f_;
+    std::vector<uint8_t> head_;
+    size_t head_pos_ = 0;
+};
+
+// gzip members back to back; anything after the last member that is not another gzip header is ignored (zlib)
+class GzipSource : public ByteSource {
+public:
+    GzipSource(std::unique_ptr<RawFile> f, const uint8_t* head, size_t head_len) : f_(std::move(f)), in_(1 << 20) {
+        std::memcpy(in_.data(), head, head_len);
+        avail_ = head_len;
+        std::memset(&zs_, 0, sizeof(zs_));
+        ok_ = inflateInit2(&zs_, 15 + 16) == Z_OK;   // gzip wrapper
+    }
+    ~GzipSource() override { if (ok_) inflateEnd(&zs_); }
+    size_t read(uint8_t* dst, size_t cap) override {
+        if (!ok_ || done_) return 0;
+        size_t produced = 0;
+        while (produced < cap) {
+            if (avail_ == 0) {
+                pos_ = 0;
+                avail_ = f_->read(in_.data(), in_.size());
+                if (avail_ == 0) { done_ = true; break; }
+            }
+            if (need_header_check_) {
+                // between members: another gzip header continues the stream, anything else is trailing garbage
+                if (avail_ < 2) {
+                    // pull more so that two bytes can be inspected
+                    std::memmove(in_.data(), in_.data() + pos_, avail_);
+                    pos_ = 0;
+                    size_t more = f_->read(in_.data() + avail_, in_.size() - avail_);
+                    avail_ += more;
+                    if (avail_ < 2) { done_ = true; break; }
+                }
+                if (!(in_[pos_] == 0x1f && in_[pos_ + 1] == 0x8b)) { done_ = true; break; }
+                inflateReset(&zs_);
+                need_header_check_ = false;
+            }
+            zs_.next_in = in_.data() + pos_;
+            zs_.avail_in = (uInt)std::min<size_t>(avail_, 1u << 30);
+            zs_.next_out = dst + produced;
+            zs_.avail_out = (uInt)std::min<size_t>(cap - produced, 1u << 30);
+            uInt in_before = zs_.avail_in, out_before = zs_.avail_out;
+            int rc = inflate(&zs_, Z_NO_FLUSH);
+            size_t used = in_before - zs_.avail_in;
+            pos_ += used; avail_ -= used;
+            produced += out_before - zs_.avail_out;
+            if (rc == Z_STREAM_END) { need_header_check_ = true; continue; }
+            if (rc != Z_OK && rc != Z_BUF_ERROR) { done_ = true; break; }   // corrupt data: stop, keep what was decoded
+            if (rc == Z_BUF_ERROR && used == 0 && out_before == zs_.avail_out && avail_ > 0) { done_ = true; break; }
+        }
+        return produced;
+    }
+    const char* kind() const override { return "gzip"; }
+private:
+    std::unique_ptr<RawFile> f_;
+    std::vector<uint8_t> in_;
+    size_t pos_ = 0, avail_ = 0;
+    z_stream zs_;
+    bool ok_ = false, done_ = false, need_header_check_ = false;
+};
+
+// zstd through dlopen (the image ships libzstd.so.1 without headers); frames back to back
+struct ZstdApi {
+    void* handle = nullptr;
+    void* (*create)() = nullptr;
+    size_t (*free_ds)(void*) = nullptr;
+    size_t (*decompress)(void*, void*, void*) = nullptr;
+    unsigned (*is_error)(size_t) = nullptr;
+    bool load() {
+        std::lock_guard<std::mutex> lk(g_zstd_mu);
+        if (handle) return true;
+        void* h = dlopen(g_zstd_path.c_str(), RTLD_NOW);
+        if (!h) h = dlopen("libzstd.so.1", RTLD_NOW);
+        if (!h) return false;
+        create = (void* (*)())dlsym(h, "ZSTD_createDStream");
+        free_ds = (size_t (*)(void*))dlsym(h, "ZSTD_freeDStream");
+        decompress = (size_t (*)(void*, void*, void*))dlsym(h, "ZSTD_decompressStream");
+        is_error = (unsigned (*)(size_t))dlsym(h, "ZSTD_isError");
+        if (!create || !free_ds || !decompress || !is_error) return false;
+        handle = h;
+        return true;
+    }
+};
+ZstdApi g_zstd;
+
+class ZstdSource : public ByteSource {
+    struct InBuf { const void* src; size_t size; size_t pos; };
+    struct OutBuf { void* dst; size_t size; size_t pos; };
+public:
+    ZstdSource(std::unique_ptr<RawFile> f, const uint8_t* head, size_t head_len) : f_(std::move(f)), in_(1 << 20) {
+        std::memcpy(in_.data(), head, head_len);
+        avail_ = head_len;
+        ds_ = g_zstd.create();
+    }
+    ~ZstdSource() override { if (ds_) g_zstd.free_ds(ds_); }
+    size_t read(uint8_t* dst, size_t cap) override {
+        if (!ds_ || done_) return 0;
+        size_t produced = 0;
+        while (produced < cap) {
+            if (avail_ == 0) {
+                pos_ = 0;
+                avail_ = f_->read(in_.data(), in_.size());
+                if (avail_ == 0) { done_ = true; break; }
+            }
+            if (frame_done_) {
+                if (avail_ < 4) {
+                    std::memmove(in_.data(), in_.data() + pos_, avail_);
+                    pos_ = 0;
+                    avail_ += f_->read(in_.data() + avail_, in_.size() - avail_);
+                    if (avail_ < 4) { done_ = true; break; }
+                }
+                const uint8_t* p = in_.data() + pos_;
+                bool zstd_frame = p[0] == 0x28 && p[1] == 0xb5 && p[2] == 0x2f && p[3] == 0xfd;
+                bool skippable = (p[0] & 0xf0) == 0x50 && p[1] == 0x2a && p[2] == 0x4d && p[3] == 0x18;
+                if (!zstd_frame && !skippable) { done_ = true; break; }
+                frame_done_ = false;
+            }
+            InBuf ib{in_.data() + pos_, avail_, 0};
+            OutBuf ob{dst + produced, cap - produced, 0};
+            size_t rc = g_zstd.decompress(ds_, &ob, &ib);
+            pos_ += ib.pos; avail_ -= ib.pos;
+            produced += ob.pos;
+            if (g_zstd.is_error(rc)) { done_ = true; break; }
+            if (rc == 0) frame_done_ = true;
+            if (ib.pos == 0 && ob.pos == 0 && rc != 0 && avail_ > 0 && produced < cap) { done_ = true; break; }
+        }
+        return produced;
+    }
+    const char* kind() const override { return "zstd"; }
+private:
+    std::unique_ptr<RawFile> f_;
+    std::vector<uint8_t> in_;
+    size_t pos_ = 0, avail_ = 0;
+    void* ds_ = nullptr;
+    bool done_ = false, frame_done_ = false;
+};
+
+}  // namespace
+
+void set_zstd_library_path(const std::string& path) {
+    std::lock_guard<std::mutex> lk(g_zstd_mu);
+    g_zstd_path = path;
+}
+
+std::unique_ptr<ByteSource> open_byte_source(const char* path, std::string& error) {
+    int fd = ::open(path, O_RDONLY | O_CLOEXEC);
+    if (fd < 0) {
+        error = std::string("cannot open ") + path + ": " + std::strerror(errno);
+        return nullptr;
+    }
+    auto raw = std::make_unique<RawFile>(fd);
+    uint8_t head[4];
+    size_t got = raw->read(head, sizeof(head));
+    if (got >= 2 && head[0] == 0x1f && head[1] == 0x8b) return std::make_unique<GzipSource>(std::move(raw), head, got);
+    if (got == 4 && head[0] == 0x28 && head[1] == 0xb5 && head[2] == 0x2f && head[3] == 0xfd) {
+        if (!g_zstd.load()) {
+            error = "zstd input but libzstd could not be loaded";
+            return nullptr;
+        }
+        return std::make_unique<ZstdSource>(std::move(raw), head, got);
+    }
+    return std::make_unique<PlainSource>(std::move(raw), head, got);
+}
+
+}  // namespace gpugrep

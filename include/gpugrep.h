@@ -15,6 +15,12 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#if defined(__GNUC__)
+#define GPUGREP_API __attribute__((visibility("default")))
+#else
+#define GPUGREP_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -53,13 +59,13 @@ typedef void (*hs_event)(hyperscanner_result_t* results, int result_count);
  * at most buffer_size-1 bytes (the reference's gzgets buffer).  buffer_count: callback batch size (clamped to
  * max_match_count when that is smaller, hyperscanner.c:259-262).  max_match_count: stop after the line on which
  * the total reaches it; 0 = unlimited. */
-int hyperscan(char* file_name, const char* const* patterns, const unsigned int* pattern_flags,
+GPUGREP_API int hyperscan(char* file_name, const char* const* patterns, const unsigned int* pattern_flags,
               const unsigned int* pattern_ids, const unsigned int elements, hs_event on_event,
               const int buffer_size, int buffer_count, unsigned long long max_match_count);
 
 /* Replaces reference hyperscanner.c:154-167 `check_patterns()`: 0 if the set compiles, else 4.
  * Never touches CUDA (safe before fork()). */
-int check_patterns(const char* const* patterns, const unsigned int* pattern_flags,
+GPUGREP_API int check_patterns(const char* const* patterns, const unsigned int* pattern_flags,
                    const unsigned int* pattern_ids, const unsigned int elements);
 
 /* ------------------------------------------------------------------------------------------------------------
@@ -89,31 +95,40 @@ typedef struct gpugrep_stats {
 /* Scan a memory buffer holding the (decompressed) file contents; same pattern, batching and callback
  * semantics as hyperscan().  on_event may be NULL: matches are then only counted (no line bytes are copied).
  * `stream` is an optional cudaStream_t (as void*) to enqueue on, NULL = the library's own stream. */
-int gpugrep_scan_buffer(const void* data, size_t size, int location, const char* const* patterns,
+GPUGREP_API int gpugrep_scan_buffer(const void* data, size_t size, int location, const char* const* patterns,
                         const unsigned int* pattern_flags, const unsigned int* pattern_ids, unsigned int elements,
                         hs_event on_event, int buffer_size, int buffer_count, unsigned long long max_match_count,
                         void* stream, gpugrep_stats* stats);
 
 /* hyperscan() plus statistics. */
-int gpugrep_scan_file(const char* file_name, const char* const* patterns, const unsigned int* pattern_flags,
+GPUGREP_API int gpugrep_scan_file(const char* file_name, const char* const* patterns, const unsigned int* pattern_flags,
                       const unsigned int* pattern_ids, unsigned int elements, hs_event on_event, int buffer_size,
                       int buffer_count, unsigned long long max_match_count, gpugrep_stats* stats);
+
+/* An hs_event that discards its batch (benchmarks: full delivery path without a Python frame per batch). */
+GPUGREP_API void gpugrep_discard_results(hyperscanner_result_t* results, int result_count);
 
 /* Byte-range sharding helper for multi-GPU runs: rank r of `world` scans
  * [gpugrep_shard_begin(r), gpugrep_shard_begin(r+1)) where each boundary is advanced to just past the next '\n'.
  * `data` is host memory. */
-size_t gpugrep_shard_begin(const void* data, size_t size, unsigned int rank, unsigned int world);
+GPUGREP_API size_t gpugrep_shard_begin(const void* data, size_t size, unsigned int rank, unsigned int world);
 
 /* Select the CUDA device used by subsequent calls from this thread's process (default: $GPUGREP_DEVICE,
  * else $LOCAL_RANK, else 0). */
-void gpugrep_set_device(int device);
+GPUGREP_API void gpugrep_set_device(int device);
 
 /* Path of the libzstd shared object used for .zst ingest (default "libzstd.so.1"). */
-void gpugrep_set_zstd_path(const char* path);
+GPUGREP_API void gpugrep_set_zstd_path(const char* path);
 
 /* Human-readable reason of the last failure on this thread ("" if none). */
-const char* gpugrep_last_error(void);
-const char* gpugrep_version(void);
+GPUGREP_API const char* gpugrep_last_error(void);
+GPUGREP_API const char* gpugrep_version(void);
+
+/* Seeded synthetic syslog-shaped text for bench.py and the parity tests: fills out[0,size) with
+ * complete '\n'-terminated lines (80-250 bytes, ~145 mean) and returns the line count.  `plants`: optional
+ * indicator strings (each < 100 bytes), one appended to a line with probability plant_ppm / 1e6. */
+GPUGREP_API size_t gpugrep_synth_syslog(unsigned long long seed, char* out, size_t size, const char* const* plants,
+                                        unsigned int nplants, unsigned int plant_ppm);
 
 /* ---- compiled-database introspection (pattern compiler tests) ---- */
 typedef struct gpugrep_db gpugrep_db;
@@ -144,20 +159,20 @@ typedef struct gpugrep_group_info {
     unsigned int members;
 } gpugrep_group_info;
 
-gpugrep_db* gpugrep_db_compile(const char* const* patterns, const unsigned int* pattern_flags,
+GPUGREP_API gpugrep_db* gpugrep_db_compile(const char* const* patterns, const unsigned int* pattern_flags,
                                const unsigned int* pattern_ids, unsigned int elements, int* rc);
-void gpugrep_db_free(gpugrep_db* db);
-int gpugrep_db_get_info(const gpugrep_db* db, gpugrep_db_info* out);
-int gpugrep_db_get_group(const gpugrep_db* db, unsigned int group, gpugrep_group_info* out);
+GPUGREP_API void gpugrep_db_free(gpugrep_db* db);
+GPUGREP_API int gpugrep_db_get_info(const gpugrep_db* db, gpugrep_db_info* out);
+GPUGREP_API int gpugrep_db_get_group(const gpugrep_db* db, unsigned int group, gpugrep_group_info* out);
 /* Copies the tables of one group: byte_class[256], trans[states*stride], accept_of[states]. */
-int gpugrep_db_copy_group(const gpugrep_db* db, unsigned int group, uint8_t* byte_class, uint32_t* trans,
+GPUGREP_API int gpugrep_db_copy_group(const gpugrep_db* db, unsigned int group, uint8_t* byte_class, uint32_t* trans,
                           uint32_t* accept_of);
 /* Reports of accept set `accept` of `group`: writes up to cap (id, singlematch) pairs, returns the count. */
-int gpugrep_db_accept_reports(const gpugrep_db* db, unsigned int group, unsigned int accept, unsigned int* ids,
+GPUGREP_API int gpugrep_db_accept_reports(const gpugrep_db* db, unsigned int group, unsigned int accept, unsigned int* ids,
                               unsigned int* singlematch, unsigned int cap);
 /* Copies the prefilter bitmap ((1 << log2_bits) / 32 words); returns words copied, 0 if disabled. */
-size_t gpugrep_db_copy_prefilter(const gpugrep_db* db, uint32_t* words, size_t cap_words, uint32_t* hash_mul);
-const char* gpugrep_db_prefilter_note(const gpugrep_db* db);
+GPUGREP_API size_t gpugrep_db_copy_prefilter(const gpugrep_db* db, uint32_t* words, size_t cap_words, uint32_t* hash_mul);
+GPUGREP_API const char* gpugrep_db_prefilter_note(const gpugrep_db* db);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,78 @@
+"""Differential harness: any library with the reference ABI vs the CPU oracle, on the same inputs."""
+
+from __future__ import annotations
+
+import gzip
+import os
+import random
+import tempfile
+
+from oracle_api import run_scan
+from regex_gen import gen_regex, gen_text
+
+
+def compare(lib, oracle, data: bytes | None, patterns, flags=None, ids=None, buffer_size=262140, buffer_count=16,
+            max_match_count=0, path: str | None = None):
+    """Run both libraries on the same file and assert identical return code, records, order and batch sizes."""
+    own = path is None
+    if own:
+        with tempfile.NamedTemporaryFile(suffix=".log", delete=False) as handle:
+            handle.write(data)
+            path = handle.name
+    try:
+        kw = {"flags": flags, "ids": ids, "buffer_size": buffer_size, "buffer_count": buffer_count, "max_match_count": max_match_count}
+        exp_rc, exp, exp_batches = run_scan(oracle, path, patterns, **kw)
+        got_rc, got, got_batches = run_scan(lib, path, patterns, **kw)
+    finally:
+        if own:
+            os.unlink(path)
+    assert got_rc == exp_rc, f"return code {got_rc} != oracle {exp_rc} for {patterns}"
+    if got != exp:
+        for k, (a, b) in enumerate(zip(got, exp)):
+            if a != b:
+                raise AssertionError(f"record {k}: got {a} expected {b}; patterns={patterns} flags={flags} ids={ids} bs={buffer_size}")
+        raise AssertionError(f"record count {len(got)} != oracle {len(exp)}; patterns={patterns} flags={flags} ids={ids} bs={buffer_size}")
+    assert got_batches == exp_batches, f"batch sizes differ: {got_batches[:8]} vs {exp_batches[:8]}"
+    return len(exp)
+
+
+def has_all_nul_pseudo_line(data: bytes, buffer_size: int) -> bool:
+    """The reference reads stale buffer bytes for a pseudo-line made only of NULs (SURVEY.md §8a-2 rule 8): excluded."""
+    pos, lim = 0, buffer_size - 1
+    while pos < len(data):
+        nl = data.find(b"\n", pos, pos + lim)
+        end = nl + 1 if nl >= 0 else min(len(data), pos + lim)
+        chunk = data[pos:end]
+        if chunk and chunk[0] == 0 and not chunk.strip(b"\0"):
+            return True
+        pos = end
+    return False
+
+
+def random_case(seed: int):
+    """One seeded random pattern set / text / parameter combination (patterns may be rejected by both sides)."""
+    rng = random.Random(seed)
+    k = rng.choice([1, 1, 1, 2, 3, 5])
+    patterns = [gen_regex(rng) for _ in range(k)]
+    mode = rng.choice(["simple", "simple", "ids", "nosm", "mixed"])
+    base = rng.choice([14, 14, 14, 10, 12, 8, 15, 14])
+    flags = [base] * k
+    if mode == "simple":
+        ids = [rng.choice([0, 7])] * k
+    elif mode == "ids":
+        ids = [rng.randint(0, 2) for _ in range(k)]
+    elif mode == "nosm":
+        flags = [f & ~8 for f in flags]
+        ids = [rng.randint(0, 1) for _ in range(k)]
+    else:
+        ids = list(range(k))
+        flags = [f & ~8 if i % 2 else f for i, f in enumerate(flags)]
+    buffer_size = rng.choice([262140, 262140, 64, 9, 5])
+    data = gen_text(rng, rng.choice([0, 1, 30, 200]), nul_rate=rng.choice([0, 0, 0.05]))
+    buffer_count = rng.choice([16, 1, 3])
+    max_match = rng.choice([0, 0, 0, 1, 4])
+    return patterns, flags, ids, buffer_size, data, buffer_count, max_match
+
+
+def gz_members(parts: list[bytes]) -> bytes:
+    return b"".join(gzip.compress(p) for p in parts)

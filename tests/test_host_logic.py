@@ -1,0 +1,68 @@
+"""Host logic (capi.cpp segment cutting / batching / stop rule, ingest, pattern compiler) against the oracle, on CPU,
+through the mock engine.  The same cases run against the CUDA engine in test_gpu_parity.py."""
+
+import os
+
+import pytest
+
+import parity
+from hypergrep_b200 import synth
+
+
+@pytest.mark.parametrize("seed", range(120))
+def test_random_cases_match_oracle(seed, hostmock_lib, oracle_lib):
+    patterns, flags, ids, buffer_size, data, buffer_count, max_match = parity.random_case(seed)
+    if parity.has_all_nul_pseudo_line(data, buffer_size):
+        pytest.skip("all-NUL pseudo-line: reference reads stale bytes, excluded from parity")
+    parity.compare(hostmock_lib, oracle_lib, data, patterns, flags, ids, buffer_size, buffer_count, max_match)
+
+
+EDGE_TEXTS = {
+    "empty": b"",
+    "one_line_no_newline": b"foo bar",
+    "only_newlines": b"\n\n\n\n",
+    "crlf": b"foo\r\nbar foo\r\n\r\nfoo",
+    "leading_nuls": b"\0\0foo\nbar\n\0foo bar\n",
+    "embedded_nul": b"foo\0bar\nbar\0foo\nfoo\n",
+    "long_line": b"x" * 700 + b"foo" + b"y" * 300 + b"\nfoo\n",
+    "boundary_lengths": b"a" * 62 + b"\n" + b"b" * 63 + b"\n" + b"c" * 64 + b"\n" + b"foo" * 21 + b"\n" + b"foo" * 42 + b"\nfoo",
+    "match_split_by_buffer": b"0123456fo" + b"obar\n" + b"foobar\n",
+}
+
+
+@pytest.mark.parametrize("name", sorted(EDGE_TEXTS))
+@pytest.mark.parametrize("buffer_size", [262140, 64, 8])
+def test_edge_texts(name, buffer_size, hostmock_lib, oracle_lib):
+    for patterns in (["foo"], ["foo$", "^bar"], ["o+b", "x{3}"], ["foo."]):
+        parity.compare(hostmock_lib, oracle_lib, EDGE_TEXTS[name], patterns, buffer_size=buffer_size)
+    parity.compare(hostmock_lib, oracle_lib, EDGE_TEXTS[name], ["foo", "bar", "o"], flags=[14, 14, 6], ids=[1, 2, 3], buffer_size=buffer_size)
+
+
+def test_multi_segment_syslog(hostmock_lib, oracle_lib, monkeypatch, tmp_path):
+    """3 MiB of syslog text cut into ~530 KiB segments: line numbers and records must not depend on the cuts."""
+    monkeypatch.setenv("GPUGREP_CHUNK_BYTES", "1")
+    data = synth.syslog_bytes(3 << 20, seed=5, lib=hostmock_lib)
+    n = parity.compare(hostmock_lib, oracle_lib, data, synth.C1_PATTERNS)
+    assert n > 100
+    parity.compare(hostmock_lib, oracle_lib, data, synth.C2_PATTERNS)
+    parity.compare(hostmock_lib, oracle_lib, data, synth.C2_PATTERNS, max_match_count=1000, buffer_count=7)
+    parity.compare(hostmock_lib, oracle_lib, data[: 1 << 20], ["ERROR", "port [0-9]+", "WARN"], flags=[14, 14, 14], ids=[3, 1, 2])
+    # small gzgets buffer: every line is split into pseudo-lines, across segment cuts as well
+    parity.compare(hostmock_lib, oracle_lib, data[: 1 << 20], ["ERROR", "ssh2$"], buffer_size=50)
+
+
+def test_compressed_inputs(hostmock_lib, oracle_lib, tmp_path):
+    text = synth.syslog_bytes(1 << 20, seed=9, lib=hostmock_lib)
+    half = text.rfind(b"\n", 0, len(text) // 2) + 1
+    multi = tmp_path / "multi.log.gz"
+    multi.write_bytes(parity.gz_members([text[:half], text[half:]]))
+    parity.compare(hostmock_lib, oracle_lib, None, ["ERROR"], path=str(multi))
+    garbage = tmp_path / "garbage.log.gz"
+    garbage.write_bytes(parity.gz_members([text[:half]]) + b"this is not gzip")
+    parity.compare(hostmock_lib, oracle_lib, None, ["ERROR"], path=str(garbage))
+
+
+def test_missing_file_and_directory(hostmock_lib, oracle_lib, tmp_path):
+    parity.compare(hostmock_lib, oracle_lib, None, ["foo"], path=str(tmp_path / "nope.txt"))   # both: 6 (GZ_OPEN)
+    parity.compare(hostmock_lib, oracle_lib, None, ["foo"], path=str(tmp_path))                # both: 0, no lines
+    assert os.path.isdir(tmp_path)
