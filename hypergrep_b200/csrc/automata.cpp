@@ -218,7 +218,7 @@ struct Determinizer {
 
 }  // namespace
 
-static void minimise(Dfa& d);
+static void minimise(Dfa& d, const std::vector<char>& idle);
 
 bool build_dfa(const Nfa& nfa, const DfaBuildOptions& opt, Dfa& out) {
     Determinizer det(nfa, opt);
@@ -239,7 +239,7 @@ bool build_dfa(const Nfa& nfa, const DfaBuildOptions& opt, Dfa& out) {
     accept_sets.push_back({});
     accept_ids[{}] = 0;
     std::vector<uint32_t> trans;
-    const int SINK = 1;  // simple mode only
+    int sink_state = -1;  // simple mode only
 
     auto accept_id = [&](const std::vector<int>& m) {
         auto it = accept_ids.find(m);
@@ -268,17 +268,18 @@ bool build_dfa(const Nfa& nfa, const DfaBuildOptions& opt, Dfa& out) {
     Ctx start_ctx{true, false, false};
     if (!nfa.uses_line_ctx) start_ctx.at_start = false;  // nobody can observe it: fewer states
     intern({}, start_ctx, 0);
+    const int mid_other = intern({}, Ctx{false, false, false}, 0);
+    const int mid_word = intern({}, Ctx{false, false, nfa.uses_word_ctx}, 0);
     if (opt.simple) {
-        int s = intern({-1, -1}, Ctx{false, false, false}, accept_id({0}));
-        (void)s;  // == SINK
+        sink_state = intern({-1, -1}, Ctx{false, false, false}, accept_id({0}));
     }
 
     std::vector<int> bytes, matched, next_kernel;
     std::vector<int> look_bytes[4], look_matched[4];
     for (int s = 0; s < (int)kernels.size(); s++) {
         if ((size_t)kernels.size() > opt.max_states) return false;
-        if (opt.simple && s == SINK) {
-            for (int c = 0; c < stride; c++) trans[(size_t)s * stride + c] = SINK;
+        if (opt.simple && s == sink_state) {
+            for (int c = 0; c < stride; c++) trans[(size_t)s * stride + c] = (uint32_t)sink_state;
             continue;
         }
         std::vector<int> kernel = kernels[s];
@@ -299,7 +300,7 @@ bool build_dfa(const Nfa& nfa, const DfaBuildOptions& opt, Dfa& out) {
             const std::vector<int>& m = look_matched[slot];
             int target;
             if (opt.simple && !m.empty()) {
-                target = SINK;
+                target = sink_state;
             } else {
                 next_kernel.clear();
                 for (int pc : look_bytes[slot]) {
@@ -320,7 +321,7 @@ bool build_dfa(const Nfa& nfa, const DfaBuildOptions& opt, Dfa& out) {
             }
             const std::vector<int>& m = look_matched[slot];
             int target;
-            if (opt.simple && !m.empty()) target = SINK;
+            if (opt.simple && !m.empty()) target = sink_state;
             else target = intern({-1}, Ctx{false, false, false}, accept_id(m));
             trans[(size_t)s * stride + ncls] = (uint32_t)target;
         }
@@ -335,15 +336,21 @@ bool build_dfa(const Nfa& nfa, const DfaBuildOptions& opt, Dfa& out) {
     out.accept_of = std::move(accept_of);
     out.accept_sets = std::move(accept_sets);
     out.simple = opt.simple;
-    out.sink_match = opt.simple ? SINK : -1;
-    minimise(out);
+    out.sink_match = opt.simple ? sink_state : -1;
+    out.entry_mid_other = mid_other;
+    out.entry_mid_word = mid_word;
+    // idle = empty kernel (no partial match in progress); recorded per state for minimise() to carry over
+    out.idle_end = 0;
+    std::vector<char> idle(kernels.size(), 0);
+    for (size_t k = 0; k < kernels.size(); k++) idle[k] = kernels[k].empty() && out.accept_of[k] == 0;
+    minimise(out, idle);
     return true;
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // Moore partition refinement + merging of identical alphabet columns + renumbering (accepting states last)
 // ------------------------------------------------------------------------------------------------------------
-static void minimise(Dfa& d) {
+static void minimise(Dfa& d, const std::vector<char>& idle) {
     const int n = d.num_states, stride = d.stride;
     std::vector<int> blk(n);
     {
@@ -389,6 +396,12 @@ static void minimise(Dfa& d) {
     newid[blk[0]] = 0;
     bool start_accepting = d.accept_of[0] != 0;
     (void)start_accepting;  // the start state never accepts (reports are delayed by one symbol)
+    // a block is idle if it contains an idle state: equivalent states have the same future, so none of the block's
+    // partial matches can matter
+    std::vector<char> blk_idle(nblk, 0);
+    for (int s = 0; s < n; s++) if (idle[s]) blk_idle[blk[s]] = 1;
+    for (int b = 0; b < nblk; b++) if (newid[b] < 0 && d.accept_of[rep[b]] == 0 && blk_idle[b]) { newid[b] = (int)order.size(); order.push_back(b); }
+    int idle_end = (int)order.size();
     for (int b = 0; b < nblk; b++) if (newid[b] < 0 && d.accept_of[rep[b]] == 0) { newid[b] = (int)order.size(); order.push_back(b); }
     int first_accept = (int)order.size();
     for (int b = 0; b < nblk; b++) if (newid[b] < 0) { newid[b] = (int)order.size(); order.push_back(b); }
@@ -426,6 +439,9 @@ static void minimise(Dfa& d) {
     d.num_states = nblk;
     d.first_accept = first_accept;
     if (d.sink_match >= 0) d.sink_match = newid[blk[d.sink_match]];
+    d.entry_mid_other = newid[blk[d.entry_mid_other]];
+    d.entry_mid_word = newid[blk[d.entry_mid_word]];
+    d.idle_end = idle_end;
     d.dead = -1;
     for (int s = 0; s < nblk; s++) {
         if (d.accept_of[s] != 0) continue;

@@ -49,6 +49,12 @@ struct Dfa {
     int sink_match = -1;             // simple mode: absorbing "line matched" state, else -1
     int dead = -1;                   // absorbing non-accepting state that can never reach an accept, else -1
     bool simple = false;
+    // Entry states for a walk that starts in the middle of a line (local verification): the byte before the first
+    // consumed byte was a non-word / a word character.  Equal to 0 when the patterns cannot observe the difference.
+    int entry_mid_other = 0, entry_mid_word = 0;
+    // States < idle_end have no partial match in progress (only the implicit ".*" restart): once a walk is idle
+    // past a prefilter hit, no match containing that hit can still complete.  State 0 is always idle.
+    int idle_end = 1;
 };
 
 struct DfaBuildOptions {

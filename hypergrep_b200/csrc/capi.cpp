@@ -15,6 +15,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <list>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -95,9 +97,51 @@ private:
     std::vector<std::vector<char>> lines_;
 };
 
+constexpr size_t kSampleBytes = 512 << 10;   // head of the input used to tune the prefilter windows
+
+// Sample-tuned prefilter tables, cached per (database, device, sample fingerprint).
+std::shared_ptr<DevicePrefilter> tuned_prefilter(const std::shared_ptr<Database>& db, const uint8_t* sample, size_t len, std::string& error) {
+    if (!db->simple || !db->factors.usable) return nullptr;
+    struct Entry { const Database* db; int device; uint64_t fp; std::shared_ptr<Database> keep; std::shared_ptr<DevicePrefilter> pf; };
+    static std::mutex mu;
+    static std::list<Entry> cache;
+    len = std::min(len, kSampleBytes);
+    uint64_t fp = 1469598103934665603ull ^ len;
+    for (size_t i = 0; i + 8 <= std::min<size_t>(len, 64 << 10); i += 8) {
+        uint64_t w;
+        std::memcpy(&w, sample + i, 8);
+        fp = (fp ^ w) * 1099511628211ull;
+    }
+    const int device = engine_current_device();
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto it = cache.begin(); it != cache.end(); ++it) {
+            if (it->db == db.get() && it->device == device && it->fp == fp) {
+                cache.splice(cache.begin(), cache, it);
+                return cache.front().pf;
+            }
+        }
+    }
+    Prefilter pf;
+    if (len >= 4096 && std::getenv("GPUGREP_NO_TUNE") == nullptr) {
+        GramHistogram hist;
+        hist.add_sample(sample, len);
+        build_prefilter(db->factors, &hist, pf);
+    } else {
+        pf = db->prefilter;
+    }
+    auto dpf = engine_upload_prefilter(pf, error);
+    if (!dpf) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    cache.push_front(Entry{db.get(), device, fp, db, dpf});
+    while (cache.size() > 16) cache.pop_back();
+    return dpf;
+}
+
 struct Job {
     std::shared_ptr<Database> db;
     std::shared_ptr<DeviceDb> ddb;
+    std::shared_ptr<DevicePrefilter> dpf;   // null: general path
     int buffer_size = 0;
     unsigned long long max_match = 0;
     Deliverer* out = nullptr;
@@ -138,7 +182,23 @@ struct Job {
     }
 
     int deliver_simple(const SegmentResult& r, const uint8_t* host, ScanSlot* slot) {
-        size_t take = r.num_line_recs;
+        // fast-path records may repeat a line (marked by several candidate chunks) or carry kInvalid length (a line
+        // with NULs that failed the exact re-check): keep the first valid record of every line
+        const LineRec* recs = r.lines;
+        size_t count = r.num_line_recs;
+        if (r.stats.path & 1) {
+            unique_.clear();
+            unique_.reserve(count);
+            uint32_t last_start = 0xffffffffu;
+            for (size_t i = 0; i < count; i++) {
+                if (recs[i].len == 0xffffffffu || recs[i].start == last_start) continue;
+                last_start = recs[i].start;
+                unique_.push_back(recs[i]);
+            }
+            recs = unique_.data();
+            count = unique_.size();
+        }
+        size_t take = count;
         if (max_match > 0) {
             unsigned long long room = max_match > out->count() ? max_match - out->count() : 0;
             if ((unsigned long long)take >= room) { take = (size_t)room; stop = true; }
@@ -150,18 +210,19 @@ struct Job {
             std::vector<uint32_t> starts(take), lens(take);
             unsigned long long total = 0;
             goff.resize(take);
-            for (size_t i = 0; i < take; i++) { starts[i] = r.lines[i].start; lens[i] = r.lines[i].len; goff[i] = total; total += lens[i] + 1ull; }
+            for (size_t i = 0; i < take; i++) { starts[i] = recs[i].start; lens[i] = recs[i].len; goff[i] = total; total += lens[i] + 1ull; }
             gathered.resize((size_t)total);
             int rc = slot_gather_lines(slot, starts.data(), lens.data(), take, gathered.data(), error);
             if (rc) return rc;
         }
         for (size_t i = 0; i < take; i++) {
-            const LineRec& lr = r.lines[i];
+            const LineRec& lr = recs[i];
             const uint8_t* bytes = host ? host + lr.start : gathered.data() + goff[i];
             out->emit(db->simple_id, line_base + lr.line, bytes, lr.len);
         }
         return 0;
     }
+    std::vector<LineRec> unique_;
 
     int deliver_events(const SegmentResult& r, const uint8_t* host, ScanSlot* slot) {
         // events arrive grouped by pseudo-line in file order; inside a line they are grouped by DFA group
@@ -297,6 +358,7 @@ int scan_file(const char* path, const Params& pr, gpugrep_stats* stats_out) {
     int k = 0;
     int inflight = -1;
     size_t inflight_len = 0;
+    bool tuned = false;
     size_t carry = 0;
     const uint8_t* carry_src = nullptr;
     bool eof = false;
@@ -315,7 +377,8 @@ int scan_file(const char* path, const Params& pr, gpugrep_stats* stats_out) {
         if (cut == 0 && !eof) cut = have;   // cannot happen (chunk >= 2*limit): defensive
         job.stats.bytes_scanned += cut;
         if (cut > 0) {
-            rc = slot_submit(slots[k], *job.ddb, buf, nullptr, cut, pr.buffer_size, nullptr, job.error);
+            if (!tuned) { job.dpf = tuned_prefilter(job.db, buf, cut, job.error); tuned = true; }
+            rc = slot_submit(slots[k], *job.ddb, job.dpf.get(), buf, nullptr, cut, pr.buffer_size, nullptr, job.error);
             if (rc) break;
         }
         carry = have - cut;
@@ -394,6 +457,8 @@ int scan_memory(const uint8_t* data, size_t size, int location, const Params& pr
     if (!slots[0] || !slots[1]) { engine_release_slot(slots[0]); engine_release_slot(slots[1]); set_last_error(err); return GPUGREP_SCRATCH; }
     const uint8_t* seg_host[2] = {nullptr, nullptr};
     int k = 0, inflight = -1;
+    bool tuned = false;
+    std::vector<uint8_t> sample;
     size_t pos = 0;
     while (pos < size && !job.stop && rc == 0) {
         size_t have = std::min(chunk, size - pos);
@@ -416,7 +481,18 @@ int scan_memory(const uint8_t* data, size_t size, int location, const Params& pr
                 host_src = stage;
             }
         }
-        rc = slot_submit(slots[k], *job.ddb, host_src, on_device ? data + pos : nullptr, cut, pr.buffer_size, pr.user_stream, job.error);
+        if (!tuned) {
+            tuned = true;
+            if (on_device) {
+                sample.resize(std::min(cut, kSampleBytes));
+                if (cudaMemcpy(sample.data(), data, sample.size(), cudaMemcpyDeviceToHost) != cudaSuccess) { job.error = "cudaMemcpy of the tuning sample failed"; rc = GPUGREP_SCAN; break; }
+                job.stats.d2h_bytes += sample.size();
+                job.dpf = tuned_prefilter(job.db, sample.data(), sample.size(), job.error);
+            } else {
+                job.dpf = tuned_prefilter(job.db, data, cut, job.error);
+            }
+        }
+        rc = slot_submit(slots[k], *job.ddb, job.dpf.get(), host_src, on_device ? data + pos : nullptr, cut, pr.buffer_size, pr.user_stream, job.error);
         if (rc) break;
         seg_host[k] = on_device ? nullptr : data + pos;
         job.stats.bytes_scanned += cut;

@@ -60,9 +60,11 @@ int gpugrep_db_get_info(const gpugrep_db* h, gpugrep_db_info* out) {
     out->prefilter = db.prefilter.enabled;
     out->prefilter_stride = (unsigned)db.prefilter.stride;
     out->prefilter_fold = db.prefilter.fold_case;
-    out->prefilter_log2_bits = (unsigned)db.prefilter.log2_bits;
+    out->prefilter_log2_bits = (unsigned)(db.prefilter.exact ? db.prefilter.log2_buckets : db.prefilter.log2_bits);
+    out->reserved = db.prefilter.exact ? 1u : 0u;
     out->prefilter_grams = (unsigned)db.prefilter.num_grams;
     out->prefilter_min_factor = (unsigned)db.prefilter.min_factor_len;
+    out->prefilter_lookback = db.prefilter.lookback;
     for (auto& g : db.groups) out->total_states += (unsigned)g.dfa.num_states;
     return 0;
 }
@@ -78,6 +80,10 @@ int gpugrep_db_get_group(const gpugrep_db* h, unsigned int group, gpugrep_group_
     out->dead = d.dead;
     out->accept_sets = (unsigned)d.accept_sets.size();
     out->members = (unsigned)h->db->groups[group].members.size();
+    out->entry_mid_other = (unsigned)d.entry_mid_other;
+    out->entry_mid_word = (unsigned)d.entry_mid_word;
+    out->idle_end = (unsigned)d.idle_end;
+    out->reserved = 0;
     return 0;
 }
 
@@ -112,6 +118,22 @@ size_t gpugrep_db_copy_prefilter(const gpugrep_db* h, uint32_t* words, size_t ca
     if (words) std::memcpy(words, pf.bitmap.data(), n * sizeof(uint32_t));
     if (hash_mul) *hash_mul = pf.hash_mul;
     return n;
+}
+
+size_t gpugrep_db_copy_grams(const gpugrep_db* h, uint32_t* out, size_t cap) {
+    if (!h) return 0;
+    const auto& g = h->db->prefilter.grams;
+    size_t n = std::min(cap, g.size());
+    if (out) std::memcpy(out, g.data(), n * sizeof(uint32_t));
+    return g.size();
+}
+
+int gpugrep_db_tune(gpugrep_db* h, const void* sample, size_t size) {
+    if (!h || !h->db->factors.usable) return -1;
+    gpugrep::GramHistogram hist;
+    hist.add_sample((const uint8_t*)sample, size);
+    gpugrep::build_prefilter(h->db->factors, &hist, h->db->prefilter);
+    return h->db->prefilter.enabled ? 0 : -1;
 }
 
 const char* gpugrep_db_prefilter_note(const gpugrep_db* h) { return h ? h->db->prefilter.note.c_str() : ""; }

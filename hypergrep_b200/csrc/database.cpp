@@ -112,10 +112,13 @@ int compile_database(const char* const* patterns, const unsigned* flags, const u
     }
 
     std::vector<const Node*> raw;
-    std::vector<unsigned> fl;
-    for (unsigned i = 0; i < n; i++) { raw.push_back(asts[i].get()); fl.push_back(db->patterns[i].flags); }
-    if (env_size("GPUGREP_NO_PREFILTER", 0) == 0) build_prefilter(raw, fl, db->prefilter);
-    else db->prefilter.note = "disabled by GPUGREP_NO_PREFILTER";
+    for (unsigned i = 0; i < n; i++) raw.push_back(asts[i].get());
+    if (env_size("GPUGREP_NO_PREFILTER", 0) == 0) {
+        db->factors = analyse_factors(raw);
+        build_prefilter(db->factors, nullptr, db->prefilter);
+    } else {
+        db->prefilter.note = db->factors.note = "disabled by GPUGREP_NO_PREFILTER";
+    }
     out = db;
     return 0;
 }

@@ -37,7 +37,8 @@ struct Database {
     // event mode: accept set k of group g -> reports[report_begin[g][k] .. report_begin[g][k+1])
     std::vector<std::vector<uint32_t>> report_begin;
     std::vector<ReportDesc> reports;
-    Prefilter prefilter;
+    FactorSet factors;       // required factors per pattern (input of the prefilter builder)
+    Prefilter prefilter;     // statically chosen windows (used when no input sample is available)
     std::string key;   // cache key: patterns + flags + ids
 };
 

@@ -29,7 +29,7 @@ struct GroupDev {
     const uint16_t* trans;      // [states][stride]
     const uint8_t* cls;         // [256] byte -> class
     const uint32_t* accept_of;  // [states] (general mode)
-    uint32_t stride, eod, first_accept, dead, accept_base, pad;
+    uint32_t stride, eod, first_accept, dead, accept_base, idle_end, mid_other, mid_word;
 };
 
 struct DbView {
@@ -37,11 +37,7 @@ struct DbView {
     int ngroups;
 };
 
-struct CandRes {
-    uint32_t first_line;    // pseudo-line number (inside the segment) of the line containing the chunk's first byte
-    uint32_t first_start;   // its start offset
-    uint32_t mask;          // bit j: the j-th line intersecting the chunk matched (and is owned by this chunk)
-};
+constexpr uint32_t kInvalidLen = 0xffffffffu;   // LineRec.len of a record the host must drop (NUL re-check failed)
 
 struct Totals {
     unsigned long long meta_total;   // candidates << 32 | newlines
@@ -148,14 +144,16 @@ __device__ uint32_t count_newlines(const uint8_t* data, size_t from, size_t to) 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K1: streaming kernel.  One warp owns a 512-byte block per step: 32 x 16-byte coalesced loads, newline count
-// (SWAR + popc + warp reduce) and, when the prefilter is on, one hashed-bitmap probe per sampled 4-byte gram.
+// K1: streaming kernel.  One warp owns four consecutive 512-byte blocks per step: 4 x (32 x 16-byte) coalesced
+// loads in flight, newline count (SWAR + popc + warp reduce) and, when the prefilter is on, one gram-table lookup
+// per sampled 4-byte gram (shared-memory table of exact keys, or a bloom bitmap for huge gram sets).
 // Output: meta[block] = newline_count << 32 | ballot(lanes whose 16-byte chunk has a gram hit).
-// STRIDE: 0 = no prefilter, else sample every STRIDE-th byte position (4, 2, 1).  Algorithmic traffic: 1 byte
-// read per input byte + 8 bytes written per 512.
+// STRIDE: sample every STRIDE-th byte position (4, 2, 1).  MODE: 0 no prefilter, 1 exact keys, 2 bloom bitmap.
+// Algorithmic traffic: 1 byte read per input byte + 8 bytes written per 512.
 // ------------------------------------------------------------------------------------------------------------
-template <int STRIDE, bool FOLD>
-__device__ __forceinline__ uint32_t probe_chunk(const uint4& v, uint32_t next, const uint32_t* __restrict__ bm, uint32_t mul, int shift) {
+template <int STRIDE, bool FOLD, int MODE>
+__device__ __forceinline__ uint32_t probe_chunk(const uint4& v, uint32_t next, const uint32_t* __restrict__ tab, uint32_t mul, int shift) {
+    if (MODE == 0) return 0;
     uint32_t w[5] = {v.x, v.y, v.z, v.w, next};
     if (FOLD) {
 #pragma unroll
@@ -168,62 +166,101 @@ __device__ __forceinline__ uint32_t probe_chunk(const uint4& v, uint32_t next, c
         for (int s = 0; s < 4; s += STRIDE) {
             uint32_t gram = s == 0 ? w[i] : __funnelshift_r(w[i], w[i + 1], 8 * s);
             uint32_t h = (gram * mul) >> shift;
-            hit |= bm[h >> 5] >> (h & 31);
-        }
-    }
-    return hit & 1u;
-}
-
-template <int STRIDE, bool FOLD>
-__global__ void __launch_bounds__(256) k_stream(const uint8_t* __restrict__ data, size_t n, size_t nblk, unsigned long long* __restrict__ meta,
-                                                const uint32_t* __restrict__ bitmap, int log2_bits, uint32_t mul) {
-    extern __shared__ uint32_t s_bitmap[];
-    if (STRIDE > 0) {
-        const int words = 1 << (log2_bits - 5);
-        for (int i = threadIdx.x; i < words; i += blockDim.x) s_bitmap[i] = bitmap[i];
-        __syncthreads();
-    }
-    const int lane = threadIdx.x & 31;
-    const int shift = 32 - log2_bits;
-    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    constexpr int U = 4;   // 512-byte blocks in flight per warp
-    for (size_t g0 = warp * U; g0 < nblk; g0 += nwarps * U) {
-        uint4 v[U];
-        uint32_t nx[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            size_t off = (g0 + u) * 512 + (size_t)lane * 16;
-            if (off + 16 <= n) v[u] = ld_stream16(data + off);
-            else if (off < n) v[u] = ld_chunk(data, off, n);
-            else v[u] = make_uint4(0, 0, 0, 0);
-            nx[u] = 0;
-        }
-        if (STRIDE > 0 && STRIDE < 4) {
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                // first word of the following chunk: the next lane's, or (lane 31) the next block's first word
-                uint32_t down = __shfl_down_sync(0xffffffffu, v[u].x, 1);
-                if (lane == 31) {
-                    size_t off = (g0 + u + 1) * 512;
-                    down = 0;
-                    if (off < n) down = ld_chunk(data, off, n).x;
-                }
-                nx[u] = down;
+            if (MODE == 1) {
+                uint2 e = reinterpret_cast<const uint2*>(tab)[h];   // bucket of two exact keys
+                hit |= (uint32_t)(e.x == gram) | (uint32_t)(e.y == gram);
+            } else {
+                hit |= (tab[h >> 5] >> (h & 31)) & 1u;
             }
         }
+    }
+    return hit;
+}
+
+// newlines in a 16-byte chunk: four flag words (bit 7 of matching bytes) are merged into one 64-bit word with three
+// multiply-adds (FMA pipe) instead of shifts and ORs (ALU pipe, the pipe this kernel saturates first)
+__device__ __forceinline__ uint32_t newline_count16_fma(const uint4& v) {
+    uint32_t a = eq_mask4(v.x, 0x0a0a0a0au), b = eq_mask4(v.y, 0x0a0a0a0au), c = eq_mask4(v.z, 0x0a0a0a0au), d = eq_mask4(v.w, 0x0a0a0a0au);
+    unsigned long long acc = a;
+    asm("mad.wide.u32 %0, %1, 2, %0;" : "+l"(acc) : "r"(b));
+    asm("mad.wide.u32 %0, %1, 4, %0;" : "+l"(acc) : "r"(c));
+    asm("mad.wide.u32 %0, %1, 8, %0;" : "+l"(acc) : "r"(d));
+    return __popcll(acc);
+}
+
+constexpr int kStreamU = 4;   // 512-byte blocks per warp step
+
+template <int STRIDE, bool FOLD, int MODE>
+__global__ void __launch_bounds__(1024) k_stream(const uint8_t* __restrict__ data, size_t n, unsigned long long* __restrict__ meta,
+                                                 const uint32_t* __restrict__ table, int table_words, int shift, uint32_t mul) {
+    extern __shared__ __align__(16) uint32_t s_tab[];
+    if (MODE != 0) {
+        for (int i = threadIdx.x; i < table_words; i += blockDim.x) s_tab[i] = table[i];
+        __syncthreads();
+    }
+    constexpr int U = kStreamU;
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const size_t nblk = (n + 511) >> 9;
+    const size_t nfull = n >> 9;   // blocks that lie entirely inside [0, n)
+
+    // ---- main loop: groups of U full blocks, no bounds checks on the data loads
+    for (size_t g0 = warp * U; g0 + U <= nfull; g0 += nwarps * U) {
+        const uint8_t* p = data + (g0 << 9) + lane * 16;
+        uint4 v[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            if (g0 + u >= nblk) break;
-            uint32_t cnt = newline_count16(v[u]);
-            uint32_t hit = 0;
-            if (STRIDE > 0) hit = probe_chunk<(STRIDE > 0 ? STRIDE : 4), FOLD>(v[u], nx[u], s_bitmap, mul, shift);
-            // chunks that start at or beyond n can never be candidates
-            if ((g0 + u) * 512 + (size_t)lane * 16 >= n) hit = 0;
-            uint32_t mask = __ballot_sync(0xffffffffu, hit != 0);
-            uint32_t total = __reduce_add_sync(0xffffffffu, cnt);
-            if (lane == 0) meta[g0 + u] = ((unsigned long long)total << 32) | mask;
+        for (int u = 0; u < U; u++) v[u] = ld_stream16(p + u * 512);
+        uint32_t after = 0;   // first word after the group (only lane 31 needs it, for grams that straddle the end)
+        if (MODE != 0 && STRIDE < 4 && lane == 31) {
+            size_t off = (g0 + U) << 9;
+            if (off + 4 <= n) after = *reinterpret_cast<const uint32_t*>(data + off);
+            else if (off < n) after = ld_chunk(data, off, n).x;
         }
+        uint32_t cnt01, cnt23, masks[U];
+        {
+            uint32_t c[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                c[u] = newline_count16_fma(v[u]);
+                uint32_t nx = 0;
+                if (MODE != 0 && STRIDE < 4) {
+                    // first word of the next chunk: lane+1's word of this block, or (lane 31) lane 0's word of the next block
+                    uint32_t give = (u + 1 < U && lane == 0) ? v[u + 1 < U ? u + 1 : u].x : v[u].x;
+                    nx = __shfl_sync(0xffffffffu, give, (lane + 1) & 31);
+                    if (u + 1 == U && lane == 31) nx = after;
+                }
+                uint32_t hit = probe_chunk<STRIDE, FOLD, MODE>(v[u], nx, s_tab, mul, shift);
+                masks[u] = __ballot_sync(0xffffffffu, hit != 0);
+            }
+            cnt01 = __reduce_add_sync(0xffffffffu, c[0] | (c[1] << 16));
+            cnt23 = __reduce_add_sync(0xffffffffu, c[2] | (c[3] << 16));
+        }
+        if (lane == 0) {
+            uint4* out = reinterpret_cast<uint4*>(meta + g0);   // g0 is a multiple of 4: 32-byte aligned
+            out[0] = make_uint4(masks[0], cnt01 & 0xffffu, masks[1], cnt01 >> 16);
+            out[1] = make_uint4(masks[2], cnt23 & 0xffffu, masks[3], cnt23 >> 16);
+        }
+    }
+
+    // ---- tail: the last (< U) full blocks and the partial block, one block per warp step, bounds-checked
+    for (size_t g = (nfull / U) * U + warp; g < nblk; g += nwarps) {
+        size_t off = (g << 9) + (size_t)lane * 16;
+        uint4 v = off < n ? ld_chunk(data, off, n) : make_uint4(0, 0, 0, 0);
+        uint32_t nx = 0;
+        if (MODE != 0 && STRIDE < 4) {
+            nx = __shfl_down_sync(0xffffffffu, v.x, 1);
+            if (lane == 31) {
+                size_t o2 = (g + 1) << 9;
+                nx = o2 < n ? ld_chunk(data, o2, n).x : 0u;
+            }
+        }
+        uint32_t cnt = newline_count16_fma(v);
+        uint32_t hit = probe_chunk<STRIDE, FOLD, MODE>(v, nx, s_tab, mul, shift);
+        if (off >= n) hit = 0;   // chunks that start at or beyond n can never be candidates
+        uint32_t mask = __ballot_sync(0xffffffffu, hit != 0);
+        uint32_t total = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0) meta[g] = ((unsigned long long)total << 32) | mask;
     }
 }
 
@@ -266,14 +303,14 @@ struct LoadMeta {   // meta word -> candidates << 32 | newlines
         return ((unsigned long long)__popc((uint32_t)m) << 32) | (m >> 32);
     }
 };
-struct LoadResMask {   // records per candidate; *count (device) bounds the valid prefix
-    const CandRes* res;
+struct LoadMarks {   // records per candidate; *meta_total (device) bounds the valid prefix
+    const uint32_t* marks;
     const unsigned long long* meta_total;
     size_t cap;
     __device__ unsigned long long operator()(size_t i) const {
         size_t cnt = (size_t)(*meta_total >> 32);
         if (cnt > cap) cnt = cap;
-        return i < cnt ? (unsigned long long)__popc(res[i].mask) : 0ull;
+        return i < cnt ? (unsigned long long)__popc(marks[i]) : 0ull;
     }
 };
 struct LoadU8 {
@@ -448,73 +485,133 @@ __global__ void k_list_candidates(const unsigned long long* __restrict__ meta, c
     }
 }
 
-// One thread per candidate chunk: verify every line that intersects the chunk; the line that starts before the
-// chunk is owned by the FIRST flagged chunk it intersects (exact de-duplication without sorting).
-__global__ void __launch_bounds__(128) k_verify_simple(DbView db, const uint8_t* __restrict__ data, size_t n, const unsigned long long* __restrict__ meta,
-                                                       const unsigned long long* __restrict__ prefix, const uint32_t* __restrict__ cand,
-                                                       const unsigned long long* meta_total, size_t cap, CandRes* __restrict__ res) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t ncand = (size_t)(*meta_total >> 32);
-    if (ncand > cap) ncand = cap;
-    if (i >= ncand) return;
-    const uint32_t c = cand[i];
-    const size_t o = (size_t)c * 16;
-    uint4 v = ld_chunk(data, o, n);
-    uint32_t nlm = newline_mask16(v);
-    if (o + 16 > n) nlm &= (1u << (n - o)) - 1u;
-    const size_t ls = line_start_of(data, o);
-    // ownership of the first line: no flagged chunk in [ls/16, c)
-    bool owned = true;
-    {
-        size_t c0 = ls >> 4;
-        if (c0 < c) {
-            for (size_t gb = c0 >> 5; gb <= ((size_t)c >> 5) && owned; gb++) {
-                uint32_t m = (uint32_t)meta[gb];
-                if (gb == (c0 >> 5)) m &= ~((1u << (c0 & 31)) - 1u);
-                if (gb == ((size_t)c >> 5)) m &= (1u << (c & 31)) - 1u;
-                if (m) owned = false;
-            }
-        }
-    }
-    const size_t lb = ls >> 9;
-    const uint32_t line_no = (uint32_t)prefix[lb] + count_newlines(data, lb << 9, ls);
-    uint32_t mask = 0;
-    if (owned && block_matches(db, data, ls, n)) mask |= 1u;
-    int j = 1;
-    uint32_t m = nlm;
-    while (m) {
-        int b = __ffs(m) - 1;
-        m &= m - 1;
-        size_t st = o + b + 1;
-        if (st >= n || st >= o + 16) break;
-        if (block_matches(db, data, st, n)) mask |= 1u << j;
-        j++;
-    }
-    res[i] = CandRes{line_no, (uint32_t)ls, mask};
+__device__ __forceinline__ bool is_word_dev(uint32_t b) {
+    return (b - '0' < 10u) || ((b | 0x20u) - 'a' < 26u) || b == '_';
 }
 
-__global__ void __launch_bounds__(128) k_emit_simple(const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
-                                                     const CandRes* __restrict__ res, const unsigned long long* __restrict__ recoff,
-                                                     const unsigned long long* meta_total, size_t cap, LineRec* __restrict__ recs, size_t rec_cap,
-                                                     Totals* totals) {
+// LOCAL verification walk of one DFA group around candidate chunk [o, o+16).
+//  - starts at t (at most `lookback` bytes before the chunk, never before the line start) in the start-of-line state
+//    or in the mid-line entry state that matches the previous byte;
+//  - a NUL acts as end-of-data followed by a restart (lines with NULs are re-checked exactly by k_emit_simple);
+//  - a '\n' ends the line: the walk continues with the next line only if that line starts inside the chunk;
+//  - once past every gram of the chunk (o+19) the walk stops as soon as the automaton is idle: a match that
+//    contains a gram hit of this chunk would still be in progress.
+// Returns bit j set if the j-th line intersecting the chunk matched.
+__device__ uint32_t walk_local(const GroupDev& G, const uint8_t* __restrict__ data, size_t n, size_t o, size_t t, bool at_line_start) {
+    uint32_t s = 0;
+    if (!at_line_start) s = is_word_dev(data[t - 1]) ? G.mid_word : G.mid_other;
+    uint32_t mask = 0;
+    int line = 0;
+    bool done = false;
+    const size_t chunk_end = o + 16, idle_from = o + 19;
+    ByteCursor c(data, t, n);
+    while (c.pos < n) {
+        const uint32_t b = c.get();
+        if (!done) {
+            bool hit;
+            if (b == 0) {
+                hit = G.trans[s * G.stride + G.eod] >= G.first_accept;
+                s = 0;
+            } else {
+                s = G.trans[s * G.stride + G.cls[b]];
+                hit = s >= G.first_accept;
+                if (!hit && b == '\n') hit = G.trans[s * G.stride + G.eod] >= G.first_accept;
+            }
+            if (hit) { mask |= 1u << line; done = true; }
+        }
+        c.next();
+        if (b == '\n') {
+            if (c.pos >= chunk_end || c.pos >= n) return mask;
+            line++;
+            done = false;
+            s = 0;
+            continue;
+        }
+        if (c.pos >= idle_from && (done || s < G.idle_end)) return mask;
+        if (done && c.pos >= chunk_end) return mask;
+    }
+    if (!done && G.trans[s * G.stride + G.eod] >= G.first_accept) mask |= 1u << line;
+    return mask;
+}
+
+// One thread per candidate chunk: local verification (see walk_local); writes the bitmask of matched lines.
+__global__ void __launch_bounds__(128) k_verify_local(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
+                                                      const unsigned long long* meta_total, size_t cap, uint32_t lookback,
+                                                      uint32_t* __restrict__ marks) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t ncand = (size_t)(*meta_total >> 32);
     if (ncand > cap) ncand = cap;
     if (i >= ncand) return;
-    CandRes r = res[i];
-    if (!r.mask) return;
+    const size_t o = (size_t)cand[i] * 16;
+    size_t t;
+    bool at_line_start;
+    if (lookback == 0xffffffffu) {
+        t = line_start_of(data, o);
+        at_line_start = true;
+    } else {
+        const size_t lo = o > lookback ? o - lookback : 0;
+        t = lo;
+        at_line_start = lo == 0;
+        size_t p = o;   // 16-byte aligned; scan words [p-4, p) downwards for the last '\n' in [lo, o)
+        while (p > lo) {
+            uint32_t z = eq_mask4(*reinterpret_cast<const uint32_t*>(data + p - 4), 0x0a0a0a0au);
+            if (p - 4 < lo) z &= ~((1u << (8 * (uint32_t)(lo - (p - 4)))) - 1u);
+            if (z) {
+                t = (p - 4) + ((31 - __clz(z)) >> 3) + 1;
+                at_line_start = true;
+                break;
+            }
+            p -= 4;
+        }
+    }
+    uint32_t mask = 0;
+    for (int g = 0; g < db.ngroups; g++) mask |= walk_local(db.groups[g], data, n, o, t, at_line_start);
+    marks[i] = mask;
+}
+
+__device__ bool range_has_nul(const uint8_t* __restrict__ data, size_t st, size_t en, size_t n) {
+    for (size_t base = st & ~(size_t)15; base < en; base += 16) {
+        uint4 v = ld_chunk(data, base, n);
+        uint32_t m = movemask4(eq_mask4(v.x, 0u)) | (movemask4(eq_mask4(v.y, 0u)) << 4) | (movemask4(eq_mask4(v.z, 0u)) << 8) |
+                     (movemask4(eq_mask4(v.w, 0u)) << 12);
+        uint32_t lo = base < st ? (uint32_t)(st - base) : 0u;
+        uint32_t hi = en - base < 16 ? (uint32_t)(en - base) : 16u;
+        m &= (hi == 16 ? 0xffffu : (1u << hi) - 1u) & ~((1u << lo) - 1u);
+        if (m) return true;
+    }
+    return false;
+}
+
+// One thread per candidate with marked lines: line extents, line numbers and the exact re-check of lines with NULs.
+// The same line can be marked by several candidate chunks; records come out ordered by line start, so the host
+// drops adjacent duplicates.
+__global__ void __launch_bounds__(128) k_emit_simple(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
+                                                     const uint32_t* __restrict__ marks, const unsigned long long* __restrict__ recoff,
+                                                     const unsigned long long* __restrict__ prefix, const unsigned long long* meta_total, size_t cap,
+                                                     LineRec* __restrict__ recs, size_t rec_cap, Totals* totals) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t ncand = (size_t)(*meta_total >> 32);
+    if (ncand > cap) ncand = cap;
+    if (i >= ncand) return;
+    uint32_t mask = marks[i];
+    if (!mask) return;
     size_t at = (size_t)recoff[i];
     const size_t o = (size_t)cand[i] * 16;
     uint4 v = ld_chunk(data, o, n);
     uint32_t nlm = newline_mask16(v);
     if (o + 16 > n) nlm &= (1u << (n - o)) - 1u;
-    uint32_t mask = r.mask;
     int j = 0;
-    size_t st = r.first_start;
+    size_t st = 0;
+    bool first = true;
     while (true) {
         if (mask & (1u << j)) {
+            if (first) st = line_start_of(data, o);
             size_t en = line_end_of(data, st, n);
-            if (at < rec_cap) recs[at] = LineRec{r.first_line + (uint32_t)j, (uint32_t)st, (uint32_t)(en - st)};
+            bool ok = true;
+            if (range_has_nul(data, st, en, n)) ok = block_matches(db, data, st, en);
+            const size_t lb = st >> 9;
+            const uint32_t line_no = (uint32_t)prefix[lb] + count_newlines(data, lb << 9, st);
+            if (at < rec_cap) recs[at] = LineRec{line_no, (uint32_t)st, ok ? (uint32_t)(en - st) : kInvalidLen};
             else atomicOr(&totals->flags, 4u);
             at++;
         }
@@ -522,6 +619,7 @@ __global__ void __launch_bounds__(128) k_emit_simple(const uint8_t* __restrict__
         int b = __ffs(nlm) - 1;
         nlm &= nlm - 1;
         st = o + b + 1;
+        first = false;
         j++;
         if ((mask >> j) == 0) break;
     }
@@ -681,9 +779,21 @@ struct DeviceDb {
     std::vector<void*> allocs;
     GroupDev* d_groups = nullptr;
     int ngroups = 0;
-    uint32_t* d_bitmap = nullptr;
     bool simple = false;
     ~DeviceDb() { for (void* p : allocs) cudaFree(p); }
+};
+
+struct DevicePrefilter {
+    int device = 0;
+    uint32_t* d_table = nullptr;
+    int table_words = 0;
+    int stride = 4;
+    bool fold = false;
+    int mode = 0;        // 1 exact keys, 2 bloom bitmap
+    int shift = 0;       // 32 - log2(buckets | bits)
+    uint32_t mul = 0;
+    uint32_t lookback = 0xffffffffu;
+    ~DevicePrefilter() { if (d_table) cudaFree(d_table); }
 };
 
 class ScanSlot {
@@ -765,6 +875,9 @@ std::shared_ptr<DeviceDb> engine_upload(const std::shared_ptr<Database>& db, std
         G.eod = (uint32_t)d.num_classes;
         G.first_accept = (uint32_t)d.first_accept;
         G.dead = d.dead >= 0 ? (uint32_t)d.dead : 0xffffffffu;
+        G.idle_end = (uint32_t)d.idle_end;
+        G.mid_other = (uint32_t)d.entry_mid_other;
+        G.mid_word = (uint32_t)d.entry_mid_word;
         G.accept_base = db->report_begin.empty() ? 0u : 0u;
         groups.push_back(G);
     }
@@ -777,12 +890,28 @@ std::shared_ptr<DeviceDb> engine_upload(const std::shared_ptr<Database>& db, std
     out->d_groups = (GroupDev*)upload(groups.data(), groups.size() * sizeof(GroupDev));
     out->ngroups = (int)groups.size();
     if (!out->d_groups) { error = "cudaMalloc failed for group table"; return nullptr; }
-    if (db->prefilter.enabled) {
-        out->d_bitmap = (uint32_t*)upload(db->prefilter.bitmap.data(), db->prefilter.bitmap.size() * sizeof(uint32_t));
-        if (!out->d_bitmap) { error = "cudaMalloc failed for prefilter bitmap"; return nullptr; }
-    }
     cache.emplace_back(db, out);
     if (cache.size() > 8) cache.erase(cache.begin());
+    return out;
+}
+
+std::shared_ptr<DevicePrefilter> engine_upload_prefilter(const Prefilter& pf, std::string& error) {
+    if (!pf.enabled) return nullptr;
+    auto out = std::make_shared<DevicePrefilter>();
+    cudaGetDevice(&out->device);
+    const std::vector<uint32_t>& src = pf.exact ? pf.keys : pf.bitmap;
+    out->table_words = (int)src.size();
+    out->stride = pf.stride;
+    out->fold = pf.fold_case;
+    out->mode = pf.exact ? 1 : 2;
+    out->shift = 32 - (pf.exact ? pf.log2_buckets : pf.log2_bits);
+    out->mul = pf.hash_mul;
+    out->lookback = pf.lookback;
+    if (cudaMalloc((void**)&out->d_table, src.size() * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMemcpy(out->d_table, src.data(), src.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+        error = "cudaMalloc/cudaMemcpy failed for the prefilter table";
+        return nullptr;
+    }
     return out;
 }
 
@@ -838,19 +967,34 @@ static void launch_scan(cudaStream_t st, Load load, size_t n, unsigned long long
     stats.launches += 3;
 }
 
-template <int STRIDE, bool FOLD>
-static cudaError_t launch_stream(cudaStream_t st, int grid, size_t smem, const uint8_t* data, size_t n, size_t nblk, unsigned long long* meta,
-                                 const uint32_t* bitmap, int log2_bits, uint32_t mul) {
+template <int STRIDE, bool FOLD, int MODE>
+static cudaError_t launch_stream_t(cudaStream_t st, int grid, int block, size_t smem, const uint8_t* data, size_t n, unsigned long long* meta,
+                                   const DevicePrefilter* pf) {
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_stream<STRIDE, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_stream<STRIDE, FOLD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k_stream<STRIDE, FOLD><<<grid, 256, smem, st>>>(data, n, nblk, meta, bitmap, log2_bits, mul);
+    k_stream<STRIDE, FOLD, MODE><<<grid, block, smem, st>>>(data, n, meta, pf ? pf->d_table : nullptr, pf ? pf->table_words : 0,
+                                                            pf ? pf->shift : 0, pf ? pf->mul : 0);
     return cudaGetLastError();
 }
 
-int slot_submit(ScanSlot* s, const DeviceDb& ddb, const uint8_t* host_data, const uint8_t* dev_data, size_t n, int buffer_size,
-                void* user_stream, std::string& error) {
+template <int MODE>
+static cudaError_t launch_stream_m(cudaStream_t st, int grid, int block, size_t smem, const uint8_t* data, size_t n, unsigned long long* meta,
+                                   const DevicePrefilter* pf) {
+    int key = pf->stride * 2 + (pf->fold ? 1 : 0);
+    switch (key) {
+        case 8: return launch_stream_t<4, false, MODE>(st, grid, block, smem, data, n, meta, pf);
+        case 9: return launch_stream_t<4, true, MODE>(st, grid, block, smem, data, n, meta, pf);
+        case 4: return launch_stream_t<2, false, MODE>(st, grid, block, smem, data, n, meta, pf);
+        case 5: return launch_stream_t<2, true, MODE>(st, grid, block, smem, data, n, meta, pf);
+        case 2: return launch_stream_t<1, false, MODE>(st, grid, block, smem, data, n, meta, pf);
+        default: return launch_stream_t<1, true, MODE>(st, grid, block, smem, data, n, meta, pf);
+    }
+}
+
+int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, const uint8_t* host_data, const uint8_t* dev_data, size_t n,
+                int buffer_size, void* user_stream, std::string& error) {
     if (n >= ((size_t)1 << 32) - 1024) { error = "segment too large"; return 7; }
     s->stream = user_stream ? (cudaStream_t)user_stream : s->own_stream;
     cudaStream_t st = s->stream;
@@ -859,7 +1003,6 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const uint8_t* host_data, cons
     s->buffer_size = buffer_size;
     s->stats = SegmentStats();
     s->nblk = (n + 511) / 512;
-    const Prefilter& pf = ddb.db->prefilter;
     // fast path: simple mode + prefilter + buffer large enough that "a super-block without newline" is a cheap
     // sufficient test for "no line needs gzgets splitting"
     size_t super_bytes = 0;
@@ -867,7 +1010,7 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const uint8_t* host_data, cons
         super_bytes = 512;
         while (super_bytes * 4 <= (size_t)buffer_size && super_bytes < 65536) super_bytes *= 2;   // 2*super-1 <= buffer_size-1
     }
-    s->fast = ddb.simple && pf.enabled && super_bytes >= 512 && std::getenv("GPUGREP_FORCE_GENERAL") == nullptr;
+    s->fast = ddb.simple && pf != nullptr && super_bytes >= 512 && std::getenv("GPUGREP_FORCE_GENERAL") == nullptr;
 
     if (host_data) {
         if (s->d_input.reserve(n + 1024) != cudaSuccess) { error = "cudaMalloc failed for the input segment"; return 3; }
@@ -885,7 +1028,7 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const uint8_t* host_data, cons
     if (s->d_meta.reserve((s->nblk + 8) * 8) != cudaSuccess || s->d_prefix.reserve((s->nblk + 8) * 8) != cudaSuccess ||
         s->d_sums.reserve(nb_scan * 8) != cudaSuccess) { error = "cudaMalloc failed for scan scratch"; return 3; }
     if (s->fast) {
-        if (s->d_cand.reserve(s->cand_cap * 4) != cudaSuccess || s->d_res.reserve(s->cand_cap * sizeof(CandRes)) != cudaSuccess ||
+        if (s->d_cand.reserve(s->cand_cap * 4) != cudaSuccess || s->d_res.reserve(s->cand_cap * sizeof(uint32_t)) != cudaSuccess ||
             s->d_recoff.reserve(s->cand_cap * 8) != cudaSuccess || s->d_recs.reserve(s->rec_cap * sizeof(LineRec)) != cudaSuccess) {
             error = "cudaMalloc failed for candidate scratch"; return 3;
         }
@@ -898,28 +1041,19 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const uint8_t* host_data, cons
         return 0;
     }
     // ---- K1 ----
-    int grid = g_num_sms * 8;
-    size_t max_grid = (s->nblk + 31) / 32;   // 8 warps x 4 blocks per CTA step
+    // persistent grid: enough CTAs to fill every SM, each warp strides over groups of kStreamU blocks
+    size_t smem = s->fast ? (size_t)pf->table_words * 4 : 0;
+    int block = smem > 32 * 1024 ? 1024 : 256;
+    int ctas_per_sm = smem > 100 * 1024 ? 1 : (smem > 32 * 1024 ? 2 : 6);
+    int grid = g_num_sms * ctas_per_sm;
+    size_t groups = (s->nblk + kStreamU - 1) / kStreamU;
+    size_t max_grid = (groups + (block / 32) - 1) / (block / 32);
     if ((size_t)grid > max_grid) grid = (int)std::max<size_t>(1, max_grid);
     unsigned long long* meta = s->d_meta.as<unsigned long long>();
     CUDA_TRY(cudaEventRecord(s->ev[2], st));
     cudaError_t le;
-    if (s->fast) {
-        size_t smem = ((size_t)1 << pf.log2_bits) / 8;
-        if (smem > 64 * 1024) grid = g_num_sms * (smem > 100 * 1024 ? 1 : 2);
-        if ((size_t)grid > max_grid) grid = (int)std::max<size_t>(1, max_grid);
-        int key = pf.stride * 2 + (pf.fold_case ? 1 : 0);
-        switch (key) {
-            case 8: le = launch_stream<4, false>(st, grid, smem, s->data, n, s->nblk, meta, ddb.d_bitmap, pf.log2_bits, pf.hash_mul); break;
-            case 9: le = launch_stream<4, true>(st, grid, smem, s->data, n, s->nblk, meta, ddb.d_bitmap, pf.log2_bits, pf.hash_mul); break;
-            case 4: le = launch_stream<2, false>(st, grid, smem, s->data, n, s->nblk, meta, ddb.d_bitmap, pf.log2_bits, pf.hash_mul); break;
-            case 5: le = launch_stream<2, true>(st, grid, smem, s->data, n, s->nblk, meta, ddb.d_bitmap, pf.log2_bits, pf.hash_mul); break;
-            case 2: le = launch_stream<1, false>(st, grid, smem, s->data, n, s->nblk, meta, ddb.d_bitmap, pf.log2_bits, pf.hash_mul); break;
-            default: le = launch_stream<1, true>(st, grid, smem, s->data, n, s->nblk, meta, ddb.d_bitmap, pf.log2_bits, pf.hash_mul); break;
-        }
-    } else {
-        le = launch_stream<0, false>(st, grid, 0, s->data, n, s->nblk, meta, nullptr, 13, 0);
-    }
+    if (s->fast) le = pf->mode == 1 ? launch_stream_m<1>(st, grid, block, smem, s->data, n, meta, pf) : launch_stream_m<2>(st, grid, block, smem, s->data, n, meta, pf);
+    else le = launch_stream_t<4, false, 0>(st, grid, block, 0, s->data, n, meta, nullptr);
     if (le != cudaSuccess) { error = std::string("k_stream launch: ") + cudaGetErrorString(le); return 7; }
     CUDA_TRY(cudaEventRecord(s->ev[3], st));
     s->stats.launches++;
@@ -937,12 +1071,12 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const uint8_t* host_data, cons
         k_list_candidates<<<(unsigned)((s->nblk + 255) / 256), 256, 0, st>>>(meta, prefix, s->nblk, s->d_cand.as<uint32_t>(), s->cand_cap, dT);
         DbView view{ddb.d_groups, ddb.ngroups};
         unsigned vgrid = (unsigned)((s->cand_cap + 127) / 128);
-        k_verify_simple<<<vgrid, 128, 0, st>>>(view, s->data, n, meta, prefix, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap,
-                                               s->d_res.as<CandRes>());
-        launch_scan(st, LoadResMask{s->d_res.as<CandRes>(), &dT->meta_total, s->cand_cap}, s->cand_cap, s->d_recoff.as<unsigned long long>(),
+        k_verify_local<<<vgrid, 128, 0, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->lookback,
+                                              s->d_res.as<uint32_t>());
+        launch_scan(st, LoadMarks{s->d_res.as<uint32_t>(), &dT->meta_total, s->cand_cap}, s->cand_cap, s->d_recoff.as<unsigned long long>(),
                     s->d_sums.as<unsigned long long>(), &dT->rec_total, s->stats);
-        k_emit_simple<<<vgrid, 128, 0, st>>>(s->data, n, s->d_cand.as<uint32_t>(), s->d_res.as<CandRes>(), s->d_recoff.as<unsigned long long>(),
-                                             &dT->meta_total, s->cand_cap, s->d_recs.as<LineRec>(), s->rec_cap, dT);
+        k_emit_simple<<<vgrid, 128, 0, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), s->d_res.as<uint32_t>(), s->d_recoff.as<unsigned long long>(),
+                                             prefix, &dT->meta_total, s->cand_cap, s->d_recs.as<LineRec>(), s->rec_cap, dT);
         s->stats.launches += 3;
         CUDA_TRY(cudaEventRecord(s->ev[1], st));
     }

@@ -42,7 +42,8 @@ struct SegmentResult {
     SegmentStats stats;
 };
 
-struct DeviceDb;   // device-resident tables of one Database on one device
+struct DeviceDb;          // device-resident DFA tables of one Database on one device
+struct DevicePrefilter;   // device-resident gram table of one (sample-tuned) Prefilter
 class ScanSlot;    // stream + scratch + pinned result buffers for one in-flight segment
 
 // All functions return 0 or a reference return code (3 = scratch allocation, 7 = CUDA failure) and set `error`.
@@ -50,6 +51,7 @@ int engine_select_device(int device, std::string& error);
 int engine_current_device();
 
 std::shared_ptr<DeviceDb> engine_upload(const std::shared_ptr<Database>& db, std::string& error);
+std::shared_ptr<DevicePrefilter> engine_upload_prefilter(const Prefilter& pf, std::string& error);
 
 ScanSlot* engine_acquire_slot(std::string& error);   // pooled per device; never returns a slot in use
 void engine_release_slot(ScanSlot* slot);
@@ -61,7 +63,8 @@ uint8_t* slot_host_buffer(ScanSlot* slot, size_t capacity, std::string& error);
 //  host_data: host memory (pinned => direct H2D; pageable => cudaMemcpyAsync stages it), n bytes.
 //  dev_data : device pointer, 16-byte aligned, n bytes, stays valid until slot_collect returns.
 //  user_stream: optional cudaStream_t to run on instead of the slot's own stream.
-int slot_submit(ScanSlot* slot, const DeviceDb& ddb, const uint8_t* host_data, const uint8_t* dev_data, size_t n,
+//  pf: gram table for the fast path, or nullptr (general path).
+int slot_submit(ScanSlot* slot, const DeviceDb& ddb, const DevicePrefilter* pf, const uint8_t* host_data, const uint8_t* dev_data, size_t n,
                 int buffer_size, void* user_stream, std::string& error);
 // Wait for the segment and expose its results (valid until the next slot_submit on this slot).
 int slot_collect(ScanSlot* slot, SegmentResult& out, std::string& error);

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <set>
 
 namespace gpugrep {
@@ -15,14 +16,25 @@ constexpr size_t kMaxGramsTotal = 131072;
 
 using Alts = std::vector<ClassString>;
 
-struct Lits {
-    bool exact_ok = false;
-    Alts exact;    // the node matches exactly one of these (valid iff exact_ok)
-    Alts prefix;   // every match starts with one of these ({""} = nothing known)
-    Alts suffix;   // every match ends with one of these
-    Alts best;     // required factor: every match contains one of these (empty = none found)
+constexpr size_t kInf = SIZE_MAX / 4;
+size_t sat_add(size_t a, size_t b) { return (a >= kInf || b >= kInf) ? kInf : a + b; }
+
+// A required factor together with the largest distance (bytes) from the start of the enclosing match to the start
+// of the factor occurrence that the match is guaranteed to contain (kInf: unbounded).
+struct Cand {
+    std::vector<ClassString> alts;
+    size_t before = 0;
 };
 
+struct Lits {
+    bool exact_ok = false;
+    std::vector<ClassString> exact;    // the node matches exactly one of these (valid iff exact_ok)
+    std::vector<ClassString> prefix;   // every match starts with one of these ({""} = nothing known)
+    std::vector<ClassString> suffix;   // every match ends with one of these
+    Cand best;                         // required factor (empty = none found)
+};
+
+using Alts = std::vector<ClassString>;
 const Alts kEpsilon = {ClassString{}};
 
 size_t max_len(const Alts& a) { size_t m = 0; for (auto& s : a) m = std::max(m, s.size()); return m; }
@@ -41,18 +53,11 @@ Alts cross(const Alts& a, const Alts& b) {
     dedupe(r);
     return r;
 }
-// products that may be truncated: prefixes keep their head, suffixes keep their tail
+// product that may be truncated: a prefix keeps its head
 Alts cross_head(const Alts& a, const Alts& b) {
     if (a.size() * b.size() > kMaxSet) return a;
     Alts r = cross(a, b);
     for (auto& s : r) if (s.size() > kMaxLen) s.resize(kMaxLen);
-    dedupe(r);
-    return r;
-}
-Alts cross_tail(const Alts& a, const Alts& b) {
-    if (a.size() * b.size() > kMaxSet) return b;
-    Alts r = cross(a, b);
-    for (auto& s : r) if (s.size() > kMaxLen) s.erase(s.begin(), s.end() - kMaxLen);
     dedupe(r);
     return r;
 }
@@ -74,15 +79,32 @@ double window_prob(const ClassString& s, size_t w) {
 double cost(const Alts& a) {
     if (a.empty()) return INFINITY;
     size_t ml = min_len(a);
-    if (ml < 4) return INFINITY;   // the filter hashes 4-byte grams
+    if (ml < 4) return INFINITY;   // the filter looks up 4-byte grams
     double tier = ml >= 7 ? 1.0 : (ml >= 5 ? 2.0 : 4.0);   // stride 4 / 2 / 1 in the streaming kernel
     double p = 0;
     for (auto& s : a) p += window_prob(s, 4);
     return p * tier;
 }
+double cost(const Cand& c) { return cost(c.alts) * (c.before >= kInf ? 1.5 : 1.0); }   // bounded look-back verifies cheaper
 
-void consider(Alts& best, const Alts& cand) {
+void consider(Cand& best, const Cand& cand) {
     if (cost(cand) < cost(best)) best = cand;
+}
+
+size_t node_maxlen(const Node& n) {
+    switch (n.kind) {
+        case NodeKind::Empty: case NodeKind::Assert: return 0;
+        case NodeKind::Set: return 1;
+        case NodeKind::Concat: { size_t t = 0; for (auto& k : n.kids) t = sat_add(t, node_maxlen(*k)); return t; }
+        case NodeKind::Alt: { size_t t = 0; for (auto& k : n.kids) t = std::max(t, node_maxlen(*k)); return std::min(t, kInf); }
+        case NodeKind::Repeat: {
+            size_t c = node_maxlen(*n.kids[0]);
+            if (c == 0) return 0;
+            if (n.max < 0 || c >= kInf) return kInf;
+            return std::min(kInf, c * (size_t)n.max);
+        }
+    }
+    return kInf;
 }
 
 Lits analyse(const Node& n) {
@@ -100,25 +122,30 @@ Lits analyse(const Node& n) {
         }
         case NodeKind::Concat: {
             Alts run = kEpsilon;
+            size_t run_before = 0;   // bytes of this concatenation that can precede the start of `run`
+            size_t acc = 0;          // bytes that can precede the current kid
             bool whole = true;       // everything so far is inside `run`
             r.prefix = kEpsilon;
             for (auto& kid : n.kids) {
                 Lits k = analyse(*kid);
-                if (k.exact_ok && fits(run, k.exact)) { run = cross(run, k.exact); continue; }
+                size_t km = node_maxlen(*kid);
+                if (k.exact_ok && fits(run, k.exact)) { run = cross(run, k.exact); acc = sat_add(acc, km); continue; }
                 Alts closed = cross_head(run, k.exact_ok ? k.exact : k.prefix);
-                consider(r.best, closed);
-                consider(r.best, k.best);
-                if (k.exact_ok) consider(r.best, k.exact);
+                consider(r.best, Cand{closed, run_before});
+                if (!k.best.alts.empty()) consider(r.best, Cand{k.best.alts, sat_add(acc, k.best.before)});
+                if (k.exact_ok) consider(r.best, Cand{k.exact, acc});
                 if (whole) r.prefix = closed;
                 whole = false;
                 run = k.exact_ok ? k.exact : k.suffix;
-                if (k.exact_ok) for (auto& s : run) if (s.size() > kMaxLen) s.erase(s.begin(), s.end() - kMaxLen);
+                for (auto& s : run) if (s.size() > kMaxLen) s.erase(s.begin(), s.end() - kMaxLen);
+                dedupe(run);
+                run_before = km >= kInf ? kInf : sat_add(acc, km - std::min(km, min_len(run)));
+                acc = sat_add(acc, km);
             }
             if (whole) {
                 r.exact_ok = true; r.exact = run; r.prefix = run; r.suffix = run;
-                for (auto& s : r.prefix) if (s.size() > kMaxLen) s.resize(kMaxLen);
             } else {
-                consider(r.best, run);
+                consider(r.best, Cand{run, run_before});
                 r.suffix = run;
             }
             return r;
@@ -127,23 +154,23 @@ Lits analyse(const Node& n) {
             r.exact_ok = true;
             bool all_factor = true;
             Alts pre, suf, fac;
-            bool pre_ok = true, suf_ok = true;
+            size_t before = 0;
             for (auto& kid : n.kids) {
                 Lits k = analyse(*kid);
                 if (k.exact_ok && r.exact_ok && r.exact.size() + k.exact.size() <= kMaxSet) r.exact.insert(r.exact.end(), k.exact.begin(), k.exact.end());
                 else r.exact_ok = false;
-                const Alts& f = (k.exact_ok && cost(k.exact) <= cost(k.best)) ? k.exact : k.best;
-                if (std::isinf(cost(f))) all_factor = false; else fac.insert(fac.end(), f.begin(), f.end());
+                Cand as_exact{k.exact, 0};
+                const Cand& f = (k.exact_ok && cost(as_exact) <= cost(k.best)) ? as_exact : k.best;
+                if (std::isinf(cost(f))) all_factor = false;
+                else { fac.insert(fac.end(), f.alts.begin(), f.alts.end()); before = std::max(before, f.before); }
                 pre.insert(pre.end(), k.prefix.begin(), k.prefix.end());
                 suf.insert(suf.end(), k.suffix.begin(), k.suffix.end());
             }
             dedupe(pre); dedupe(suf); dedupe(fac);
-            if (pre.size() > kMaxSet) pre_ok = false;
-            if (suf.size() > kMaxSet) suf_ok = false;
-            r.prefix = pre_ok ? pre : kEpsilon;
-            r.suffix = suf_ok ? suf : kEpsilon;
+            r.prefix = pre.size() <= kMaxSet ? pre : kEpsilon;
+            r.suffix = suf.size() <= kMaxSet ? suf : kEpsilon;
             if (r.exact_ok) dedupe(r.exact); else r.exact.clear();
-            if (all_factor && fac.size() <= 4 * kMaxSet) r.best = fac;
+            if (all_factor && fac.size() <= 4 * kMaxSet) r.best = Cand{fac, before};
             return r;
         }
         case NodeKind::Repeat: {
@@ -155,15 +182,15 @@ Lits analyse(const Node& n) {
                 }
                 return r;
             }
-            // min >= 1: the child occurs at least `min` times in a row
+            // min >= 1: the child occurs at least `min` times in a row; the first iteration starts the match
             if (k.exact_ok) {
                 Alts pow = k.exact;
                 int reps = 1;
                 while (reps < n.min && fits(pow, k.exact)) { pow = cross(pow, k.exact); reps++; }
                 if (reps == n.min && n.max == n.min) { r.exact_ok = true; r.exact = pow; r.prefix = r.suffix = pow; return r; }
                 r.prefix = r.suffix = pow;
-                r.best = pow;
-                if (std::isinf(cost(r.best))) r.best.clear();
+                r.best = Cand{pow, 0};
+                if (std::isinf(cost(r.best))) r.best = Cand{};
                 return r;
             }
             r.prefix = k.prefix; r.suffix = k.suffix; r.best = k.best;
@@ -193,49 +220,185 @@ double grams_in_window(const ClassString& s, size_t t, int stride, bool fold) {
 
 }  // namespace
 
-bool extract_factor(const Node& ast, std::vector<ClassString>& alternatives) {
+static bool extract_cand(const Node& ast, Cand& out) {
     Lits l = analyse(ast);
-    Alts best = l.best;
-    if (l.exact_ok) consider(best, l.exact);
-    consider(best, l.prefix);
-    consider(best, l.suffix);
+    Cand best = l.best;
+    if (l.exact_ok) consider(best, Cand{l.exact, 0});
+    consider(best, Cand{l.prefix, 0});
+    size_t total = node_maxlen(ast);
+    consider(best, Cand{l.suffix, total >= kInf ? kInf : total - std::min(total, min_len(l.suffix))});
     if (std::isinf(cost(best))) return false;
-    alternatives = best;
+    out = best;
     return true;
 }
 
-void build_prefilter(const std::vector<const Node*>& asts, const std::vector<unsigned>& flags, Prefilter& out) {
-    out = Prefilter();
-    std::vector<Alts> factors(asts.size());
+bool extract_factor(const Node& ast, std::vector<ClassString>& alternatives) {
+    Cand c;
+    if (!extract_cand(ast, c)) return false;
+    alternatives = c.alts;
+    return true;
+}
+
+FactorSet analyse_factors(const std::vector<const Node*>& asts) {
+    FactorSet fs;
+    fs.factors.resize(asts.size());
     size_t ml = SIZE_MAX;
+    fs.before.resize(asts.size());
     for (size_t i = 0; i < asts.size(); i++) {
-        if (!extract_factor(*asts[i], factors[i])) {
-            out.note = "pattern " + std::to_string(i) + " has no required factor of >= 4 bytes";
-            return;
+        Cand c;
+        bool ok = extract_cand(*asts[i], c);
+        fs.factors[i] = c.alts;
+        fs.before[i] = c.before >= kInf ? SIZE_MAX : c.before;
+        if (!ok) {
+            fs.note = "pattern " + std::to_string(i) + " has no required factor of >= 4 bytes";
+            fs.factors.clear();
+            return fs;
         }
-        ml = std::min(ml, min_len(factors[i]));
+        ml = std::min(ml, min_len(fs.factors[i]));
     }
-    (void)flags;
-    out.min_factor_len = (int)ml;
-    int first_stride = ml >= 7 ? 4 : (ml >= 5 ? 2 : 1);
+    fs.usable = true;
+    fs.min_len = ml;
+    return fs;
+}
+
+// ---- sample histogram ----------------------------------------------------------------------------------------
+void GramHistogram::Table::init(size_t capacity_pow2) {
+    keys.assign(capacity_pow2, 0);
+    counts.assign(capacity_pow2, 0);
+    mask = (uint32_t)capacity_pow2 - 1;
+}
+void GramHistogram::Table::add(uint32_t key) {
+    uint32_t h = (key * 0x9E3779B1u) >> 7;
+    for (;;) {
+        h &= mask;
+        if (counts[h] == 0) { keys[h] = key; counts[h] = 1; return; }
+        if (keys[h] == key) { counts[h]++; return; }
+        h++;
+    }
+}
+uint32_t GramHistogram::Table::get(uint32_t key) const {
+    if (keys.empty()) return 0;
+    uint32_t h = (key * 0x9E3779B1u) >> 7;
+    for (;;) {
+        h &= mask;
+        if (counts[h] == 0) return 0;
+        if (keys[h] == key) return counts[h];
+        h++;
+    }
+}
+void GramHistogram::add_sample(const uint8_t* text, size_t n) {
+    if (n < 4) return;
+    size_t cap = 1;
+    while (cap < 2 * n) cap <<= 1;   // load factor <= 0.5
+    raw_.init(cap);
+    folded_.init(cap);
+    uint64_t fp = 1469598103934665603ull ^ n;
+    for (size_t i = 0; i + 4 <= n; i++) {
+        uint32_t g;
+        std::memcpy(&g, text + i, 4);
+        raw_.add(g);
+        folded_.add(g | 0x20202020u);
+        if ((i & 63) == 0) fp = (fp ^ g) * 1099511628211ull;
+    }
+    positions_ = n - 3;
+    fingerprint_ = fp;
+}
+uint32_t GramHistogram::count(uint32_t gram, bool folded) const { return folded ? folded_.get(gram) : raw_.get(gram); }
+
+namespace {
+
+ByteSet effective(const ByteSet& b, bool fold) {
+    if (!fold) return b;
+    ByteSet f;
+    for (unsigned v = 0; v < 256; v++) if (b.test(v)) f.set(v | 0x20);
+    return f;
+}
+
+void expand_gram(const ClassString& s, size_t at, bool fold, std::vector<uint32_t>& out) {
+    std::vector<uint32_t> cur = {0};
+    for (int i = 0; i < 4; i++) {
+        ByteSet eff = effective(s[at + i], fold);
+        std::vector<uint32_t> next;
+        next.reserve(cur.size() * eff.count());
+        for (uint32_t g : cur) for (unsigned v = 0; v < 256; v++) if (eff.test(v)) next.push_back(g | (v << (8 * i)));
+        cur.swap(next);
+    }
+    out.insert(out.end(), cur.begin(), cur.end());
+}
+
+// Expected filter hits in the sample if window [t, t+3+stride) of s is used: each gram of alignment j is looked up
+// at 1/stride of the text positions.
+double window_hits(const ClassString& s, size_t t, int stride, bool fold, const GramHistogram& h) {
+    std::vector<uint32_t> grams;
+    double hits = 0;
+    for (int j = 0; j < stride; j++) {
+        grams.clear();
+        expand_gram(s, t + j, fold, grams);
+        for (uint32_t g : grams) hits += h.count(g, fold);
+    }
+    return hits / stride;
+}
+
+bool build_exact_table(const std::vector<uint32_t>& grams, Prefilter& out) {
+    // buckets of two keys; find a multiplier for which no bucket receives a third key
+    static const uint32_t muls[] = {0x9E3779B1u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Cu, 0xFD7046C5u, 0xB55A4F09u,
+                                    0x7FEB352Du, 0x846CA68Bu, 0x9E3779B9u, 0xCC9E2D51u, 0x1B873593u, 0xE6546B64u, 0x2545F491u, 0x5851F42Du};
+    int lb = 9;   // 512 buckets = 4 KiB minimum
+    while (lb < 14 && ((size_t)1 << lb) < grams.size() * 2) lb++;
+    for (; lb <= 14; lb++) {   // at most 16384 buckets = 128 KiB of shared memory
+        for (uint32_t mul : muls) {
+            std::vector<uint32_t> keys((size_t)2 << lb, 0);
+            bool ok = true;
+            for (uint32_t g : grams) {
+                uint32_t b = prefilter_hash(g, mul, lb);
+                if (keys[2 * b] == 0) keys[2 * b] = g;
+                else if (keys[2 * b + 1] == 0) keys[2 * b + 1] = g;
+                else { ok = false; break; }
+            }
+            if (ok) {
+                out.exact = true;
+                out.log2_buckets = lb;
+                out.hash_mul = mul;
+                out.keys.swap(keys);
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
+}  // namespace
+
+void build_prefilter(const FactorSet& fs, const GramHistogram* sample, Prefilter& out) {
+    out = Prefilter();
+    if (!fs.usable) { out.note = fs.note; return; }
+    out.min_factor_len = (int)fs.min_len;
+    int first_stride = fs.min_len >= 7 ? 4 : (fs.min_len >= 5 ? 2 : 1);
     for (int stride = first_stride; stride >= 1; stride /= 2) {
         size_t w = 3 + (size_t)stride;
-        // pick, per alternative, the window with the fewest grams; decide on folding from the totals
         for (int pass = 0; pass < 2; pass++) {
             bool fold = pass == 1;
             std::vector<Window> wins;
-            double total = 0;
+            double total = 0, hits = 0;
             bool ok = true;
-            for (auto& alts : factors) {
+            size_t lookback = 0;
+            for (size_t pi = 0; pi < fs.factors.size(); pi++) {
+                auto& alts = fs.factors[pi];
                 for (auto& s : alts) {
-                    double best = INFINITY; size_t bt = 0;
+                    double best = INFINITY, best_grams = 0; size_t bt = 0;
                     for (size_t t = 0; t + w <= s.size(); t++) {
                         double g = grams_in_window(s, t, stride, fold);
-                        if (g < best) { best = g; bt = t; }
+                        if (g > kMaxGramsPerWindow * stride) continue;
+                        // score: expected hits in the sample first, table growth second
+                        double score = sample ? window_hits(s, t, stride, fold, *sample) * 1000.0 + g : g;
+                        if (score < best) { best = score; best_grams = g; bt = t; }
                     }
-                    if (best > kMaxGramsPerWindow * stride) { ok = false; break; }
-                    total += best;
+                    if (std::isinf(best)) { ok = false; break; }
+                    total += best_grams;
+                    if (sample) hits += (best - best_grams) / 1000.0;
                     wins.push_back(Window{&s, bt});
+                    size_t lb = fs.before[pi] == SIZE_MAX ? SIZE_MAX : fs.before[pi] + bt + (size_t)stride - 1;
+                    lookback = std::max(lookback, lb);
                 }
                 if (!ok) break;
             }
@@ -246,38 +409,35 @@ void build_prefilter(const std::vector<const Node*>& asts, const std::vector<uns
                 for (auto& wn : wins) folded_total += grams_in_window(*wn.s, wn.start, stride, true);
                 if (total > 3.0 * folded_total && total > 2048) continue;
             }
-            // materialise the grams
-            std::set<uint32_t> grams;
-            for (auto& wn : wins) {
-                for (int j = 0; j < stride; j++) {
-                    std::vector<uint32_t> cur = {0};
-                    for (int i = 0; i < 4; i++) {
-                        const ByteSet& b = (*wn.s)[wn.start + j + i];
-                        ByteSet eff;
-                        if (fold) { for (unsigned v = 0; v < 256; v++) if (b.test(v)) eff.set(v | 0x20); } else eff = b;
-                        std::vector<uint32_t> next;
-                        next.reserve(cur.size() * eff.count());
-                        for (uint32_t g : cur) for (unsigned v = 0; v < 256; v++) if (eff.test(v)) next.push_back(g | (v << (8 * i)));
-                        cur.swap(next);
-                    }
-                    grams.insert(cur.begin(), cur.end());
-                }
-            }
-            size_t need = grams.size() * 64;
-            int lb = 13;
-            while (lb < 20 && (1ull << lb) < need) lb++;
+            std::vector<uint32_t> all;
+            for (auto& wn : wins)
+                for (int j = 0; j < stride; j++) expand_gram(*wn.s, wn.start + j, fold, all);
+            std::sort(all.begin(), all.end());
+            all.erase(std::unique(all.begin(), all.end()), all.end());
+            // a gram equal to the empty-slot marker cannot be stored exactly; it can only be "\0\0\0\0"
+            all.erase(std::remove(all.begin(), all.end(), 0u), all.end());
             out.enabled = true;
             out.stride = stride;
             out.fold_case = fold;
-            out.log2_bits = lb;
-            out.bitmap.assign((1u << lb) / 32, 0);
-            for (uint32_t g : grams) {
-                uint32_t h = prefilter_hash(g, out.hash_mul, lb);
-                out.bitmap[h >> 5] |= 1u << (h & 31);
+            out.num_grams = all.size();
+            out.grams = all;
+            out.lookback = lookback > 4096 ? 0xffffffffu : (uint32_t)lookback;
+            if (sample && sample->positions()) out.expected_hits_per_mib = hits * 1048576.0 / (double)sample->positions();
+            if (!build_exact_table(all, out)) {
+                size_t need = all.size() * 64;
+                int lb = 16;
+                while (lb < 20 && (1ull << lb) < need) lb++;
+                out.log2_bits = lb;
+                out.hash_mul = 0x9E3779B1u;
+                out.bitmap.assign((1u << lb) / 32, 0);
+                for (uint32_t g : all) {
+                    uint32_t h = prefilter_hash(g, out.hash_mul, lb);
+                    out.bitmap[h >> 5] |= 1u << (h & 31);
+                }
             }
-            out.num_grams = grams.size();
-            out.note = "stride " + std::to_string(stride) + (fold ? ", folded" : "") + ", " + std::to_string(grams.size()) + " grams, " +
-                       std::to_string(1u << lb) + " bits";
+            out.note = "stride " + std::to_string(stride) + (fold ? ", folded" : "") + ", " + std::to_string(all.size()) + " grams, " +
+                       (out.exact ? "exact table of " + std::to_string(2u << out.log2_buckets) + " keys" : "bloom bitmap of " + std::to_string(1u << out.log2_bits) + " bits") +
+                       (sample ? ", sample-tuned" : "");
             return;
         }
     }

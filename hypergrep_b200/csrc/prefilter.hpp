@@ -1,10 +1,12 @@
 // Literal-factor prefilter: the role Hyperscan's FDR/Teddy literal matchers play in front of its automata,
-// re-designed for a SIMT machine with no byte shuffle: every pattern contributes a REQUIRED FACTOR (a set of
-// short class-strings one of which occurs in every match); all 4-byte windows of those factors that can land
-// on a sampled text position are inserted into a hashed bitmap that lives in shared memory.  The streaming
-// kernel hashes one 4-byte gram per sampled position (every 4th, 2nd or every byte, depending on the shortest
-// factor) and flags 16-byte chunks whose grams hit the bitmap; only lines touching flagged chunks are walked
-// by the DFA.  The filter is a superset filter: it may flag lines that do not match, never the reverse.
+// re-designed for a SIMT machine with no byte shuffle.  Every pattern contributes a REQUIRED FACTOR (a set of short
+// class-strings one of which occurs in every match).  For a sampling stride k (4, 2 or 1) a window of 3+k bytes is
+// chosen inside every factor alternative; the k four-byte grams of that window - one for each alignment the
+// window can have against the sampled text positions - go into a gram table that lives in shared memory.  The
+// streaming kernel looks up one gram per sampled position and flags 16-byte chunks with a hit; only lines
+// touching flagged chunks are walked by the DFA.  The filter is a superset filter: it may flag lines that do not
+// match, never the reverse - so WHICH window is chosen only affects speed, and it is chosen against a histogram of
+// the grams in a sample of the input (a window made of "host" or "dur=" would flag every syslog line).
 #pragma once
 #include <cstdint>
 #include <string>
@@ -16,24 +18,65 @@ namespace gpugrep {
 
 using ClassString = std::vector<ByteSet>;
 
+// Required factors of a pattern set (static, part of the compiled database).
+struct FactorSet {
+    bool usable = false;                               // every pattern has a factor of >= 4 bytes
+    std::vector<std::vector<ClassString>> factors;     // per pattern: alternatives
+    std::vector<size_t> before;                        // per pattern: max bytes between match start and factor start (SIZE_MAX: unbounded)
+    size_t min_len = 0;
+    std::string note;
+};
+
+// 4-gram histogram of a text sample (raw and case-folded), used to pick selective windows.
+class GramHistogram {
+public:
+    void add_sample(const uint8_t* text, size_t n);
+    uint32_t count(uint32_t gram, bool folded) const;
+    size_t positions() const { return positions_; }
+    uint64_t fingerprint() const { return fingerprint_; }
+private:
+    struct Table {
+        std::vector<uint32_t> keys, counts;
+        uint32_t mask = 0;
+        void init(size_t capacity_pow2);
+        void add(uint32_t key);
+        uint32_t get(uint32_t key) const;
+    };
+    Table raw_, folded_;
+    size_t positions_ = 0;
+    uint64_t fingerprint_ = 0;
+};
+
 struct Prefilter {
     bool enabled = false;
     int stride = 4;             // text positions sampled: multiples of `stride` (4, 2 or 1)
-    bool fold_case = false;     // text bytes are OR-ed with 0x20 before hashing (grams stored folded)
-    uint32_t hash_mul = 0x9E3779B1u;
-    int log2_bits = 13;         // bitmap holds 1 << log2_bits bits
+    bool fold_case = false;     // text bytes are OR-ed with 0x20 before lookup (grams stored folded)
+    // exact mode: buckets of two 32-bit keys, bucket = (gram * hash_mul) >> (32 - log2_buckets); 0 = empty slot
+    bool exact = false;
+    int log2_buckets = 0;
+    std::vector<uint32_t> keys;       // 2 << log2_buckets entries
+    // bloom mode (very large gram sets): bit = (gram * hash_mul) >> (32 - log2_bits)
+    int log2_bits = 13;
     std::vector<uint32_t> bitmap;
+    uint32_t hash_mul = 0x9E3779B1u;
+    std::vector<uint32_t> grams;      // the exact gram set (sorted)
     size_t num_grams = 0;
     int min_factor_len = 0;
+    // A match whose window hit sits at text position q starts at or after q - lookback (0xffffffff: unbounded, verify
+    // from the line start).
+    uint32_t lookback = 0xffffffffu;
+    double expected_hits_per_mib = -1;   // from the sample histogram, -1 without a sample
     std::string note;           // why it is disabled, or a one-line summary
 };
 
 // Required-factor analysis of one pattern.  Returns false if no usable factor exists.
 bool extract_factor(const Node& ast, std::vector<ClassString>& alternatives);
 
-// Build the shared prefilter of a pattern set (one entry per pattern, in order).
-void build_prefilter(const std::vector<const Node*>& asts, const std::vector<unsigned>& flags, Prefilter& out);
+FactorSet analyse_factors(const std::vector<const Node*>& asts);
 
-inline uint32_t prefilter_hash(uint32_t gram, uint32_t mul, int log2_bits) { return (gram * mul) >> (32 - log2_bits); }
+// Build the gram tables.  `sample` may be null (static choice: fewest grams per window).
+void build_prefilter(const FactorSet& fs, const GramHistogram* sample, Prefilter& out);
+
+inline uint32_t prefilter_hash(uint32_t gram, uint32_t mul, int log2_size) { return (gram * mul) >> (32 - log2_size); }
 
 }  // namespace gpugrep

@@ -62,7 +62,8 @@ struct ParseResult {
 // Parse one pattern (raw bytes, NUL-free) under HS_FLAG_{CASELESS,DOTALL,MULTILINE}.
 ParseResult parse_regex(const std::string& pattern, unsigned flags);
 
-// True if the pattern can match the empty buffer (Hyperscan: "Pattern matches empty buffer; use HS_FLAG_ALLOWEMPTY").
+// True if the pattern can match without consuming a byte, assertions aside (Hyperscan: "Pattern matches empty
+// buffer; use HS_FLAG_ALLOWEMPTY").
 bool matches_empty_buffer(const Node& n);
 
 bool is_word_byte(unsigned b);

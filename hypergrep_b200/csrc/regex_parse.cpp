@@ -526,8 +526,8 @@ bool matches_empty_buffer(const Node& n) {
         case NodeKind::Empty: return true;
         case NodeKind::Set: return false;
         case NodeKind::Assert:
-            // on an empty buffer: ^ \A $ \z hold, \B holds, \b does not
-            return n.assert_kind != AssertKind::WordBoundary;
+            // structural test (a start->accept path that consumes nothing), as in Hyperscan: assertions do not count
+            return true;
         case NodeKind::Concat:
             for (auto& k : n.kids) if (!matches_empty_buffer(*k)) return false;
             return true;

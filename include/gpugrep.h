@@ -141,11 +141,12 @@ typedef struct gpugrep_db_info {
     unsigned int prefilter;       /* 1: literal prefilter enabled                                   */
     unsigned int prefilter_stride;
     unsigned int prefilter_fold;
-    unsigned int prefilter_log2_bits;
+    unsigned int prefilter_log2_bits;   /* log2 of buckets (exact table) or of bits (bloom bitmap) */
     unsigned int prefilter_grams;
     unsigned int prefilter_min_factor;
+    unsigned int prefilter_lookback;    /* a match with a gram hit at q starts at or after q - lookback; 0xffffffff = unbounded */
     unsigned int total_states;
-    unsigned int reserved;
+    unsigned int reserved;              /* 1: exact gram table, 0: bloom bitmap */
 } gpugrep_db_info;
 
 typedef struct gpugrep_group_info {
@@ -157,6 +158,10 @@ typedef struct gpugrep_group_info {
     int dead;                    /* absorbing non-reporting state, else -1                   */
     unsigned int accept_sets;
     unsigned int members;
+    unsigned int entry_mid_other; /* entry state of a walk that starts after a non-word byte inside a line */
+    unsigned int entry_mid_word;  /* ... after a word byte                                                  */
+    unsigned int idle_end;        /* states < idle_end have no partial match in progress                   */
+    unsigned int reserved;
 } gpugrep_group_info;
 
 GPUGREP_API gpugrep_db* gpugrep_db_compile(const char* const* patterns, const unsigned int* pattern_flags,
@@ -172,6 +177,11 @@ GPUGREP_API int gpugrep_db_accept_reports(const gpugrep_db* db, unsigned int gro
                               unsigned int* singlematch, unsigned int cap);
 /* Copies the prefilter bitmap ((1 << log2_bits) / 32 words); returns words copied, 0 if disabled. */
 GPUGREP_API size_t gpugrep_db_copy_prefilter(const gpugrep_db* db, uint32_t* words, size_t cap_words, uint32_t* hash_mul);
+/* Copies up to cap exact prefilter grams (little-endian 4-byte windows); returns the total gram count. */
+GPUGREP_API size_t gpugrep_db_copy_grams(const gpugrep_db* db, uint32_t* out, size_t cap);
+/* Re-chooses the prefilter windows of a handle against the 4-gram histogram of a text sample (what the scan entry
+ * points do with the head of their input); 0 on success. */
+GPUGREP_API int gpugrep_db_tune(gpugrep_db* db, const void* sample, size_t size);
 GPUGREP_API const char* gpugrep_db_prefilter_note(const gpugrep_db* db);
 
 #ifdef __cplusplus

@@ -74,6 +74,7 @@ static struct {
     p2_md* (*md_create_from)(const p2_code*, void*);
     void (*md_free)(p2_md*);
     size_t* (*ovector)(p2_md*);
+    int (*pattern_info)(const p2_code*, uint32_t, void*);
 } P2;
 
 static int p2_load(void) {
@@ -84,7 +85,7 @@ static int p2_load(void) {
     SYM(compile, "pcre2_compile_8"); SYM(code_free, "pcre2_code_free_8"); SYM(jit_compile, "pcre2_jit_compile_8");
     SYM(match, "pcre2_match_8"); SYM(dfa_match, "pcre2_dfa_match_8"); SYM(md_create, "pcre2_match_data_create_8");
     SYM(md_create_from, "pcre2_match_data_create_from_pattern_8"); SYM(md_free, "pcre2_match_data_free_8");
-    SYM(ovector, "pcre2_get_ovector_pointer_8");
+    SYM(ovector, "pcre2_get_ovector_pointer_8"); SYM(pattern_info, "pcre2_pattern_info_8");
 #undef SYM
     P2.h = h;
     return 0;
@@ -123,6 +124,14 @@ static int hs_would_reject(const char* p) {
             if (i + 1 < n && p[i + 1] == '^') i++;
             if (i + 1 < n && p[i + 1] == ']') i++; /* leading ] is literal */
             continue;
+        }
+        if (c == '{') { /* Hyperscan: "Bounded repeat is too large" above 32767 */
+            size_t j = i + 1; unsigned long v = 0; int digits = 0, big = 0;
+            while (j < n && ((p[j] >= '0' && p[j] <= '9') || p[j] == ',')) {
+                if (p[j] == ',') { v = 0; } else { v = v * 10 + (unsigned long)(p[j] - '0'); digits++; if (v > 32767) big = 1; }
+                j++;
+            }
+            if (j < n && p[j] == '}' && digits && big) return 1;
         }
         if (c == '(' && i + 1 < n && p[i + 1] == '*') return 1;      /* (*VERB) / (*UTF) */
         if (c == '(' && i + 1 < n && p[i + 1] == '?') {
@@ -212,8 +221,13 @@ static port_db_t* port_compile(const char* const* patterns, const unsigned* flag
         db->code[i] = P2.compile((const unsigned char*)patterns[i], strlen(patterns[i]), p2_options(f), &err, &eoff, NULL);
         if (!db->code[i]) goto fail;
         db->md[i] = P2.md_create(2048, NULL);
-        /* "Pattern matches empty buffer; use HS_FLAG_ALLOWEMPTY" */
-        if (P2.match(db->code[i], (const unsigned char*)"", 0, 0, 0, db->md[i], NULL) >= 0) goto fail;
+        /* "Pattern matches empty buffer; use HS_FLAG_ALLOWEMPTY": Hyperscan tests its graph for a start->accept
+           edge, i.e. whether the pattern can match without consuming a byte, assertions notwithstanding (so a bare
+           \b or ^ is vacuous too).  PCRE2_INFO_MATCHEMPTY (13) answers the same structural question. */
+        {
+            uint32_t can_be_empty = 0;
+            if (P2.pattern_info(db->code[i], 13u, &can_be_empty) != 0 || can_be_empty) goto fail;
+        }
         P2.jit_compile(db->code[i], P2_JIT_COMPLETE);
         if (!(f & HS_FLAG_SINGLEMATCH) || db->ids[i] != db->ids[0]) db->simple = 0;
     }

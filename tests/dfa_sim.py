@@ -18,13 +18,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 class DbInfo(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint) for n in (
         "patterns", "groups", "simple", "simple_id", "prefilter", "prefilter_stride", "prefilter_fold",
-        "prefilter_log2_bits", "prefilter_grams", "prefilter_min_factor", "total_states", "reserved")]
+        "prefilter_log2_bits", "prefilter_grams", "prefilter_min_factor", "prefilter_lookback", "total_states", "reserved")]
 
 
 class GroupInfo(ctypes.Structure):
     _fields_ = [("states", ctypes.c_uint), ("classes", ctypes.c_uint), ("stride", ctypes.c_uint),
                 ("first_accept", ctypes.c_uint), ("sink_match", ctypes.c_int), ("dead", ctypes.c_int),
-                ("accept_sets", ctypes.c_uint), ("members", ctypes.c_uint)]
+                ("accept_sets", ctypes.c_uint), ("members", ctypes.c_uint), ("entry_mid_other", ctypes.c_uint),
+                ("entry_mid_word", ctypes.c_uint), ("idle_end", ctypes.c_uint), ("reserved", ctypes.c_uint)]
 
 
 def marshal(patterns, flags=None, ids=None):
@@ -72,14 +73,26 @@ class CompiledDb:
                 reports.append([(ids_buf[i], sm_buf[i]) for i in range(cnt)])
             self.groups.append((gi, cls, trans.reshape(gi.states, gi.stride), acc, reports))
         self.prefilter_note = lib.gpugrep_db_prefilter_note(h).decode()
-        self.bitmap = None
+        self._load_grams()
+
+    def retune(self, sample: bytes) -> None:
+        """Re-choose the prefilter windows against a text sample (what the scan entry points do with their input)."""
+        self.lib.gpugrep_db_tune.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
+        self.lib.gpugrep_db_tune(ctypes.c_void_p(self.handle), sample, len(sample))
+        self.lib.gpugrep_db_get_info(ctypes.c_void_p(self.handle), ctypes.byref(self.info))
+        self.prefilter_note = self.lib.gpugrep_db_prefilter_note(ctypes.c_void_p(self.handle)).decode()
+        self._load_grams()
+
+    def _load_grams(self) -> None:
+        lib = self.lib
+        h = ctypes.c_void_p(self.handle)
+        self.grams = None
         if self.info.prefilter:
-            words = (1 << self.info.prefilter_log2_bits) // 32
-            bm = np.zeros(words, dtype=np.uint32)
-            mul = ctypes.c_uint32(0)
-            lib.gpugrep_db_copy_prefilter(h, bm.ctypes.data_as(ctypes.c_void_p), words, ctypes.byref(mul))
-            self.bitmap = bm
-            self.hash_mul = mul.value
+            lib.gpugrep_db_copy_grams.restype = ctypes.c_size_t
+            count = lib.gpugrep_db_copy_grams(h, None, 0)
+            grams = np.zeros(count, dtype=np.uint32)
+            lib.gpugrep_db_copy_grams(h, grams.ctypes.data_as(ctypes.c_void_p), count)
+            self.grams = set(int(g) for g in grams)
 
     def __del__(self):
         if getattr(self, "handle", None):
@@ -137,20 +150,113 @@ class CompiledDb:
         return out
 
     def prefilter_hits(self, text: bytes) -> bool:
-        """True if any sampled 4-gram of `text` hits the bitmap (superset test used by the streaming kernel)."""
-        if self.bitmap is None:
+        """True if some 4-gram of `text` is in the gram set at EVERY alignment of the sampling grid (superset test)."""
+        if self.grams is None:
             return True
         st = self.info.prefilter_stride
-        lb = self.info.prefilter_log2_bits
-        for q in range(0, max(0, len(text) - 3), 1):
-            gram = int.from_bytes(text[q:q + 4], "little")
-            if self.info.prefilter_fold:
-                gram |= 0x20202020
-            h = ((gram * self.hash_mul) & 0xFFFFFFFF) >> (32 - lb)
-            if (int(self.bitmap[h >> 5]) >> (h & 31)) & 1:
-                if q % st == 0:
-                    return True
-        return False
+        fold = 0x20202020 if self.info.prefilter_fold else 0
+        for phase in range(st):
+            hit = False
+            for q in range(phase, max(0, len(text) - 3), st):
+                if (int.from_bytes(text[q:q + 4], "little") | fold) in self.grams:
+                    hit = True
+                    break
+            if not hit:
+                return False
+        return True
+
+
+def _is_word(b: int) -> bool:
+    return (48 <= b <= 57) or (65 <= b <= 90) or (97 <= b <= 122) or b == 95
+
+
+def fast_path_matched_line_starts(db: "CompiledDb", data: bytes) -> set:
+    """CPU model of the fast path (simple mode): gram hits flag 16-byte chunks; every flagged chunk is verified by a
+    LOCAL DFA walk that starts `lookback` bytes before the chunk (or at the line start if that is nearer), treats NUL
+    as end-of-data + restart, follows lines that start inside the chunk and stops once the automaton is idle past
+    the chunk.  Lines containing NUL are re-checked exactly.  Returns the start offsets of the matched lines."""
+    n = len(data)
+    st = db.info.prefilter_stride
+    fold = 0x20202020 if db.info.prefilter_fold else 0
+    lookback = db.info.prefilter_lookback
+    flagged = set()
+    for q in range(0, n, st):
+        gram = int.from_bytes(data[q:q + 4].ljust(4, b"\0"), "little") | fold
+        if gram in db.grams:
+            flagged.add(q >> 4)
+    marked = set()
+    for c in sorted(flagged):
+        o = c * 16
+        lo = 0 if lookback == 0xFFFFFFFF else max(0, o - lookback)
+        nl = data.rfind(b"\n", lo, o)
+        if lookback == 0xFFFFFFFF:
+            nl = data.rfind(b"\n", 0, o)
+        at_line_start = nl >= 0 or lo == 0
+        t = nl + 1 if nl >= 0 else lo
+        line_start = data.rfind(b"\n", 0, o) + 1   # bookkeeping for the model only
+        states = []
+        for gi, cls, trans, acc, reports in db.groups:
+            if at_line_start:
+                states.append(0)
+            else:
+                states.append(gi.entry_mid_word if _is_word(data[t - 1]) else gi.entry_mid_other)
+        pos = t
+        cur_line = line_start
+        done_line = False
+        while pos < n:
+            b = data[pos]
+            if not done_line:
+                if b == 0:
+                    hit = False
+                    for k, (gi, cls, trans, acc, reports) in enumerate(db.groups):
+                        s = int(trans[states[k], gi.classes])
+                        hit |= s >= gi.first_accept
+                        states[k] = 0
+                    if hit:
+                        marked.add(cur_line)
+                        done_line = True
+                else:
+                    hit = False
+                    for k, (gi, cls, trans, acc, reports) in enumerate(db.groups):
+                        s = int(trans[states[k], cls[b]])
+                        if s >= gi.first_accept:
+                            hit = True
+                        states[k] = s
+                    if not hit and b == 10:
+                        for k, (gi, cls, trans, acc, reports) in enumerate(db.groups):
+                            if int(trans[states[k], gi.classes]) >= gi.first_accept:
+                                hit = True
+                    if hit:
+                        marked.add(cur_line)
+                        done_line = True
+            pos += 1
+            if b == 10:
+                if pos >= o + 16 or pos >= n:
+                    break
+                cur_line = pos
+                done_line = False
+                states = [0] * len(db.groups)
+                continue
+            if pos >= o + 19 and (done_line or all(states[k] < g[0].idle_end for k, g in enumerate(db.groups))):
+                break
+            if done_line and pos >= o + 16:
+                break
+        else:
+            if not done_line:
+                for k, (gi, cls, trans, acc, reports) in enumerate(db.groups):
+                    if int(trans[states[k], gi.classes]) >= gi.first_accept:
+                        marked.add(cur_line)
+    # exact re-check of marked lines that contain NUL bytes
+    out = set()
+    for ls in marked:
+        end = data.find(b"\n", ls)
+        line = data[ls:end + 1] if end >= 0 else data[ls:]
+        if b"\0" in line:
+            if db.line_reports(line):
+                out.add(ls)
+        else:
+            out.add(ls)
+    return out
 
 
 def split_pseudo_lines(data: bytes, buffer_size: int):

@@ -16,6 +16,9 @@ namespace gpugrep {
 struct DeviceDb {
     std::shared_ptr<Database> db;
 };
+struct DevicePrefilter {
+    int unused = 0;
+};
 
 class ScanSlot {
 public:
@@ -37,6 +40,10 @@ std::shared_ptr<DeviceDb> engine_upload(const std::shared_ptr<Database>& db, std
     return d;
 }
 
+std::shared_ptr<DevicePrefilter> engine_upload_prefilter(const Prefilter& pf, std::string&) {
+    return pf.enabled ? std::make_shared<DevicePrefilter>() : nullptr;
+}
+
 ScanSlot* engine_acquire_slot(std::string&) { return new ScanSlot(); }
 void engine_release_slot(ScanSlot* s) { delete s; }
 
@@ -45,8 +52,8 @@ uint8_t* slot_host_buffer(ScanSlot* s, size_t capacity, std::string&) {
     return s->stage.data();
 }
 
-int slot_submit(ScanSlot* s, const DeviceDb& ddb, const uint8_t* host_data, const uint8_t* dev_data, size_t n, int buffer_size, void*,
-                std::string& error) {
+int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter*, const uint8_t* host_data, const uint8_t* dev_data, size_t n,
+                int buffer_size, void*, std::string& error) {
     if (!host_data) { (void)dev_data; error = "mock engine: device-resident input is not supported"; return 7; }
     s->ddb = &ddb; s->data = host_data; s->n = n; s->buffer_size = buffer_size;
     return 0;

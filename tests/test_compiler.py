@@ -1,0 +1,97 @@
+"""Pattern compiler checks on CPU: the tables libgpugrep.so emits, walked by tests/dfa_sim.py, against the oracle."""
+
+import ctypes
+import random
+
+import pytest
+
+import parity
+from dfa_sim import CompiledDb, fast_path_matched_line_starts, split_pseudo_lines
+from oracle_api import check, scan_bytes
+from regex_gen import gen_regex, gen_text
+
+ACCEPTED = ["foobar", "fo{2}bar", "fo+bar", "^foo$", r"\bfoo\b", "[[:alpha:]]+[0-9]", r"a\x41\n", r"\Qa.b\E+", "(?i)abc", "(?x) a b c # comment",
+            "(?P<name>ab)+c", "a{2,3}?b", r"[^\n]x", r"\d{1,3}\.\d{1,3}", "(a|b)*abb", r"x\z", r"x\Z", r"\Afoo", "(?s:a.b)", "a(?#note)b"]
+REJECTED = ["(?<!foo)bar", "(?=a)b", "(?!a)b", "(?<=a)b", r"(a)\1", "(?>ab)c", "a*+", "a++", "(?(1)a|b)", "(?R)", r"a\Kb", r"\X", r"\C", r"\R",
+            "(*UTF)a", "a*", "foo|", "^", "$", r"\b", "(a", "a)", "[a", "a{3,2}", r"\p{L}", "(?C1)a", "a{40000}", r"\x{100}", "(?P=n)", "", "x*?"]
+
+
+def test_accept_reject_table(gpu_lib, oracle_lib):
+    """Accept/reject decisions (reference check_patterns, hyperscanner.c:154-167) agree with the oracle's Hyperscan rules."""
+    for pattern in ACCEPTED:
+        assert CompiledDb(gpu_lib, [pattern]).rc == 0, pattern
+        assert check(oracle_lib, [pattern]) == 0, pattern
+    for pattern in REJECTED:
+        if pattern == "":
+            continue
+        assert CompiledDb(gpu_lib, [pattern]).rc == 4, pattern
+        assert check(oracle_lib, [pattern]) == 4, pattern
+    # ids sharing SINGLEMATCH inconsistently, unknown flag bits
+    assert CompiledDb(gpu_lib, ["a", "b"], [14, 6], [1, 1]).rc == 4
+    assert CompiledDb(gpu_lib, ["a"], [14 | 32]).rc == 4
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_tables_match_oracle(seed, gpu_lib, oracle_lib):
+    """DFA tables (all groups, accept sets, report lists) reproduce the oracle's per-line reports, incl. multiple ids,
+    non-SINGLEMATCH patterns, NULs and gzgets splitting."""
+    patterns, flags, ids, buffer_size, data, _, _ = parity.random_case(1000 + seed)
+    if parity.has_all_nul_pseudo_line(data, buffer_size):
+        pytest.skip("all-NUL pseudo-line")
+    db = CompiledDb(gpu_lib, patterns, flags, ids)
+    assert (db.rc == 0) == (check(oracle_lib, patterns, flags, ids) == 0)
+    if db.rc:
+        return
+    _, got, _ = scan_bytes(oracle_lib, data, patterns, flags=flags, ids=ids, buffer_size=buffer_size)
+    expected = [(i, ln) for (i, ln, _line) in got]
+    mine = []
+    for ln, pl in enumerate(split_pseudo_lines(data, buffer_size)):
+        reports = db.line_reports(pl)
+        mine += [(rid, ln) for rid in reports]
+        assert not reports or db.prefilter_hits(db.block_of(pl)), "prefilter must be a superset filter"
+    assert mine == expected
+
+
+LITS = ["abc", "bca", "a b", "Ab1", "x_1", "c.a", "ab", "bb", "1x"]
+
+
+def _factor_pattern(rng: random.Random) -> str:
+    core = "".join(rng.choice(LITS) for _ in range(rng.randint(2, 3)))
+    pre = rng.choice(["", "", "^", r"\b", "x?", "[ab]{0,2}", "(?:a|b_)", r"\w+", ".*", "a{2,}"])
+    suf = rng.choice(["", "", "$", r"\b", "c*", "[^a]", "(?:x|1)+", r"\s", r"\d{1,2}", ".b"])
+    return pre + core.replace(".", r"\.") + suf
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_fast_path_model_is_exact(seed, gpu_lib):
+    """The fast-path ALGORITHM (gram hits -> local DFA walk with look-back, mid-line entry states, idle stop, NUL
+    re-check), modelled on CPU over the compiler's tables, finds exactly the lines the full per-line walk finds."""
+    rng = random.Random(seed)
+    k = rng.choice([1, 2, 4])
+    patterns = [_factor_pattern(rng) for _ in range(k)]
+    db = CompiledDb(gpu_lib, patterns, [rng.choice([14, 14, 15, 10])] * k, [0] * k)
+    assert db.rc == 0
+    if not db.info.prefilter:
+        pytest.skip("no usable factor")
+    lines = []
+    for _ in range(40):
+        text = "".join(rng.choice("abcAB _x1.\t") for _ in range(rng.randint(0, 50)))
+        if rng.random() < 0.5:
+            at = rng.randint(0, len(text))
+            text = text[:at] + "".join(rng.choice(LITS) for _ in range(rng.randint(1, 3))) + text[at:]
+        if rng.random() < 0.1:
+            at = rng.randint(0, len(text))
+            text = text[:at] + "\0" + text[at:]
+        lines.append(text)
+    data = ("\n".join(lines) + ("\n" if rng.random() < 0.7 else "")).encode("latin1")
+    if parity.has_all_nul_pseudo_line(data, 262140):
+        pytest.skip("all-NUL pseudo-line")
+    if rng.random() < 0.5:
+        gpu_lib.gpugrep_db_tune.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
+        db.retune(data[: max(8, len(data) // 2)])
+    truth, pos = set(), 0
+    for pl in split_pseudo_lines(data, 262140):
+        if db.line_reports(pl):
+            truth.add(pos)
+        pos += len(pl)
+    assert fast_path_matched_line_starts(db, data) == truth

@@ -1,0 +1,38 @@
+#!/usr/bin/env python3
+"""Small device-resident scan used under ncu (profiles/): one warm-up pass and one measured pass over --mib MiB."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+
+from gpu_api import scan_buffer  # noqa: E402
+from hypergrep_b200 import synth, utils  # noqa: E402
+
+parser = argparse.ArgumentParser()
+parser.add_argument("--mib", type=int, default=1024)
+parser.add_argument("--set", default="c2")
+parser.add_argument("--passes", type=int, default=2)
+args = parser.parse_args()
+lib = utils._get_hyperscanner_lib()
+plants = None
+if args.set == "c1":
+    patterns = synth.C1_PATTERNS
+elif args.set == "c3":
+    patterns, plants = synth.c3_patterns()
+else:
+    patterns = synth.C2_PATTERNS
+host = torch.empty(args.mib << 20, dtype=torch.uint8).pin_memory()
+synth.fill_syslog(host.numpy(), seed=1234, plants=plants, plant_ppm=1000 if plants else 0, lib=lib)
+dev = host.cuda()
+torch.cuda.synchronize()
+for _ in range(args.passes):
+    rc, _, st = scan_buffer(lib, dev.data_ptr(), dev.numel(), 1, patterns, collect=False)
+    assert rc == 0
+    print(f"set={args.set} bytes={st.bytes_scanned} lines={st.lines} matches={st.matches} candidates={st.candidates} "
+          f"gpu_ms={st.gpu_ms:.3f} stream_ms={st.stream_kernel_ms:.3f} launches={st.launches} path={st.path} "
+          f"GB/s={st.bytes_scanned / st.gpu_ms / 1e6:.1f} stream_GB/s={st.bytes_scanned / st.stream_kernel_ms / 1e6:.1f}")
