@@ -60,7 +60,7 @@ int gpugrep_db_get_info(const gpugrep_db* h, gpugrep_db_info* out) {
     out->prefilter = db.prefilter.enabled;
     out->prefilter_stride = (unsigned)db.prefilter.stride;
     out->prefilter_fold = db.prefilter.fold_case;
-    out->prefilter_log2_bits = (unsigned)(db.prefilter.exact ? db.prefilter.log2_buckets : db.prefilter.log2_bits);
+    out->prefilter_log2_bits = (unsigned)(db.prefilter.exact ? db.prefilter.log2_slots : db.prefilter.log2_bits);
     out->reserved = db.prefilter.exact ? 1u : 0u;
     out->prefilter_grams = (unsigned)db.prefilter.num_grams;
     out->prefilter_min_factor = (unsigned)db.prefilter.min_factor_len;

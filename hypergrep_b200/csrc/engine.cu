@@ -69,6 +69,15 @@ __device__ __forceinline__ uint32_t eq_mask4(uint32_t w, uint32_t rep) {
     uint32_t t = u - 0x01010101u;
     return ~(t | w) & 0x80808080u;   // valid for rep bytes < 0x80 ('\n' = 0x0a, NUL = 0x00)
 }
+// same test with the constants held in registers so that each step is ONE three-input LOP3 (the compiler otherwise
+// splits the two-immediate forms): 3 instructions per word instead of 4 on the pipe this kernel saturates
+__device__ __forceinline__ uint32_t eq_mask4_r(uint32_t w, uint32_t rep, uint32_t c80) {
+    uint32_t u, z;
+    asm("lop3.b32 %0, %1, %2, %3, 0xBE;" : "=r"(u) : "r"(w), "r"(rep), "r"(c80));   // (w ^ rep) | 0x80808080
+    uint32_t t = u - 0x01010101u;
+    asm("lop3.b32 %0, %1, %2, %3, 0x02;" : "=r"(z) : "r"(t), "r"(w), "r"(c80));     // ~(t | w) & 0x80808080
+    return z;
+}
 // 4 flag bits (0x80 per byte) -> 4 contiguous bits
 __device__ __forceinline__ uint32_t movemask4(uint32_t z) { return ((z >> 7) * 0x01020408u) >> 24 & 0xFu; }
 
@@ -103,42 +112,75 @@ __device__ __forceinline__ uint4 ld_chunk(const uint8_t* data, size_t off, size_
     return v;
 }
 
+// cheap existence tests on a 16-byte chunk (exact: the borrow trick can only flag a byte above a real hit)
+__device__ __forceinline__ uint32_t any_newline16(const uint4& v) {
+    return eq_mask4(v.x, 0x0a0a0a0au) | eq_mask4(v.y, 0x0a0a0a0au) | eq_mask4(v.z, 0x0a0a0a0au) | eq_mask4(v.w, 0x0a0a0a0au);
+}
+__device__ __forceinline__ uint32_t haszero4(uint32_t w) { return (w - 0x01010101u) & ~w & 0x80808080u; }
+
 // index just past the last '\n' strictly before `pos` (0 if none): start of the line containing byte `pos`
 __device__ size_t line_start_of(const uint8_t* data, size_t pos) {
     while (pos > 0) {
         size_t base = (pos - 1) & ~(size_t)15;
         uint4 v = *reinterpret_cast<const uint4*>(data + base);
-        uint32_t m = newline_mask16(v);
         uint32_t span = (uint32_t)(pos - base);   // bytes [base, pos) are candidates, 1..16
-        if (span < 16) m &= (1u << span) - 1u;
-        if (m) return base + (32 - __clz(m));
+        if (any_newline16(v)) {
+            uint32_t m = newline_mask16(v);
+            if (span < 16) m &= (1u << span) - 1u;
+            if (m) return base + (32 - __clz(m));
+        }
         pos = base;
     }
     return 0;
 }
 
-// index just past the first '\n' at or after `pos`, or n if there is none
-__device__ size_t line_end_of(const uint8_t* data, size_t pos, size_t n) {
+// index just past the first '\n' at or after `pos`, or n if there is none; *has_nul is set if a NUL byte lies in
+// [pos, returned end)
+__device__ size_t line_end_of(const uint8_t* data, size_t pos, size_t n, bool* has_nul) {
     size_t base = pos & ~(size_t)15;
     uint32_t skip = (uint32_t)(pos - base);
+    bool nul = false;
+    size_t end = n;
     while (base < n) {
         uint4 v = ld_chunk(data, base, n);
-        uint32_t m = newline_mask16(v) & ~((1u << skip) - 1u);
-        if (m) return base + __ffs(m);
+        const bool edge = skip != 0 || base + 16 > n;
+        uint32_t zero_any = haszero4(v.x) | haszero4(v.y) | haszero4(v.z) | haszero4(v.w);
+        uint32_t nl_any = any_newline16(v);
+        if (nl_any || edge) {
+            uint32_t valid = (base + 16 > n ? (1u << (n - base)) - 1u : 0xffffu) & ~((1u << skip) - 1u);
+            uint32_t m = newline_mask16(v) & valid;
+            if (m) {
+                end = base + __ffs(m);
+                if (zero_any) {
+                    uint32_t zm = movemask4(eq_mask4(v.x, 0u)) | (movemask4(eq_mask4(v.y, 0u)) << 4) | (movemask4(eq_mask4(v.z, 0u)) << 8) |
+                                  (movemask4(eq_mask4(v.w, 0u)) << 12);
+                    if (zm & valid & ((1u << __ffs(m)) - 1u)) nul = true;
+                }
+                break;
+            }
+            if (zero_any) {
+                uint32_t zm = movemask4(eq_mask4(v.x, 0u)) | (movemask4(eq_mask4(v.y, 0u)) << 4) | (movemask4(eq_mask4(v.z, 0u)) << 8) |
+                              (movemask4(eq_mask4(v.w, 0u)) << 12);
+                if (zm & valid) nul = true;
+            }
+        } else if (zero_any) {
+            nul = true;
+        }
         skip = 0;
         base += 16;
     }
-    return n;
+    if (has_nul) *has_nul = nul;
+    return end;
 }
 
 // newlines in [from, to), from 16-byte aligned
 __device__ uint32_t count_newlines(const uint8_t* data, size_t from, size_t to) {
     uint32_t c = 0;
-    for (size_t b = from; b < to; b += 16) {
+    size_t b = from;
+    for (; b + 16 <= to; b += 16) c += newline_count16(*reinterpret_cast<const uint4*>(data + b));
+    if (b < to) {
         uint4 v = *reinterpret_cast<const uint4*>(data + b);
-        uint32_t m = newline_mask16(v);
-        if (b + 16 > to) m &= (1u << (to - b)) - 1u;
-        c += __popc(m);
+        c += __popc(newline_mask16(v) & ((1u << (to - b)) - 1u));
     }
     return c;
 }
@@ -151,36 +193,59 @@ __device__ uint32_t count_newlines(const uint8_t* data, size_t from, size_t to) 
 // STRIDE: sample every STRIDE-th byte position (4, 2, 1).  MODE: 0 no prefilter, 1 exact keys, 2 bloom bitmap.
 // Algorithmic traffic: 1 byte read per input byte + 8 bytes written per 512.
 // ------------------------------------------------------------------------------------------------------------
+struct ProbeParams {
+    uint32_t mul, mul2;   // hash multipliers (mul2: second choice of the exact table)
+    int shift;            // bloom: 32 - log2(bits).  exact: shift that turns the product into a BYTE offset (see below)
+    uint32_t amask;       // exact: keeps the slot bits of the byte offset, clears the replica / word bits
+    uint32_t half_bytes;  // exact: byte offset of the second half of the table
+    int rshift;           // exact: log2 of the replication factor (copies interleaved across banks)
+};
+
+// Gram lookups of one 16-byte chunk.  MODE 1: two-choice table of exact 32-bit keys; the table is replicated
+// 2^rshift times with the copies interleaved word by word, and a lane only ever reads copy (lane mod 2^rshift):
+// with 32 copies every lane stays in its own shared-memory bank and the loads are conflict-free.
+// Byte offset of slot h for this lane = ((gram * mul) >> shift) & amask | replica4, where replica4 = 4 * copy.
+__device__ __forceinline__ uint32_t lds32(uint32_t shared_addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(shared_addr));
+    return v;
+}
+
+// c1 / c2: shared-window address of table half 1 / 2 (aligned to the size of a half) OR-ed with 4 * copy of this lane,
+// so that an address is formed by ONE logic op: ((product >> shift) & amask) | c.
 template <int STRIDE, bool FOLD, int MODE>
-__device__ __forceinline__ uint32_t probe_chunk(const uint4& v, uint32_t next, const uint32_t* __restrict__ tab, uint32_t mul, int shift) {
-    if (MODE == 0) return 0;
+__device__ __forceinline__ bool probe_chunk(const uint4& v, uint32_t next, const uint32_t* __restrict__ tab, const ProbeParams& pp, uint32_t c1,
+                                            uint32_t c2) {
+    if (MODE == 0) return false;
     uint32_t w[5] = {v.x, v.y, v.z, v.w, next};
     if (FOLD) {
 #pragma unroll
         for (int i = 0; i < 5; i++) w[i] |= 0x20202020u;
     }
-    uint32_t hit = 0;
+    uint32_t miss = 0xffffffffu;   // min over all lookups of (key ^ gram): 0 iff some key matched
+    uint32_t bits = 0;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
 #pragma unroll
         for (int s = 0; s < 4; s += STRIDE) {
             uint32_t gram = s == 0 ? w[i] : __funnelshift_r(w[i], w[i + 1], 8 * s);
-            uint32_t h = (gram * mul) >> shift;
             if (MODE == 1) {
-                uint2 e = reinterpret_cast<const uint2*>(tab)[h];   // bucket of two exact keys
-                hit |= (uint32_t)(e.x == gram) | (uint32_t)(e.y == gram);
+                uint32_t e1 = lds32((((gram * pp.mul) >> pp.shift) & pp.amask) | c1);
+                uint32_t e2 = lds32((((gram * pp.mul2) >> pp.shift) & pp.amask) | c2);
+                miss = __vimin3_u32(miss, e1 ^ gram, e2 ^ gram);
             } else {
-                hit |= (tab[h >> 5] >> (h & 31)) & 1u;
+                uint32_t h = (gram * pp.mul) >> pp.shift;
+                bits |= tab[h >> 5] >> (h & 31);
             }
         }
     }
-    return hit;
+    return MODE == 1 ? miss == 0u : (bits & 1u) != 0u;
 }
 
 // newlines in a 16-byte chunk: four flag words (bit 7 of matching bytes) are merged into one 64-bit word with three
 // multiply-adds (FMA pipe) instead of shifts and ORs (ALU pipe, the pipe this kernel saturates first)
-__device__ __forceinline__ uint32_t newline_count16_fma(const uint4& v) {
-    uint32_t a = eq_mask4(v.x, 0x0a0a0a0au), b = eq_mask4(v.y, 0x0a0a0a0au), c = eq_mask4(v.z, 0x0a0a0a0au), d = eq_mask4(v.w, 0x0a0a0a0au);
+__device__ __forceinline__ uint32_t newline_count16_fma(const uint4& v, uint32_t cnl, uint32_t c80) {
+    uint32_t a = eq_mask4_r(v.x, cnl, c80), b = eq_mask4_r(v.y, cnl, c80), c = eq_mask4_r(v.z, cnl, c80), d = eq_mask4_r(v.w, cnl, c80);
     unsigned long long acc = a;
     asm("mad.wide.u32 %0, %1, 2, %0;" : "+l"(acc) : "r"(b));
     asm("mad.wide.u32 %0, %1, 4, %0;" : "+l"(acc) : "r"(c));
@@ -192,14 +257,29 @@ constexpr int kStreamU = 4;   // 512-byte blocks per warp step
 
 template <int STRIDE, bool FOLD, int MODE>
 __global__ void __launch_bounds__(1024) k_stream(const uint8_t* __restrict__ data, size_t n, unsigned long long* __restrict__ meta,
-                                                 const uint32_t* __restrict__ table, int table_words, int shift, uint32_t mul) {
-    extern __shared__ __align__(16) uint32_t s_tab[];
+                                                 const uint32_t* __restrict__ table, int table_words, ProbeParams pp) {
+    extern __shared__ __align__(16) uint32_t s_raw[];
+    // exact tables are placed at an address aligned to the size of one half (see probe_chunk); the launch reserves the slack
+    uint32_t* s_tab = s_raw;
+    uint32_t saddr = (uint32_t)__cvta_generic_to_shared(s_raw);
+    if (MODE == 1) {
+        uint32_t aligned = (saddr + pp.half_bytes - 1u) & ~(pp.half_bytes - 1u);
+        s_tab = s_raw + ((aligned - saddr) >> 2);
+        saddr = aligned;
+    }
     if (MODE != 0) {
         for (int i = threadIdx.x; i < table_words; i += blockDim.x) s_tab[i] = table[i];
         __syncthreads();
     }
     constexpr int U = kStreamU;
     const uint32_t lane = threadIdx.x & 31;
+    const uint32_t replica4 = (lane & ((1u << pp.rshift) - 1u)) << 2;
+    uint32_t c1 = saddr | replica4, c2 = (saddr + pp.half_bytes) | replica4;
+    asm volatile("mov.u32 %0, %0;" : "+r"(c1));   // materialise: each table address is then a single (x & amask) | c
+    asm volatile("mov.u32 %0, %0;" : "+r"(c2));
+    uint32_t cnl, c80;   // opaque to the optimiser so that they stay in registers (see eq_mask4_r)
+    asm volatile("mov.u32 %0, 0x0a0a0a0a;" : "=r"(cnl));
+    asm volatile("mov.u32 %0, 0x80808080;" : "=r"(c80));
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
     const size_t nblk = (n + 511) >> 9;
@@ -222,7 +302,7 @@ __global__ void __launch_bounds__(1024) k_stream(const uint8_t* __restrict__ dat
             uint32_t c[U];
 #pragma unroll
             for (int u = 0; u < U; u++) {
-                c[u] = newline_count16_fma(v[u]);
+                c[u] = newline_count16_fma(v[u], cnl, c80);
                 uint32_t nx = 0;
                 if (MODE != 0 && STRIDE < 4) {
                     // first word of the next chunk: lane+1's word of this block, or (lane 31) lane 0's word of the next block
@@ -230,8 +310,8 @@ __global__ void __launch_bounds__(1024) k_stream(const uint8_t* __restrict__ dat
                     nx = __shfl_sync(0xffffffffu, give, (lane + 1) & 31);
                     if (u + 1 == U && lane == 31) nx = after;
                 }
-                uint32_t hit = probe_chunk<STRIDE, FOLD, MODE>(v[u], nx, s_tab, mul, shift);
-                masks[u] = __ballot_sync(0xffffffffu, hit != 0);
+                bool hit = probe_chunk<STRIDE, FOLD, MODE>(v[u], nx, s_tab, pp, c1, c2);
+                masks[u] = __ballot_sync(0xffffffffu, hit);
             }
             cnt01 = __reduce_add_sync(0xffffffffu, c[0] | (c[1] << 16));
             cnt23 = __reduce_add_sync(0xffffffffu, c[2] | (c[3] << 16));
@@ -255,10 +335,10 @@ __global__ void __launch_bounds__(1024) k_stream(const uint8_t* __restrict__ dat
                 nx = o2 < n ? ld_chunk(data, o2, n).x : 0u;
             }
         }
-        uint32_t cnt = newline_count16_fma(v);
-        uint32_t hit = probe_chunk<STRIDE, FOLD, MODE>(v, nx, s_tab, mul, shift);
-        if (off >= n) hit = 0;   // chunks that start at or beyond n can never be candidates
-        uint32_t mask = __ballot_sync(0xffffffffu, hit != 0);
+        uint32_t cnt = newline_count16_fma(v, cnl, c80);
+        bool hit = probe_chunk<STRIDE, FOLD, MODE>(v, nx, s_tab, pp, c1, c2);
+        if (off >= n) hit = false;   // chunks that start at or beyond n can never be candidates
+        uint32_t mask = __ballot_sync(0xffffffffu, hit);
         uint32_t total = __reduce_add_sync(0xffffffffu, cnt);
         if (lane == 0) meta[g] = ((unsigned long long)total << 32) | mask;
     }
@@ -322,10 +402,17 @@ struct LoadU32 {
     __device__ unsigned long long operator()(size_t i) const { return p[i]; }
 };
 
+// `limit` (optional): device word whose high 32 bits bound the meaningful prefix of the input (candidate count);
+// tiles entirely beyond it contribute zero and are skipped.
 template <class Load>
-__global__ void __launch_bounds__(kScanThreads) k_scan_sums(Load load, size_t n, unsigned long long* __restrict__ sums) {
+__global__ void __launch_bounds__(kScanThreads) k_scan_sums(Load load, size_t n, unsigned long long* __restrict__ sums, const unsigned long long* limit) {
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_total;
+    if (limit) {
+        size_t lim = (size_t)(*limit >> 32);
+        if (lim < n) n = lim;
+        if ((size_t)blockIdx.x * kScanTile >= n) { if (threadIdx.x == 0) sums[blockIdx.x] = 0; return; }
+    }
     size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
     unsigned long long acc = 0;
 #pragma unroll
@@ -352,9 +439,14 @@ __global__ void __launch_bounds__(1024) k_scan_top(unsigned long long* __restric
 
 template <class Load>
 __global__ void __launch_bounds__(kScanThreads) k_scan_write(Load load, size_t n, const unsigned long long* __restrict__ sums,
-                                                             unsigned long long* __restrict__ out) {
+                                                             unsigned long long* __restrict__ out, const unsigned long long* limit) {
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_total;
+    if (limit) {
+        size_t lim = (size_t)(*limit >> 32);
+        if (lim < n) n = lim;
+        if ((size_t)blockIdx.x * kScanTile >= n) return;
+    }
     size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
     unsigned long long vals[kScanItems];
     unsigned long long acc = 0;
@@ -569,59 +661,61 @@ __global__ void __launch_bounds__(128) k_verify_local(DbView db, const uint8_t* 
     marks[i] = mask;
 }
 
-__device__ bool range_has_nul(const uint8_t* __restrict__ data, size_t st, size_t en, size_t n) {
-    for (size_t base = st & ~(size_t)15; base < en; base += 16) {
-        uint4 v = ld_chunk(data, base, n);
-        uint32_t m = movemask4(eq_mask4(v.x, 0u)) | (movemask4(eq_mask4(v.y, 0u)) << 4) | (movemask4(eq_mask4(v.z, 0u)) << 8) |
-                     (movemask4(eq_mask4(v.w, 0u)) << 12);
-        uint32_t lo = base < st ? (uint32_t)(st - base) : 0u;
-        uint32_t hi = en - base < 16 ? (uint32_t)(en - base) : 16u;
-        m &= (hi == 16 ? 0xffffu : (1u << hi) - 1u) & ~((1u << lo) - 1u);
-        if (m) return true;
-    }
-    return false;
-}
-
-// One thread per candidate with marked lines: line extents, line numbers and the exact re-check of lines with NULs.
+// Candidates with marked lines are first compacted per block (few candidates carry a match), then one thread per
+// marked candidate computes line extents, line numbers and the exact re-check of lines with NULs.
 // The same line can be marked by several candidate chunks; records come out ordered by line start, so the host
 // drops adjacent duplicates.
-__global__ void __launch_bounds__(128) k_emit_simple(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
-                                                     const uint32_t* __restrict__ marks, const unsigned long long* __restrict__ recoff,
-                                                     const unsigned long long* __restrict__ prefix, const unsigned long long* meta_total, size_t cap,
-                                                     LineRec* __restrict__ recs, size_t rec_cap, Totals* totals) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+constexpr int kEmitThreads = 256;
+__global__ void __launch_bounds__(kEmitThreads) k_emit_simple(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
+                                                              const uint32_t* __restrict__ marks, const unsigned long long* __restrict__ recoff,
+                                                              const unsigned long long* __restrict__ prefix, const unsigned long long* meta_total,
+                                                              size_t cap, LineRec* __restrict__ recs, size_t rec_cap, Totals* totals) {
+    __shared__ uint32_t s_list[kEmitThreads];
+    __shared__ uint32_t s_count;
     size_t ncand = (size_t)(*meta_total >> 32);
     if (ncand > cap) ncand = cap;
-    if (i >= ncand) return;
-    uint32_t mask = marks[i];
-    if (!mask) return;
-    size_t at = (size_t)recoff[i];
-    const size_t o = (size_t)cand[i] * 16;
-    uint4 v = ld_chunk(data, o, n);
-    uint32_t nlm = newline_mask16(v);
-    if (o + 16 > n) nlm &= (1u << (n - o)) - 1u;
-    int j = 0;
-    size_t st = 0;
-    bool first = true;
-    while (true) {
-        if (mask & (1u << j)) {
-            if (first) st = line_start_of(data, o);
-            size_t en = line_end_of(data, st, n);
-            bool ok = true;
-            if (range_has_nul(data, st, en, n)) ok = block_matches(db, data, st, en);
-            const size_t lb = st >> 9;
-            const uint32_t line_no = (uint32_t)prefix[lb] + count_newlines(data, lb << 9, st);
-            if (at < rec_cap) recs[at] = LineRec{line_no, (uint32_t)st, ok ? (uint32_t)(en - st) : kInvalidLen};
-            else atomicOr(&totals->flags, 4u);
-            at++;
+    const size_t block_base = (size_t)blockIdx.x * kEmitThreads;
+    if (block_base >= ncand) return;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    {
+        size_t i = block_base + threadIdx.x;
+        if (i < ncand && marks[i] != 0) s_list[atomicAdd(&s_count, 1u)] = threadIdx.x;
+    }
+    __syncthreads();
+    const uint32_t todo = s_count;
+    for (uint32_t k = threadIdx.x; k < todo; k += kEmitThreads) {
+        const size_t i = block_base + s_list[k];
+        uint32_t mask = marks[i];
+        size_t at = (size_t)recoff[i];
+        const size_t o = (size_t)cand[i] * 16;
+        uint4 v = ld_chunk(data, o, n);
+        uint32_t nlm = newline_mask16(v);
+        if (o + 16 > n) nlm &= (1u << (n - o)) - 1u;
+        int j = 0;
+        size_t st = 0;
+        bool first = true;
+        while (true) {
+            if (mask & (1u << j)) {
+                if (first) st = line_start_of(data, o);
+                bool has_nul = false;
+                size_t en = line_end_of(data, st, n, &has_nul);
+                bool ok = true;
+                if (has_nul) ok = block_matches(db, data, st, en);
+                const size_t lb = st >> 9;
+                const uint32_t line_no = (uint32_t)prefix[lb] + count_newlines(data, lb << 9, st);
+                if (at < rec_cap) recs[at] = LineRec{line_no, (uint32_t)st, ok ? (uint32_t)(en - st) : kInvalidLen};
+                else atomicOr(&totals->flags, 4u);
+                at++;
+            }
+            if (!nlm) break;
+            int b = __ffs(nlm) - 1;
+            nlm &= nlm - 1;
+            st = o + b + 1;
+            first = false;
+            j++;
+            if ((mask >> j) == 0) break;
         }
-        if (!nlm) break;
-        int b = __ffs(nlm) - 1;
-        nlm &= nlm - 1;
-        st = o + b + 1;
-        first = false;
-        j++;
-        if ((mask >> j) == 0) break;
     }
 }
 
@@ -790,8 +884,7 @@ struct DevicePrefilter {
     int stride = 4;
     bool fold = false;
     int mode = 0;        // 1 exact keys, 2 bloom bitmap
-    int shift = 0;       // 32 - log2(buckets | bits)
-    uint32_t mul = 0;
+    ProbeParams pp{};
     uint32_t lookback = 0xffffffffu;
     ~DevicePrefilter() { if (d_table) cudaFree(d_table); }
 };
@@ -899,16 +992,35 @@ std::shared_ptr<DevicePrefilter> engine_upload_prefilter(const Prefilter& pf, st
     if (!pf.enabled) return nullptr;
     auto out = std::make_shared<DevicePrefilter>();
     cudaGetDevice(&out->device);
-    const std::vector<uint32_t>& src = pf.exact ? pf.keys : pf.bitmap;
-    out->table_words = (int)src.size();
+    std::vector<uint32_t> replicated;
+    const std::vector<uint32_t>* src = &pf.bitmap;
     out->stride = pf.stride;
     out->fold = pf.fold_case;
     out->mode = pf.exact ? 1 : 2;
-    out->shift = 32 - (pf.exact ? pf.log2_buckets : pf.log2_bits);
-    out->mul = pf.hash_mul;
+    out->pp.mul = pf.hash_mul;
+    out->pp.mul2 = pf.hash_mul2;
+    out->pp.shift = 32 - (pf.exact ? pf.log2_slots : pf.log2_bits);
     out->lookback = pf.lookback;
-    if (cudaMalloc((void**)&out->d_table, src.size() * sizeof(uint32_t)) != cudaSuccess ||
-        cudaMemcpy(out->d_table, src.data(), src.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+    if (pf.exact) {
+        // replicate so that a lane reads copy (lane mod R): as many copies as fit ~160 KiB of shared memory, at most 32
+        const size_t slots = (size_t)1 << pf.log2_slots;
+        int rshift = 5;
+        while (rshift > 0 && (3 * slots * 4) << rshift > 200 * 1024) rshift--;   // two halves + alignment slack of one half
+        const size_t copies = (size_t)1 << rshift;
+        replicated.resize(2 * slots * copies);
+        for (size_t half = 0; half < 2; half++)
+            for (size_t h = 0; h < slots; h++)
+                for (size_t r = 0; r < copies; r++) replicated[half * slots * copies + h * copies + r] = pf.keys[half * slots + h];
+        out->pp.rshift = rshift;
+        out->pp.half_bytes = (uint32_t)(slots * copies * 4);
+        // byte offset of slot h, copy r: ((h << rshift) | r) * 4.  h = product >> (32 - log2_slots), hence:
+        out->pp.shift = 32 - pf.log2_slots - rshift - 2;
+        out->pp.amask = (uint32_t)((slots - 1) << (rshift + 2));
+        src = &replicated;
+    }
+    out->table_words = (int)src->size();
+    if (cudaMalloc((void**)&out->d_table, src->size() * sizeof(uint32_t)) != cudaSuccess ||
+        cudaMemcpy(out->d_table, src->data(), src->size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
         error = "cudaMalloc/cudaMemcpy failed for the prefilter table";
         return nullptr;
     }
@@ -958,12 +1070,12 @@ uint8_t* slot_host_buffer(ScanSlot* slot, size_t capacity, std::string& error) {
 
 template <class Load>
 static void launch_scan(cudaStream_t st, Load load, size_t n, unsigned long long* out, unsigned long long* sums, unsigned long long* total,
-                        SegmentStats& stats) {
+                        SegmentStats& stats, const unsigned long long* limit = nullptr) {
     size_t nb = (n + kScanTile - 1) / kScanTile;
     if (nb == 0) nb = 1;
-    k_scan_sums<Load><<<(unsigned)nb, kScanThreads, 0, st>>>(load, n, sums);
+    k_scan_sums<Load><<<(unsigned)nb, kScanThreads, 0, st>>>(load, n, sums, limit);
     k_scan_top<<<1, 1024, 0, st>>>(sums, nb, total);
-    k_scan_write<Load><<<(unsigned)nb, kScanThreads, 0, st>>>(load, n, sums, out);
+    k_scan_write<Load><<<(unsigned)nb, kScanThreads, 0, st>>>(load, n, sums, out, limit);
     stats.launches += 3;
 }
 
@@ -975,7 +1087,7 @@ static cudaError_t launch_stream_t(cudaStream_t st, int grid, int block, size_t 
         if (e != cudaSuccess) return e;
     }
     k_stream<STRIDE, FOLD, MODE><<<grid, block, smem, st>>>(data, n, meta, pf ? pf->d_table : nullptr, pf ? pf->table_words : 0,
-                                                            pf ? pf->shift : 0, pf ? pf->mul : 0);
+                                                            pf ? pf->pp : ProbeParams{});
     return cudaGetLastError();
 }
 
@@ -1042,7 +1154,7 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
     }
     // ---- K1 ----
     // persistent grid: enough CTAs to fill every SM, each warp strides over groups of kStreamU blocks
-    size_t smem = s->fast ? (size_t)pf->table_words * 4 : 0;
+    size_t smem = s->fast ? (size_t)pf->table_words * 4 + (pf->mode == 1 ? pf->pp.half_bytes : 0) : 0;
     int block = smem > 32 * 1024 ? 1024 : 256;
     int ctas_per_sm = smem > 100 * 1024 ? 1 : (smem > 32 * 1024 ? 2 : 6);
     int grid = g_num_sms * ctas_per_sm;
@@ -1074,8 +1186,8 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
         k_verify_local<<<vgrid, 128, 0, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->lookback,
                                               s->d_res.as<uint32_t>());
         launch_scan(st, LoadMarks{s->d_res.as<uint32_t>(), &dT->meta_total, s->cand_cap}, s->cand_cap, s->d_recoff.as<unsigned long long>(),
-                    s->d_sums.as<unsigned long long>(), &dT->rec_total, s->stats);
-        k_emit_simple<<<vgrid, 128, 0, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), s->d_res.as<uint32_t>(), s->d_recoff.as<unsigned long long>(),
+                    s->d_sums.as<unsigned long long>(), &dT->rec_total, s->stats, &dT->meta_total);
+        k_emit_simple<<<(unsigned)((s->cand_cap + kEmitThreads - 1) / kEmitThreads), kEmitThreads, 0, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), s->d_res.as<uint32_t>(), s->d_recoff.as<unsigned long long>(),
                                              prefix, &dT->meta_total, s->cand_cap, s->d_recs.as<LineRec>(), s->rec_cap, dT);
         s->stats.launches += 3;
         CUDA_TRY(cudaEventRecord(s->ev[1], st));

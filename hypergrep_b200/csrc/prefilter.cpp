@@ -340,25 +340,42 @@ double window_hits(const ClassString& s, size_t t, int stride, bool fold, const 
 }
 
 bool build_exact_table(const std::vector<uint32_t>& grams, Prefilter& out) {
-    // buckets of two keys; find a multiplier for which no bucket receives a third key
+    // Two-choice hashing: every key has one candidate slot in each half; insertion evicts (cuckoo) until everything
+    // is placed.  Small tables matter: the engine replicates the table across shared-memory banks so that lookups
+    // are conflict-free, and the replication factor is what fits.
     static const uint32_t muls[] = {0x9E3779B1u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Cu, 0xFD7046C5u, 0xB55A4F09u,
                                     0x7FEB352Du, 0x846CA68Bu, 0x9E3779B9u, 0xCC9E2D51u, 0x1B873593u, 0xE6546B64u, 0x2545F491u, 0x5851F42Du};
-    int lb = 9;   // 512 buckets = 4 KiB minimum
-    while (lb < 14 && ((size_t)1 << lb) < grams.size() * 2) lb++;
-    for (; lb <= 14; lb++) {   // at most 16384 buckets = 128 KiB of shared memory
-        for (uint32_t mul : muls) {
-            std::vector<uint32_t> keys((size_t)2 << lb, 0);
+    const int nmul = (int)(sizeof(muls) / sizeof(muls[0]));
+    int lb = 4;
+    while (lb < 14 && ((size_t)2 << lb) * 2 < grams.size() * 5) lb++;   // total slots >= 2.5 x keys
+    for (; lb <= 14; lb++) {   // at most 2 x 16384 slots = 128 KiB unreplicated
+        const size_t slots = (size_t)1 << lb;
+        for (int a = 0; a + 1 < nmul; a += 2) {
+            const uint32_t m1 = muls[a], m2 = muls[a + 1];
+            std::vector<uint32_t> keys(2 * slots, 0);
             bool ok = true;
             for (uint32_t g : grams) {
-                uint32_t b = prefilter_hash(g, mul, lb);
-                if (keys[2 * b] == 0) keys[2 * b] = g;
-                else if (keys[2 * b + 1] == 0) keys[2 * b + 1] = g;
-                else { ok = false; break; }
+                uint32_t cur = g;
+                int side = 0;
+                int kicks = 0;
+                while (true) {
+                    size_t at = side == 0 ? prefilter_hash(cur, m1, lb) : slots + prefilter_hash(cur, m2, lb);
+                    if (keys[at] == 0) { keys[at] = cur; break; }
+                    if (kicks == 0 && side == 0) {   // try the other side before evicting
+                        size_t alt = slots + prefilter_hash(cur, m2, lb);
+                        if (keys[alt] == 0) { keys[alt] = cur; break; }
+                    }
+                    std::swap(cur, keys[at]);
+                    side ^= 1;
+                    if (++kicks > 200) { ok = false; break; }
+                }
+                if (!ok) break;
             }
             if (ok) {
                 out.exact = true;
-                out.log2_buckets = lb;
-                out.hash_mul = mul;
+                out.log2_slots = lb;
+                out.hash_mul = m1;
+                out.hash_mul2 = m2;
                 out.keys.swap(keys);
                 return true;
             }
@@ -436,7 +453,7 @@ void build_prefilter(const FactorSet& fs, const GramHistogram* sample, Prefilter
                 }
             }
             out.note = "stride " + std::to_string(stride) + (fold ? ", folded" : "") + ", " + std::to_string(all.size()) + " grams, " +
-                       (out.exact ? "exact table of " + std::to_string(2u << out.log2_buckets) + " keys" : "bloom bitmap of " + std::to_string(1u << out.log2_bits) + " bits") +
+                       (out.exact ? "exact two-choice table of 2 x " + std::to_string(1u << out.log2_slots) + " slots" : "bloom bitmap of " + std::to_string(1u << out.log2_bits) + " bits") +
                        (sample ? ", sample-tuned" : "");
             return;
         }

@@ -51,10 +51,12 @@ struct Prefilter {
     bool enabled = false;
     int stride = 4;             // text positions sampled: multiples of `stride` (4, 2 or 1)
     bool fold_case = false;     // text bytes are OR-ed with 0x20 before lookup (grams stored folded)
-    // exact mode: buckets of two 32-bit keys, bucket = (gram * hash_mul) >> (32 - log2_buckets); 0 = empty slot
+    // exact mode: two-choice (cuckoo) table of 32-bit keys.  A gram lives in keys[h1] or keys[slots + h2] with
+    // h1 = (gram * hash_mul) >> (32 - log2_slots), h2 = (gram * hash_mul2) >> (32 - log2_slots); 0 = empty slot.
     bool exact = false;
-    int log2_buckets = 0;
-    std::vector<uint32_t> keys;       // 2 << log2_buckets entries
+    int log2_slots = 0;
+    uint32_t hash_mul2 = 0x85EBCA6Bu;
+    std::vector<uint32_t> keys;       // 2 << log2_slots entries
     // bloom mode (very large gram sets): bit = (gram * hash_mul) >> (32 - log2_bits)
     int log2_bits = 13;
     std::vector<uint32_t> bitmap;
