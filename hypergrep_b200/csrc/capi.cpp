@@ -182,22 +182,8 @@ struct Job {
     }
 
     int deliver_simple(const SegmentResult& r, const uint8_t* host, ScanSlot* slot) {
-        // fast-path records may repeat a line (marked by several candidate chunks) or carry kInvalid length (a line
-        // with NULs that failed the exact re-check): keep the first valid record of every line
         const LineRec* recs = r.lines;
         size_t count = r.num_line_recs;
-        if (r.stats.path & 1) {
-            unique_.clear();
-            unique_.reserve(count);
-            uint32_t last_start = 0xffffffffu;
-            for (size_t i = 0; i < count; i++) {
-                if (recs[i].len == 0xffffffffu || recs[i].start == last_start) continue;
-                last_start = recs[i].start;
-                unique_.push_back(recs[i]);
-            }
-            recs = unique_.data();
-            count = unique_.size();
-        }
         size_t take = count;
         if (max_match > 0) {
             unsigned long long room = max_match > out->count() ? max_match - out->count() : 0;
@@ -222,7 +208,6 @@ struct Job {
         }
         return 0;
     }
-    std::vector<LineRec> unique_;
 
     int deliver_events(const SegmentResult& r, const uint8_t* host, ScanSlot* slot) {
         // events arrive grouped by pseudo-line in file order; inside a line they are grouped by DFA group
@@ -422,11 +407,19 @@ int device_cut(const uint8_t* dev, size_t have, bool final, size_t limit, size_t
     while (true) {
         tail.resize(span);
         if (cudaMemcpy(tail.data(), dev + have - span, span, cudaMemcpyDeviceToHost) != cudaSuccess) { error = "cudaMemcpy failed while locating a segment boundary"; return GPUGREP_SCAN; }
-        const void* nl = memrchr(tail.data(), '\n', span);
-        if (nl) {
-            size_t c = have - span + (size_t)((const uint8_t*)nl - tail.data()) + 1;
+        // prefer a line end that leaves the next segment 16-byte aligned (the kernels use 16-byte loads)
+        size_t base = have - span;
+        size_t best = 0, any = 0;
+        for (size_t p = span; p > 0; p--) {
+            if (tail[p - 1] != '\n') continue;
+            if (!any) any = base + p;
+            if (((base + p) & 15) == 0) { best = base + p; break; }
+            if (span - p > (64 << 10)) break;
+        }
+        if (best || any) {
+            size_t c = best ? best : any;
             size_t rest = have - c;
-            if (rest >= limit) c += (rest / limit) * limit;
+            if (!best && rest >= limit) c += (rest / limit) * limit;
             cut = c;
             return 0;
         }
@@ -459,12 +452,21 @@ int scan_memory(const uint8_t* data, size_t size, int location, const Params& pr
     int k = 0, inflight = -1;
     bool tuned = false;
     std::vector<uint8_t> sample;
+    // device-resident input: all segment ends come from one small kernel instead of one synchronous copy per segment
+    std::vector<size_t> dev_cuts;
+    size_t dev_cut_index = 0;
+    if (on_device && size > chunk) {
+        chunk = std::min(chunk, kMaxSegmentBytes - ((size_t)16 << 20));
+        if (engine_find_cuts(data, size, chunk, dev_cuts, job.error) != 0) dev_cuts.clear();
+    }
     size_t pos = 0;
     while (pos < size && !job.stop && rc == 0) {
         size_t have = std::min(chunk, size - pos);
         bool final = pos + have == size;
         size_t cut = 0;
-        if (on_device) {
+        if (on_device && !dev_cuts.empty()) {
+            cut = dev_cuts[dev_cut_index++] - pos;
+        } else if (on_device) {
             rc = device_cut(data + pos, have, final, limit, cut, job.error);
             if (rc) break;
         } else {

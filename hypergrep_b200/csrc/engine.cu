@@ -232,7 +232,7 @@ __device__ __forceinline__ bool probe_chunk(const uint4& v, uint32_t next, const
             if (MODE == 1) {
                 uint32_t e1 = lds32((((gram * pp.mul) >> pp.shift) & pp.amask) | c1);
                 uint32_t e2 = lds32((((gram * pp.mul2) >> pp.shift) & pp.amask) | c2);
-                miss = __vimin3_u32(miss, e1 ^ gram, e2 ^ gram);
+                miss = __vimin3_u32(miss, e1 - gram, e2 - gram);   // differences, not XORs: ptxas can place subtractions on the FMA pipe
             } else {
                 uint32_t h = (gram * pp.mul) >> pp.shift;
                 bits |= tab[h >> 5] >> (h & 31);
@@ -402,14 +402,14 @@ struct LoadU32 {
     __device__ unsigned long long operator()(size_t i) const { return p[i]; }
 };
 
-// `limit` (optional): device word whose high 32 bits bound the meaningful prefix of the input (candidate count);
-// tiles entirely beyond it contribute zero and are skipped.
+// `limit` (optional): device word that bounds the meaningful prefix of the input (value >> limit_shift: 32 selects the
+// candidate count of Totals::meta_total, 0 a plain count); tiles entirely beyond it contribute zero and are skipped.
 template <class Load>
-__global__ void __launch_bounds__(kScanThreads) k_scan_sums(Load load, size_t n, unsigned long long* __restrict__ sums, const unsigned long long* limit) {
+__global__ void __launch_bounds__(kScanThreads) k_scan_sums(Load load, size_t n, unsigned long long* __restrict__ sums, const unsigned long long* limit, int limit_shift) {
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_total;
     if (limit) {
-        size_t lim = (size_t)(*limit >> 32);
+        size_t lim = (size_t)(*limit >> limit_shift);
         if (lim < n) n = lim;
         if ((size_t)blockIdx.x * kScanTile >= n) { if (threadIdx.x == 0) sums[blockIdx.x] = 0; return; }
     }
@@ -439,11 +439,11 @@ __global__ void __launch_bounds__(1024) k_scan_top(unsigned long long* __restric
 
 template <class Load>
 __global__ void __launch_bounds__(kScanThreads) k_scan_write(Load load, size_t n, const unsigned long long* __restrict__ sums,
-                                                             unsigned long long* __restrict__ out, const unsigned long long* limit) {
+                                                             unsigned long long* __restrict__ out, const unsigned long long* limit, int limit_shift) {
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_total;
     if (limit) {
-        size_t lim = (size_t)(*limit >> 32);
+        size_t lim = (size_t)(*limit >> limit_shift);
         if (lim < n) n = lim;
         if ((size_t)blockIdx.x * kScanTile >= n) return;
     }
@@ -719,6 +719,46 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit_simple(DbView db, const u
     }
 }
 
+// Records arrive ordered by line start; a line marked by several candidate chunks appears several times in a row,
+// and a record whose NUL re-check failed carries kInvalidLen.  Keep the first valid record of every line.
+struct LoadKeep {
+    const LineRec* recs;
+    const unsigned long long* rec_total;
+    size_t cap;
+    __device__ unsigned long long operator()(size_t k) const {
+        size_t cnt = (size_t)*rec_total;
+        if (cnt > cap) cnt = cap;
+        if (k >= cnt) return 0ull;
+        LineRec r = recs[k];
+        if (r.len == kInvalidLen) return 0ull;
+        return (k == 0 || recs[k - 1].start != r.start) ? 1ull : 0ull;
+    }
+};
+
+__global__ void k_compact_records(LoadKeep keep, const unsigned long long* __restrict__ off, size_t cap, LineRec* __restrict__ out) {
+    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t cnt = (size_t)*keep.rec_total;
+    if (cnt > cap) cnt = cap;
+    if (k >= cnt) return;
+    if (keep(k)) out[off[k]] = keep.recs[k];
+}
+
+// Device-resident inputs: the end of segment j is the byte after a '\n' before boundary (j+1)*chunk, chosen so that the
+// NEXT segment starts 16-byte aligned (the kernels use 16-byte loads): one line end in 16 qualifies on average.
+// One thread per boundary scans backwards (gives up after `window` bytes -> 0 = not found).
+__global__ void k_find_cuts(const uint8_t* __restrict__ data, size_t size, size_t chunk, size_t window, size_t ncuts, unsigned long long* __restrict__ cuts) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncuts) return;
+    size_t b = (j + 1) * chunk;
+    if (b >= size) { cuts[j] = size; return; }
+    size_t lo = b > window ? b - window : 0;
+    unsigned long long found = 0;
+    for (size_t p = b; p > lo; p--) {
+        if ((p & 15) == 0 && data[p - 1] == '\n') { found = p; break; }
+    }
+    cuts[j] = found;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // GENERAL PATH kernels
 // ------------------------------------------------------------------------------------------------------------
@@ -893,8 +933,10 @@ class ScanSlot {
 public:
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // result D2H, so that it does not queue behind the next segment's kernels
+    cudaEvent_t done = nullptr;           // all kernels of the segment + the totals copy have finished
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // 0/1: whole segment, 2/3: streaming kernel
-    DevBuf d_input, d_meta, d_prefix, d_sums, d_cand, d_res, d_recoff, d_recs, d_totals;
+    DevBuf d_input, d_meta, d_prefix, d_sums, d_cand, d_res, d_recoff, d_recs, d_recs2, d_keepoff, d_totals;
     DevBuf d_nlpos, d_npl, d_ploff, d_plstart, d_pllen, d_flags, d_counts, d_events, d_gather, d_gidx;
     PinBuf h_totals, h_recs, h_stage, h_gather;
     // state of the in-flight segment
@@ -903,6 +945,7 @@ public:
     size_t n = 0, nblk = 0, cand_cap = 0, rec_cap = 0;
     int buffer_size = 0;
     bool fast = false;
+    bool want_records = true;   // false: the caller only counts matches (no callback, no limit): skip the record D2H
     SegmentStats stats;
     bool in_use = false;
 
@@ -1049,6 +1092,9 @@ ScanSlot* engine_acquire_slot(std::string& error) {
     s->device = dev;
     if (cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking) != cudaSuccess) { error = "cudaStreamCreate failed"; delete s; return nullptr; }
     for (auto& e : s->ev) if (cudaEventCreate(&e) != cudaSuccess) { error = "cudaEventCreate failed"; delete s; return nullptr; }
+    if (cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming) != cudaSuccess) {
+        error = "cudaStreamCreate/cudaEventCreate failed"; delete s; return nullptr;
+    }
     if (s->d_totals.reserve(sizeof(Totals)) != cudaSuccess || s->h_totals.reserve(sizeof(Totals)) != cudaSuccess) {
         error = "scratch allocation failed"; delete s; return nullptr;
     }
@@ -1070,12 +1116,12 @@ uint8_t* slot_host_buffer(ScanSlot* slot, size_t capacity, std::string& error) {
 
 template <class Load>
 static void launch_scan(cudaStream_t st, Load load, size_t n, unsigned long long* out, unsigned long long* sums, unsigned long long* total,
-                        SegmentStats& stats, const unsigned long long* limit = nullptr) {
+                        SegmentStats& stats, const unsigned long long* limit = nullptr, int limit_shift = 32) {
     size_t nb = (n + kScanTile - 1) / kScanTile;
     if (nb == 0) nb = 1;
-    k_scan_sums<Load><<<(unsigned)nb, kScanThreads, 0, st>>>(load, n, sums, limit);
+    k_scan_sums<Load><<<(unsigned)nb, kScanThreads, 0, st>>>(load, n, sums, limit, limit_shift);
     k_scan_top<<<1, 1024, 0, st>>>(sums, nb, total);
-    k_scan_write<Load><<<(unsigned)nb, kScanThreads, 0, st>>>(load, n, sums, out, limit);
+    k_scan_write<Load><<<(unsigned)nb, kScanThreads, 0, st>>>(load, n, sums, out, limit, limit_shift);
     stats.launches += 3;
 }
 
@@ -1131,17 +1177,25 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
         s->data = s->d_input.as<uint8_t>();
         s->stats.h2d_bytes += n;
     } else {
-        if (((uintptr_t)dev_data & 15) != 0) { error = "device buffers must be 16-byte aligned"; return 7; }
-        s->data = dev_data;
+        if (((uintptr_t)dev_data & 15) != 0) {
+            // unaligned device segment (no aligned line end was available for the cut): stage it once, device to device
+            if (s->d_input.reserve(n + 1024) != cudaSuccess) { error = "cudaMalloc failed for the input segment"; return 3; }
+            CUDA_TRY(cudaMemcpyAsync(s->d_input.p, dev_data, n, cudaMemcpyDeviceToDevice, st));
+            CUDA_TRY(cudaMemsetAsync(s->d_input.as<uint8_t>() + n, 0, 1024, st));
+            s->data = s->d_input.as<uint8_t>();
+        } else {
+            s->data = dev_data;
+        }
     }
     s->cand_cap = n / 64 + 4096;
     s->rec_cap = n / 48 + 4096;
-    size_t nb_scan = (std::max(s->nblk, s->cand_cap) + kScanTile - 1) / kScanTile + 1;
+    size_t nb_scan = (std::max(std::max(s->nblk, s->cand_cap), s->rec_cap) + kScanTile - 1) / kScanTile + 1;
     if (s->d_meta.reserve((s->nblk + 8) * 8) != cudaSuccess || s->d_prefix.reserve((s->nblk + 8) * 8) != cudaSuccess ||
         s->d_sums.reserve(nb_scan * 8) != cudaSuccess) { error = "cudaMalloc failed for scan scratch"; return 3; }
     if (s->fast) {
         if (s->d_cand.reserve(s->cand_cap * 4) != cudaSuccess || s->d_res.reserve(s->cand_cap * sizeof(uint32_t)) != cudaSuccess ||
-            s->d_recoff.reserve(s->cand_cap * 8) != cudaSuccess || s->d_recs.reserve(s->rec_cap * sizeof(LineRec)) != cudaSuccess) {
+            s->d_recoff.reserve(s->cand_cap * 8) != cudaSuccess || s->d_recs.reserve(s->rec_cap * sizeof(LineRec)) != cudaSuccess ||
+            s->d_recs2.reserve(s->rec_cap * sizeof(LineRec)) != cudaSuccess || s->d_keepoff.reserve(s->rec_cap * 8) != cudaSuccess) {
             error = "cudaMalloc failed for candidate scratch"; return 3;
         }
     }
@@ -1150,6 +1204,7 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
     CUDA_TRY(cudaEventRecord(s->ev[0], st));
     if (n == 0) {
         CUDA_TRY(cudaEventRecord(s->ev[1], st));
+        CUDA_TRY(cudaEventRecord(s->done, st));
         return 0;
     }
     // ---- K1 ----
@@ -1189,11 +1244,16 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
                     s->d_sums.as<unsigned long long>(), &dT->rec_total, s->stats, &dT->meta_total);
         k_emit_simple<<<(unsigned)((s->cand_cap + kEmitThreads - 1) / kEmitThreads), kEmitThreads, 0, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), s->d_res.as<uint32_t>(), s->d_recoff.as<unsigned long long>(),
                                              prefix, &dT->meta_total, s->cand_cap, s->d_recs.as<LineRec>(), s->rec_cap, dT);
-        s->stats.launches += 3;
+        LoadKeep keep{s->d_recs.as<LineRec>(), &dT->rec_total, s->rec_cap};
+        launch_scan(st, keep, s->rec_cap, s->d_keepoff.as<unsigned long long>(), s->d_sums.as<unsigned long long>(), &dT->aux_total, s->stats,
+                    &dT->rec_total, 0);
+        k_compact_records<<<(unsigned)((s->rec_cap + 255) / 256), 256, 0, st>>>(keep, s->d_keepoff.as<unsigned long long>(), s->rec_cap, s->d_recs2.as<LineRec>());
+        s->stats.launches += 4;
         CUDA_TRY(cudaEventRecord(s->ev[1], st));
     }
     CUDA_TRY(cudaMemcpyAsync(&dT->last_byte, s->data + n - 1, 1, cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(s->h_totals.p, dT, sizeof(Totals), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(s->done, st));
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -1302,7 +1362,8 @@ int ScanSlot::run_general(SegmentResult& out, std::string& error) {
 int slot_collect(ScanSlot* s, SegmentResult& out, std::string& error) {
     cudaStream_t st = s->stream;
     out = SegmentResult();
-    CUDA_TRY(cudaStreamSynchronize(st));
+    // wait for THIS segment only: the stream may already hold the next segment's kernels
+    CUDA_TRY(cudaEventSynchronize(s->done));
     s->stats.d2h_bytes += sizeof(Totals);
     if (s->n == 0) { out.stats = s->stats; return 0; }
     Totals* hT = s->h_totals.as<Totals>();
@@ -1311,13 +1372,13 @@ int slot_collect(ScanSlot* s, SegmentResult& out, std::string& error) {
         s->stats.candidates = hT->meta_total >> 32;
         if (hT->flags == 0) {
             s->stats.path |= 1;
-            size_t nrec = (size_t)hT->rec_total;
+            size_t nrec = (size_t)hT->aux_total;   // unique valid records (k_compact_records)
             const size_t nl_total = (size_t)(uint32_t)hT->meta_total;
             out.num_lines = nl_total + ((hT->last_byte & 0xff) != '\n' ? 1 : 0);
-            if (nrec) {
+            if (nrec && s->want_records) {
                 if (s->h_recs.reserve(nrec * sizeof(LineRec)) != cudaSuccess) { error = "cudaHostAlloc failed"; return 3; }
-                CUDA_TRY(cudaMemcpyAsync(s->h_recs.p, s->d_recs.p, nrec * sizeof(LineRec), cudaMemcpyDeviceToHost, st));
-                CUDA_TRY(cudaStreamSynchronize(st));
+                CUDA_TRY(cudaMemcpyAsync(s->h_recs.p, s->d_recs2.p, nrec * sizeof(LineRec), cudaMemcpyDeviceToHost, s->copy_stream));
+                CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
                 s->stats.d2h_bytes += nrec * sizeof(LineRec);
             }
             out.lines = s->h_recs.as<LineRec>();
@@ -1333,6 +1394,26 @@ int slot_collect(ScanSlot* s, SegmentResult& out, std::string& error) {
     if (cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]) == cudaSuccess) s->stats.gpu_ms = ms;
     if (cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]) == cudaSuccess) s->stats.stream_ms = ms;
     out.stats = s->stats;
+    return 0;
+}
+
+int engine_find_cuts(const uint8_t* dev_data, size_t size, size_t chunk, std::vector<size_t>& cuts, std::string& error) {
+    cuts.clear();
+    if (size == 0 || chunk == 0) return 0;
+    size_t ncuts = (size + chunk - 1) / chunk;
+    unsigned long long* d = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d, ncuts * sizeof(unsigned long long)));
+    k_find_cuts<<<(unsigned)((ncuts + 63) / 64), 64>>>(dev_data, size, chunk, (size_t)4 << 20, ncuts, d);
+    std::vector<unsigned long long> h(ncuts);
+    cudaError_t e = cudaMemcpy(h.data(), d, ncuts * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { error = std::string("k_find_cuts: ") + cudaGetErrorString(e); return 7; }
+    size_t prev = 0;
+    for (size_t j = 0; j < ncuts; j++) {
+        if (h[j] == 0 || h[j] <= prev) { cuts.clear(); return 0; }   // no newline near a boundary: caller falls back
+        cuts.push_back((size_t)h[j]);
+        prev = (size_t)h[j];
+    }
     return 0;
 }
 

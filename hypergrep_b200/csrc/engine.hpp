@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "database.hpp"
 
@@ -73,6 +74,10 @@ int slot_collect(ScanSlot* slot, SegmentResult& out, std::string& error);
 // with a callback).  `recs` are LineRec-like (start,len) pairs already on the host; out must hold sum(len)+count.
 int slot_gather_lines(ScanSlot* slot, const uint32_t* starts, const uint32_t* lens, size_t count, uint8_t* out,
                       std::string& error);
+
+// Segment ends for a device-resident input: cuts[j] = offset just past the last '\n' before (j+1)*chunk (the last
+// entry is `size`).  Left empty when some boundary has no newline nearby (the caller then cuts sequentially).
+int engine_find_cuts(const uint8_t* dev_data, size_t size, size_t chunk, std::vector<size_t>& cuts, std::string& error);
 
 constexpr size_t kMaxSegmentBytes = (size_t)1 << 30;
 
