@@ -29,6 +29,8 @@ struct GroupDev {
     const uint16_t* trans;      // [states][stride]
     const uint8_t* cls;         // [256] byte -> class
     const uint32_t* accept_of;  // [states] (general mode)
+    const uint16_t* flat;       // [states][256] byte-indexed transitions (local verification: one load per byte), or null
+    const uint16_t* eod_next;   // [states] transition on end-of-data (with `flat`)
     uint32_t stride, eod, first_accept, dead, accept_base, idle_end, mid_other, mid_word;
 };
 
@@ -211,6 +213,12 @@ __device__ __forceinline__ uint32_t lds32(uint32_t shared_addr) {
     return v;
 }
 
+__device__ __forceinline__ uint32_t lds8(uint32_t shared_addr) {
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(shared_addr));
+    return v;
+}
+
 // c1 / c2: shared-window address of table half 1 / 2 (aligned to the size of a half) OR-ed with 4 * copy of this lane,
 // so that an address is formed by ONE logic op: ((product >> shift) & amask) | c.
 template <int STRIDE, bool FOLD, int MODE>
@@ -234,8 +242,11 @@ __device__ __forceinline__ bool probe_chunk(const uint4& v, uint32_t next, const
                 uint32_t e2 = lds32((((gram * pp.mul2) >> pp.shift) & pp.amask) | c2);
                 miss = __vimin3_u32(miss, e1 - gram, e2 - gram);   // differences, not XORs: ptxas can place subtractions on the FMA pipe
             } else {
-                uint32_t h = (gram * pp.mul) >> pp.shift;
-                bits |= tab[h >> 5] >> (h & 31);
+                // bloom: one byte load, bit (p & 7) of it.  The byte is replicated into all four bytes of a word (one
+                // multiply on the FMA pipe) so that the wrap-around shift by p itself lands on the right bit.
+                uint32_t p = gram * pp.mul;
+                uint32_t b = lds8((p >> pp.shift) + c1);
+                bits |= (b * 0x01010101u) >> (p & 31u);
             }
         }
     }
@@ -274,7 +285,7 @@ __global__ void __launch_bounds__(1024) k_stream(const uint8_t* __restrict__ dat
     constexpr int U = kStreamU;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t replica4 = (lane & ((1u << pp.rshift) - 1u)) << 2;
-    uint32_t c1 = saddr | replica4, c2 = (saddr + pp.half_bytes) | replica4;
+    uint32_t c1 = MODE == 1 ? (saddr | replica4) : saddr, c2 = (saddr + pp.half_bytes) | replica4;
     asm volatile("mov.u32 %0, %0;" : "+r"(c1));   // materialise: each table address is then a single (x & amask) | c
     asm volatile("mov.u32 %0, %0;" : "+r"(c2));
     uint32_t cnl, c80;   // opaque to the optimiser so that they stay in registers (see eq_mask4_r)
@@ -405,20 +416,24 @@ struct LoadU32 {
 // `limit` (optional): device word that bounds the meaningful prefix of the input (value >> limit_shift: 32 selects the
 // candidate count of Totals::meta_total, 0 a plain count); tiles entirely beyond it contribute zero and are skipped.
 template <class Load>
-__global__ void __launch_bounds__(kScanThreads) k_scan_sums(Load load, size_t n, unsigned long long* __restrict__ sums, const unsigned long long* limit, int limit_shift) {
+__global__ void __launch_bounds__(kScanThreads) k_scan_sums(Load load, size_t n, unsigned long long* __restrict__ sums, size_t ntiles,
+                                                            const unsigned long long* limit, int limit_shift) {
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_total;
     if (limit) {
         size_t lim = (size_t)(*limit >> limit_shift);
         if (lim < n) n = lim;
-        if ((size_t)blockIdx.x * kScanTile >= n) { if (threadIdx.x == 0) sums[blockIdx.x] = 0; return; }
     }
-    size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
-    unsigned long long acc = 0;
+    for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (tile * kScanTile >= n) { if (threadIdx.x == 0) sums[tile] = 0; continue; }
+        size_t base = tile * kScanTile + (size_t)threadIdx.x * kScanItems;
+        unsigned long long acc = 0;
 #pragma unroll
-    for (int k = 0; k < kScanItems; k++) if (base + k < n) acc += load(base + k);
-    block_exclusive_scan(acc, s_warp, &s_total);
-    if (threadIdx.x == 0) sums[blockIdx.x] = s_total;
+        for (int k = 0; k < kScanItems; k++) if (base + k < n) acc += load(base + k);
+        block_exclusive_scan(acc, s_warp, &s_total);
+        if (threadIdx.x == 0) sums[tile] = s_total;
+        __syncthreads();
+    }
 }
 
 __global__ void __launch_bounds__(1024) k_scan_top(unsigned long long* __restrict__ sums, size_t nb, unsigned long long* __restrict__ total) {
@@ -439,27 +454,30 @@ __global__ void __launch_bounds__(1024) k_scan_top(unsigned long long* __restric
 
 template <class Load>
 __global__ void __launch_bounds__(kScanThreads) k_scan_write(Load load, size_t n, const unsigned long long* __restrict__ sums,
-                                                             unsigned long long* __restrict__ out, const unsigned long long* limit, int limit_shift) {
+                                                             unsigned long long* __restrict__ out, size_t ntiles, const unsigned long long* limit,
+                                                             int limit_shift) {
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_total;
     if (limit) {
         size_t lim = (size_t)(*limit >> limit_shift);
         if (lim < n) n = lim;
-        if ((size_t)blockIdx.x * kScanTile >= n) return;
     }
-    size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
-    unsigned long long vals[kScanItems];
-    unsigned long long acc = 0;
+    for (size_t tile = blockIdx.x; tile < ntiles && tile * kScanTile < n; tile += gridDim.x) {
+        size_t base = tile * kScanTile + (size_t)threadIdx.x * kScanItems;
+        unsigned long long vals[kScanItems];
+        unsigned long long acc = 0;
 #pragma unroll
-    for (int k = 0; k < kScanItems; k++) {
-        vals[k] = base + k < n ? load(base + k) : 0ull;
-        acc += vals[k];
-    }
-    unsigned long long run = block_exclusive_scan(acc, s_warp, &s_total) + sums[blockIdx.x];
+        for (int k = 0; k < kScanItems; k++) {
+            vals[k] = base + k < n ? load(base + k) : 0ull;
+            acc += vals[k];
+        }
+        unsigned long long run = block_exclusive_scan(acc, s_warp, &s_total) + sums[tile];
 #pragma unroll
-    for (int k = 0; k < kScanItems; k++) {
-        if (base + k < n) out[base + k] = run;
-        run += vals[k];
+        for (int k = 0; k < kScanItems; k++) {
+            if (base + k < n) out[base + k] = run;
+            run += vals[k];
+        }
+        __syncthreads();
     }
 }
 
@@ -563,17 +581,17 @@ __global__ void k_check_long(const unsigned long long* __restrict__ prefix, size
 // meta/prefix -> ordered list of candidate chunk indices
 __global__ void k_list_candidates(const unsigned long long* __restrict__ meta, const unsigned long long* __restrict__ prefix, size_t nblk,
                                   uint32_t* __restrict__ cand, size_t cap, Totals* totals) {
-    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= nblk) return;
-    uint32_t mask = (uint32_t)meta[g];
-    if (!mask) return;
-    size_t at = (size_t)(prefix[g] >> 32);
-    while (mask) {
-        int b = __ffs(mask) - 1;
-        mask &= mask - 1;
-        if (at < cap) cand[at] = (uint32_t)(g * 32 + b);
-        else { atomicOr(&totals->flags, 2u); return; }
-        at++;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < nblk; g += (size_t)gridDim.x * blockDim.x) {
+        uint32_t mask = (uint32_t)meta[g];
+        if (!mask) continue;
+        size_t at = (size_t)(prefix[g] >> 32);
+        while (mask) {
+            int b = __ffs(mask) - 1;
+            mask &= mask - 1;
+            if (at < cap) cand[at] = (uint32_t)(g * 32 + b);
+            else { atomicOr(&totals->flags, 2u); break; }
+            at++;
+        }
     }
 }
 
@@ -597,17 +615,18 @@ __device__ uint32_t walk_local(const GroupDev& G, const uint8_t* __restrict__ da
     bool done = false;
     const size_t chunk_end = o + 16, idle_from = o + 19;
     ByteCursor c(data, t, n);
+    const uint16_t* __restrict__ flat = G.flat;
     while (c.pos < n) {
         const uint32_t b = c.get();
         if (!done) {
             bool hit;
             if (b == 0) {
-                hit = G.trans[s * G.stride + G.eod] >= G.first_accept;
+                hit = (flat ? G.eod_next[s] : G.trans[s * G.stride + G.eod]) >= G.first_accept;
                 s = 0;
             } else {
-                s = G.trans[s * G.stride + G.cls[b]];
+                s = flat ? flat[(s << 8) | b] : G.trans[s * G.stride + G.cls[b]];
                 hit = s >= G.first_accept;
-                if (!hit && b == '\n') hit = G.trans[s * G.stride + G.eod] >= G.first_accept;
+                if (!hit && b == '\n') hit = (flat ? G.eod_next[s] : G.trans[s * G.stride + G.eod]) >= G.first_accept;
             }
             if (hit) { mask |= 1u << line; done = true; }
         }
@@ -622,7 +641,7 @@ __device__ uint32_t walk_local(const GroupDev& G, const uint8_t* __restrict__ da
         if (c.pos >= idle_from && (done || s < G.idle_end)) return mask;
         if (done && c.pos >= chunk_end) return mask;
     }
-    if (!done && G.trans[s * G.stride + G.eod] >= G.first_accept) mask |= 1u << line;
+    if (!done && (flat ? G.eod_next[s] : G.trans[s * G.stride + G.eod]) >= G.first_accept) mask |= 1u << line;
     return mask;
 }
 
@@ -630,10 +649,9 @@ __device__ uint32_t walk_local(const GroupDev& G, const uint8_t* __restrict__ da
 __global__ void __launch_bounds__(128) k_verify_local(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
                                                       const unsigned long long* meta_total, size_t cap, uint32_t lookback,
                                                       uint32_t* __restrict__ marks) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t ncand = (size_t)(*meta_total >> 32);
     if (ncand > cap) ncand = cap;
-    if (i >= ncand) return;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncand; i += (size_t)gridDim.x * blockDim.x) {
     const size_t o = (size_t)cand[i] * 16;
     size_t t;
     bool at_line_start;
@@ -659,6 +677,7 @@ __global__ void __launch_bounds__(128) k_verify_local(DbView db, const uint8_t* 
     uint32_t mask = 0;
     for (int g = 0; g < db.ngroups; g++) mask |= walk_local(db.groups[g], data, n, o, t, at_line_start);
     marks[i] = mask;
+    }
 }
 
 // Candidates with marked lines are first compacted per block (few candidates carry a match), then one thread per
@@ -666,21 +685,22 @@ __global__ void __launch_bounds__(128) k_verify_local(DbView db, const uint8_t* 
 // The same line can be marked by several candidate chunks; records come out ordered by line start, so the host
 // drops adjacent duplicates.
 constexpr int kEmitThreads = 256;
+constexpr int kEmitTile = 2048;   // candidates compacted per block step: enough marked ones to keep every warp busy
 __global__ void __launch_bounds__(kEmitThreads) k_emit_simple(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
                                                               const uint32_t* __restrict__ marks, const unsigned long long* __restrict__ recoff,
                                                               const unsigned long long* __restrict__ prefix, const unsigned long long* meta_total,
                                                               size_t cap, LineRec* __restrict__ recs, size_t rec_cap, Totals* totals) {
-    __shared__ uint32_t s_list[kEmitThreads];
+    __shared__ uint32_t s_list[kEmitTile];
     __shared__ uint32_t s_count;
     size_t ncand = (size_t)(*meta_total >> 32);
     if (ncand > cap) ncand = cap;
-    const size_t block_base = (size_t)blockIdx.x * kEmitThreads;
-    if (block_base >= ncand) return;
+    for (size_t block_base = (size_t)blockIdx.x * kEmitTile; block_base < ncand; block_base += (size_t)gridDim.x * kEmitTile) {
+    __syncthreads();
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
-    {
-        size_t i = block_base + threadIdx.x;
-        if (i < ncand && marks[i] != 0) s_list[atomicAdd(&s_count, 1u)] = threadIdx.x;
+    for (uint32_t k = threadIdx.x; k < (uint32_t)kEmitTile; k += kEmitThreads) {
+        size_t i = block_base + k;
+        if (i < ncand && marks[i] != 0) s_list[atomicAdd(&s_count, 1u)] = k;
     }
     __syncthreads();
     const uint32_t todo = s_count;
@@ -717,6 +737,7 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit_simple(DbView db, const u
             if ((mask >> j) == 0) break;
         }
     }
+    }
 }
 
 // Records arrive ordered by line start; a line marked by several candidate chunks appears several times in a row,
@@ -736,11 +757,10 @@ struct LoadKeep {
 };
 
 __global__ void k_compact_records(LoadKeep keep, const unsigned long long* __restrict__ off, size_t cap, LineRec* __restrict__ out) {
-    size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t cnt = (size_t)*keep.rec_total;
     if (cnt > cap) cnt = cap;
-    if (k >= cnt) return;
-    if (keep(k)) out[off[k]] = keep.recs[k];
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < cnt; k += (size_t)gridDim.x * blockDim.x)
+        if (keep(k)) out[off[k]] = keep.recs[k];
 }
 
 // Device-resident inputs: the end of segment j is the byte after a '\n' before boundary (j+1)*chunk, chosen so that the
@@ -1007,6 +1027,16 @@ std::shared_ptr<DeviceDb> engine_upload(const std::shared_ptr<Database>& db, std
         G.cls = (const uint8_t*)upload(d.byte_class, 256);
         G.accept_of = (const uint32_t*)upload(d.accept_of.data(), d.accept_of.size() * sizeof(uint32_t));
         if (!G.trans || !G.cls || !G.accept_of) { error = "cudaMalloc/cudaMemcpy failed while uploading DFA tables"; return nullptr; }
+        if (db->simple && (size_t)d.num_states * 512 <= ((size_t)256 << 20)) {
+            std::vector<uint16_t> flat((size_t)d.num_states * 256), eod((size_t)d.num_states);
+            for (int st = 0; st < d.num_states; st++) {
+                for (int b = 0; b < 256; b++) flat[(size_t)st * 256 + b] = (uint16_t)d.trans[(size_t)st * d.stride + d.byte_class[b]];
+                eod[st] = (uint16_t)d.trans[(size_t)st * d.stride + d.num_classes];
+            }
+            G.flat = (const uint16_t*)upload(flat.data(), flat.size() * sizeof(uint16_t));
+            G.eod_next = (const uint16_t*)upload(eod.data(), eod.size() * sizeof(uint16_t));
+            if (!G.flat || !G.eod_next) { error = "cudaMalloc/cudaMemcpy failed while uploading DFA tables"; return nullptr; }
+        }
         G.stride = (uint32_t)d.stride;
         G.eod = (uint32_t)d.num_classes;
         G.first_accept = (uint32_t)d.first_accept;
@@ -1037,14 +1067,16 @@ std::shared_ptr<DevicePrefilter> engine_upload_prefilter(const Prefilter& pf, st
     cudaGetDevice(&out->device);
     std::vector<uint32_t> replicated;
     const std::vector<uint32_t>* src = &pf.bitmap;
+    const char* want = std::getenv("GPUGREP_FILTER");
+    const bool use_exact = pf.exact && want && std::strcmp(want, "exact") == 0;
     out->stride = pf.stride;
     out->fold = pf.fold_case;
-    out->mode = pf.exact ? 1 : 2;
-    out->pp.mul = pf.hash_mul;
+    out->mode = use_exact ? 1 : 2;
+    out->pp.mul = use_exact ? pf.hash_mul : pf.bloom_mul;
     out->pp.mul2 = pf.hash_mul2;
-    out->pp.shift = 32 - (pf.exact ? pf.log2_slots : pf.log2_bits);
+    out->pp.shift = 32 - (pf.log2_bits - 3);   // bloom: product -> byte index
     out->lookback = pf.lookback;
-    if (pf.exact) {
+    if (use_exact) {
         // replicate so that a lane reads copy (lane mod R): as many copies as fit ~160 KiB of shared memory, at most 32
         const size_t slots = (size_t)1 << pf.log2_slots;
         int rshift = 5;
@@ -1119,9 +1151,11 @@ static void launch_scan(cudaStream_t st, Load load, size_t n, unsigned long long
                         SegmentStats& stats, const unsigned long long* limit = nullptr, int limit_shift = 32) {
     size_t nb = (n + kScanTile - 1) / kScanTile;
     if (nb == 0) nb = 1;
-    k_scan_sums<Load><<<(unsigned)nb, kScanThreads, 0, st>>>(load, n, sums, limit, limit_shift);
+    // persistent grid: with a device-side `limit` most tiles are empty, and empty blocks are not free to schedule
+    unsigned grid = (unsigned)std::min<size_t>(nb, (size_t)g_num_sms * 8);
+    k_scan_sums<Load><<<grid, kScanThreads, 0, st>>>(load, n, sums, nb, limit, limit_shift);
     k_scan_top<<<1, 1024, 0, st>>>(sums, nb, total);
-    k_scan_write<Load><<<(unsigned)nb, kScanThreads, 0, st>>>(load, n, sums, out, limit, limit_shift);
+    k_scan_write<Load><<<grid, kScanThreads, 0, st>>>(load, n, sums, out, nb, limit, limit_shift);
     stats.launches += 3;
 }
 
@@ -1235,19 +1269,19 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
             k_check_long<<<(unsigned)((nsuper + 255) / 256), 256, 0, st>>>(prefix, s->nblk, bps, &dT->meta_total, dT);
             s->stats.launches++;
         }
-        k_list_candidates<<<(unsigned)((s->nblk + 255) / 256), 256, 0, st>>>(meta, prefix, s->nblk, s->d_cand.as<uint32_t>(), s->cand_cap, dT);
+        k_list_candidates<<<(unsigned)std::min<size_t>((s->nblk + 255) / 256, (size_t)g_num_sms * 16), 256, 0, st>>>(meta, prefix, s->nblk, s->d_cand.as<uint32_t>(), s->cand_cap, dT);
         DbView view{ddb.d_groups, ddb.ngroups};
-        unsigned vgrid = (unsigned)((s->cand_cap + 127) / 128);
+        unsigned vgrid = (unsigned)std::min<size_t>((s->cand_cap + 127) / 128, (size_t)g_num_sms * 16);
         k_verify_local<<<vgrid, 128, 0, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->lookback,
                                               s->d_res.as<uint32_t>());
         launch_scan(st, LoadMarks{s->d_res.as<uint32_t>(), &dT->meta_total, s->cand_cap}, s->cand_cap, s->d_recoff.as<unsigned long long>(),
                     s->d_sums.as<unsigned long long>(), &dT->rec_total, s->stats, &dT->meta_total);
-        k_emit_simple<<<(unsigned)((s->cand_cap + kEmitThreads - 1) / kEmitThreads), kEmitThreads, 0, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), s->d_res.as<uint32_t>(), s->d_recoff.as<unsigned long long>(),
+        k_emit_simple<<<(unsigned)std::min<size_t>((s->cand_cap + kEmitTile - 1) / kEmitTile, (size_t)g_num_sms * 8), kEmitThreads, 0, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), s->d_res.as<uint32_t>(), s->d_recoff.as<unsigned long long>(),
                                              prefix, &dT->meta_total, s->cand_cap, s->d_recs.as<LineRec>(), s->rec_cap, dT);
         LoadKeep keep{s->d_recs.as<LineRec>(), &dT->rec_total, s->rec_cap};
         launch_scan(st, keep, s->rec_cap, s->d_keepoff.as<unsigned long long>(), s->d_sums.as<unsigned long long>(), &dT->aux_total, s->stats,
                     &dT->rec_total, 0);
-        k_compact_records<<<(unsigned)((s->rec_cap + 255) / 256), 256, 0, st>>>(keep, s->d_keepoff.as<unsigned long long>(), s->rec_cap, s->d_recs2.as<LineRec>());
+        k_compact_records<<<(unsigned)(g_num_sms * 8), 256, 0, st>>>(keep, s->d_keepoff.as<unsigned long long>(), s->rec_cap, s->d_recs2.as<LineRec>());
         s->stats.launches += 4;
         CUDA_TRY(cudaEventRecord(s->ev[1], st));
     }

@@ -32,9 +32,11 @@ class GramHistogram {
 public:
     void add_sample(const uint8_t* text, size_t n);
     uint32_t count(uint32_t gram, bool folded) const;
+    // distinct grams of the sample with their counts
+    const std::vector<uint32_t>& keys(bool folded) const { return folded ? folded_.keys : raw_.keys; }
+    const std::vector<uint32_t>& counts(bool folded) const { return folded ? folded_.counts : raw_.counts; }
     size_t positions() const { return positions_; }
     uint64_t fingerprint() const { return fingerprint_; }
-private:
     struct Table {
         std::vector<uint32_t> keys, counts;
         uint32_t mask = 0;
@@ -42,6 +44,7 @@ private:
         void add(uint32_t key);
         uint32_t get(uint32_t key) const;
     };
+private:
     Table raw_, folded_;
     size_t positions_ = 0;
     uint64_t fingerprint_ = 0;
@@ -57,8 +60,10 @@ struct Prefilter {
     int log2_slots = 0;
     uint32_t hash_mul2 = 0x85EBCA6Bu;
     std::vector<uint32_t> keys;       // 2 << log2_slots entries
-    // bloom mode (very large gram sets): bit = (gram * hash_mul) >> (32 - log2_bits)
-    int log2_bits = 13;
+    // bloom bitmap (default in the streaming kernel: one lookup per gram): with p = gram * bloom_mul,
+    // byte = p >> (32 - (log2_bits - 3)), bit = p & 7
+    int log2_bits = 16;
+    uint32_t bloom_mul = 0x9E3779B1u;
     std::vector<uint32_t> bitmap;
     uint32_t hash_mul = 0x9E3779B1u;
     std::vector<uint32_t> grams;      // the exact gram set (sorted)
