@@ -437,7 +437,7 @@ int scan_memory(const uint8_t* data, size_t size, int location, const Params& pr
     std::string err;
     const size_t limit = clamp_limit(pr.buffer_size);
     const bool on_device = location == GPUGREP_LOC_DEVICE;
-    size_t chunk = on_device ? env_mb("GPUGREP_DEVICE_SEGMENT_MB", 1024) : env_mb("GPUGREP_CHUNK_MB", 64);
+    size_t chunk = on_device ? env_mb("GPUGREP_DEVICE_SEGMENT_MB", 2048) : env_mb("GPUGREP_CHUNK_MB", 64);
     chunk = std::max(chunk, 2 * limit + 4096);
     chunk = std::min(chunk, kMaxSegmentBytes);
     bool pinned = false;

@@ -611,37 +611,76 @@ __device__ uint32_t walk_local(const GroupDev& G, const uint8_t* __restrict__ da
     uint32_t s = 0;
     if (!at_line_start) s = is_word_dev(data[t - 1]) ? G.mid_word : G.mid_other;
     uint32_t mask = 0;
-    int line = 0;
-    bool done = false;
+    uint32_t line_bit = 1u;
     const size_t chunk_end = o + 16, idle_from = o + 19;
-    ByteCursor c(data, t, n);
     const uint16_t* __restrict__ flat = G.flat;
+    const uint32_t first_accept = G.first_accept, idle_end = G.idle_end;
+    if (flat) {
+        // fast form: '\n' and NUL are ordinary columns of the table (see engine_upload)
+        size_t pos = t;
+        uint32_t word = *reinterpret_cast<const uint32_t*>(data + (pos & ~(size_t)3)) >> (8 * (pos & 3));
+        while (pos < n) {
+            const uint32_t b = word & 0xffu;
+            s = flat[(s << 8) | b];
+            pos++;
+            word >>= 8;
+            if ((pos & 3) == 0 && pos < n) word = *reinterpret_cast<const uint32_t*>(data + pos);
+            if (s >= first_accept) {
+                // the line matched: mark it, then only look for line ends inside the chunk
+                mask |= line_bit;
+                if (b != '\n') {
+                    bool more = false;
+                    while (pos < n && pos < chunk_end) {
+                        uint32_t c = data[pos++];
+                        if (c == '\n') { more = pos < chunk_end && pos < n; break; }
+                    }
+                    if (!more) return mask;
+                    word = *reinterpret_cast<const uint32_t*>(data + (pos & ~(size_t)3)) >> (8 * (pos & 3));
+                } else if (pos >= chunk_end || pos >= n) {
+                    return mask;
+                }
+                line_bit <<= 1;
+                s = 0;
+                continue;
+            }
+            if (b == '\n') {
+                if (pos >= chunk_end || pos >= n) return mask;
+                line_bit <<= 1;   // flat['\n'] already reset s to 0
+                continue;
+            }
+            if (pos >= idle_from && s < idle_end) return mask;
+        }
+        if (G.eod_next[s] >= first_accept) mask |= line_bit;
+        return mask;
+    }
+    bool done = false;
+    ByteCursor c(data, t, n);
     while (c.pos < n) {
         const uint32_t b = c.get();
         if (!done) {
             bool hit;
             if (b == 0) {
-                hit = (flat ? G.eod_next[s] : G.trans[s * G.stride + G.eod]) >= G.first_accept;
+                hit = G.trans[s * G.stride + G.eod] >= first_accept;
                 s = 0;
             } else {
-                s = flat ? flat[(s << 8) | b] : G.trans[s * G.stride + G.cls[b]];
-                hit = s >= G.first_accept;
-                if (!hit && b == '\n') hit = (flat ? G.eod_next[s] : G.trans[s * G.stride + G.eod]) >= G.first_accept;
+                s = G.trans[s * G.stride + G.cls[b]];
+                hit = s >= first_accept;
+                if (!hit && b == '\n') hit = G.trans[s * G.stride + G.eod] >= first_accept;
             }
-            if (hit) { mask |= 1u << line; done = true; }
+            if (hit) { mask |= line_bit; done = true; }
         }
         c.next();
         if (b == '\n') {
             if (c.pos >= chunk_end || c.pos >= n) return mask;
-            line++;
+            line_bit <<= 1;
             done = false;
             s = 0;
             continue;
         }
-        if (c.pos >= idle_from && (done || s < G.idle_end)) return mask;
+        if (c.pos >= idle_from && (done || s < idle_end)) return mask;
         if (done && c.pos >= chunk_end) return mask;
     }
-    if (!done && (flat ? G.eod_next[s] : G.trans[s * G.stride + G.eod]) >= G.first_accept) mask |= 1u << line;
+    if (!done && G.trans[s * G.stride + G.eod] >= first_accept) mask |= line_bit;
     return mask;
 }
 
@@ -1028,10 +1067,20 @@ std::shared_ptr<DeviceDb> engine_upload(const std::shared_ptr<Database>& db, std
         G.accept_of = (const uint32_t*)upload(d.accept_of.data(), d.accept_of.size() * sizeof(uint32_t));
         if (!G.trans || !G.cls || !G.accept_of) { error = "cudaMalloc/cudaMemcpy failed while uploading DFA tables"; return nullptr; }
         if (db->simple && (size_t)d.num_states * 512 <= ((size_t)256 << 20)) {
+            // Byte-indexed table for local verification with the line rules folded in (one load per byte, no special
+            // cases in the walk): '\n' and NUL end the scanned block, so their columns hold either the absorbing
+            // "matched" state (the block matched at its end) or state 0 (restart: next line / text after the NUL).
             std::vector<uint16_t> flat((size_t)d.num_states * 256), eod((size_t)d.num_states);
+            const uint16_t sink = (uint16_t)d.sink_match;
             for (int st = 0; st < d.num_states; st++) {
-                for (int b = 0; b < 256; b++) flat[(size_t)st * 256 + b] = (uint16_t)d.trans[(size_t)st * d.stride + d.byte_class[b]];
-                eod[st] = (uint16_t)d.trans[(size_t)st * d.stride + d.num_classes];
+                const uint32_t at_eod = d.trans[(size_t)st * d.stride + d.num_classes];
+                eod[st] = (uint16_t)at_eod;
+                for (int b = 0; b < 256; b++) {
+                    uint32_t nx = d.trans[(size_t)st * d.stride + d.byte_class[b]];
+                    if (b == 0) nx = (int)at_eod >= d.first_accept ? sink : 0;
+                    else if (b == '\n') nx = ((int)nx >= d.first_accept || (int)d.trans[(size_t)nx * d.stride + d.num_classes] >= d.first_accept) ? sink : 0;
+                    flat[(size_t)st * 256 + b] = (uint16_t)nx;
+                }
             }
             G.flat = (const uint16_t*)upload(flat.data(), flat.size() * sizeof(uint16_t));
             G.eod_next = (const uint16_t*)upload(eod.data(), eod.size() * sizeof(uint16_t));

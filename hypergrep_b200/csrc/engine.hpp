@@ -79,6 +79,6 @@ int slot_gather_lines(ScanSlot* slot, const uint32_t* starts, const uint32_t* le
 // entry is `size`).  Left empty when some boundary has no newline nearby (the caller then cuts sequentially).
 int engine_find_cuts(const uint8_t* dev_data, size_t size, size_t chunk, std::vector<size_t>& cuts, std::string& error);
 
-constexpr size_t kMaxSegmentBytes = (size_t)1 << 30;
+constexpr size_t kMaxSegmentBytes = (size_t)3 << 30;   // offsets inside a segment are 32-bit
 
 }  // namespace gpugrep
