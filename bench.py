@@ -226,7 +226,9 @@ def main() -> None:  # pylint: disable=too-many-locals,too-many-statements
     gen_s = time.perf_counter() - t0
     dev = host.cuda(non_blocking=False)
     torch.cuda.synchronize()
-    stream = torch.cuda.current_stream()
+    # a dedicated (non-default) stream: the library enqueues every kernel of the device-resident passes on it, so the
+    # CUDA events below bracket exactly the work that is timed
+    stream = torch.cuda.Stream()
 
     def scan(ptr: int, location: int, callback) -> Stats:
         st = Stats()
@@ -265,6 +267,7 @@ def main() -> None:  # pylint: disable=too-many-locals,too-many-statements
     launches = stream_launches = 0
     stream_ms = gpu_ms = 0.0
     matches = 0
+    stream.wait_stream(torch.cuda.current_stream())
     begin.record(stream)
     for _ in range(args.steps):
         st = scan(dev.data_ptr(), 1, None)

@@ -65,13 +65,15 @@ public:
     }
     // `bytes`/`len`: the pseudo-line as it sits in the file.  The delivered text is what the reference strcpy()s:
     // leading NULs skipped, cut at the next NUL (hyperscanner.c:205-214, :92).
-    void emit(unsigned id, unsigned long long line_number, const uint8_t* bytes, size_t len) {
+    void emit(unsigned id, unsigned long long line_number, const uint8_t* bytes, size_t len, bool may_have_nul = true) {
         count_++;
         if (!cb_) return;
-        size_t a = 0;
-        while (a < len && bytes[a] == 0) a++;
-        const void* z = std::memchr(bytes + a, 0, len - a);
-        size_t b = z ? (size_t)((const uint8_t*)z - bytes) : len;
+        size_t a = 0, b = len;
+        if (may_have_nul) {
+            while (a < len && bytes[a] == 0) a++;
+            const void* z = std::memchr(bytes + a, 0, len - a);
+            if (z) b = (size_t)((const uint8_t*)z - bytes);
+        }
         std::vector<char>& slot = lines_[(size_t)fill_];
         slot.assign((const char*)bytes + a, (const char*)bytes + b);
         slot.push_back('\0');
@@ -196,7 +198,7 @@ struct Job {
             std::vector<uint32_t> starts(take), lens(take);
             unsigned long long total = 0;
             goff.resize(take);
-            for (size_t i = 0; i < take; i++) { starts[i] = recs[i].start; lens[i] = recs[i].len; goff[i] = total; total += lens[i] + 1ull; }
+            for (size_t i = 0; i < take; i++) { starts[i] = recs[i].start; lens[i] = recs[i].len & kLineLenMask; goff[i] = total; total += lens[i] + 1ull; }
             gathered.resize((size_t)total);
             int rc = slot_gather_lines(slot, starts.data(), lens.data(), take, gathered.data(), error);
             if (rc) return rc;
@@ -204,7 +206,8 @@ struct Job {
         for (size_t i = 0; i < take; i++) {
             const LineRec& lr = recs[i];
             const uint8_t* bytes = host ? host + lr.start : gathered.data() + goff[i];
-            out->emit(db->simple_id, line_base + lr.line, bytes, lr.len);
+            const bool fast_rec = (r.stats.path & 1) != 0;   // fast-path records carry the NUL hint, general-path ones do not
+            out->emit(db->simple_id, line_base + lr.line, bytes, lr.len & kLineLenMask, fast_rec ? (lr.len & kLineHasNul) != 0 : true);
         }
         return 0;
     }

@@ -40,6 +40,7 @@ struct DbView {
 };
 
 constexpr uint32_t kInvalidLen = 0xffffffffu;   // LineRec.len of a record the host must drop (NUL re-check failed)
+constexpr uint32_t kHasNulBit = 0x80000000u;    // LineRec.len flag: the line contains NUL bytes (host applies the strip/cut rule)
 
 struct Totals {
     unsigned long long meta_total;   // candidates << 32 | newlines
@@ -763,7 +764,7 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit_simple(DbView db, const u
                 if (has_nul) ok = block_matches(db, data, st, en);
                 const size_t lb = st >> 9;
                 const uint32_t line_no = (uint32_t)prefix[lb] + count_newlines(data, lb << 9, st);
-                if (at < rec_cap) recs[at] = LineRec{line_no, (uint32_t)st, ok ? (uint32_t)(en - st) : kInvalidLen};
+                if (at < rec_cap) recs[at] = LineRec{line_no, (uint32_t)st, ok ? ((uint32_t)(en - st) | (has_nul ? kHasNulBit : 0u)) : kInvalidLen};
                 else atomicOr(&totals->flags, 4u);
                 at++;
             }

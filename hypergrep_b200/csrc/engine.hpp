@@ -16,8 +16,10 @@ namespace gpugrep {
 struct LineRec {
     uint32_t line;    // pseudo-line index inside the segment
     uint32_t start;   // byte offset of the pseudo-line inside the segment
-    uint32_t len;     // bytes, trailing '\n' included when present
+    uint32_t len;     // bytes, trailing '\n' included when present; bit 31 (fast path only): the line contains NUL bytes
 };
+constexpr uint32_t kLineLenMask = 0x7fffffffu;
+constexpr uint32_t kLineHasNul = 0x80000000u;
 
 // One automaton report (general mode): some accept set fired at `end` inside pseudo-line `line`.
 struct EventRec {

@@ -17,6 +17,7 @@ parser = argparse.ArgumentParser()
 parser.add_argument("--mib", type=int, default=1024)
 parser.add_argument("--set", default="c2")
 parser.add_argument("--passes", type=int, default=2)
+parser.add_argument("--quiet", action="store_true")
 args = parser.parse_args()
 lib = utils._get_hyperscanner_lib()
 plants = None
