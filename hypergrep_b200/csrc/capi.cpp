@@ -186,6 +186,17 @@ struct Job {
     int deliver_simple(const SegmentResult& r, const uint8_t* host, ScanSlot* slot) {
         const LineRec* recs = r.lines;
         size_t count = r.num_line_recs;
+        const bool fast_rec = (r.stats.path & 1) != 0;   // fast-path records: NUL hint in len, dropped ones marked kLineInvalid
+        if (fast_rec) {
+            if (!out->wants_lines() && max_match == 0) { out->emit_count_only(r.num_valid_recs); return 0; }
+            if (r.num_valid_recs != count) {
+                unique_.clear();
+                unique_.reserve(r.num_valid_recs);
+                for (size_t i = 0; i < count; i++) if (recs[i].len != kLineInvalid) unique_.push_back(recs[i]);
+                recs = unique_.data();
+                count = unique_.size();
+            }
+        }
         size_t take = count;
         if (max_match > 0) {
             unsigned long long room = max_match > out->count() ? max_match - out->count() : 0;
@@ -206,11 +217,12 @@ struct Job {
         for (size_t i = 0; i < take; i++) {
             const LineRec& lr = recs[i];
             const uint8_t* bytes = host ? host + lr.start : gathered.data() + goff[i];
-            const bool fast_rec = (r.stats.path & 1) != 0;   // fast-path records carry the NUL hint, general-path ones do not
             out->emit(db->simple_id, line_base + lr.line, bytes, lr.len & kLineLenMask, fast_rec ? (lr.len & kLineHasNul) != 0 : true);
         }
         return 0;
     }
+
+    std::vector<LineRec> unique_;
 
     int deliver_events(const SegmentResult& r, const uint8_t* host, ScanSlot* slot) {
         // events arrive grouped by pseudo-line in file order; inside a line they are grouped by DFA group

@@ -388,13 +388,31 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long
     return s_warp[wid] + incl - v;
 }
 
-struct LoadMeta {   // meta word -> candidates << 32 | newlines
+// Prefix sums are kept per GROUP of four 512-byte blocks (the unit one warp step of k_stream writes): a quarter of the
+// scan work; consumers add the in-group part from the (adjacent) meta words.
+constexpr int kGroupBlocks = 4;
+struct LoadMetaGroup {   // sum over the group's blocks of: candidates << 32 | newlines
     const unsigned long long* meta;
-    __device__ unsigned long long operator()(size_t i) const {
-        unsigned long long m = meta[i];
-        return ((unsigned long long)__popc((uint32_t)m) << 32) | (m >> 32);
+    size_t nblk;
+    __device__ unsigned long long operator()(size_t g) const {
+        unsigned long long acc = 0;
+        size_t b0 = g * kGroupBlocks;
+#pragma unroll
+        for (int u = 0; u < kGroupBlocks; u++) {
+            if (b0 + u < nblk) {
+                unsigned long long m = meta[b0 + u];
+                acc += ((unsigned long long)__popc((uint32_t)m) << 32) | (m >> 32);
+            }
+        }
+        return acc;
     }
 };
+// newlines before block `blk`: group prefix + the earlier blocks of its group
+__device__ __forceinline__ uint32_t newlines_before_block(const unsigned long long* __restrict__ prefix_g, const unsigned long long* __restrict__ meta, size_t blk) {
+    uint32_t c = (uint32_t)prefix_g[blk / kGroupBlocks];
+    for (size_t b = blk - blk % kGroupBlocks; b < blk; b++) c += (uint32_t)(meta[b] >> 32);
+    return c;
+}
 struct LoadMarks {   // records per candidate; *meta_total (device) bounds the valid prefix
     const uint32_t* marks;
     const unsigned long long* meta_total;
@@ -574,24 +592,26 @@ __global__ void k_check_long(const unsigned long long* __restrict__ prefix, size
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t lo = j * blocks_per_super, hi = lo + blocks_per_super;
     if (hi > nblk) return;   // partial trailing super-block cannot hide a full one
-    uint32_t a = (uint32_t)prefix[lo];
-    uint32_t b = hi < nblk ? (uint32_t)prefix[hi] : (uint32_t)*meta_total;
+    uint32_t a = (uint32_t)prefix[lo / kGroupBlocks];   // blocks_per_super is a multiple of kGroupBlocks
+    uint32_t b = hi < nblk ? (uint32_t)prefix[hi / kGroupBlocks] : (uint32_t)*meta_total;
     if (a == b) atomicOr(&totals->flags, 1u);
 }
 
 // meta/prefix -> ordered list of candidate chunk indices
 __global__ void k_list_candidates(const unsigned long long* __restrict__ meta, const unsigned long long* __restrict__ prefix, size_t nblk,
                                   uint32_t* __restrict__ cand, size_t cap, Totals* totals) {
-    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < nblk; g += (size_t)gridDim.x * blockDim.x) {
-        uint32_t mask = (uint32_t)meta[g];
-        if (!mask) continue;
-        size_t at = (size_t)(prefix[g] >> 32);
-        while (mask) {
-            int b = __ffs(mask) - 1;
-            mask &= mask - 1;
-            if (at < cap) cand[at] = (uint32_t)(g * 32 + b);
-            else { atomicOr(&totals->flags, 2u); break; }
-            at++;
+    const size_t ngroups = (nblk + kGroupBlocks - 1) / kGroupBlocks;
+    for (size_t grp = (size_t)blockIdx.x * blockDim.x + threadIdx.x; grp < ngroups; grp += (size_t)gridDim.x * blockDim.x) {
+        size_t at = (size_t)(prefix[grp] >> 32);
+        for (size_t g = grp * kGroupBlocks; g < nblk && g < (grp + 1) * kGroupBlocks; g++) {
+            uint32_t mask = (uint32_t)meta[g];
+            while (mask) {
+                int b = __ffs(mask) - 1;
+                mask &= mask - 1;
+                if (at < cap) cand[at] = (uint32_t)(g * 32 + b);
+                else atomicOr(&totals->flags, 2u);
+                at++;
+            }
         }
     }
 }
@@ -728,9 +748,11 @@ constexpr int kEmitThreads = 256;
 constexpr int kEmitTile = 2048;   // candidates compacted per block step: enough marked ones to keep every warp busy
 __global__ void __launch_bounds__(kEmitThreads) k_emit_simple(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
                                                               const uint32_t* __restrict__ marks, const unsigned long long* __restrict__ recoff,
-                                                              const unsigned long long* __restrict__ prefix, const unsigned long long* meta_total,
-                                                              size_t cap, LineRec* __restrict__ recs, size_t rec_cap, Totals* totals) {
+                                                              const unsigned long long* __restrict__ meta, const unsigned long long* __restrict__ prefix,
+                                                              const unsigned long long* meta_total, size_t cap, LineRec* __restrict__ recs, size_t rec_cap,
+                                                              Totals* totals) {
     __shared__ uint32_t s_list[kEmitTile];
+    uint32_t valid = 0;
     __shared__ uint32_t s_count;
     size_t ncand = (size_t)(*meta_total >> 32);
     if (ncand > cap) ncand = cap;
@@ -761,9 +783,23 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit_simple(DbView db, const u
                 bool has_nul = false;
                 size_t en = line_end_of(data, st, n, &has_nul);
                 bool ok = true;
-                if (has_nul) ok = block_matches(db, data, st, en);
+                if (first) {
+                    // the line started before this chunk: an earlier candidate chunk that intersects it may have marked it
+                    // already (the line is the LAST line of such a chunk); only the first marking is kept
+                    for (size_t k = i; k-- > 0;) {
+                        const size_t ok_off = (size_t)cand[k] * 16;
+                        if (ok_off + 16 <= st) break;
+                        const uint32_t mk = marks[k];
+                        if (!mk) continue;
+                        uint4 pv = ld_chunk(data, ok_off, n);
+                        const uint32_t last_idx = __popc(newline_mask16(pv) & 0x7fffu);   // line starts inside that chunk
+                        if ((mk >> last_idx) & 1u) { ok = false; break; }
+                    }
+                }
+                if (ok && has_nul) ok = block_matches(db, data, st, en);
+                valid += ok ? 1u : 0u;
                 const size_t lb = st >> 9;
-                const uint32_t line_no = (uint32_t)prefix[lb] + count_newlines(data, lb << 9, st);
+                const uint32_t line_no = newlines_before_block(prefix, meta, lb) + count_newlines(data, lb << 9, st);
                 if (at < rec_cap) recs[at] = LineRec{line_no, (uint32_t)st, ok ? ((uint32_t)(en - st) | (has_nul ? kHasNulBit : 0u)) : kInvalidLen};
                 else atomicOr(&totals->flags, 4u);
                 at++;
@@ -778,29 +814,9 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit_simple(DbView db, const u
         }
     }
     }
-}
-
-// Records arrive ordered by line start; a line marked by several candidate chunks appears several times in a row,
-// and a record whose NUL re-check failed carries kInvalidLen.  Keep the first valid record of every line.
-struct LoadKeep {
-    const LineRec* recs;
-    const unsigned long long* rec_total;
-    size_t cap;
-    __device__ unsigned long long operator()(size_t k) const {
-        size_t cnt = (size_t)*rec_total;
-        if (cnt > cap) cnt = cap;
-        if (k >= cnt) return 0ull;
-        LineRec r = recs[k];
-        if (r.len == kInvalidLen) return 0ull;
-        return (k == 0 || recs[k - 1].start != r.start) ? 1ull : 0ull;
-    }
-};
-
-__global__ void k_compact_records(LoadKeep keep, const unsigned long long* __restrict__ off, size_t cap, LineRec* __restrict__ out) {
-    size_t cnt = (size_t)*keep.rec_total;
-    if (cnt > cap) cnt = cap;
-    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < cnt; k += (size_t)gridDim.x * blockDim.x)
-        if (keep(k)) out[off[k]] = keep.recs[k];
+    // unique valid records of the segment (count-only callers need nothing else)
+    valid = __reduce_add_sync(0xffffffffu, valid);
+    if ((threadIdx.x & 31) == 0 && valid) atomicAdd(&totals->aux_total, (unsigned long long)valid);
 }
 
 // Device-resident inputs: the end of segment j is the byte after a '\n' before boundary (j+1)*chunk, chosen so that the
@@ -823,7 +839,7 @@ __global__ void k_find_cuts(const uint8_t* __restrict__ data, size_t size, size_
 // GENERAL PATH kernels
 // ------------------------------------------------------------------------------------------------------------
 // warp per 512-byte block: write the offset of every '\n' at its global rank
-__global__ void __launch_bounds__(256) k_newline_positions(const uint8_t* __restrict__ data, size_t n, size_t nblk,
+__global__ void __launch_bounds__(256) k_newline_positions(const uint8_t* __restrict__ data, size_t n, size_t nblk, const unsigned long long* __restrict__ meta,
                                                            const unsigned long long* __restrict__ prefix, uint32_t* __restrict__ nlpos) {
     const int lane = threadIdx.x & 31;
     size_t g = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -841,7 +857,7 @@ __global__ void __launch_bounds__(256) k_newline_positions(const uint8_t* __rest
         uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += t;
     }
-    size_t at = (size_t)(uint32_t)prefix[g] + (incl - cnt);
+    size_t at = (size_t)newlines_before_block(prefix, meta, g) + (incl - cnt);
     while (m) {
         int b = __ffs(m) - 1;
         m &= m - 1;
@@ -996,7 +1012,7 @@ public:
     cudaStream_t copy_stream = nullptr;   // result D2H, so that it does not queue behind the next segment's kernels
     cudaEvent_t done = nullptr;           // all kernels of the segment + the totals copy have finished
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // 0/1: whole segment, 2/3: streaming kernel
-    DevBuf d_input, d_meta, d_prefix, d_sums, d_cand, d_res, d_recoff, d_recs, d_recs2, d_keepoff, d_totals;
+    DevBuf d_input, d_meta, d_prefix, d_sums, d_cand, d_res, d_recoff, d_recs, d_totals;
     DevBuf d_nlpos, d_npl, d_ploff, d_plstart, d_pllen, d_flags, d_counts, d_events, d_gather, d_gidx;
     PinBuf h_totals, h_recs, h_stage, h_gather;
     // state of the in-flight segment
@@ -1248,11 +1264,11 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
     // fast path: simple mode + prefilter + buffer large enough that "a super-block without newline" is a cheap
     // sufficient test for "no line needs gzgets splitting"
     size_t super_bytes = 0;
-    if (buffer_size >= 1024) {
-        super_bytes = 512;
+    if (buffer_size >= 4096) {
+        super_bytes = 2048;
         while (super_bytes * 4 <= (size_t)buffer_size && super_bytes < 65536) super_bytes *= 2;   // 2*super-1 <= buffer_size-1
     }
-    s->fast = ddb.simple && pf != nullptr && super_bytes >= 512 && std::getenv("GPUGREP_FORCE_GENERAL") == nullptr;
+    s->fast = ddb.simple && pf != nullptr && super_bytes >= 2048 && std::getenv("GPUGREP_FORCE_GENERAL") == nullptr;
 
     if (host_data) {
         if (s->d_input.reserve(n + 1024) != cudaSuccess) { error = "cudaMalloc failed for the input segment"; return 3; }
@@ -1273,13 +1289,12 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
     }
     s->cand_cap = n / 64 + 4096;
     s->rec_cap = n / 48 + 4096;
-    size_t nb_scan = (std::max(std::max(s->nblk, s->cand_cap), s->rec_cap) + kScanTile - 1) / kScanTile + 1;
+    size_t nb_scan = (std::max(s->nblk, s->cand_cap) + kScanTile - 1) / kScanTile + 1;
     if (s->d_meta.reserve((s->nblk + 8) * 8) != cudaSuccess || s->d_prefix.reserve((s->nblk + 8) * 8) != cudaSuccess ||
         s->d_sums.reserve(nb_scan * 8) != cudaSuccess) { error = "cudaMalloc failed for scan scratch"; return 3; }
     if (s->fast) {
         if (s->d_cand.reserve(s->cand_cap * 4) != cudaSuccess || s->d_res.reserve(s->cand_cap * sizeof(uint32_t)) != cudaSuccess ||
-            s->d_recoff.reserve(s->cand_cap * 8) != cudaSuccess || s->d_recs.reserve(s->rec_cap * sizeof(LineRec)) != cudaSuccess ||
-            s->d_recs2.reserve(s->rec_cap * sizeof(LineRec)) != cudaSuccess || s->d_keepoff.reserve(s->rec_cap * 8) != cudaSuccess) {
+            s->d_recoff.reserve(s->cand_cap * 8) != cudaSuccess || s->d_recs.reserve(s->rec_cap * sizeof(LineRec)) != cudaSuccess) {
             error = "cudaMalloc failed for candidate scratch"; return 3;
         }
     }
@@ -1311,7 +1326,8 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
     s->stats.stream_launches++;
     // ---- scan of (candidates, newlines) ----
     unsigned long long* prefix = s->d_prefix.as<unsigned long long>();
-    launch_scan(st, LoadMeta{meta}, s->nblk, prefix, s->d_sums.as<unsigned long long>(), &dT->meta_total, s->stats);
+    launch_scan(st, LoadMetaGroup{meta, s->nblk}, (s->nblk + kGroupBlocks - 1) / kGroupBlocks, prefix, s->d_sums.as<unsigned long long>(),
+                &dT->meta_total, s->stats);
     if (s->fast) {
         size_t bps = super_bytes / 512;
         size_t nsuper = s->nblk / bps;
@@ -1326,13 +1342,10 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
                                               s->d_res.as<uint32_t>());
         launch_scan(st, LoadMarks{s->d_res.as<uint32_t>(), &dT->meta_total, s->cand_cap}, s->cand_cap, s->d_recoff.as<unsigned long long>(),
                     s->d_sums.as<unsigned long long>(), &dT->rec_total, s->stats, &dT->meta_total);
-        k_emit_simple<<<(unsigned)std::min<size_t>((s->cand_cap + kEmitTile - 1) / kEmitTile, (size_t)g_num_sms * 8), kEmitThreads, 0, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), s->d_res.as<uint32_t>(), s->d_recoff.as<unsigned long long>(),
-                                             prefix, &dT->meta_total, s->cand_cap, s->d_recs.as<LineRec>(), s->rec_cap, dT);
-        LoadKeep keep{s->d_recs.as<LineRec>(), &dT->rec_total, s->rec_cap};
-        launch_scan(st, keep, s->rec_cap, s->d_keepoff.as<unsigned long long>(), s->d_sums.as<unsigned long long>(), &dT->aux_total, s->stats,
-                    &dT->rec_total, 0);
-        k_compact_records<<<(unsigned)(g_num_sms * 8), 256, 0, st>>>(keep, s->d_keepoff.as<unsigned long long>(), s->rec_cap, s->d_recs2.as<LineRec>());
-        s->stats.launches += 4;
+        k_emit_simple<<<(unsigned)std::min<size_t>((s->cand_cap + kEmitTile - 1) / kEmitTile, (size_t)g_num_sms * 8), kEmitThreads, 0, st>>>(
+            view, s->data, n, s->d_cand.as<uint32_t>(), s->d_res.as<uint32_t>(), s->d_recoff.as<unsigned long long>(), meta, prefix, &dT->meta_total,
+            s->cand_cap, s->d_recs.as<LineRec>(), s->rec_cap, dT);
+        s->stats.launches += 3;
         CUDA_TRY(cudaEventRecord(s->ev[1], st));
     }
     CUDA_TRY(cudaMemcpyAsync(&dT->last_byte, s->data + n - 1, 1, cudaMemcpyDeviceToDevice, st));
@@ -1353,7 +1366,7 @@ int ScanSlot::run_general(SegmentResult& out, std::string& error) {
     unsigned long long* prefix = d_prefix.as<unsigned long long>();
     if (d_nlpos.reserve((nl_total + 1) * 4) != cudaSuccess) { error = "cudaMalloc failed for newline index"; return 3; }
     if (nblk) {
-        k_newline_positions<<<(unsigned)((nblk * 32 + 255) / 256), 256, 0, st>>>(data, n, nblk, prefix, d_nlpos.as<uint32_t>());
+        k_newline_positions<<<(unsigned)((nblk * 32 + 255) / 256), 256, 0, st>>>(data, n, nblk, d_meta.as<unsigned long long>(), prefix, d_nlpos.as<uint32_t>());
         stats.launches++;
     }
     const uint32_t limit = (uint32_t)std::max(1, buffer_size - 1);
@@ -1456,12 +1469,13 @@ int slot_collect(ScanSlot* s, SegmentResult& out, std::string& error) {
         s->stats.candidates = hT->meta_total >> 32;
         if (hT->flags == 0) {
             s->stats.path |= 1;
-            size_t nrec = (size_t)hT->aux_total;   // unique valid records (k_compact_records)
+            size_t nrec = (size_t)hT->rec_total;   // includes records marked kInvalidLen (repeats of a line, failed NUL re-checks)
+            out.num_valid_recs = (size_t)hT->aux_total;
             const size_t nl_total = (size_t)(uint32_t)hT->meta_total;
             out.num_lines = nl_total + ((hT->last_byte & 0xff) != '\n' ? 1 : 0);
             if (nrec && s->want_records) {
                 if (s->h_recs.reserve(nrec * sizeof(LineRec)) != cudaSuccess) { error = "cudaHostAlloc failed"; return 3; }
-                CUDA_TRY(cudaMemcpyAsync(s->h_recs.p, s->d_recs2.p, nrec * sizeof(LineRec), cudaMemcpyDeviceToHost, s->copy_stream));
+                CUDA_TRY(cudaMemcpyAsync(s->h_recs.p, s->d_recs.p, nrec * sizeof(LineRec), cudaMemcpyDeviceToHost, s->copy_stream));
                 CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
                 s->stats.d2h_bytes += nrec * sizeof(LineRec);
             }

@@ -20,6 +20,7 @@ struct LineRec {
 };
 constexpr uint32_t kLineLenMask = 0x7fffffffu;
 constexpr uint32_t kLineHasNul = 0x80000000u;
+constexpr uint32_t kLineInvalid = 0xffffffffu;   // fast path: repeat of a line already reported, or a failed NUL re-check
 
 // One automaton report (general mode): some accept set fired at `end` inside pseudo-line `line`.
 struct EventRec {
@@ -40,6 +41,7 @@ struct SegmentResult {
     uint64_t num_lines = 0;        // pseudo-lines in the segment
     const LineRec* lines = nullptr;   // simple mode, file order (pinned host memory owned by the slot)
     size_t num_line_recs = 0;
+    size_t num_valid_recs = 0;        // fast path: records whose len is not kLineInvalid (the others must be skipped)
     const EventRec* events = nullptr; // general mode, grouped by line in file order
     size_t num_events = 0;
     SegmentStats stats;
