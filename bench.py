@@ -299,6 +299,30 @@ def main() -> None:  # pylint: disable=too-many-locals,too-many-statements
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = total_bytes * args.steps / e2e_s / 1e9
 
+    # ---- the reference-facing call itself: hyperscan(path) on a file in tmpfs (read() into pinned memory + H2D + ...)
+    e2e_file = None
+    if world == 1:
+        try:
+            file_bytes = min(size, 4 << 30)
+            while file_bytes > 1 and host[file_bytes - 1].item() != 10:
+                file_bytes -= 1
+            shm = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+            path = os.path.join(shm, f"gpugrep_bench_{os.getpid()}.log")
+            host.numpy()[:file_bytes].tofile(path)
+            lib.gpugrep_scan_file.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p,
+                                              ctypes.c_int, ctypes.c_int, ctypes.c_ulonglong, ctypes.c_void_p]
+            fst = Stats()
+            for it in range(3):
+                t0 = time.perf_counter()
+                rc = lib.gpugrep_scan_file(path.encode(), pa, fa, ia, npat, discard, 262140, 4096, 0, ctypes.byref(fst))
+                file_s = time.perf_counter() - t0
+                assert rc == 0
+            os.unlink(path)
+            e2e_file = {"value": file_bytes / file_s / 1e9, "unit": "GB/s", "bytes": file_bytes, "matches": int(fst.matches),
+                        "source": "hyperscan(path)-equivalent gpugrep_scan_file on a tmpfs file, native discard callback, third of 3 runs"}
+        except Exception as error:  # pylint: disable=broad-except
+            e2e_file = {"value": None, "error": str(error)}
+
     peak, peak_source = load_peaks()
     kernel_bytes = size / max(1, stream_launches // max(1, args.steps))   # algorithmic bytes per k_stream launch
     avg_launch_ms = stream_ms / max(1, stream_launches)
@@ -317,6 +341,7 @@ def main() -> None:  # pylint: disable=too-many-locals,too-many-statements
         "matched_lines_per_step": total_matches, "lines_per_step": sum_over_ranks(float(lines)) if world == 1 else None,
         "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_s * 1e3 / args.steps, "source": "pinned host memory -> gpugrep_scan_buffer (C ABI) -> native discard callback"},
+        "e2e_file": e2e_file,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                      "kernel": "k_stream (newline count + literal prefilter)", "peak_source": peak_source,

@@ -186,7 +186,8 @@ struct Determinizer {
 
     // Epsilon closure.  `strong` items descend from consumed bytes (their Match counts); `weak` items are the
     // fresh ".*" restarts whose zero-width matches must not be reported.
-    void closure(const std::vector<int>& kernel, const Ctx& ctx, int look, std::vector<int>& bytes, std::vector<int>& matched) {
+    void closure(const std::vector<int>& kernel, const Ctx& ctx, int look, std::vector<int>& bytes, std::vector<int>& matched,
+                 bool with_kernel = true, bool with_starts = true) {
         bytes.clear(); matched.clear();
         stamp++;
         if (stamp == 0) { std::fill(seen_strong.begin(), seen_strong.end(), 0); std::fill(seen_weak.begin(), seen_weak.end(), 0); stamp = 1; }
@@ -207,8 +208,8 @@ struct Determinizer {
                 }
             }
         };
-        for (int pc : kernel) run(pc, true);
-        for (int pc : nfa.starts) run(pc, false);
+        if (with_kernel) for (int pc : kernel) run(pc, true);
+        if (with_starts) for (int pc : nfa.starts) run(pc, false);
         std::sort(bytes.begin(), bytes.end());
         bytes.erase(std::unique(bytes.begin(), bytes.end()), bytes.end());
         std::sort(matched.begin(), matched.end());
@@ -276,6 +277,25 @@ bool build_dfa(const Nfa& nfa, const DfaBuildOptions& opt, Dfa& out) {
 
     std::vector<int> bytes, matched, next_kernel;
     std::vector<int> look_bytes[4], look_matched[4];
+    // per (context, look-ahead): for every byte class, the kernel items contributed by matches that START here
+    std::map<int, std::vector<std::vector<int>>> start_cache;
+    auto start_targets = [&](int ctx_bits, const Ctx& ctx, int slot, int look) -> const std::vector<std::vector<int>>& {
+        int key = ctx_bits * 4 + slot;
+        auto it = start_cache.find(key);
+        if (it != start_cache.end()) return it->second;
+        std::vector<int> sb, sm;
+        det.closure({}, ctx, look, sb, sm, false, true);
+        std::vector<std::vector<int>> per_class(ncls);
+        for (int c = 0; c < ncls; c++) {
+            for (int pc : sb) {
+                const NfaInst& in = nfa.prog[pc];
+                if ((det.set_classes[in.arg][c >> 6] >> (c & 63)) & 1) per_class[c].push_back(in.x);
+            }
+            std::sort(per_class[c].begin(), per_class[c].end());
+            per_class[c].erase(std::unique(per_class[c].begin(), per_class[c].end()), per_class[c].end());
+        }
+        return start_cache.emplace(key, std::move(per_class)).first->second;
+    };
     for (int s = 0; s < (int)kernels.size(); s++) {
         if ((size_t)kernels.size() > opt.max_states) return false;
         if (opt.simple && s == sink_state) {
@@ -291,9 +311,12 @@ bool build_dfa(const Nfa& nfa, const DfaBuildOptions& opt, Dfa& out) {
         bool have[4] = {false, false, false, false};
         auto get = [&](int look) {
             int slot = nfa.uses_lookahead ? look : 0;
-            if (!have[slot]) { det.closure(kernel, ctx, look, look_bytes[slot], look_matched[slot]); have[slot] = true; }
+            // only the items that descend from consumed bytes: the ".*" restarts are the same for every state with this
+            // context and are merged in from start_targets() below (what keeps large pattern sets tractable)
+            if (!have[slot]) { det.closure(kernel, ctx, look, look_bytes[slot], look_matched[slot], true, false); have[slot] = true; }
             return slot;
         };
+        const int ctx_bits = (ctx.at_start ? 1 : 0) | (ctx.prev_nl ? 2 : 0) | (ctx.prev_word ? 4 : 0);
         for (int c = 0; c < ncls; c++) {
             int look = det.class_look[c];
             int slot = get(look);
@@ -307,6 +330,8 @@ bool build_dfa(const Nfa& nfa, const DfaBuildOptions& opt, Dfa& out) {
                     const NfaInst& in = nfa.prog[pc];
                     if ((det.set_classes[in.arg][c >> 6] >> (c & 63)) & 1) next_kernel.push_back(in.x);
                 }
+                const std::vector<int>& fresh = start_targets(ctx_bits, ctx, nfa.uses_lookahead ? look : 0, look)[c];
+                next_kernel.insert(next_kernel.end(), fresh.begin(), fresh.end());
                 std::sort(next_kernel.begin(), next_kernel.end());
                 next_kernel.erase(std::unique(next_kernel.begin(), next_kernel.end()), next_kernel.end());
                 Ctx nctx{false, nfa.uses_line_ctx && look == LookNewline, nfa.uses_word_ctx && look == LookWord};

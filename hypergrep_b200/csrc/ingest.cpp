@@ -6,9 +6,12 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include <sys/stat.h>
+
 #include <cerrno>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 namespace gpugrep {
@@ -36,9 +39,12 @@ private:
     int fd_;
 };
 
+// Plain files.  Large reads of regular files are split over a few threads (pread into disjoint slices of the pinned
+// destination): one thread copying out of the page cache tops out far below what the PCIe link can take.
 class PlainSource : public ByteSource {
 public:
-    PlainSource(std::unique_ptr<RawFile> f, const uint8_t* head, size_t head_len) : f_(std::move(f)), head_(head, head + head_len) {}
+    PlainSource(std::unique_ptr<RawFile> f, const uint8_t* head, size_t head_len, int fd, bool regular)
+        : f_(std::move(f)), head_(head, head + head_len), fd_(fd), regular_(regular), offset_(head_len) {}
     size_t read(uint8_t* dst, size_t cap) override {
         size_t got = 0;
         if (head_pos_ < head_.size()) {
@@ -46,14 +52,52 @@ public:
             std::memcpy(dst, head_.data() + head_pos_, got);
             head_pos_ += got;
         }
-        if (got < cap) got += f_->read(dst + got, cap - got);
-        return got;
+        if (got == cap) return got;
+        if (!regular_) return got + f_->read(dst + got, cap - got);
+        size_t want = cap - got;
+        unsigned hw = std::thread::hardware_concurrency();
+        size_t nthreads = want >= ((size_t)8 << 20) ? std::min<size_t>(8, std::max(1u, hw / 2)) : 1;
+        if (nthreads <= 1) {
+            size_t r = pread_all(dst + got, want, offset_);
+            offset_ += r;
+            return got + r;
+        }
+        size_t slice = ((want / nthreads) + 4095) & ~(size_t)4095;
+        std::vector<size_t> done(nthreads, 0);
+        std::vector<std::thread> pool;
+        for (size_t t = 0; t < nthreads; t++) {
+            size_t lo = t * slice;
+            if (lo >= want) break;
+            size_t len = std::min(slice, want - lo);
+            pool.emplace_back([this, dst, got, lo, len, t, &done] { done[t] = pread_all(dst + got + lo, len, offset_ + lo); });
+        }
+        for (auto& th : pool) th.join();
+        size_t total = 0;
+        for (size_t t = 0; t < pool.size(); t++) {
+            total += done[t];
+            if (done[t] < std::min(slice, want - t * slice)) break;   // end of file inside this slice
+        }
+        offset_ += total;
+        return got + total;
     }
     const char* kind() const override { return "plain"; }
 private:
+    size_t pread_all(uint8_t* dst, size_t len, size_t off) const {
+        size_t got = 0;
+        while (got < len) {
+            ssize_t r = ::pread(fd_, dst + got, len - got, (off_t)(off + got));
+            if (r < 0) { if (errno == EINTR) continue; break; }
+            if (r == 0) break;
+            got += (size_t)r;
+        }
+        return got;
+    }
     std::unique_ptr<RawFile> f_;
     std::vector<uint8_t> head_;
     size_t head_pos_ = 0;
+    int fd_;
+    bool regular_;
+    size_t offset_;
 };
 
 // gzip members back to back; anything after the last member that is not another gzip header is ignored (zlib)
@@ -213,7 +257,9 @@ std::unique_ptr<ByteSource> open_byte_source(const char* path, std::string& erro
         }
         return std::make_unique<ZstdSource>(std::move(raw), head, got);
     }
-    return std::make_unique<PlainSource>(std::move(raw), head, got);
+    struct stat sb;
+    bool regular = ::fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode);
+    return std::make_unique<PlainSource>(std::move(raw), head, got, fd, regular);
 }
 
 }  // namespace gpugrep

@@ -144,3 +144,31 @@ def c5_patterns(count: int = 10000, seed: int = 99) -> list[str]:
         else:
             out.add(rf"{noun}-{verb}-{num}\}}$")
     return sorted(out)
+
+
+def jsonish_bytes(size: int, seed: int = 4321, patterns_to_plant: list[str] | None = None, plant_rate: float = 0.02) -> bytes:
+    """configs[4] text: long JSON-ish lines (2-16 KiB each).  `patterns_to_plant` are literal strings sprinkled into
+    about `plant_rate` of the lines.  Pure Python: meant for parity-test sizes, not for the 10 GiB bench."""
+    rng = random.Random(seed)
+    nouns = ["session", "request", "payment", "invoice", "shipment", "account", "device", "cluster", "tenant", "gateway"]
+    out = bytearray()
+    while len(out) < size:
+        fields = [f'{{"ts":{rng.randint(1_600_000_000, 1_800_000_000)},"svc":"{rng.choice(nouns)}{rng.randint(0, 999)}"']
+        target = rng.randint(2048, 16384)
+        length = len(fields[0])
+        while length < target:
+            key = f'{rng.choice(nouns)}{rng.choice(["Id", "State", "Code", "Note"])}'
+            kind = rng.random()
+            if kind < 0.4:
+                value = '"' + "".join(rng.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(rng.randint(3, 12))) + str(rng.randint(100, 99999)) + '"'
+            elif kind < 0.7:
+                value = str(rng.randint(0, 10 ** 9))
+            else:
+                value = '"' + " ".join(rng.choice(nouns) for _ in range(rng.randint(1, 6))) + '"'
+            field = f'"{key}":{value}'
+            if patterns_to_plant and rng.random() < plant_rate / 8:
+                field += ',"evt":"' + rng.choice(patterns_to_plant) + '"'
+            fields.append(field)
+            length += len(field) + 1
+        out += (",".join(fields) + "}\n").encode()
+    return bytes(out[:size].rsplit(b"\n", 1)[0] + b"\n")

@@ -53,6 +53,46 @@ def test_ioc_set_with_plants(gpu_lib, oracle_lib):
     assert parity.compare(gpu_lib, oracle_lib, data, patterns) > 50
 
 
+def test_caseless_template_set_on_long_lines(gpu_lib, oracle_lib):
+    """configs[4] shape at oracle-friendly size: caseless patterns with alternation, bounded repeats and anchors over
+    2-16 KiB JSON-ish lines (several DFA groups; lines far longer than a prefilter look-back)."""
+    patterns = synth.c5_patterns(300)
+    plants = ["session_10247 failed", "code=E4242abc", "REQUEST-EXPIRED-777}", "payment_555 REVOKED", "stalled xxxx31337"]
+    data = synth.jsonish_bytes(3 << 20, seed=3, patterns_to_plant=plants, plant_rate=0.2)
+    extra = [r"session_\d+ (?:failed|expired)", r"code=(?:E|W)\d{4}[a-f0-9]{2,6}", r"request-expired-\d+\}$", r"^\{\"ts\":\d{10},\"svc\":\"gateway",
+             r"stalled x{2,8}\d+", r"payment_\d{3} revoked"]
+    flags = [15] * (len(patterns) + len(extra))
+    assert parity.compare(gpu_lib, oracle_lib, data, patterns + extra, flags=flags) > 3
+    # the same set with distinct ids on a smaller slice (general path: events, SINGLEMATCH per id)
+    small = data[: 256 << 10]
+    small = small[: small.rfind(b"\n") + 1]
+    parity.compare(gpu_lib, oracle_lib, small, extra, flags=[15] * len(extra), ids=list(range(len(extra))))
+
+
+def test_multiscanner_over_compressed_files(gpu_lib, oracle_lib, tmp_path, monkeypatch, capsys):
+    """configs[3] shape: the CLI entry (parallel_grep) over gzip + zstd + plain files, one hyperscan() job per file
+    (spread over the visible GPUs), counts checked against the oracle."""
+    import gzip
+
+    from hypergrep_b200 import multiscanner, utils
+    from oracle_api import run_scan
+
+    monkeypatch.setattr(utils, "_get_hyperscanner_lib", lambda: gpu_lib)
+    files, expected = [], []
+    for k in range(4):
+        text = synth.syslog_bytes(1 << 20, seed=100 + k, lib=gpu_lib)
+        path = tmp_path / f"part{k}.log{'.gz' if k % 2 == 0 else ''}"
+        path.write_bytes(gzip.compress(text, 6) if k % 2 == 0 else text)
+        files.append(str(path))
+        rc, got, _ = run_scan(oracle_lib, str(path), synth.C2_PATTERNS)
+        assert rc == 0
+        expected.append(len(got))
+    code = multiscanner.parallel_grep(files, synth.C2_PATTERNS, count_results=True, with_file_name=True)
+    lines = capsys.readouterr().out.splitlines()
+    assert code == 0
+    assert lines == [f"{name}:{count}" for name, count in zip(files, expected)]
+
+
 def test_compressed_inputs(gpu_lib, oracle_lib, tmp_path):
     text = synth.syslog_bytes(1 << 20, seed=9, lib=gpu_lib)
     half = text.rfind(b"\n", 0, len(text) // 2) + 1
