@@ -221,6 +221,54 @@ struct Determinizer {
 
 static void minimise(Dfa& d, const std::vector<char>& idle);
 
+bool build_nfa_tables(const Nfa& nfa, NfaTables& out) {
+    DfaBuildOptions opt;
+    Determinizer det(nfa, opt);
+    det.seen_strong.assign(nfa.prog.size(), 0);
+    det.seen_weak.assign(nfa.prog.size(), 0);
+    std::vector<int> pos_of(nfa.prog.size(), -1);
+    std::vector<int> pcs;
+    for (size_t pc = 0; pc < nfa.prog.size(); pc++)
+        if (nfa.prog[pc].op == NfaInst::Byte) { pos_of[pc] = (int)pcs.size(); pcs.push_back((int)pc); }
+    const int P = (int)pcs.size();
+    if (P == 0 || P > 128 * 32) return false;
+    const int W = (P + 31) / 32;
+    out = NfaTables();
+    out.positions = P;
+    out.words = W;
+    out.reach.assign((size_t)256 * W, 0);
+    out.follow.assign((size_t)P * 12 * W, 0);
+    out.follow_match.assign((size_t)P * 12, 0);
+    out.restart.assign((size_t)16 * W, 0);
+    for (int p = 0; p < P; p++) {
+        const ByteSet& set = nfa.sets[nfa.prog[pcs[p]].arg];
+        for (int b = 0; b < 256; b++) if (set.test(b)) out.reach[(size_t)b * W + (p >> 5)] |= 1u << (p & 31);
+    }
+    std::vector<int> bytes, matched;
+    for (int p = 0; p < P; p++) {
+        std::vector<int> kernel = {nfa.prog[pcs[p]].x};
+        for (int kind = 0; kind < 3; kind++) {          // the byte just consumed: word / other / newline
+            Ctx ctx{false, kind == 2, kind == 0};
+            for (int look = 0; look < 4; look++) {      // Look enum order: word, other, newline, end of data
+                det.closure(kernel, ctx, look, bytes, matched, true, false);
+                size_t combo = (size_t)kind * 4 + look;
+                uint32_t* f = &out.follow[((size_t)p * 12 + combo) * W];
+                for (int pc : bytes) { int q = pos_of[pc]; f[q >> 5] |= 1u << (q & 31); }
+                out.follow_match[(size_t)p * 12 + combo] = matched.empty() ? 0u : 1u;
+            }
+        }
+    }
+    for (int prev = 0; prev < 4; prev++) {              // word / other / newline / start of block
+        Ctx ctx{prev == 3, prev == 2, prev == 0};
+        for (int look = 0; look < 4; look++) {
+            det.closure({}, ctx, look, bytes, matched, false, true);
+            uint32_t* r = &out.restart[((size_t)prev * 4 + look) * W];
+            for (int pc : bytes) { int q = pos_of[pc]; r[q >> 5] |= 1u << (q & 31); }
+        }
+    }
+    return true;
+}
+
 bool build_dfa(const Nfa& nfa, const DfaBuildOptions& opt, Dfa& out) {
     Determinizer det(nfa, opt);
     det.build_classes();

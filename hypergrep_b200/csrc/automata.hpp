@@ -62,6 +62,17 @@ struct DfaBuildOptions {
     size_t max_states = 60000;
 };
 
+// Tables of the bit-parallel NFA fallback (see nfa_sim.hpp) for ONE pattern.
+struct NfaTables {
+    int positions = 0, words = 0;
+    std::vector<uint32_t> reach;          // [256][words]
+    std::vector<uint32_t> follow;         // [positions][12][words]
+    std::vector<uint32_t> follow_match;   // [positions][12]
+    std::vector<uint32_t> restart;        // [4][4][words]
+};
+// `nfa` must hold exactly one pattern.  Returns false if it has more positions than the simulation supports.
+bool build_nfa_tables(const Nfa& nfa, NfaTables& out);
+
 // Returns false when the state budget is exceeded (caller splits the group).
 bool build_dfa(const Nfa& nfa, const DfaBuildOptions& opt, Dfa& out);
 

@@ -159,6 +159,8 @@ struct Job {
             // every group's list ends with a sentinel; keep [begin, next begin) pairs addressable by flat index
             for (size_t k = 0; k + 1 < rb.size(); k++) { report_begin_flat.push_back(rb[k]); report_end_flat.push_back(rb[k + 1]); }
         }
+        // NFA-fallback patterns follow, one report each (engine: NfaView::report)
+        for (auto& np : db->nfas) { report_begin_flat.push_back(np.report_begin); report_end_flat.push_back(np.report_begin + 1); }
     }
     std::vector<uint32_t> report_end_flat;
 

@@ -21,7 +21,7 @@ size_t env_size(const char* name, size_t dflt) {
 
 // Build DFA groups for patterns[lo, hi) by recursive bisection until every group fits the state budget.
 bool build_groups(const std::vector<NodePtr>& asts, const std::vector<int>& idx, size_t lo, size_t hi, bool simple,
-                  size_t max_states, std::vector<DfaGroup>& out, std::string& error) {
+                  size_t max_states, std::vector<DfaGroup>& out, std::vector<NfaPattern>& nfas, std::string& error) {
     Nfa nfa;
     bool ok = true;
     for (size_t k = lo; k < hi && ok; k++) ok = nfa_add_pattern(nfa, *asts[idx[k]], (int)(k - lo), kMaxNfaInsts);
@@ -38,12 +38,21 @@ bool build_groups(const std::vector<NodePtr>& asts, const std::vector<int>& idx,
         return true;
     }
     if (hi - lo == 1) {
-        error = "pattern " + std::to_string(idx[lo]) + " exceeds the DFA state budget (" + std::to_string(max_states) + " states)";
-        return false;
+        // this pattern alone explodes as a DFA: bit-parallel NFA fallback
+        Nfa single;
+        NfaPattern np;
+        np.pattern = idx[lo];
+        if (!nfa_add_pattern(single, *asts[idx[lo]], 0, kMaxNfaInsts) || !build_nfa_tables(single, np.tables)) {
+            error = "pattern " + std::to_string(idx[lo]) + " exceeds both the DFA state budget (" + std::to_string(max_states) +
+                    " states) and the NFA position limit (4096)";
+            return false;
+        }
+        nfas.push_back(std::move(np));
+        return true;
     }
     size_t mid = lo + (hi - lo) / 2;
-    return build_groups(asts, idx, lo, mid, simple, max_states, out, error) &&
-           build_groups(asts, idx, mid, hi, simple, max_states, out, error);
+    return build_groups(asts, idx, lo, mid, simple, max_states, out, nfas, error) &&
+           build_groups(asts, idx, mid, hi, simple, max_states, out, nfas, error);
 }
 
 }  // namespace
@@ -91,7 +100,7 @@ int compile_database(const char* const* patterns, const unsigned* flags, const u
     std::vector<int> idx(n);
     for (unsigned i = 0; i < n; i++) idx[i] = (int)i;
     size_t max_states = env_size("GPUGREP_MAX_DFA_STATES", 40000);
-    if (!build_groups(asts, idx, 0, n, db->simple, max_states, db->groups, error)) return kDbError;
+    if (!build_groups(asts, idx, 0, n, db->simple, max_states, db->groups, db->nfas, error)) return kDbError;
 
     // flatten accept sets into (id, singlematch) report lists
     db->report_begin.resize(db->groups.size());
@@ -109,6 +118,12 @@ int compile_database(const char* const* patterns, const unsigned* flags, const u
             for (auto& r : reps) db->reports.push_back(ReportDesc{r.first, r.second});
         }
         db->report_begin[g].push_back((uint32_t)db->reports.size());
+    }
+
+    for (auto& np : db->nfas) {
+        np.report_begin = (uint32_t)db->reports.size();
+        const PatternInfo& p = db->patterns[np.pattern];
+        db->reports.push_back(ReportDesc{p.id, (p.flags & FLAG_SINGLEMATCH) ? 1u : 0u});
     }
 
     std::vector<const Node*> raw;
@@ -138,6 +153,7 @@ std::shared_ptr<Database> cached_database(const char* const* patterns, const uns
         key.push_back('\0');
     }
     key.append(std::getenv("GPUGREP_NO_PREFILTER") ? "np" : "");
+    if (const char* b = std::getenv("GPUGREP_MAX_DFA_STATES")) key.append(b);
     {
         std::lock_guard<std::mutex> lk(mu);
         for (auto it = cache.begin(); it != cache.end(); ++it) {

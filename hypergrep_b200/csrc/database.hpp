@@ -28,8 +28,16 @@ struct ReportDesc {
     unsigned singlematch;
 };
 
+// A pattern whose own DFA exceeds the state budget: simulated as a bit-parallel NFA (general path only).
+struct NfaPattern {
+    int pattern = 0;          // index into Database::patterns
+    NfaTables tables;
+    uint32_t report_begin = 0;   // its single report: Database::reports[report_begin]
+};
+
 struct Database {
     std::vector<PatternInfo> patterns;
+    std::vector<NfaPattern> nfas;
     // simple: every pattern has SINGLEMATCH and all share one id -> "does any pattern match this line?"
     bool simple = false;
     unsigned simple_id = 0;

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "engine.hpp"
+#include "nfa_sim.hpp"
 
 namespace gpugrep {
 
@@ -37,6 +38,8 @@ struct GroupDev {
 struct DbView {
     const GroupDev* groups;
     int ngroups;
+    const NfaView* nfas;   // patterns simulated as bit-parallel NFAs (general path only)
+    int nnfa;
 };
 
 constexpr uint32_t kInvalidLen = 0xffffffffu;   // LineRec.len of a record the host must drop (NUL re-check failed)
@@ -524,6 +527,18 @@ __device__ __forceinline__ size_t skip_leading_nuls(const uint8_t* data, size_t 
     return c.pos;
 }
 
+// end of the scanned block that starts at p0: just past the first '\n', or at the first NUL, or lim
+__device__ size_t scanned_block_end(const uint8_t* data, size_t p0, size_t lim) {
+    size_t e = p0;
+    while (e < lim) {
+        uint32_t b = data[e];
+        if (b == 0) break;
+        e++;
+        if (b == '\n') break;
+    }
+    return e;
+}
+
 // simple mode: does any pattern match the block?
 __device__ bool block_matches(const DbView& db, const uint8_t* data, size_t start, size_t lim) {
     size_t p0 = skip_leading_nuls(data, start, lim);
@@ -545,6 +560,11 @@ __device__ bool block_matches(const DbView& db, const uint8_t* data, size_t star
             s = G.trans[s * G.stride + G.eod];
             if (s >= G.first_accept) return true;
         }
+    }
+    if (db.nnfa) {
+        const size_t e = scanned_block_end(data, p0, lim);
+        for (int k = 0; k < db.nnfa; k++)
+            if (nfa_scan_block(db.nfas[k], data + p0, e - p0, [](size_t) { return true; })) return true;
     }
     return false;
 }
@@ -577,6 +597,17 @@ __device__ uint32_t block_events(const DbView& db, const uint8_t* data, size_t s
                 if (out) out[k] = EventRec{line, pl_start, pl_len, (uint32_t)(c.pos - p0), G.accept_base + G.accept_of[s]};
                 k++;
             }
+        }
+    }
+    if (db.nnfa) {
+        const size_t e = scanned_block_end(data, p0, lim);
+        for (int q = 0; q < db.nnfa; q++) {
+            const uint32_t report = db.nfas[q].report;
+            nfa_scan_block(db.nfas[q], data + p0, e - p0, [&](size_t end) {
+                if (out) out[k] = EventRec{line, pl_start, pl_len, (uint32_t)end, report};
+                k++;
+                return false;
+            });
         }
     }
     return k;
@@ -989,6 +1020,8 @@ struct DeviceDb {
     std::vector<void*> allocs;
     GroupDev* d_groups = nullptr;
     int ngroups = 0;
+    NfaView* d_nfas = nullptr;
+    int nnfa = 0;
     bool simple = false;
     ~DeviceDb() { for (void* p : allocs) cudaFree(p); }
 };
@@ -1122,6 +1155,22 @@ std::shared_ptr<DeviceDb> engine_upload(const std::shared_ptr<Database>& db, std
     out->d_groups = (GroupDev*)upload(groups.data(), groups.size() * sizeof(GroupDev));
     out->ngroups = (int)groups.size();
     if (!out->d_groups) { error = "cudaMalloc failed for group table"; return nullptr; }
+    std::vector<NfaView> nfas;
+    for (size_t k = 0; k < db->nfas.size(); k++) {
+        const NfaTables& t = db->nfas[k].tables;
+        NfaView v;
+        v.positions = t.positions;
+        v.words = t.words;
+        v.reach = (const uint32_t*)upload(t.reach.data(), t.reach.size() * 4);
+        v.follow = (const uint32_t*)upload(t.follow.data(), t.follow.size() * 4);
+        v.follow_match = (const uint32_t*)upload(t.follow_match.data(), t.follow_match.size() * 4);
+        v.restart = (const uint32_t*)upload(t.restart.data(), t.restart.size() * 4);
+        v.report = base + (uint32_t)k;   // flattened report index: after the accept sets of all DFA groups
+        if (!v.reach || !v.follow || !v.follow_match || !v.restart) { error = "cudaMalloc failed for NFA tables"; return nullptr; }
+        nfas.push_back(v);
+    }
+    out->d_nfas = (NfaView*)upload(nfas.data(), nfas.size() * sizeof(NfaView));
+    out->nnfa = (int)nfas.size();
     cache.emplace_back(db, out);
     if (cache.size() > 8) cache.erase(cache.begin());
     return out;
@@ -1268,7 +1317,7 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
         super_bytes = 2048;
         while (super_bytes * 4 <= (size_t)buffer_size && super_bytes < 65536) super_bytes *= 2;   // 2*super-1 <= buffer_size-1
     }
-    s->fast = ddb.simple && pf != nullptr && super_bytes >= 2048 && std::getenv("GPUGREP_FORCE_GENERAL") == nullptr;
+    s->fast = ddb.simple && ddb.nnfa == 0 && pf != nullptr && super_bytes >= 2048 && std::getenv("GPUGREP_FORCE_GENERAL") == nullptr;
 
     if (host_data) {
         if (s->d_input.reserve(n + 1024) != cudaSuccess) { error = "cudaMalloc failed for the input segment"; return 3; }
@@ -1336,7 +1385,7 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
             s->stats.launches++;
         }
         k_list_candidates<<<(unsigned)std::min<size_t>((s->nblk + 255) / 256, (size_t)g_num_sms * 16), 256, 0, st>>>(meta, prefix, s->nblk, s->d_cand.as<uint32_t>(), s->cand_cap, dT);
-        DbView view{ddb.d_groups, ddb.ngroups};
+        DbView view{ddb.d_groups, ddb.ngroups, ddb.d_nfas, ddb.nnfa};
         unsigned vgrid = (unsigned)std::min<size_t>((s->cand_cap + 127) / 128, (size_t)g_num_sms * 16);
         k_verify_local<<<vgrid, 128, 0, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->lookback,
                                               s->d_res.as<uint32_t>());
@@ -1400,7 +1449,7 @@ int ScanSlot::run_general(SegmentResult& out, std::string& error) {
         CUDA_TRY(cudaStreamSynchronize(st));
         return 0;
     }
-    DbView view{ddb->d_groups, ddb->ngroups};
+    DbView view{ddb->d_groups, ddb->ngroups, ddb->d_nfas, ddb->nnfa};
     size_t nb_scan = (npl_total + kScanTile - 1) / kScanTile + 1;
     if (d_sums.reserve(nb_scan * 8) != cudaSuccess || d_recoff.reserve(npl_total * 8) != cudaSuccess) { error = "cudaMalloc failed"; return 3; }
     unsigned mgrid = (unsigned)((npl_total + 127) / 128);

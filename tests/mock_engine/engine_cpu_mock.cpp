@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "engine.hpp"
+#include "nfa_sim.hpp"
 
 namespace gpugrep {
 
@@ -88,6 +89,22 @@ static void walk(const Database& db, const uint8_t* p, size_t len, uint32_t line
             }
         }
         base += (uint32_t)d.accept_sets.size();
+    }
+    if (!db.nfas.empty()) {
+        size_t e = a;
+        while (e < len) { uint8_t b = p[e]; if (b == 0) break; e++; if (b == '\n') break; }
+        for (size_t k = 0; k < db.nfas.size(); k++) {
+            const NfaTables& t = db.nfas[k].tables;
+            NfaView v;
+            v.positions = t.positions; v.words = t.words; v.reach = t.reach.data(); v.follow = t.follow.data();
+            v.follow_match = t.follow_match.data(); v.restart = t.restart.data(); v.report = base + (uint32_t)k;
+            bool stop = nfa_scan_block(v, p + a, e - a, [&](size_t end) {
+                if (simple) { hit = true; return true; }
+                ev.push_back(EventRec{line, start, (uint32_t)len, (uint32_t)end, v.report});
+                return false;
+            });
+            if (stop) return;
+        }
     }
 }
 

@@ -66,3 +66,21 @@ def test_missing_file_and_directory(hostmock_lib, oracle_lib, tmp_path):
     parity.compare(hostmock_lib, oracle_lib, None, ["foo"], path=str(tmp_path / "nope.txt"))   # both: 6 (GZ_OPEN)
     parity.compare(hostmock_lib, oracle_lib, None, ["foo"], path=str(tmp_path))                # both: 0, no lines
     assert os.path.isdir(tmp_path)
+
+
+@pytest.mark.parametrize("seed", range(200, 240))
+def test_nfa_fallback_random_cases(seed, hostmock_lib, oracle_lib, monkeypatch):
+    """Every pattern forced through the bit-parallel NFA fallback (DFA state budget of 3): same reports as the oracle."""
+    monkeypatch.setenv("GPUGREP_MAX_DFA_STATES", "3")
+    patterns, flags, ids, buffer_size, data, buffer_count, max_match = parity.random_case(seed)
+    if parity.has_all_nul_pseudo_line(data, buffer_size):
+        pytest.skip("all-NUL pseudo-line")
+    parity.compare(hostmock_lib, oracle_lib, data, patterns, flags, ids, buffer_size, buffer_count, max_match)
+
+
+def test_nfa_fallback_for_exploding_patterns(hostmock_lib, oracle_lib):
+    """Patterns whose DFA is exponential (a gap of n arbitrary bytes) take the NFA path next to ordinary DFA patterns."""
+    text = synth.syslog_bytes(256 << 10, seed=13, lib=hostmock_lib)
+    patterns = [r"e.{60}d\b", r"ERROR", r"\bport .{40,80}x"]
+    assert parity.compare(hostmock_lib, oracle_lib, text, patterns) > 10
+    parity.compare(hostmock_lib, oracle_lib, text[: 64 << 10], patterns, flags=[14, 14, 6], ids=[1, 2, 3])
