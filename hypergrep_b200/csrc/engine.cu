@@ -539,7 +539,9 @@ __device__ size_t scanned_block_end(const uint8_t* data, size_t p0, size_t lim) 
     return e;
 }
 
-// simple mode: does any pattern match the block?
+// simple mode: does any pattern match the block?  WITH_NFA = false keeps the (1 KiB of local memory) NFA state out of
+// kernels that can never see NFA patterns (the fast path is only taken without them).
+template <bool WITH_NFA>
 __device__ bool block_matches(const DbView& db, const uint8_t* data, size_t start, size_t lim) {
     size_t p0 = skip_leading_nuls(data, start, lim);
     for (int g = 0; g < db.ngroups; g++) {
@@ -561,7 +563,7 @@ __device__ bool block_matches(const DbView& db, const uint8_t* data, size_t star
             if (s >= G.first_accept) return true;
         }
     }
-    if (db.nnfa) {
+    if (WITH_NFA && db.nnfa) {
         const size_t e = scanned_block_end(data, p0, lim);
         for (int k = 0; k < db.nnfa; k++)
             if (nfa_scan_block(db.nfas[k], data + p0, e - p0, [](size_t) { return true; })) return true;
@@ -827,7 +829,7 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit_simple(DbView db, const u
                         if ((mk >> last_idx) & 1u) { ok = false; break; }
                     }
                 }
-                if (ok && has_nul) ok = block_matches(db, data, st, en);
+                if (ok && has_nul) ok = block_matches<false>(db, data, st, en);
                 valid += ok ? 1u : 0u;
                 const size_t lb = st >> 9;
                 const uint32_t line_no = newlines_before_block(prefix, meta, lb) + count_newlines(data, lb << 9, st);
@@ -935,7 +937,7 @@ __global__ void __launch_bounds__(128) k_match_pl_simple(DbView db, const uint8_
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npl) return;
     size_t st = pl_start[i];
-    flags[i] = block_matches(db, data, st, st + pl_len[i]) ? 1 : 0;
+    flags[i] = block_matches<true>(db, data, st, st + pl_len[i]) ? 1 : 0;
 }
 
 __global__ void k_emit_pl_simple(const uint32_t* __restrict__ pl_start, const uint32_t* __restrict__ pl_len, size_t npl, const uint8_t* __restrict__ flags,
