@@ -670,39 +670,58 @@ __device__ uint32_t walk_local(const GroupDev& G, const uint8_t* __restrict__ da
     const uint16_t* __restrict__ flat = G.flat;
     const uint32_t first_accept = G.first_accept, idle_end = G.idle_end;
     if (flat) {
-        // fast form: '\n' and NUL are ordinary columns of the table (see engine_upload)
-        size_t pos = t;
-        uint32_t word = *reinterpret_cast<const uint32_t*>(data + (pos & ~(size_t)3)) >> (8 * (pos & 3));
-        while (pos < n) {
-            const uint32_t b = word & 0xffu;
-            s = flat[(s << 8) | b];
-            pos++;
-            word >>= 8;
-            if ((pos & 3) == 0 && pos < n) word = *reinterpret_cast<const uint32_t*>(data + pos);
-            if (s >= first_accept) {
-                // the line matched: mark it, then only look for line ends inside the chunk
-                mask |= line_bit;
-                if (b != '\n') {
-                    bool more = false;
-                    while (pos < n && pos < chunk_end) {
-                        uint32_t c = data[pos++];
-                        if (c == '\n') { more = pos < chunk_end && pos < n; break; }
+        // Fast form: '\n' and NUL are ordinary columns of the table (see engine_upload), offsets are 32-bit.
+        // Aligned words without a newline take four chained lookups and ONE test (max of the four states against
+        // first_accept); a word with a newline or a hit is replayed byte by byte.
+        const uint32_t end = (uint32_t)n, cend = (uint32_t)chunk_end, ifrom = (uint32_t)idle_from;
+        uint32_t pos = (uint32_t)t;
+        while (pos < end) {
+            if ((pos & 3u) == 0 && pos + 4 <= end) {
+                const uint32_t word = *reinterpret_cast<const uint32_t*>(data + pos);
+                const uint32_t x = word ^ 0x0a0a0a0au;
+                if (((x - 0x01010101u) & ~x & 0x80808080u) == 0) {
+                    const uint32_t s1 = flat[(s << 8) | (word & 0xffu)];
+                    const uint32_t s2 = flat[(s1 << 8) | ((word >> 8) & 0xffu)];
+                    const uint32_t s3 = flat[(s2 << 8) | ((word >> 16) & 0xffu)];
+                    const uint32_t s4 = flat[(s3 << 8) | (word >> 24)];
+                    if (max(max(s1, s2), max(s3, s4)) < first_accept) {
+                        s = s4;
+                        pos += 4;
+                        if (pos >= ifrom && s < idle_end) return mask;
+                        continue;
                     }
-                    if (!more) return mask;
-                    word = *reinterpret_cast<const uint32_t*>(data + (pos & ~(size_t)3)) >> (8 * (pos & 3));
-                } else if (pos >= chunk_end || pos >= n) {
+                }
+            }
+            // byte-wise: the rest of the current word (or the tail of the segment)
+            uint32_t stop = (pos | 3u) + 1u;
+            if (stop > end) stop = end;
+            while (pos < stop) {
+                const uint32_t b = data[pos];
+                s = flat[(s << 8) | b];
+                pos++;
+                if (s >= first_accept) {
+                    // the line matched: mark it, then only look for the next line start inside the chunk
+                    mask |= line_bit;
+                    if (b != '\n') {
+                        bool more = false;
+                        while (pos < end && pos < cend) {
+                            if (data[pos++] == '\n') { more = pos < cend && pos < end; break; }
+                        }
+                        if (!more) return mask;
+                    } else if (pos >= cend || pos >= end) {
+                        return mask;
+                    }
+                    line_bit <<= 1;
+                    s = 0;
+                    break;   // re-enter the outer loop at the new position
+                }
+                if (b == '\n') {
+                    if (pos >= cend || pos >= end) return mask;
+                    line_bit <<= 1;   // flat['\n'] already reset s to 0
+                } else if (pos >= ifrom && s < idle_end) {
                     return mask;
                 }
-                line_bit <<= 1;
-                s = 0;
-                continue;
             }
-            if (b == '\n') {
-                if (pos >= chunk_end || pos >= n) return mask;
-                line_bit <<= 1;   // flat['\n'] already reset s to 0
-                continue;
-            }
-            if (pos >= idle_from && s < idle_end) return mask;
         }
         if (G.eod_next[s] >= first_accept) mask |= line_bit;
         return mask;

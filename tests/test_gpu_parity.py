@@ -186,3 +186,35 @@ def test_nfa_fallback_for_exploding_patterns(gpu_lib, oracle_lib):
     patterns = [r"e.{60}d\b", r"ERROR", r"\bport .{40,80}x"]
     assert parity.compare(gpu_lib, oracle_lib, text, patterns) > 10
     parity.compare(gpu_lib, oracle_lib, text[: 64 << 10], patterns, flags=[14, 14, 6], ids=[1, 2, 3])
+
+
+def test_cli_in_fresh_processes(gpu_lib, oracle_lib, tmp_path):
+    """The `hyperscanner` command line end to end, in fresh interpreters: default thread pool and --mp (fork AFTER the
+    parent's compile check, which therefore must not have touched CUDA)."""
+    import os
+    import subprocess
+    import sys
+
+    from oracle_api import run_scan
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files, expected = [], []
+    for k in range(3):
+        text = synth.syslog_bytes(512 << 10, seed=300 + k, lib=gpu_lib)
+        path = tmp_path / f"cli{k}.log"
+        path.write_bytes(text)
+        files.append(str(path))
+        rc, got, _ = run_scan(oracle_lib, str(path), ["Failed password", "port [0-9]+"])
+        expected.append(len(got))
+    env = dict(os.environ, PYTHONPATH=root)
+    for extra in ([], ["--mp"]):
+        cmd = [sys.executable, "-m", "hypergrep_b200.multiscanner", "-E", "-c", "-e", "Failed password", "-e", "port [0-9]+"] + extra + files
+        proc = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300, check=False)
+        assert proc.returncode == 0, proc.stdout + proc.stderr
+        assert proc.stdout.splitlines() == [f"{name}:{count}" for name, count in zip(files, expected)]
+    # -n output of one file equals the oracle's (1-based numbers, lines with their text)
+    rc, got, _ = run_scan(oracle_lib, files[0], ["Failed password"])
+    proc = subprocess.run([sys.executable, "-m", "hypergrep_b200.multiscanner", "-n", "Failed password", files[0]], env=env,
+                          capture_output=True, text=True, timeout=300, check=False)
+    assert proc.returncode == 0
+    assert proc.stdout == "".join(f"{ln + 1}:{line.decode()}" for (_i, ln, line) in got)
