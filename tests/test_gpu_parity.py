@@ -218,3 +218,23 @@ def test_cli_in_fresh_processes(gpu_lib, oracle_lib, tmp_path):
                           capture_output=True, text=True, timeout=300, check=False)
     assert proc.returncode == 0
     assert proc.stdout == "".join(f"{ln + 1}:{line.decode()}" for (_i, ln, line) in got)
+
+
+def test_default_buffer_boundary_lines(gpu_lib, oracle_lib):
+    """Lines of exactly buffer_size-2, -1, 0, +1 bytes around the default gzgets buffer (262,140): the pseudo-line split
+    (SURVEY.md §8a-2 rule 1) with matches on both sides of every cut, between ordinary lines."""
+    limit = 262140 - 1
+    parts = [b"foo first\n"]
+    for total in (limit - 1, limit, limit + 1, limit + 2, 2 * limit, 2 * limit + 5):
+        body = bytearray(b"x" * (total - 1))
+        body[10:13] = b"foo"
+        body[limit - 2:limit + 1] = b"foo" if len(body) > limit + 1 else body[limit - 2:limit + 1]   # straddles the first cut
+        if len(body) > limit + 20:
+            body[limit + 5:limit + 8] = b"foo"
+        parts.append(bytes(body) + b"\n")
+        parts.append(b"bar between\n")
+    parts.append(b"foo last")
+    data = b"".join(parts)
+    assert parity.compare(gpu_lib, oracle_lib, data, ["foo"]) >= 8
+    parity.compare(gpu_lib, oracle_lib, data, ["foo", "bar"], flags=[14, 6], ids=[1, 2])
+    parity.compare(gpu_lib, oracle_lib, data, ["o{2}$", "^x+foo"])

@@ -84,3 +84,23 @@ def test_nfa_fallback_for_exploding_patterns(hostmock_lib, oracle_lib):
     patterns = [r"e.{60}d\b", r"ERROR", r"\bport .{40,80}x"]
     assert parity.compare(hostmock_lib, oracle_lib, text, patterns) > 10
     parity.compare(hostmock_lib, oracle_lib, text[: 64 << 10], patterns, flags=[14, 14, 6], ids=[1, 2, 3])
+
+
+def test_default_buffer_boundary_lines(hostmock_lib, oracle_lib):
+    """Lines of exactly buffer_size-2, -1, 0, +1 bytes around the default gzgets buffer (262,140): the pseudo-line split
+    (SURVEY.md §8a-2 rule 1) with matches on both sides of every cut, between ordinary lines."""
+    limit = 262140 - 1
+    parts = [b"foo first\n"]
+    for total in (limit - 1, limit, limit + 1, limit + 2, 2 * limit, 2 * limit + 5):
+        body = bytearray(b"x" * (total - 1))
+        body[10:13] = b"foo"
+        body[limit - 2:limit + 1] = b"foo" if len(body) > limit + 1 else body[limit - 2:limit + 1]   # straddles the first cut
+        if len(body) > limit + 20:
+            body[limit + 5:limit + 8] = b"foo"
+        parts.append(bytes(body) + b"\n")
+        parts.append(b"bar between\n")
+    parts.append(b"foo last")
+    data = b"".join(parts)
+    assert parity.compare(hostmock_lib, oracle_lib, data, ["foo"]) >= 8
+    parity.compare(hostmock_lib, oracle_lib, data, ["foo", "bar"], flags=[14, 6], ids=[1, 2])
+    parity.compare(hostmock_lib, oracle_lib, data, ["o{2}$", "^x+foo"])
