@@ -15,8 +15,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <list>
 #include <mutex>
+#include <thread>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -58,10 +61,12 @@ double now_ms() {
 }
 
 // Host batcher: the result slots of hyperscanner_state_t (hyperscanner.c:64-72) and hs_callback (:83-102).
+// The reference keeps buffer_count slots of buffer_size bytes and strcpy()s every matched line into one; here the
+// lines of a batch are packed into pooled blocks (stable addresses until the batch has been delivered).
 class Deliverer {
 public:
     Deliverer(hs_event cb, int buffer_count) : cb_(cb), cap_(std::max(1, buffer_count)) {
-        if (cb_) { results_.resize((size_t)cap_); lines_.resize((size_t)cap_); }
+        if (cb_) results_.resize((size_t)cap_);
     }
     // `bytes`/`len`: the pseudo-line as it sits in the file.  The delivered text is what the reference strcpy()s:
     // leading NULs skipped, cut at the next NUL (hyperscanner.c:205-214, :92).
@@ -74,12 +79,13 @@ public:
             const void* z = std::memchr(bytes + a, 0, len - a);
             if (z) b = (size_t)((const uint8_t*)z - bytes);
         }
-        std::vector<char>& slot = lines_[(size_t)fill_];
-        slot.assign((const char*)bytes + a, (const char*)bytes + b);
-        slot.push_back('\0');
-        results_[(size_t)fill_].id = id;
-        results_[(size_t)fill_].line_number = line_number;
-        results_[(size_t)fill_].line = slot.data();
+        char* dst = place(b - a + 1);
+        std::memcpy(dst, bytes + a, b - a);
+        dst[b - a] = '\0';
+        hyperscanner_result_t& r = results_[(size_t)fill_];
+        r.id = id;
+        r.line_number = line_number;
+        r.line = dst;
         fill_++;
         if (fill_ == cap_) flush();
     }
@@ -87,16 +93,30 @@ public:
     void flush() {
         if (cb_ && fill_ > 0) cb_(results_.data(), fill_);
         fill_ = 0;
+        block_ = 0;
+        used_ = 0;
     }
     unsigned long long count() const { return count_; }
     bool wants_lines() const { return cb_ != nullptr; }
 private:
+    static constexpr size_t kBlock = (size_t)1 << 20;
+    char* place(size_t bytes) {
+        while (true) {
+            if (block_ == blocks_.size()) blocks_.emplace_back(std::max(bytes, kBlock));
+            std::vector<char>& blk = blocks_[block_];
+            if (used_ + bytes <= blk.size()) { char* p = blk.data() + used_; used_ += bytes; return p; }
+            if (used_ == 0) { blk.resize(bytes); continue; }   // an over-long line gets the whole (grown) block
+            block_++;
+            used_ = 0;
+        }
+    }
     hs_event cb_;
     int cap_;
     int fill_ = 0;
     unsigned long long count_ = 0;
     std::vector<hyperscanner_result_t> results_;
-    std::vector<std::vector<char>> lines_;
+    std::vector<std::vector<char>> blocks_;
+    size_t block_ = 0, used_ = 0;
 };
 
 constexpr size_t kSampleBytes = 512 << 10;   // head of the input used to tune the prefilter windows
@@ -218,6 +238,12 @@ struct Job {
         }
         for (size_t i = 0; i < take; i++) {
             const LineRec& lr = recs[i];
+            if (host && i + 8 < take) {   // matched lines are scattered over the (pinned) input: hide the cache misses
+                const uint8_t* ahead = host + recs[i + 8].start;
+                __builtin_prefetch(ahead);
+                __builtin_prefetch(ahead + 64);
+                __builtin_prefetch(ahead + 128);
+            }
             const uint8_t* bytes = host ? host + lr.start : gathered.data() + goff[i];
             out->emit(db->simple_id, line_base + lr.line, bytes, lr.len & kLineLenMask, fast_rec ? (lr.len & kLineHasNul) != 0 : true);
         }
@@ -338,6 +364,18 @@ size_t clamp_limit(int buffer_size) {
 }
 
 // ---- file input -------------------------------------------------------------------------------------------
+// Reader side of scan_file(): fills pinned slot buffers with consecutive segments (each ends on a pseudo-line boundary;
+// the unfinished tail is carried into the next buffer) on its own thread, so that reading / inflating segment k+2
+// overlaps the H2D + kernels of k+1 and the delivery of k.
+struct SegmentQueue {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<int> free_slots;            // buffers the reader may fill
+    std::vector<std::pair<int, size_t>> ready;   // (slot, segment bytes), FIFO
+    bool done = false;                      // reader reached the end of the input
+    bool abort = false;                     // consumer asked the reader to stop
+};
+
 int scan_file(const char* path, const Params& pr, gpugrep_stats* stats_out) {
     double t0 = now_ms();
     Deliverer out(pr.cb, effective_batch(pr));
@@ -352,57 +390,103 @@ int scan_file(const char* path, const Params& pr, gpugrep_stats* stats_out) {
     size_t chunk = env_mb("GPUGREP_CHUNK_MB", 64);
     chunk = std::max(chunk, 2 * limit + 4096);
     chunk = std::min(chunk, kMaxSegmentBytes);
-    ScanSlot* slots[2] = {engine_acquire_slot(err), engine_acquire_slot(err)};
-    if (!slots[0] || !slots[1]) { engine_release_slot(slots[0]); engine_release_slot(slots[1]); set_last_error(err); return GPUGREP_SCRATCH; }
-    uint8_t* bufs[2] = {slot_host_buffer(slots[0], chunk, err), slot_host_buffer(slots[1], chunk, err)};
-    if (!bufs[0] || !bufs[1]) { engine_release_slot(slots[0]); engine_release_slot(slots[1]); set_last_error(err); return GPUGREP_SCRATCH; }
+    constexpr int kSlots = 3;
+    ScanSlot* slots[kSlots] = {nullptr, nullptr, nullptr};
+    uint8_t* bufs[kSlots] = {nullptr, nullptr, nullptr};
+    bool ok = true;
+    for (int i = 0; i < kSlots && ok; i++) {
+        slots[i] = engine_acquire_slot(err);
+        ok = slots[i] != nullptr;
+        if (ok) { bufs[i] = slot_host_buffer(slots[i], chunk, err); ok = bufs[i] != nullptr; }
+    }
+    if (!ok) {
+        for (ScanSlot* sl : slots) engine_release_slot(sl);
+        set_last_error(err);
+        return GPUGREP_SCRATCH;
+    }
 
-    int k = 0;
+    SegmentQueue q;
+    for (int i = 0; i < kSlots; i++) q.free_slots.push_back(i);
+    std::thread reader([&] {
+        std::vector<uint8_t> carry;
+        bool eof = false;
+        while (!eof) {
+            int slot;
+            {
+                std::unique_lock<std::mutex> lk(q.mu);
+                q.cv.wait(lk, [&] { return q.abort || !q.free_slots.empty(); });
+                if (q.abort) break;
+                slot = q.free_slots.back();
+                q.free_slots.pop_back();
+            }
+            uint8_t* buf = bufs[slot];
+            if (!carry.empty()) std::memcpy(buf, carry.data(), carry.size());
+            size_t have = carry.size();
+            size_t cut = 0;
+            while (true) {
+                size_t got = src->read(buf + have, chunk - have);
+                have += got;
+                if (got == 0) eof = true;
+                cut = cut_point(buf, have, eof, limit);
+                if (cut > 0 || eof || have == chunk) break;
+            }
+            if (cut == 0 && !eof) cut = have;   // cannot happen (chunk >= 2*limit): defensive
+            carry.assign(buf + cut, buf + have);
+            std::lock_guard<std::mutex> lk(q.mu);
+            if (cut > 0) q.ready.emplace_back(slot, cut);
+            else q.free_slots.push_back(slot);
+            q.cv.notify_all();
+        }
+        std::lock_guard<std::mutex> lk(q.mu);
+        q.done = true;
+        q.cv.notify_all();
+    });
+
+    auto release = [&](int slot) {
+        std::lock_guard<std::mutex> lk(q.mu);
+        q.free_slots.push_back(slot);
+        q.cv.notify_all();
+    };
     int inflight = -1;
-    size_t inflight_len = 0;
     bool tuned = false;
-    size_t carry = 0;
-    const uint8_t* carry_src = nullptr;
-    bool eof = false;
-    while (!eof && !job.stop && rc == 0) {
-        uint8_t* buf = bufs[k];
-        if (carry) std::memmove(buf, carry_src, carry);
-        size_t have = carry;
-        size_t cut = 0;
-        while (true) {
-            size_t got = src->read(buf + have, chunk - have);
-            have += got;
-            if (got == 0) eof = true;
-            cut = cut_point(buf, have, eof, limit);
-            if (cut > 0 || eof || have == chunk) break;
+    while (!job.stop && rc == 0) {
+        int slot = -1;
+        size_t len = 0;
+        {
+            std::unique_lock<std::mutex> lk(q.mu);
+            q.cv.wait(lk, [&] { return !q.ready.empty() || q.done; });
+            if (q.ready.empty()) break;
+            slot = q.ready.front().first;
+            len = q.ready.front().second;
+            q.ready.erase(q.ready.begin());
         }
-        if (cut == 0 && !eof) cut = have;   // cannot happen (chunk >= 2*limit): defensive
-        job.stats.bytes_scanned += cut;
-        if (cut > 0) {
-            if (!tuned) { job.dpf = tuned_prefilter(job.db, buf, cut, job.error); tuned = true; }
-            rc = slot_submit(slots[k], *job.ddb, job.dpf.get(), buf, nullptr, cut, pr.buffer_size, nullptr, job.error);
-            if (rc) break;
-        }
-        carry = have - cut;
-        carry_src = buf + cut;
+        job.stats.bytes_scanned += len;
+        if (!tuned) { job.dpf = tuned_prefilter(job.db, bufs[slot], len, job.error); tuned = true; }
+        rc = slot_submit(slots[slot], *job.ddb, job.dpf.get(), bufs[slot], nullptr, len, pr.buffer_size, nullptr, job.error);
+        if (rc) { release(slot); break; }
         if (inflight >= 0) {
             SegmentResult res;
             rc = slot_collect(slots[inflight], res, job.error);
             if (rc == 0) rc = job.deliver(res, bufs[inflight], slots[inflight]);
-            (void)inflight_len;
-            inflight = -1;
+            release(inflight);
         }
-        if (cut > 0) { inflight = k; inflight_len = cut; k ^= 1; }
+        inflight = slot;
     }
     if (inflight >= 0) {
         SegmentResult res;
-        int rc2 = slot_collect(slots[inflight], res, job.error);
+        int rc2 = slot_collect(slots[inflight], res, job.error);   // always drain the GPU before the buffers are reused
         if (rc == 0) rc = rc2;
-        if (rc == 0) rc = job.deliver(res, bufs[inflight], slots[inflight]);
+        if (rc == 0 && !job.stop) rc = job.deliver(res, bufs[inflight], slots[inflight]);
+        release(inflight);
     }
+    {
+        std::lock_guard<std::mutex> lk(q.mu);
+        q.abort = true;
+        q.cv.notify_all();
+    }
+    reader.join();
     out.flush();   // hyperscanner.c:311-313
-    engine_release_slot(slots[0]);
-    engine_release_slot(slots[1]);
+    for (ScanSlot* sl : slots) engine_release_slot(sl);
     job.stats.matches = out.count();
     job.stats.wall_ms = now_ms() - t0;
     if (stats_out) *stats_out = job.stats;

@@ -56,7 +56,7 @@ public:
         if (!regular_) return got + f_->read(dst + got, cap - got);
         size_t want = cap - got;
         unsigned hw = std::thread::hardware_concurrency();
-        size_t nthreads = want >= ((size_t)8 << 20) ? std::min<size_t>(8, std::max(1u, hw / 2)) : 1;
+        size_t nthreads = want >= ((size_t)8 << 20) ? std::min<size_t>(16, std::max(1u, hw > 2 ? hw - 2 : 1)) : 1;
         if (nthreads <= 1) {
             size_t r = pread_all(dst + got, want, offset_);
             offset_ += r;
