@@ -70,31 +70,30 @@ struct Totals {
 // 0x80 in every byte of w equal to the byte replicated in `rep`.  Exact (no borrow between bytes):
 // u = (w ^ rep) | 0x80 never borrows when 1 is subtracted per byte; bit 7 of the result is clear iff the low 7 bits
 // matched, and ~w / rep bit 7 handling below makes the top bit exact for rep < 0x80.
-__device__ __forceinline__ uint32_t eq_mask4(uint32_t w, uint32_t rep) {
-    uint32_t u = (w ^ rep) | 0x80808080u;
-    uint32_t t = u - 0x01010101u;
-    return ~(t | w) & 0x80808080u;   // valid for rep bytes < 0x80 ('\n' = 0x0a, NUL = 0x00)
-}
-// same test with the constants held in registers so that each step is ONE three-input LOP3 (the compiler otherwise
-// splits the two-immediate forms): 3 instructions per word instead of 4 on the pipe this kernel saturates
 __device__ __forceinline__ uint32_t eq_mask4_r(uint32_t w, uint32_t rep, uint32_t c80) {
+    // the constants are operands of two three-input LOP3s: 3 instructions per word instead of 4
     uint32_t u, z;
     asm("lop3.b32 %0, %1, %2, %3, 0xBE;" : "=r"(u) : "r"(w), "r"(rep), "r"(c80));   // (w ^ rep) | 0x80808080
     uint32_t t = u - 0x01010101u;
     asm("lop3.b32 %0, %1, %2, %3, 0x02;" : "=r"(z) : "r"(t), "r"(w), "r"(c80));     // ~(t | w) & 0x80808080
-    return z;
+    return z;   // valid for rep bytes < 0x80 ('\n' = 0x0a, NUL = 0x00)
 }
+__device__ __forceinline__ uint32_t eq_mask4(uint32_t w, uint32_t rep) { return eq_mask4_r(w, rep, 0x80808080u); }
 // 4 flag bits (0x80 per byte) -> 4 contiguous bits
 __device__ __forceinline__ uint32_t movemask4(uint32_t z) { return ((z >> 7) * 0x01020408u) >> 24 & 0xFu; }
+// flag words of two consecutive words -> 8 contiguous bits (one multiply gathers both: no two partial products meet)
+__device__ __forceinline__ uint32_t movemask8(uint32_t z0, uint32_t z1) { return (((z0 >> 7) | (z1 >> 3)) * 0x01020408u) >> 24; }
 
-__device__ __forceinline__ uint32_t newline_mask16(const uint4& v) {
-    return movemask4(eq_mask4(v.x, 0x0a0a0a0au)) | (movemask4(eq_mask4(v.y, 0x0a0a0a0au)) << 4) |
-           (movemask4(eq_mask4(v.z, 0x0a0a0a0au)) << 8) | (movemask4(eq_mask4(v.w, 0x0a0a0a0au)) << 12);
+__device__ __forceinline__ uint32_t byte_mask16(const uint4& v, uint32_t rep) {
+    return movemask8(eq_mask4(v.x, rep), eq_mask4(v.y, rep)) | (movemask8(eq_mask4(v.z, rep), eq_mask4(v.w, rep)) << 8);
 }
-__device__ __forceinline__ uint32_t newline_count16(const uint4& v) {
+__device__ __forceinline__ uint32_t newline_mask16(const uint4& v) { return byte_mask16(v, 0x0a0a0a0au); }
+// flags of 16 bytes packed into bits 0..3 of every byte of one word (order does not matter to a count)
+__device__ __forceinline__ uint32_t newline_flags16(const uint4& v) {
     uint32_t a = eq_mask4(v.x, 0x0a0a0a0au), b = eq_mask4(v.y, 0x0a0a0a0au), c = eq_mask4(v.z, 0x0a0a0a0au), d = eq_mask4(v.w, 0x0a0a0a0au);
-    return __popc((a >> 7) | (b >> 6) | (c >> 5) | (d >> 4));
+    return (a >> 7) | (b >> 6) | (c >> 5) | (d >> 4);
 }
+__device__ __forceinline__ uint32_t newline_count16(const uint4& v) { return __popc(newline_flags16(v)); }
 
 // streaming 16-byte load that does not pollute L1
 __device__ __forceinline__ uint4 ld_stream16(const uint8_t* p) {
@@ -149,28 +148,19 @@ __device__ size_t line_end_of(const uint8_t* data, size_t pos, size_t n, bool* h
     size_t end = n;
     while (base < n) {
         uint4 v = ld_chunk(data, base, n);
-        const bool edge = skip != 0 || base + 16 > n;
-        uint32_t zero_any = haszero4(v.x) | haszero4(v.y) | haszero4(v.z) | haszero4(v.w);
-        uint32_t nl_any = any_newline16(v);
-        if (nl_any || edge) {
-            uint32_t valid = (base + 16 > n ? (1u << (n - base)) - 1u : 0xffffu) & ~((1u << skip) - 1u);
-            uint32_t m = newline_mask16(v) & valid;
+        // one test for "a '\n' or a NUL may be here": with bits 1 and 3 cleared both become zero bytes (so do 0x02 and 0x08,
+        // which only cost the exact look below); bytes at or beyond n read as zero and take the same path
+        const uint32_t k = 0xf5f5f5f5u;
+        if ((haszero4(v.x & k) | haszero4(v.y & k) | haszero4(v.z & k) | haszero4(v.w & k)) != 0 || skip != 0) {
+            const uint32_t valid = (base + 16 > n ? (1u << (n - base)) - 1u : 0xffffu) & ~((1u << skip) - 1u);
+            const uint32_t m = newline_mask16(v) & valid;
+            uint32_t zm = byte_mask16(v, 0u) & valid;
             if (m) {
                 end = base + __ffs(m);
-                if (zero_any) {
-                    uint32_t zm = movemask4(eq_mask4(v.x, 0u)) | (movemask4(eq_mask4(v.y, 0u)) << 4) | (movemask4(eq_mask4(v.z, 0u)) << 8) |
-                                  (movemask4(eq_mask4(v.w, 0u)) << 12);
-                    if (zm & valid & ((1u << __ffs(m)) - 1u)) nul = true;
-                }
-                break;
+                zm &= (1u << __ffs(m)) - 1u;
             }
-            if (zero_any) {
-                uint32_t zm = movemask4(eq_mask4(v.x, 0u)) | (movemask4(eq_mask4(v.y, 0u)) << 4) | (movemask4(eq_mask4(v.z, 0u)) << 8) |
-                              (movemask4(eq_mask4(v.w, 0u)) << 12);
-                if (zm & valid) nul = true;
-            }
-        } else if (zero_any) {
-            nul = true;
+            if (zm) nul = true;
+            if (m) break;
         }
         skip = 0;
         base += 16;
@@ -179,15 +169,21 @@ __device__ size_t line_end_of(const uint8_t* data, size_t pos, size_t n, bool* h
     return end;
 }
 
-// newlines in [from, to), from 16-byte aligned
+// newlines in [from, to); both ends arbitrary, to <= n.  Reads whole aligned 16-byte granules that overlap the range.
 __device__ uint32_t count_newlines(const uint8_t* data, size_t from, size_t to) {
+    if (from >= to) return 0;
+    size_t b = from & ~(size_t)15;
     uint32_t c = 0;
-    size_t b = from;
-    for (; b + 16 <= to; b += 16) c += newline_count16(*reinterpret_cast<const uint4*>(data + b));
-    if (b < to) {
-        uint4 v = *reinterpret_cast<const uint4*>(data + b);
-        c += __popc(newline_mask16(v) & ((1u << (to - b)) - 1u));
+    if (b != from || b + 16 > to) {   // first granule, partially inside the range
+        uint32_t m = newline_mask16(*reinterpret_cast<const uint4*>(data + b)) & ~((1u << (from - b)) - 1u);
+        if (b + 16 > to) m &= (1u << (to - b)) - 1u;
+        c = __popc(m);
+        b += 16;
     }
+    for (; b + 32 <= to; b += 32)   // two granules per population count
+        c += __popc(newline_flags16(*reinterpret_cast<const uint4*>(data + b)) | (newline_flags16(*reinterpret_cast<const uint4*>(data + b + 16)) << 4));
+    if (b + 16 <= to) { c += newline_count16(*reinterpret_cast<const uint4*>(data + b)); b += 16; }
+    if (b < to) c += __popc(newline_mask16(*reinterpret_cast<const uint4*>(data + b)) & ((1u << (to - b)) - 1u));
     return c;
 }
 
@@ -670,60 +666,54 @@ __device__ uint32_t walk_local(const GroupDev& G, const uint8_t* __restrict__ da
     const uint16_t* __restrict__ flat = G.flat;
     const uint32_t first_accept = G.first_accept, idle_end = G.idle_end;
     if (flat) {
-        // Fast form: '\n' and NUL are ordinary columns of the table (see engine_upload), offsets are 32-bit.
-        // Aligned words without a newline take four chained lookups and ONE test (max of the four states against
-        // first_accept); a word with a newline or a hit is replayed byte by byte.
+        // Fast form: '\n' and NUL are ordinary columns of the table and "matched" is an absorbing state (see
+        // engine_upload), offsets are 32-bit.  The walk advances one ALIGNED WORD per step:
+        //  - a full word without a newline is four chained lookups and nothing else (no per-byte tests: a match
+        //    sticks until the line ends);
+        //  - a word with a newline, the first word of an unaligned start and the last word of the segment take the
+        //    byte-wise form below, straight-line code without inner loops (threads of a warp diverge here, so it is short).
+        // The line bit is set when the line ends in the matched state, or at the end of the walk.
         const uint32_t end = (uint32_t)n, cend = (uint32_t)chunk_end, ifrom = (uint32_t)idle_from;
         uint32_t pos = (uint32_t)t;
-        while (pos < end) {
-            if ((pos & 3u) == 0 && pos + 4 <= end) {
-                const uint32_t word = *reinterpret_cast<const uint32_t*>(data + pos);
-                const uint32_t x = word ^ 0x0a0a0a0au;
-                if (((x - 0x01010101u) & ~x & 0x80808080u) == 0) {
-                    const uint32_t s1 = flat[(s << 8) | (word & 0xffu)];
-                    const uint32_t s2 = flat[(s1 << 8) | ((word >> 8) & 0xffu)];
-                    const uint32_t s3 = flat[(s2 << 8) | ((word >> 16) & 0xffu)];
-                    const uint32_t s4 = flat[(s3 << 8) | (word >> 24)];
-                    if (max(max(s1, s2), max(s3, s4)) < first_accept) {
-                        s = s4;
-                        pos += 4;
-                        if (pos >= ifrom && s < idle_end) return mask;
-                        continue;
-                    }
-                }
-            }
-            // byte-wise: the rest of the current word (or the tail of the segment)
-            uint32_t stop = (pos | 3u) + 1u;
-            if (stop > end) stop = end;
-            while (pos < stop) {
-                const uint32_t b = data[pos];
-                s = flat[(s << 8) | b];
-                pos++;
-                if (s >= first_accept) {
-                    // the line matched: mark it, then only look for the next line start inside the chunk
-                    mask |= line_bit;
-                    if (b != '\n') {
-                        bool more = false;
-                        while (pos < end && pos < cend) {
-                            if (data[pos++] == '\n') { more = pos < cend && pos < end; break; }
+        if (pos >= end) return G.eod_next[s] >= first_accept ? line_bit : 0u;
+        uint32_t wpos = pos & ~3u;
+        uint32_t word = *reinterpret_cast<const uint32_t*>(data + wpos);   // the buffer is padded to a multiple of 16 bytes
+        while (true) {
+            // the next word is requested before the (dependent) table lookups of this one
+            const uint32_t next_word = wpos + 4 < end ? *reinterpret_cast<const uint32_t*>(data + wpos + 4) : 0u;
+            const uint32_t x = word ^ 0x0a0a0a0au;
+            if (((x - 0x01010101u) & ~x & 0x80808080u) == 0 && pos == wpos && wpos + 4 <= end) {
+                s = flat[(s << 8) | (word & 0xffu)];
+                s = flat[(s << 8) | ((word >> 8) & 0xffu)];
+                s = flat[(s << 8) | ((word >> 16) & 0xffu)];
+                s = flat[(s << 8) | (word >> 24)];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t p = wpos + k;
+                    if (p >= pos && p < end) {
+                        const uint32_t b = (word >> (8 * k)) & 0xffu;
+                        s = flat[(s << 8) | b];
+                        if (b == '\n') {
+                            if (s >= first_accept) mask |= line_bit;
+                            if (p + 1 >= cend) return mask;   // the next line starts outside the chunk
+                            line_bit <<= 1;
+                            s = 0;
                         }
-                        if (!more) return mask;
-                    } else if (pos >= cend || pos >= end) {
-                        return mask;
                     }
-                    line_bit <<= 1;
-                    s = 0;
-                    break;   // re-enter the outer loop at the new position
-                }
-                if (b == '\n') {
-                    if (pos >= cend || pos >= end) return mask;
-                    line_bit <<= 1;   // flat['\n'] already reset s to 0
-                } else if (pos >= ifrom && s < idle_end) {
-                    return mask;
                 }
             }
+            pos = wpos + 4;
+            if (s >= first_accept) {
+                if (pos >= cend) return mask | line_bit;   // matched, and no further line starts inside the chunk
+            } else if (pos >= ifrom && s < idle_end) {
+                return mask;
+            }
+            if (pos >= end) break;
+            wpos = pos;
+            word = next_word;
         }
-        if (G.eod_next[s] >= first_accept) mask |= line_bit;
+        if (s >= first_accept || G.eod_next[s] >= first_accept) mask |= line_bit;
         return mask;
     }
     bool done = false;
@@ -758,7 +748,7 @@ __device__ uint32_t walk_local(const GroupDev& G, const uint8_t* __restrict__ da
 }
 
 // One thread per candidate chunk: local verification (see walk_local); writes the bitmask of matched lines.
-__global__ void __launch_bounds__(128) k_verify_local(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
+__global__ void __launch_bounds__(128, 16) k_verify_local(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
                                                       const unsigned long long* meta_total, size_t cap, uint32_t lookback,
                                                       uint32_t* __restrict__ marks) {
     size_t ncand = (size_t)(*meta_total >> 32);
@@ -850,8 +840,12 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit_simple(DbView db, const u
                 }
                 if (ok && has_nul) ok = block_matches<false>(db, data, st, en);
                 valid += ok ? 1u : 0u;
+                // line number = newlines before the line start: whole blocks from the scan, then the part of the line's own
+                // 512-byte block, counted from whichever end of the block is nearer (the block's total is in meta)
                 const size_t lb = st >> 9;
-                const uint32_t line_no = newlines_before_block(prefix, meta, lb) + count_newlines(data, lb << 9, st);
+                uint32_t line_no = newlines_before_block(prefix, meta, lb);
+                if ((st & 511) <= 256) line_no += count_newlines(data, lb << 9, st);
+                else line_no += (uint32_t)(meta[lb] >> 32) - count_newlines(data, st, min((lb + 1) << 9, n));
                 if (at < rec_cap) recs[at] = LineRec{line_no, (uint32_t)st, ok ? ((uint32_t)(en - st) | (has_nul ? kHasNulBit : 0u)) : kInvalidLen};
                 else atomicOr(&totals->flags, 4u);
                 at++;
@@ -1142,14 +1136,18 @@ std::shared_ptr<DeviceDb> engine_upload(const std::shared_ptr<Database>& db, std
             // cases in the walk): '\n' and NUL end the scanned block, so their columns hold either the absorbing
             // "matched" state (the block matched at its end) or state 0 (restart: next line / text after the NUL).
             std::vector<uint16_t> flat((size_t)d.num_states * 256), eod((size_t)d.num_states);
+            // Every accepting state is replaced by ONE absorbing "matched" state that also survives '\n' and NUL: the
+            // walk tests for it only where a line ends (see walk_local), never per byte.
             const uint16_t sink = (uint16_t)d.sink_match;
             for (int st = 0; st < d.num_states; st++) {
                 const uint32_t at_eod = d.trans[(size_t)st * d.stride + d.num_classes];
                 eod[st] = (uint16_t)at_eod;
                 for (int b = 0; b < 256; b++) {
                     uint32_t nx = d.trans[(size_t)st * d.stride + d.byte_class[b]];
-                    if (b == 0) nx = (int)at_eod >= d.first_accept ? sink : 0;
+                    if (st >= d.first_accept) nx = sink;
+                    else if (b == 0) nx = (int)at_eod >= d.first_accept ? sink : 0;
                     else if (b == '\n') nx = ((int)nx >= d.first_accept || (int)d.trans[(size_t)nx * d.stride + d.num_classes] >= d.first_accept) ? sink : 0;
+                    else if ((int)nx >= d.first_accept) nx = sink;
                     flat[(size_t)st * 256 + b] = (uint16_t)nx;
                 }
             }
@@ -1282,13 +1280,26 @@ uint8_t* slot_host_buffer(ScanSlot* slot, size_t capacity, std::string& error) {
     return slot->h_stage.as<uint8_t>();
 }
 
+// Grid of a persistent (grid-stride) kernel: exactly as many blocks as can be resident at once.  A larger grid runs a
+// second, partly empty wave in which the late blocks repeat the full per-block share of the work.
+template <class Kernel>
+static unsigned resident_grid(Kernel kernel, int block, size_t smem = 0) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1) {
+        (void)cudaGetLastError();
+        per_sm = 1;
+    }
+    return (unsigned)(per_sm * g_num_sms);
+}
+
 template <class Load>
 static void launch_scan(cudaStream_t st, Load load, size_t n, unsigned long long* out, unsigned long long* sums, unsigned long long* total,
                         SegmentStats& stats, const unsigned long long* limit = nullptr, int limit_shift = 32) {
     size_t nb = (n + kScanTile - 1) / kScanTile;
     if (nb == 0) nb = 1;
     // persistent grid: with a device-side `limit` most tiles are empty, and empty blocks are not free to schedule
-    unsigned grid = (unsigned)std::min<size_t>(nb, (size_t)g_num_sms * 8);
+    static const unsigned resident = resident_grid(k_scan_sums<Load>, kScanThreads);
+    unsigned grid = (unsigned)std::min<size_t>(nb, resident);
     k_scan_sums<Load><<<grid, kScanThreads, 0, st>>>(load, n, sums, nb, limit, limit_shift);
     k_scan_top<<<1, 1024, 0, st>>>(sums, nb, total);
     k_scan_write<Load><<<grid, kScanThreads, 0, st>>>(load, n, sums, out, nb, limit, limit_shift);
@@ -1405,14 +1416,17 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
             k_check_long<<<(unsigned)((nsuper + 255) / 256), 256, 0, st>>>(prefix, s->nblk, bps, &dT->meta_total, dT);
             s->stats.launches++;
         }
-        k_list_candidates<<<(unsigned)std::min<size_t>((s->nblk + 255) / 256, (size_t)g_num_sms * 16), 256, 0, st>>>(meta, prefix, s->nblk, s->d_cand.as<uint32_t>(), s->cand_cap, dT);
+        static const unsigned list_resident = resident_grid(k_list_candidates, 256);
+        k_list_candidates<<<(unsigned)std::min<size_t>((s->nblk + 255) / 256, list_resident), 256, 0, st>>>(meta, prefix, s->nblk, s->d_cand.as<uint32_t>(), s->cand_cap, dT);
         DbView view{ddb.d_groups, ddb.ngroups, ddb.d_nfas, ddb.nnfa};
-        unsigned vgrid = (unsigned)std::min<size_t>((s->cand_cap + 127) / 128, (size_t)g_num_sms * 16);
+        static const unsigned verify_resident = resident_grid(k_verify_local, 128);
+        unsigned vgrid = (unsigned)std::min<size_t>((s->cand_cap + 127) / 128, verify_resident);
         k_verify_local<<<vgrid, 128, 0, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->lookback,
                                               s->d_res.as<uint32_t>());
         launch_scan(st, LoadMarks{s->d_res.as<uint32_t>(), &dT->meta_total, s->cand_cap}, s->cand_cap, s->d_recoff.as<unsigned long long>(),
                     s->d_sums.as<unsigned long long>(), &dT->rec_total, s->stats, &dT->meta_total);
-        k_emit_simple<<<(unsigned)std::min<size_t>((s->cand_cap + kEmitTile - 1) / kEmitTile, (size_t)g_num_sms * 8), kEmitThreads, 0, st>>>(
+        static const unsigned emit_resident = resident_grid(k_emit_simple, kEmitThreads);
+        k_emit_simple<<<(unsigned)std::min<size_t>((s->cand_cap + kEmitTile - 1) / kEmitTile, emit_resident), kEmitThreads, 0, st>>>(
             view, s->data, n, s->d_cand.as<uint32_t>(), s->d_res.as<uint32_t>(), s->d_recoff.as<unsigned long long>(), meta, prefix, &dT->meta_total,
             s->cand_cap, s->d_recs.as<LineRec>(), s->rec_cap, dT);
         s->stats.launches += 3;

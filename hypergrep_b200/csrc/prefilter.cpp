@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <set>
 
@@ -384,6 +385,58 @@ bool build_exact_table(const std::vector<uint32_t>& grams, Prefilter& out) {
     return false;
 }
 
+// Fills the gram tables of `out` (exact two-choice table and bloom byte table) from the final gram list.
+void finish_tables(std::vector<uint32_t>& all, bool fold, const GramHistogram* sample, Prefilter& out) {
+    std::sort(all.begin(), all.end());
+    all.erase(std::unique(all.begin(), all.end()), all.end());
+    // a gram equal to the empty-slot marker cannot be stored exactly; it can only be "\0\0\0\0"
+    all.erase(std::remove(all.begin(), all.end(), 0u), all.end());
+    out.enabled = true;
+    out.fold_case = fold;
+    out.num_grams = all.size();
+    out.grams = all;
+    build_exact_table(all, out);
+    // bloom bitmap, one probe per gram: byte = product >> (32 - log2_bytes), bit = product & 7.  Sized so that
+    // a false hit is rare next to real gram occurrences (<= 2^20 bits = 128 KiB of shared memory).
+    size_t need = all.size() * 2048;
+    int lb = 17;
+    while (lb < 20 && (1ull << lb) < need) lb++;
+    if (sample) lb = 20;   // streaming scans: always the largest table (128 KiB), false hits cost DFA walks
+    out.log2_bits = lb;
+    // One unlucky collision with a FREQUENT text gram ("INFO", " hos") would flag a large share of all chunks:
+    // pick, among a few multipliers, the one whose table is hit least by the non-member grams of the sample.
+    static const uint32_t muls[] = {0x9E3779B1u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u};
+    double best_false = INFINITY;
+    std::vector<uint32_t> best_map;
+    for (uint32_t mul : muls) {
+        std::vector<uint32_t> map((1u << lb) / 32, 0);
+        uint8_t* bytes = reinterpret_cast<uint8_t*>(map.data());
+        for (uint32_t g : all) {
+            uint32_t p = g * mul;
+            bytes[p >> (32 - (lb - 3))] |= (uint8_t)(1u << (p & 7));
+        }
+        double false_hits = 0;
+        if (sample) {
+            const auto& keys = sample->keys(fold);
+            const auto& counts = sample->counts(fold);
+            for (size_t k = 0; k < keys.size(); k++) {
+                if (!counts[k]) continue;
+                uint32_t p = keys[k] * mul;
+                if ((bytes[p >> (32 - (lb - 3))] >> (p & 7)) & 1)
+                    if (!std::binary_search(all.begin(), all.end(), keys[k])) false_hits += counts[k];
+            }
+        }
+        if (false_hits < best_false) { best_false = false_hits; best_map.swap(map); out.bloom_mul = mul; }
+        if (!sample || false_hits == 0) break;
+    }
+    out.bitmap.swap(best_map);
+}
+
+std::string describe(const Prefilter& out, bool tuned) {
+    return "stride " + std::to_string(out.stride) + (out.fold_case ? ", folded" : "") + ", " + std::to_string(out.num_grams) + " grams, bloom bitmap of " + std::to_string(1u << out.log2_bits) +
+           " bits" + (out.exact ? ", exact two-choice table of 2 x " + std::to_string(1u << out.log2_slots) + " slots" : "") + (tuned ? ", sample-tuned" : "");
+}
+
 }  // namespace
 
 void build_prefilter(const FactorSet& fs, const GramHistogram* sample, Prefilter& out) {
@@ -429,57 +482,11 @@ void build_prefilter(const FactorSet& fs, const GramHistogram* sample, Prefilter
             std::vector<uint32_t> all;
             for (auto& wn : wins)
                 for (int j = 0; j < stride; j++) expand_gram(*wn.s, wn.start + j, fold, all);
-            std::sort(all.begin(), all.end());
-            all.erase(std::unique(all.begin(), all.end()), all.end());
-            // a gram equal to the empty-slot marker cannot be stored exactly; it can only be "\0\0\0\0"
-            all.erase(std::remove(all.begin(), all.end(), 0u), all.end());
-            out.enabled = true;
             out.stride = stride;
-            out.fold_case = fold;
-            out.num_grams = all.size();
-            out.grams = all;
             out.lookback = lookback > 4096 ? 0xffffffffu : (uint32_t)lookback;
             if (sample && sample->positions()) out.expected_hits_per_mib = hits * 1048576.0 / (double)sample->positions();
-            build_exact_table(all, out);
-            {
-                // bloom bitmap, one probe per gram: byte = product >> (32 - log2_bytes), bit = product & 7.  Sized so that
-                // a false hit is rare next to real gram occurrences (<= 2^20 bits = 128 KiB of shared memory).
-                size_t need = all.size() * 2048;
-                int lb = 17;
-                while (lb < 20 && (1ull << lb) < need) lb++;
-                if (sample) lb = 20;   // streaming scans: always the largest table (128 KiB), false hits cost DFA walks
-                out.log2_bits = lb;
-                // One unlucky collision with a FREQUENT text gram ("INFO", " hos") would flag a large share of all chunks:
-                // pick, among a few multipliers, the one whose table is hit least by the non-member grams of the sample.
-                static const uint32_t muls[] = {0x9E3779B1u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u};
-                double best_false = INFINITY;
-                std::vector<uint32_t> best_map;
-                for (uint32_t mul : muls) {
-                    std::vector<uint32_t> map((1u << lb) / 32, 0);
-                    uint8_t* bytes = reinterpret_cast<uint8_t*>(map.data());
-                    for (uint32_t g : all) {
-                        uint32_t p = g * mul;
-                        bytes[p >> (32 - (lb - 3))] |= (uint8_t)(1u << (p & 7));
-                    }
-                    double false_hits = 0;
-                    if (sample) {
-                        const auto& keys = sample->keys(fold);
-                        const auto& counts = sample->counts(fold);
-                        for (size_t k = 0; k < keys.size(); k++) {
-                            if (!counts[k]) continue;
-                            uint32_t p = keys[k] * mul;
-                            if ((bytes[p >> (32 - (lb - 3))] >> (p & 7)) & 1)
-                                if (!std::binary_search(all.begin(), all.end(), keys[k])) false_hits += counts[k];
-                        }
-                    }
-                    if (false_hits < best_false) { best_false = false_hits; best_map.swap(map); out.bloom_mul = mul; }
-                    if (!sample || false_hits == 0) break;
-                }
-                out.bitmap.swap(best_map);
-            }
-            out.note = "stride " + std::to_string(stride) + (fold ? ", folded" : "") + ", " + std::to_string(all.size()) + " grams, " +
-                       "bloom bitmap of " + std::to_string(1u << out.log2_bits) + " bits" + (out.exact ? ", exact two-choice table of 2 x " + std::to_string(1u << out.log2_slots) + " slots" : "") +
-                       (sample ? ", sample-tuned" : "");
+            finish_tables(all, fold, sample, out);
+            out.note = describe(out, sample != nullptr);
             return;
         }
     }

@@ -25,6 +25,8 @@ if args.set == "c1":
     patterns = synth.C1_PATTERNS
 elif args.set == "c3":
     patterns, plants = synth.c3_patterns()
+elif args.set == "lit":   # literals of >= 9 bytes only: the prefilter samples at stride 4
+    patterns = [p for p in synth.C2_LITERALS if len(p) >= 9]
 else:
     patterns = synth.C2_PATTERNS
 host = torch.empty(args.mib << 20, dtype=torch.uint8).pin_memory()
