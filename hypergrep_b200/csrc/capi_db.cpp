@@ -128,6 +128,13 @@ size_t gpugrep_db_copy_grams(const gpugrep_db* h, uint32_t* out, size_t cap) {
     return g.size();
 }
 
+size_t gpugrep_db_copy_odd_compares(const gpugrep_db* h, uint32_t* out, size_t cap) {
+    if (!h) return 0;
+    const auto& odd = h->db->prefilter.odd;
+    for (size_t k = 0; k < odd.size() && k < cap && out; k++) { out[2 * k] = odd[k].mul; out[2 * k + 1] = odd[k].add; }
+    return odd.size();
+}
+
 int gpugrep_db_tune(gpugrep_db* h, const void* sample, size_t size) {
     if (!h || !h->db->factors.usable) return -1;
     gpugrep::GramHistogram hist;

@@ -201,6 +201,9 @@ struct ProbeParams {
     uint32_t amask;       // exact: keeps the slot bits of the byte offset, clears the replica / word bits
     uint32_t half_bytes;  // exact: byte offset of the second half of the table
     int rshift;           // exact: log2 of the replication factor (copies interleaved across banks)
+    // mixed sampling (Prefilter::odd): gram * odd_mul[k] + odd_add[k] == 0 at text offsets = 2 (mod 4).  Unused entries repeat
+    // a used one.  The multipliers come from here (the parameter bank) so that the test stays ONE multiply-add on the FMA pipe.
+    uint32_t odd_mul[2], odd_add[2];
 };
 
 // Gram lookups of one 16-byte chunk.  MODE 1: two-choice table of exact 32-bit keys; the table is replicated
@@ -221,7 +224,7 @@ __device__ __forceinline__ uint32_t lds8(uint32_t shared_addr) {
 
 // c1 / c2: shared-window address of table half 1 / 2 (aligned to the size of a half) OR-ed with 4 * copy of this lane,
 // so that an address is formed by ONE logic op: ((product >> shift) & amask) | c.
-template <int STRIDE, bool FOLD, int MODE>
+template <int STRIDE, bool FOLD, int MODE, int NODD>
 __device__ __forceinline__ bool probe_chunk(const uint4& v, uint32_t next, const uint32_t* __restrict__ tab, const ProbeParams& pp, uint32_t c1,
                                             uint32_t c2) {
     if (MODE == 0) return false;
@@ -250,6 +253,19 @@ __device__ __forceinline__ bool probe_chunk(const uint4& v, uint32_t next, const
             }
         }
     }
+    if (NODD > 0) {
+        // the grams at offsets 2, 6, 10, 14 of the chunk against two constants: two multiply-adds and one three-way minimum,
+        // no shared-memory traffic
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t gram = __funnelshift_r(w[i], w[i + 1], 16);
+            uint32_t x[2];
+#pragma unroll
+            for (int k = 0; k < 2; k++) asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(x[k]) : "r"(gram), "r"(pp.odd_mul[k]), "r"(pp.odd_add[k]));
+            miss = __vimin3_u32(miss, x[0], x[1]);
+        }
+        return (MODE == 1 ? false : (bits & 1u) != 0u) || miss == 0u;
+    }
     return MODE == 1 ? miss == 0u : (bits & 1u) != 0u;
 }
 
@@ -266,7 +282,7 @@ __device__ __forceinline__ uint32_t newline_count16_fma(const uint4& v, uint32_t
 
 constexpr int kStreamU = 4;   // 512-byte blocks per warp step
 
-template <int STRIDE, bool FOLD, int MODE>
+template <int STRIDE, bool FOLD, int MODE, int NODD>
 __global__ void __launch_bounds__(1024) k_stream(const uint8_t* __restrict__ data, size_t n, unsigned long long* __restrict__ meta,
                                                  const uint32_t* __restrict__ table, int table_words, ProbeParams pp) {
     extern __shared__ __align__(16) uint32_t s_raw[];
@@ -303,7 +319,7 @@ __global__ void __launch_bounds__(1024) k_stream(const uint8_t* __restrict__ dat
 #pragma unroll
         for (int u = 0; u < U; u++) v[u] = ld_stream16(p + u * 512);
         uint32_t after = 0;   // first word after the group (only lane 31 needs it, for grams that straddle the end)
-        if (MODE != 0 && STRIDE < 4 && lane == 31) {
+        if (MODE != 0 && (STRIDE < 4 || NODD > 0) && lane == 31) {
             size_t off = (g0 + U) << 9;
             if (off + 4 <= n) after = *reinterpret_cast<const uint32_t*>(data + off);
             else if (off < n) after = ld_chunk(data, off, n).x;
@@ -315,13 +331,13 @@ __global__ void __launch_bounds__(1024) k_stream(const uint8_t* __restrict__ dat
             for (int u = 0; u < U; u++) {
                 c[u] = newline_count16_fma(v[u], cnl, c80);
                 uint32_t nx = 0;
-                if (MODE != 0 && STRIDE < 4) {
+                if (MODE != 0 && (STRIDE < 4 || NODD > 0)) {
                     // first word of the next chunk: lane+1's word of this block, or (lane 31) lane 0's word of the next block
                     uint32_t give = (u + 1 < U && lane == 0) ? v[u + 1 < U ? u + 1 : u].x : v[u].x;
                     nx = __shfl_sync(0xffffffffu, give, (lane + 1) & 31);
                     if (u + 1 == U && lane == 31) nx = after;
                 }
-                bool hit = probe_chunk<STRIDE, FOLD, MODE>(v[u], nx, s_tab, pp, c1, c2);
+                bool hit = probe_chunk<STRIDE, FOLD, MODE, NODD>(v[u], nx, s_tab, pp, c1, c2);
                 masks[u] = __ballot_sync(0xffffffffu, hit);
             }
             cnt01 = __reduce_add_sync(0xffffffffu, c[0] | (c[1] << 16));
@@ -339,7 +355,7 @@ __global__ void __launch_bounds__(1024) k_stream(const uint8_t* __restrict__ dat
         size_t off = (g << 9) + (size_t)lane * 16;
         uint4 v = off < n ? ld_chunk(data, off, n) : make_uint4(0, 0, 0, 0);
         uint32_t nx = 0;
-        if (MODE != 0 && STRIDE < 4) {
+        if (MODE != 0 && (STRIDE < 4 || NODD > 0)) {
             nx = __shfl_down_sync(0xffffffffu, v.x, 1);
             if (lane == 31) {
                 size_t o2 = (g + 1) << 9;
@@ -347,7 +363,7 @@ __global__ void __launch_bounds__(1024) k_stream(const uint8_t* __restrict__ dat
             }
         }
         uint32_t cnt = newline_count16_fma(v, cnl, c80);
-        bool hit = probe_chunk<STRIDE, FOLD, MODE>(v, nx, s_tab, pp, c1, c2);
+        bool hit = probe_chunk<STRIDE, FOLD, MODE, NODD>(v, nx, s_tab, pp, c1, c2);
         if (off >= n) hit = false;   // chunks that start at or beyond n can never be candidates
         uint32_t mask = __ballot_sync(0xffffffffu, hit);
         uint32_t total = __reduce_add_sync(0xffffffffu, cnt);
@@ -757,6 +773,8 @@ struct ReprobeParams {
     int shift;              // byte index = (gram * mul) >> shift, bit = product & 7
     int stride;
     int fold;
+    int nodd;               // mixed sampling: compares at offsets 2 mod 4 (see ProbeParams)
+    uint32_t odd_mul[2], odd_add[2];
 };
 
 // One thread per candidate chunk: local verification (see walk_local); writes the bitmask of matched lines.
@@ -793,6 +811,11 @@ __global__ void __launch_bounds__(128, 16) k_verify_local(DbView db, const uint8
                     const uint32_t gram = __funnelshift_r(w[k], w[k + 1], 8 * sft);
                     const uint32_t prod = gram * rp.mul;
                     if ((rp.bloom[prod >> rp.shift] >> (prod & 7u)) & 1u) hits |= 1u << (4 * k + sft);
+                }
+                if (rp.nodd) {
+                    const uint32_t gram = __funnelshift_r(w[k], w[k + 1], 16);
+                    for (int c = 0; c < rp.nodd; c++)
+                        if (gram * rp.odd_mul[c] + rp.odd_add[c] == 0u) hits |= 1u << (4 * k + 2);
                 }
             }
             if (hits == 0) { marks[i] = 0; continue; }   // cannot happen for a chunk k_stream flagged; harmless if it does
@@ -1096,6 +1119,7 @@ struct DevicePrefilter {
     int stride = 4;
     bool fold = false;
     int mode = 0;        // 1 exact keys, 2 bloom bitmap
+    int nodd = 0;        // register compares at offsets 2 mod 4 (mixed sampling; bloom mode only)
     ProbeParams pp{};
     uint32_t lookback = 0xffffffffu;
     ~DevicePrefilter() { if (d_table) cudaFree(d_table); }
@@ -1250,7 +1274,7 @@ std::shared_ptr<DevicePrefilter> engine_upload_prefilter(const Prefilter& pf, st
     std::vector<uint32_t> replicated;
     const std::vector<uint32_t>* src = &pf.bitmap;
     const char* want = std::getenv("GPUGREP_FILTER");
-    const bool use_exact = pf.exact && want && std::strcmp(want, "exact") == 0;
+    const bool use_exact = pf.exact && pf.odd.empty() && want && std::strcmp(want, "exact") == 0;
     out->stride = pf.stride;
     out->fold = pf.fold_case;
     out->mode = use_exact ? 1 : 2;
@@ -1258,6 +1282,12 @@ std::shared_ptr<DevicePrefilter> engine_upload_prefilter(const Prefilter& pf, st
     out->pp.mul2 = pf.hash_mul2;
     out->pp.shift = 32 - (pf.log2_bits - 3);   // bloom: product -> byte index
     out->lookback = pf.lookback;
+    out->nodd = (int)std::min<size_t>(pf.odd.size(), 2);
+    for (int k = 0; k < 2; k++) {
+        const auto& c = pf.odd.empty() ? Prefilter::OddCompare{1u, 1u} : pf.odd[(size_t)k < pf.odd.size() ? (size_t)k : 0];
+        out->pp.odd_mul[k] = c.mul;
+        out->pp.odd_add[k] = c.add;
+    }
     if (use_exact) {
         // replicate so that a lane reads copy (lane mod R): as many copies as fit ~160 KiB of shared memory, at most 32
         const size_t slots = (size_t)1 << pf.log2_slots;
@@ -1354,14 +1384,14 @@ static void launch_scan(cudaStream_t st, Load load, size_t n, unsigned long long
     stats.launches += 3;
 }
 
-template <int STRIDE, bool FOLD, int MODE>
+template <int STRIDE, bool FOLD, int MODE, int NODD = 0>
 static cudaError_t launch_stream_t(cudaStream_t st, int grid, int block, size_t smem, const uint8_t* data, size_t n, unsigned long long* meta,
                                    const DevicePrefilter* pf) {
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_stream<STRIDE, FOLD, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_stream<STRIDE, FOLD, MODE, NODD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k_stream<STRIDE, FOLD, MODE><<<grid, block, smem, st>>>(data, n, meta, pf ? pf->d_table : nullptr, pf ? pf->table_words : 0,
+    k_stream<STRIDE, FOLD, MODE, NODD><<<grid, block, smem, st>>>(data, n, meta, pf ? pf->d_table : nullptr, pf ? pf->table_words : 0,
                                                             pf ? pf->pp : ProbeParams{});
     return cudaGetLastError();
 }
@@ -1370,6 +1400,8 @@ template <int MODE>
 static cudaError_t launch_stream_m(cudaStream_t st, int grid, int block, size_t smem, const uint8_t* data, size_t n, unsigned long long* meta,
                                    const DevicePrefilter* pf) {
     int key = pf->stride * 2 + (pf->fold ? 1 : 0);
+    if (MODE == 2 && pf->stride == 4 && pf->nodd > 0)
+        return pf->fold ? launch_stream_t<4, true, 2, 2>(st, grid, block, smem, data, n, meta, pf) : launch_stream_t<4, false, 2, 2>(st, grid, block, smem, data, n, meta, pf);
     switch (key) {
         case 8: return launch_stream_t<4, false, MODE>(st, grid, block, smem, data, n, meta, pf);
         case 9: return launch_stream_t<4, true, MODE>(st, grid, block, smem, data, n, meta, pf);
@@ -1469,11 +1501,16 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
         DbView view{ddb.d_groups, ddb.ngroups, ddb.d_nfas, ddb.nnfa};
         static const unsigned verify_resident = resident_grid(k_verify_local, 128);
         unsigned vgrid = (unsigned)std::min<size_t>((s->cand_cap + 127) / 128, verify_resident);
-        ReprobeParams rp{nullptr, 0, 0, 4, 0};
+        ReprobeParams rp{};
         // finding the hits again costs eight table lookups per candidate and shortens the walk of EVERY group: it pays from two
         // DFA groups on (measured: 32 patterns / 1 group 268 -> 294 us, 1,000 patterns / 4 groups 7 % faster end to end)
         if (pf->mode == 2 && ddb.ngroups >= 2 && std::getenv("GPUGREP_NO_REPROBE") == nullptr)
-            rp = ReprobeParams{reinterpret_cast<const uint8_t*>(pf->d_table), pf->pp.mul, pf->pp.shift, pf->stride, pf->fold ? 1 : 0};
+        {
+            rp.bloom = reinterpret_cast<const uint8_t*>(pf->d_table);
+            rp.mul = pf->pp.mul; rp.shift = pf->pp.shift; rp.stride = pf->stride; rp.fold = pf->fold ? 1 : 0;
+            rp.nodd = pf->nodd;
+            for (int k = 0; k < 2; k++) { rp.odd_mul[k] = pf->pp.odd_mul[k]; rp.odd_add[k] = pf->pp.odd_add[k]; }
+        }
         k_verify_local<<<vgrid, 128, 0, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->lookback, rp,
                                               s->d_res.as<uint32_t>());
         launch_scan(st, LoadMarks{s->d_res.as<uint32_t>(), &dT->meta_total, s->cand_cap}, s->cand_cap, s->d_recoff.as<unsigned long long>(),

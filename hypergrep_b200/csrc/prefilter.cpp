@@ -433,13 +433,111 @@ void finish_tables(std::vector<uint32_t>& all, bool fold, const GramHistogram* s
 }
 
 std::string describe(const Prefilter& out, bool tuned) {
-    return "stride " + std::to_string(out.stride) + (out.fold_case ? ", folded" : "") + ", " + std::to_string(out.num_grams) + " grams, bloom bitmap of " + std::to_string(1u << out.log2_bits) +
+    return "stride " + std::to_string(out.stride) + (out.odd.empty() ? "" : " + " + std::to_string(out.odd.size()) + " compares at 2 mod 4") + (out.fold_case ? ", folded" : "") + ", " + std::to_string(out.num_grams) + " grams, bloom bitmap of " + std::to_string(1u << out.log2_bits) +
            " bits" + (out.exact ? ", exact two-choice table of 2 x " + std::to_string(1u << out.log2_slots) + " slots" : "") + (tuned ? ", sample-tuned" : "");
+}
+
+// One register compare of the mixed scheme: the first `known` bytes of a 4-gram (little endian: the low bytes).
+struct OddKey {
+    uint32_t value = 0;
+    int known = 0;
+    bool operator==(const OddKey& o) const { return value == o.value && known == o.known; }
+    uint32_t mask() const { return known >= 4 ? 0xffffffffu : (1u << (8 * known)) - 1u; }
+};
+
+// the bytes of s[at, at+4) that are the same in every expansion (leading ones only)
+OddKey odd_key_of(const ClassString& s, size_t at, bool fold) {
+    OddKey k;
+    for (int i = 0; i < 4; i++) {
+        ByteSet eff = effective(s[at + i], fold);
+        if (eff.count() != 1) break;
+        for (unsigned v = 0; v < 256; v++) if (eff.test(v)) k.value |= v << (8 * i);
+        k.known++;
+    }
+    return k;
+}
+
+double odd_key_hits(const OddKey& k, bool fold, const GramHistogram& h) {
+    const auto& keys = h.keys(fold);
+    const auto& counts = h.counts(fold);
+    double hits = 0;
+    for (size_t i = 0; i < keys.size(); i++)
+        if (counts[i] && (keys[i] & k.mask()) == k.value) hits += counts[i];
+    return hits;
+}
+
+// Mixed sampling (see Prefilter::odd).  Every alternative with a usable 7-byte window is sampled at stride 4; the others
+// get a 5-byte window whose two grams go into the table (for offsets = 0 mod 4) and into the compare list (for offsets
+// = 2 mod 4).  Fails if that needs more than two compares or a compare of fewer than two known bytes.
+bool build_mixed(const FactorSet& fs, const GramHistogram* sample, bool fold, Prefilter& out) {
+    out = Prefilter();
+    out.min_factor_len = (int)fs.min_len;
+    std::vector<uint32_t> all;
+    std::vector<OddKey> odd;
+    size_t lookback = 0;
+    double hits = 0;
+    struct Short { const ClassString* s; size_t pattern; };
+    std::vector<Short> shorts;
+    for (size_t pi = 0; pi < fs.factors.size(); pi++) {
+        for (auto& s : fs.factors[pi]) {
+            double best = INFINITY; size_t bt = 0;
+            for (size_t t = 0; t + 7 <= s.size(); t++) {
+                double g = grams_in_window(s, t, 4, fold);
+                if (g > kMaxGramsPerWindow * 4) continue;
+                double score = sample ? window_hits(s, t, 4, fold, *sample) * 1000.0 + g : g;
+                if (score < best) { best = score; bt = t; }
+            }
+            if (std::isinf(best)) { shorts.push_back(Short{&s, pi}); continue; }
+            if (sample) hits += window_hits(s, bt, 4, fold, *sample);
+            for (int j = 0; j < 4; j++) expand_gram(s, bt + j, fold, all);
+            size_t lb = fs.before[pi] == SIZE_MAX ? SIZE_MAX : fs.before[pi] + bt + 3;
+            lookback = std::max(lookback, lb);
+        }
+    }
+    if (shorts.empty()) return false;   // plain stride 4 does it
+    for (auto& sh : shorts) {
+        const ClassString& s = *sh.s;
+        double best = INFINITY; size_t bt = 0;
+        for (size_t t = 0; t + 5 <= s.size(); t++) {
+            double g = grams_in_window(s, t, 2, fold);
+            if (g > kMaxGramsPerWindow * 2) continue;
+            OddKey k0 = odd_key_of(s, t, fold), k1 = odd_key_of(s, t + 1, fold);
+            if (k0.known < 2 || k1.known < 2) continue;
+            if (!sample && (k0.known < 3 || k1.known < 3)) continue;   // without a sample only selective compares
+            // fewest NEW compares first, then expected hits (table part + compare part), then table growth
+            int fresh = (std::find(odd.begin(), odd.end(), k0) == odd.end()) + (std::find(odd.begin(), odd.end(), k1) == odd.end() && !(k1 == k0));
+            double h = sample ? window_hits(s, t, 2, fold, *sample) / 2 + (odd_key_hits(k0, fold, *sample) + odd_key_hits(k1, fold, *sample)) / 4 : 0;
+            double score = fresh * 1e12 + h * 1000.0 + g;
+            if (score < best) { best = score; bt = t; }
+        }
+        if (std::isinf(best)) return false;
+        for (int j = 0; j < 2; j++) {
+            expand_gram(s, bt + j, fold, all);
+            OddKey k = odd_key_of(s, bt + j, fold);
+            if (std::find(odd.begin(), odd.end(), k) == odd.end()) odd.push_back(k);
+        }
+        if (odd.size() > 2) return false;
+        if (sample) hits += window_hits(s, bt, 2, fold, *sample) / 2;   // the table part: sampled at every fourth offset
+        size_t lb = fs.before[sh.pattern] == SIZE_MAX ? SIZE_MAX : fs.before[sh.pattern] + bt + 1;
+        lookback = std::max(lookback, lb);
+    }
+    if (all.size() > kMaxGramsTotal) return false;
+    if (sample) for (auto& k : odd) hits += odd_key_hits(k, fold, *sample) / 4;
+    for (auto& k : odd) {
+        const int shift = 8 * (4 - k.known);
+        out.odd.push_back(Prefilter::OddCompare{1u << shift, 0u - (k.value << shift)});
+    }
+    out.stride = 4;
+    out.lookback = lookback > 4096 ? 0xffffffffu : (uint32_t)lookback;
+    if (sample && sample->positions()) out.expected_hits_per_mib = hits * 1048576.0 / (double)sample->positions();
+    finish_tables(all, fold, sample, out);
+    out.note = describe(out, sample != nullptr);
+    return true;
 }
 
 }  // namespace
 
-void build_prefilter(const FactorSet& fs, const GramHistogram* sample, Prefilter& out) {
+static void build_uniform(const FactorSet& fs, const GramHistogram* sample, Prefilter& out) {
     out = Prefilter();
     if (!fs.usable) { out.note = fs.note; return; }
     out.min_factor_len = (int)fs.min_len;
@@ -491,6 +589,20 @@ void build_prefilter(const FactorSet& fs, const GramHistogram* sample, Prefilter
         }
     }
     out.note = "gram expansion too large";
+}
+
+void build_prefilter(const FactorSet& fs, const GramHistogram* sample, Prefilter& out) {
+    build_uniform(fs, sample, out);
+    // A set that is sampled at stride 2 only because of ONE short factor does better with stride 4 plus two register
+    // compares (half the shared-memory lookups of the streaming kernel; measured 0.54 -> 0.45 ms per 2 GiB), unless that
+    // flags more text or makes the verification walks longer.  (Four compares were measured too: the streaming kernel
+    // gains 8 %, verification loses more through the longer look-back of the 7-byte windows.)
+    if (out.enabled && out.stride == 2 && std::getenv("GPUGREP_NO_MIXED_STRIDE") == nullptr) {
+        Prefilter mixed;
+        if (build_mixed(fs, sample, out.fold_case, mixed) && mixed.enabled && mixed.lookback <= out.lookback + 4 &&
+            (!sample || mixed.expected_hits_per_mib <= 1.1 * out.expected_hits_per_mib + 16.0))
+            out = std::move(mixed);
+    }
 }
 
 }  // namespace gpugrep

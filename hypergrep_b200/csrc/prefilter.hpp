@@ -67,6 +67,11 @@ struct Prefilter {
     std::vector<uint32_t> bitmap;
     uint32_t hash_mul = 0x9E3779B1u;
     std::vector<uint32_t> grams;      // the exact gram set (sorted)
+    // Mixed sampling (stride == 4 only).  Factors of >= 7 bytes are found by table lookups at text offsets = 0 (mod 4).  The
+    // few factors that are too short for that are ALSO compared, in registers, at offsets = 2 (mod 4): gram * mul + add == 0
+    // tests the leading 4, 3 or 2 bytes of the gram (mul = 1, 2^8, 2^16) against a constant.  At most two compares.
+    struct OddCompare { uint32_t mul, add; };
+    std::vector<OddCompare> odd;
     size_t num_grams = 0;
     int min_factor_len = 0;
     // A match whose window hit sits at text position q starts at or after q - lookback (0xffffffff: unbounded, verify

@@ -179,6 +179,10 @@ GPUGREP_API int gpugrep_db_accept_reports(const gpugrep_db* db, unsigned int gro
 GPUGREP_API size_t gpugrep_db_copy_prefilter(const gpugrep_db* db, uint32_t* words, size_t cap_words, uint32_t* hash_mul);
 /* Copies up to cap exact prefilter grams (little-endian 4-byte windows); returns the total gram count. */
 GPUGREP_API size_t gpugrep_db_copy_grams(const gpugrep_db* db, uint32_t* out, size_t cap);
+/* Mixed sampling (prefilter_stride == 4 only): besides the table lookups at text offsets = 0 (mod 4), the streaming kernel
+ * tests gram * mul + add == 0 (mod 2^32) at offsets = 2 (mod 4) for each of these (mul, add) pairs.  Writes up to cap
+ * pairs (2 words each), returns the number of pairs (0..2). */
+GPUGREP_API size_t gpugrep_db_copy_odd_compares(const gpugrep_db* db, uint32_t* mul_add_pairs, size_t cap);
 /* Re-chooses the prefilter windows of a handle against the 4-gram histogram of a text sample (what the scan entry
  * points do with the head of their input); 0 on success. */
 GPUGREP_API int gpugrep_db_tune(gpugrep_db* db, const void* sample, size_t size);

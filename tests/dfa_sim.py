@@ -87,12 +87,18 @@ class CompiledDb:
         lib = self.lib
         h = ctypes.c_void_p(self.handle)
         self.grams = None
+        self.odd = []
         if self.info.prefilter:
             lib.gpugrep_db_copy_grams.restype = ctypes.c_size_t
             count = lib.gpugrep_db_copy_grams(h, None, 0)
             grams = np.zeros(count, dtype=np.uint32)
             lib.gpugrep_db_copy_grams(h, grams.ctypes.data_as(ctypes.c_void_p), count)
             self.grams = set(int(g) for g in grams)
+            lib.gpugrep_db_copy_odd_compares.restype = ctypes.c_size_t
+            lib.gpugrep_db_copy_odd_compares.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+            pairs = (ctypes.c_uint32 * 8)()
+            count = lib.gpugrep_db_copy_odd_compares(h, pairs, 4)
+            self.odd = [(int(pairs[2 * k]), int(pairs[2 * k + 1])) for k in range(count)]
 
     def __del__(self):
         if getattr(self, "handle", None):
@@ -149,19 +155,23 @@ class CompiledDb:
             out.append(rid)
         return out
 
+    def gram_hit(self, gram: int, offset: int) -> bool:
+        """What the streaming kernel tests at text offset `offset` (gram already case-folded if the table is)."""
+        st = self.info.prefilter_stride
+        if offset % st == 0 and gram in self.grams:
+            return True
+        if self.odd and offset % 4 == 2:   # mixed sampling: register compares between the table lookups
+            return any((gram * mul + add) & 0xFFFFFFFF == 0 for mul, add in self.odd)
+        return False
+
     def prefilter_hits(self, text: bytes) -> bool:
-        """True if some 4-gram of `text` is in the gram set at EVERY alignment of the sampling grid (superset test)."""
+        """True if some sampled 4-gram of `text` hits at EVERY alignment of the sampling grid (superset test)."""
         if self.grams is None:
             return True
-        st = self.info.prefilter_stride
         fold = 0x20202020 if self.info.prefilter_fold else 0
-        for phase in range(st):
-            hit = False
-            for q in range(phase, max(0, len(text) - 3), st):
-                if (int.from_bytes(text[q:q + 4], "little") | fold) in self.grams:
-                    hit = True
-                    break
-            if not hit:
+        for phase in range(4):
+            if not any(self.gram_hit(int.from_bytes(text[q:q + 4], "little") | fold, q + phase)
+                       for q in range(0, max(0, len(text) - 3))):
                 return False
         return True
 
@@ -180,9 +190,9 @@ def fast_path_matched_line_starts(db: "CompiledDb", data: bytes) -> set:
     fold = 0x20202020 if db.info.prefilter_fold else 0
     lookback = db.info.prefilter_lookback
     flagged = set()
-    for q in range(0, n, st):
+    for q in range(0, n, 2 if db.odd else st):
         gram = int.from_bytes(data[q:q + 4].ljust(4, b"\0"), "little") | fold
-        if gram in db.grams:
+        if db.gram_hit(gram, q):
             flagged.add(q >> 4)
     marked = set()
     for c in sorted(flagged):

@@ -95,3 +95,20 @@ def test_fast_path_model_is_exact(seed, gpu_lib):
             truth.add(pos)
         pos += len(pl)
     assert fast_path_matched_line_starts(db, data) == truth
+
+
+def test_mixed_sampling_is_chosen_for_few_short_factors(gpu_lib):
+    """One 5-byte factor next to long ones: table lookups at stride 4 plus register compares at offsets 2 (mod 4)
+    (gpugrep.h, gpugrep_db_copy_odd_compares) instead of stride 2 for everything."""
+    db = CompiledDb(gpu_lib, ["ERROR", "connection reset by peer", "segfault at"])
+    assert db.rc == 0 and db.info.prefilter_stride == 4
+    assert len(db.odd) == 2   # "ERRO" and "RROR", exact (mul == 1)
+    assert sorted((-add) & 0xFFFFFFFF for mul, add in db.odd) == sorted(
+        int.from_bytes(g, "little") for g in (b"ERRO", b"RROR"))
+    for shift in range(8):   # every alignment of the short factor is seen
+        assert db.prefilter_hits(b"x" * shift + b"an ERROR here\n")
+        assert db.prefilter_hits(b"y" * shift + b"segfault at 0\n")
+    assert not db.prefilter_hits(b"nothing to see, move along please\n")
+    # too many short factors: plain stride 2
+    many = CompiledDb(gpu_lib, ["ERROR", "WARN:", "FATAL", "PANIC", "ALERT"])
+    assert many.info.prefilter_stride == 2 and not many.odd
