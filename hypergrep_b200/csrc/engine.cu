@@ -428,16 +428,6 @@ __device__ __forceinline__ uint32_t newlines_before_block(const unsigned long lo
     for (size_t b = blk - blk % kGroupBlocks; b < blk; b++) c += (uint32_t)(meta[b] >> 32);
     return c;
 }
-struct LoadMarks {   // records per candidate; *meta_total (device) bounds the valid prefix
-    const uint32_t* marks;
-    const unsigned long long* meta_total;
-    size_t cap;
-    __device__ unsigned long long operator()(size_t i) const {
-        size_t cnt = (size_t)(*meta_total >> 32);
-        if (cnt > cap) cnt = cap;
-        return i < cnt ? (unsigned long long)__popc(marks[i]) : 0ull;
-    }
-};
 struct LoadU8 {
     const uint8_t* p;
     __device__ unsigned long long operator()(size_t i) const { return p[i]; }
@@ -765,6 +755,9 @@ __device__ uint32_t walk_local(const GroupDev& G, const uint8_t* __restrict__ da
     return mask;
 }
 
+constexpr int kEmitThreads = 256;
+constexpr int kEmitTile = 2048;   // candidates per emit step (and per record-offset entry): enough marked ones to keep every warp busy
+
 // Where the gram table lives in global memory, for k_verify_local to find the hit positions inside a candidate chunk
 // again (k_stream only reports "some sampled gram of this chunk is in the table").
 struct ReprobeParams {
@@ -782,10 +775,14 @@ struct ReprobeParams {
 // with one hit per chunk (the usual case) that is a third of walking the whole chunk.
 __global__ void __launch_bounds__(128, 16) k_verify_local(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
                                                           const unsigned long long* meta_total, size_t cap, uint32_t lookback, ReprobeParams rp,
-                                                          uint32_t* __restrict__ marks) {
+                                                          uint32_t* __restrict__ marks, uint32_t* __restrict__ tile_records) {
     size_t ncand = (size_t)(*meta_total >> 32);
     if (ncand > cap) ncand = cap;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncand; i += (size_t)gridDim.x * blockDim.x) {
+    // whole warps stay in the loop (a warp's 32 candidates are consecutive and lie in one emit tile): the records of the
+    // tile are counted with one warp reduction and one atomic
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; (i & ~(size_t)31) < ncand; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t mask = 0;
+    if (i < ncand) {
     const size_t o = (size_t)cand[i] * 16;
     size_t t;
     bool at_line_start;
@@ -818,7 +815,7 @@ __global__ void __launch_bounds__(128, 16) k_verify_local(DbView db, const uint8
                         if (gram * rp.odd_mul[c] + rp.odd_add[c] == 0u) hits |= 1u << (4 * k + 2);
                 }
             }
-            if (hits == 0) { marks[i] = 0; continue; }   // cannot happen for a chunk k_stream flagged; harmless if it does
+            if (hits == 0) hits = 0xffffu;   // cannot happen for a chunk k_stream flagged: walk the whole chunk
             const uint32_t first = __ffs(hits) - 1, last = 31 - __clz(hits);
             hi = o + first;
             idle_from = o + last + 4;
@@ -847,42 +844,77 @@ __global__ void __launch_bounds__(128, 16) k_verify_local(DbView db, const uint8
             }
         }
     }
-    uint32_t mask = 0;
     for (int g = 0; g < db.ngroups; g++) mask |= walk_local(db.groups[g], data, n, o, t, at_line_start, idle_from, line_bit);
     marks[i] = mask;
     }
+    const uint32_t records = __reduce_add_sync(0xffffffffu, __popc(mask));
+    if ((threadIdx.x & 31) == 0 && records) atomicAdd(&tile_records[i / kEmitTile], records);
+    }
+}
+
+// Exclusive scan of the per-tile record counts (a few thousand entries: one block), in place; total -> *rec_total.
+__global__ void __launch_bounds__(1024) k_tile_offsets(uint32_t* __restrict__ tile_records, const unsigned long long* meta_total, size_t cap,
+                                                       unsigned long long* rec_total) {
+    __shared__ unsigned long long s_warp[32], s_total;
+    size_t ncand = (size_t)(*meta_total >> 32);
+    if (ncand > cap) ncand = cap;
+    const size_t ntiles = (ncand + kEmitTile - 1) / kEmitTile;
+    unsigned long long running = 0;
+    for (size_t base = 0; base < ntiles; base += blockDim.x) {
+        const size_t k = base + threadIdx.x;
+        const unsigned long long v = k < ntiles ? tile_records[k] : 0ull;
+        const unsigned long long ex = block_exclusive_scan(v, s_warp, &s_total);
+        if (k < ntiles) tile_records[k] = (uint32_t)(running + ex);
+        running += s_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *rec_total = running;
 }
 
 // Candidates with marked lines are first compacted per block (few candidates carry a match), then one thread per
 // marked candidate computes line extents, line numbers and the exact re-check of lines with NULs.
 // The same line can be marked by several candidate chunks; records come out ordered by line start, so the host
 // drops adjacent duplicates.
-constexpr int kEmitThreads = 256;
-constexpr int kEmitTile = 2048;   // candidates compacted per block step: enough marked ones to keep every warp busy
 __global__ void __launch_bounds__(kEmitThreads) k_emit_simple(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
-                                                              const uint32_t* __restrict__ marks, const unsigned long long* __restrict__ recoff,
+                                                              const uint32_t* __restrict__ marks, const uint32_t* __restrict__ tile_offsets,
                                                               const unsigned long long* __restrict__ meta, const unsigned long long* __restrict__ prefix,
                                                               const unsigned long long* meta_total, size_t cap, LineRec* __restrict__ recs, size_t rec_cap,
                                                               Totals* totals) {
-    __shared__ uint32_t s_list[kEmitTile];
+    __shared__ uint32_t s_list[kEmitTile], s_at[kEmitTile];
+    __shared__ unsigned long long s_warp[kEmitThreads / 32], s_total;
     uint32_t valid = 0;
     __shared__ uint32_t s_count;
     size_t ncand = (size_t)(*meta_total >> 32);
     if (ncand > cap) ncand = cap;
+    constexpr int kPer = kEmitTile / kEmitThreads;   // consecutive candidates per thread in the compaction step
     for (size_t block_base = (size_t)blockIdx.x * kEmitTile; block_base < ncand; block_base += (size_t)gridDim.x * kEmitTile) {
     __syncthreads();
     if (threadIdx.x == 0) s_count = 0;
-    __syncthreads();
-    for (uint32_t k = threadIdx.x; k < (uint32_t)kEmitTile; k += kEmitThreads) {
-        size_t i = block_base + k;
-        if (i < ncand && marks[i] != 0) s_list[atomicAdd(&s_count, 1u)] = k;
+    // record offsets: tile offset (k_tile_offsets) + exclusive scan of the records per candidate inside the tile
+    uint32_t mk[kPer];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int j = 0; j < kPer; j++) {
+        const size_t i = block_base + (size_t)threadIdx.x * kPer + j;
+        mk[j] = i < ncand ? marks[i] : 0u;
+        mine += __popc(mk[j]);
+    }
+    uint32_t at0 = tile_offsets[block_base / kEmitTile] + (uint32_t)block_exclusive_scan(mine, s_warp, &s_total);
+#pragma unroll
+    for (int j = 0; j < kPer; j++) {
+        if (mk[j]) {
+            const uint32_t slot = atomicAdd(&s_count, 1u);
+            s_list[slot] = threadIdx.x * kPer + j;
+            s_at[slot] = at0;
+            at0 += __popc(mk[j]);
+        }
     }
     __syncthreads();
     const uint32_t todo = s_count;
     for (uint32_t k = threadIdx.x; k < todo; k += kEmitThreads) {
         const size_t i = block_base + s_list[k];
         uint32_t mask = marks[i];
-        size_t at = (size_t)recoff[i];
+        size_t at = (size_t)s_at[k];
         const size_t o = (size_t)cand[i] * 16;
         uint4 v = ld_chunk(data, o, n);
         uint32_t nlm = newline_mask16(v);
@@ -1455,7 +1487,7 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
         s->d_sums.reserve(nb_scan * 8) != cudaSuccess) { error = "cudaMalloc failed for scan scratch"; return 3; }
     if (s->fast) {
         if (s->d_cand.reserve(s->cand_cap * 4) != cudaSuccess || s->d_res.reserve(s->cand_cap * sizeof(uint32_t)) != cudaSuccess ||
-            s->d_recoff.reserve(s->cand_cap * 8) != cudaSuccess || s->d_recs.reserve(s->rec_cap * sizeof(LineRec)) != cudaSuccess) {
+            s->d_recoff.reserve((s->cand_cap / kEmitTile + 2) * sizeof(uint32_t)) != cudaSuccess || s->d_recs.reserve(s->rec_cap * sizeof(LineRec)) != cudaSuccess) {
             error = "cudaMalloc failed for candidate scratch"; return 3;
         }
     }
@@ -1511,13 +1543,15 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
             rp.nodd = pf->nodd;
             for (int k = 0; k < 2; k++) { rp.odd_mul[k] = pf->pp.odd_mul[k]; rp.odd_add[k] = pf->pp.odd_add[k]; }
         }
+        // record offsets per emit tile of kEmitTile candidates: counted by the verification kernel, scanned by one block
+        uint32_t* tile_records = s->d_recoff.as<uint32_t>();
+        CUDA_TRY(cudaMemsetAsync(tile_records, 0, (s->cand_cap / kEmitTile + 2) * sizeof(uint32_t), st));
         k_verify_local<<<vgrid, 128, 0, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->lookback, rp,
-                                              s->d_res.as<uint32_t>());
-        launch_scan(st, LoadMarks{s->d_res.as<uint32_t>(), &dT->meta_total, s->cand_cap}, s->cand_cap, s->d_recoff.as<unsigned long long>(),
-                    s->d_sums.as<unsigned long long>(), &dT->rec_total, s->stats, &dT->meta_total);
+                                              s->d_res.as<uint32_t>(), tile_records);
+        k_tile_offsets<<<1, 1024, 0, st>>>(tile_records, &dT->meta_total, s->cand_cap, &dT->rec_total);
         static const unsigned emit_resident = resident_grid(k_emit_simple, kEmitThreads);
         k_emit_simple<<<(unsigned)std::min<size_t>((s->cand_cap + kEmitTile - 1) / kEmitTile, emit_resident), kEmitThreads, 0, st>>>(
-            view, s->data, n, s->d_cand.as<uint32_t>(), s->d_res.as<uint32_t>(), s->d_recoff.as<unsigned long long>(), meta, prefix, &dT->meta_total,
+            view, s->data, n, s->d_cand.as<uint32_t>(), s->d_res.as<uint32_t>(), tile_records, meta, prefix, &dT->meta_total,
             s->cand_cap, s->d_recs.as<LineRec>(), s->rec_cap, dT);
         s->stats.launches += 3;
         CUDA_TRY(cudaEventRecord(s->ev[1], st));
