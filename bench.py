@@ -333,6 +333,16 @@ def main() -> None:  # pylint: disable=too-many-locals,too-many-statements
             dist.destroy_process_group()
         return
 
+    # DRAM traffic of the roofline kernel from the committed ncu capture (profiles/), scaled to this run's launch size
+    traffic, traffic_source = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_k_stream_traffic.json"), encoding="utf-8") as handle:
+            cap = json.load(handle)
+        traffic = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) * kernel_bytes / cap["launch_bytes"]
+        traffic_source = cap["source"]
+    except (OSError, KeyError, ValueError):
+        pass
+
     line = {
         "metric": "scanned GB/s", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
@@ -343,7 +353,8 @@ def main() -> None:  # pylint: disable=too-many-locals,too-many-statements
                 "ms_per_step": e2e_s * 1e3 / args.steps, "source": "pinned host memory -> gpugrep_scan_buffer (C ABI) -> native discard callback"},
         "e2e_file": e2e_file,
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": traffic_source,
                      "kernel": "k_stream (newline count + literal prefilter)", "peak_source": peak_source,
                      "algorithmic_bytes_per_launch": kernel_bytes, "avg_launch_ms": avg_launch_ms,
                      "kernel_share_of_gpu_time": stream_ms / gpu_ms if gpu_ms else None,

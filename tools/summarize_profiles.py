@@ -11,7 +11,8 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "smsp__thread_inst_executed_per_inst_executed.ratio", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
-        "sm__cycles_elapsed.avg.per_second"]
+        "sm__cycles_elapsed.avg.per_second", "l1tex__throughput.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts.sum"]
 STALLS = "smsp__average_warps_issue_stalled_"
 
 
@@ -28,10 +29,11 @@ def launches(path: str, last: int) -> str:
     return "\n".join(out)
 
 
-def report(path: str) -> str:
+def report(path: str, kernel: str = "") -> str:
     text = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(text.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[-1]
+    hdr, units = rows[0], rows[1]
+    vals = [r for r in rows[2:] if kernel in r[hdr.index("Kernel Name")]][-1]   # the last captured launch of that kernel
     out = [f"# ncu --set full --clock-control none, one launch: {vals[hdr.index('Kernel Name')][:100]}"]
     for h, u, v in zip(hdr, units, vals):
         if h in WANT or (h.startswith(STALLS) and h.endswith("per_issue_active.ratio")):
@@ -41,4 +43,4 @@ def report(path: str) -> str:
 
 if __name__ == "__main__":
     mode, src = sys.argv[1], sys.argv[2]
-    print(launches(src, int(sys.argv[3])) if mode == "launches" else report(src))
+    print(launches(src, int(sys.argv[3])) if mode == "launches" else report(src, sys.argv[3] if len(sys.argv) > 3 else ""))
