@@ -758,12 +758,13 @@ __device__ uint32_t walk_local(const GroupDev& G, const uint8_t* __restrict__ da
 constexpr int kEmitThreads = 256;
 constexpr int kEmitTile = 2048;   // candidates per emit step (and per record-offset entry): enough marked ones to keep every warp busy
 
-// Where the gram table lives in global memory, for k_verify_local to find the hit positions inside a candidate chunk
-// again (k_stream only reports "some sampled gram of this chunk is in the table").
+// The exact gram set in global memory (two-choice table, Prefilter::confirm_keys), for k_verify_local to find the hit
+// positions inside a candidate chunk again: k_stream only reports "some sampled gram of this chunk MAY be in the set".
 struct ReprobeParams {
-    const uint8_t* bloom;   // null: walk the whole chunk
-    uint32_t mul;
-    int shift;              // byte index = (gram * mul) >> shift, bit = product & 7
+    const uint32_t* keys;   // null: walk the whole chunk.  A gram lives in keys[h1] or keys[half + h2]
+    uint32_t mul, mul2;     // h = (gram * mul) >> shift
+    int shift;
+    uint32_t half;
     int stride;
     int fold;
     int nodd;               // mixed sampling: compares at offsets 2 mod 4 (see ProbeParams)
@@ -771,8 +772,9 @@ struct ReprobeParams {
 };
 
 // One thread per candidate chunk: local verification (see walk_local); writes the bitmask of matched lines.
-// The walk covers [first gram hit - lookback, end of the last gram hit] and then runs on until the automaton is idle;
-// with one hit per chunk (the usual case) that is a third of walking the whole chunk.
+// With the exact gram table at hand, the walk covers [first gram hit - lookback, end of the last gram hit] and then runs on
+// until the automaton is idle (with one hit per chunk, the usual case, a third of walking the whole chunk), and a chunk
+// that k_stream flagged only because of a bloom collision is dropped without a walk.
 __global__ void __launch_bounds__(128, 16) k_verify_local(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
                                                           const unsigned long long* meta_total, size_t cap, uint32_t lookback, ReprobeParams rp,
                                                           uint32_t* __restrict__ marks, uint32_t* __restrict__ tile_records) {
@@ -794,7 +796,7 @@ __global__ void __launch_bounds__(128, 16) k_verify_local(DbView db, const uint8
     } else {
         size_t hi = o;   // the walk has to start at or before hi - lookback
         uint32_t nl_in_chunk = 0;
-        if (rp.bloom) {
+        if (rp.keys) {
             const uint4 v = ld_chunk(data, o, n);
             uint32_t w[5] = {v.x, v.y, v.z, v.w, o + 16 < n ? ld_chunk(data, o + 16, n).x : 0u};
             if (rp.fold) {
@@ -806,8 +808,8 @@ __global__ void __launch_bounds__(128, 16) k_verify_local(DbView db, const uint8
             for (int k = 0; k < 4; k++) {
                 for (int sft = 0; sft < 4; sft += rp.stride) {
                     const uint32_t gram = __funnelshift_r(w[k], w[k + 1], 8 * sft);
-                    const uint32_t prod = gram * rp.mul;
-                    if ((rp.bloom[prod >> rp.shift] >> (prod & 7u)) & 1u) hits |= 1u << (4 * k + sft);
+                    const uint32_t e1 = rp.keys[(gram * rp.mul) >> rp.shift], e2 = rp.keys[rp.half + ((gram * rp.mul2) >> rp.shift)];
+                    if (e1 == gram || e2 == gram) hits |= 1u << (4 * k + sft);
                 }
                 if (rp.nodd) {
                     const uint32_t gram = __funnelshift_r(w[k], w[k + 1], 16);
@@ -815,7 +817,7 @@ __global__ void __launch_bounds__(128, 16) k_verify_local(DbView db, const uint8
                         if (gram * rp.odd_mul[c] + rp.odd_add[c] == 0u) hits |= 1u << (4 * k + 2);
                 }
             }
-            if (hits == 0) hits = 0xffffu;   // cannot happen for a chunk k_stream flagged: walk the whole chunk
+            if (hits == 0) { marks[i] = 0; goto counted; }   // a bloom collision: no gram of the set here
             const uint32_t first = __ffs(hits) - 1, last = 31 - __clz(hits);
             hi = o + first;
             idle_from = o + last + 4;
@@ -847,6 +849,7 @@ __global__ void __launch_bounds__(128, 16) k_verify_local(DbView db, const uint8
     for (int g = 0; g < db.ngroups; g++) mask |= walk_local(db.groups[g], data, n, o, t, at_line_start, idle_from, line_bit);
     marks[i] = mask;
     }
+counted:
     const uint32_t records = __reduce_add_sync(0xffffffffu, __popc(mask));
     if ((threadIdx.x & 31) == 0 && records) atomicAdd(&tile_records[i / kEmitTile], records);
     }
@@ -1154,7 +1157,11 @@ struct DevicePrefilter {
     int nodd = 0;        // register compares at offsets 2 mod 4 (mixed sampling; bloom mode only)
     ProbeParams pp{};
     uint32_t lookback = 0xffffffffu;
-    ~DevicePrefilter() { if (d_table) cudaFree(d_table); }
+    uint32_t* d_confirm = nullptr;   // exact gram set for the verification kernel (Prefilter::confirm_keys), or null
+    int confirm_log2 = 0;
+    uint32_t confirm_mul = 0, confirm_mul2 = 0;
+    double bloom_false_rate = 0;     // expected share of 16-byte chunks flagged by bloom collisions alone
+    ~DevicePrefilter() { if (d_table) cudaFree(d_table); if (d_confirm) cudaFree(d_confirm); }
 };
 
 class ScanSlot {
@@ -1337,6 +1344,17 @@ std::shared_ptr<DevicePrefilter> engine_upload_prefilter(const Prefilter& pf, st
         out->pp.amask = (uint32_t)((slots - 1) << (rshift + 2));
         src = &replicated;
     }
+    if (!pf.confirm_keys.empty()) {
+        out->confirm_log2 = pf.confirm_log2;
+        out->confirm_mul = pf.confirm_mul;
+        out->confirm_mul2 = pf.confirm_mul2;
+        if (cudaMalloc((void**)&out->d_confirm, pf.confirm_keys.size() * sizeof(uint32_t)) != cudaSuccess ||
+            cudaMemcpy(out->d_confirm, pf.confirm_keys.data(), pf.confirm_keys.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+            error = "cudaMalloc/cudaMemcpy failed for the gram confirmation table";
+            return nullptr;
+        }
+    }
+    out->bloom_false_rate = (double)pf.num_grams * (16.0 / pf.stride) / (double)((size_t)1 << pf.log2_bits);
     out->table_words = (int)src->size();
     if (cudaMalloc((void**)&out->d_table, src->size() * sizeof(uint32_t)) != cudaSuccess ||
         cudaMemcpy(out->d_table, src->data(), src->size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -1533,13 +1551,14 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
         DbView view{ddb.d_groups, ddb.ngroups, ddb.d_nfas, ddb.nnfa};
         static const unsigned verify_resident = resident_grid(k_verify_local, 128);
         unsigned vgrid = (unsigned)std::min<size_t>((s->cand_cap + 127) / 128, verify_resident);
+        // Finding the hits again costs two loads per sampled gram and candidate.  It pays when bloom collisions flag a
+        // noticeable share of chunks (large gram sets: those candidates are dropped without a walk) and when several DFA
+        // groups would each walk the whole chunk (measured: 32 patterns / 1 group / 415 grams 268 -> 294 us, so not there).
         ReprobeParams rp{};
-        // finding the hits again costs eight table lookups per candidate and shortens the walk of EVERY group: it pays from two
-        // DFA groups on (measured: 32 patterns / 1 group 268 -> 294 us, 1,000 patterns / 4 groups 7 % faster end to end)
-        if (pf->mode == 2 && ddb.ngroups >= 2 && std::getenv("GPUGREP_NO_REPROBE") == nullptr)
-        {
-            rp.bloom = reinterpret_cast<const uint8_t*>(pf->d_table);
-            rp.mul = pf->pp.mul; rp.shift = pf->pp.shift; rp.stride = pf->stride; rp.fold = pf->fold ? 1 : 0;
+        if (pf->mode == 2 && pf->d_confirm && (ddb.ngroups >= 2 || pf->bloom_false_rate > 0.005) && std::getenv("GPUGREP_NO_REPROBE") == nullptr) {
+            rp.keys = pf->d_confirm;
+            rp.mul = pf->confirm_mul; rp.mul2 = pf->confirm_mul2; rp.shift = 32 - pf->confirm_log2; rp.half = 1u << pf->confirm_log2;
+            rp.stride = pf->stride; rp.fold = pf->fold ? 1 : 0;
             rp.nodd = pf->nodd;
             for (int k = 0; k < 2; k++) { rp.odd_mul[k] = pf->pp.odd_mul[k]; rp.odd_add[k] = pf->pp.odd_add[k]; }
         }

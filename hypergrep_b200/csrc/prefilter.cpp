@@ -340,16 +340,14 @@ double window_hits(const ClassString& s, size_t t, int stride, bool fold, const 
     return hits / stride;
 }
 
-bool build_exact_table(const std::vector<uint32_t>& grams, Prefilter& out) {
-    // Two-choice hashing: every key has one candidate slot in each half; insertion evicts (cuckoo) until everything
-    // is placed.  Small tables matter: the engine replicates the table across shared-memory banks so that lookups
-    // are conflict-free, and the replication factor is what fits.
+// Two-choice hashing: every key has one candidate slot in each half; insertion evicts (cuckoo) until everything is
+// placed.  Tries table sizes 2 x 2^lb for lb in [first_lb, max_lb] and a few multiplier pairs.
+bool build_two_choice(const std::vector<uint32_t>& grams, int first_lb, int max_lb, std::vector<uint32_t>& out_keys, int& out_lb,
+                      uint32_t& out_m1, uint32_t& out_m2) {
     static const uint32_t muls[] = {0x9E3779B1u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Cu, 0xFD7046C5u, 0xB55A4F09u,
                                     0x7FEB352Du, 0x846CA68Bu, 0x9E3779B9u, 0xCC9E2D51u, 0x1B873593u, 0xE6546B64u, 0x2545F491u, 0x5851F42Du};
     const int nmul = (int)(sizeof(muls) / sizeof(muls[0]));
-    int lb = 4;
-    while (lb < 14 && ((size_t)2 << lb) * 2 < grams.size() * 5) lb++;   // total slots >= 2.5 x keys
-    for (; lb <= 14; lb++) {   // at most 2 x 16384 slots = 128 KiB unreplicated
+    for (int lb = first_lb; lb <= max_lb; lb++) {
         const size_t slots = (size_t)1 << lb;
         for (int a = 0; a + 1 < nmul; a += 2) {
             const uint32_t m1 = muls[a], m2 = muls[a + 1];
@@ -373,16 +371,32 @@ bool build_exact_table(const std::vector<uint32_t>& grams, Prefilter& out) {
                 if (!ok) break;
             }
             if (ok) {
-                out.exact = true;
-                out.log2_slots = lb;
-                out.hash_mul = m1;
-                out.hash_mul2 = m2;
-                out.keys.swap(keys);
+                out_keys.swap(keys);
+                out_lb = lb;
+                out_m1 = m1;
+                out_m2 = m2;
                 return true;
             }
         }
     }
     return false;
+}
+
+void build_exact_tables(const std::vector<uint32_t>& grams, Prefilter& out) {
+    int lb = 4;
+    while (lb < 24 && ((size_t)2 << lb) * 2 < grams.size() * 5) lb++;   // total slots >= 2.5 x keys
+    // Shared-memory variant (GPUGREP_FILTER=exact): small tables matter, the engine replicates the table across the banks so
+    // that lookups are conflict-free, and the replication factor is what fits.  At most 2 x 16384 slots = 128 KiB unreplicated.
+    out.exact = lb <= 14 && build_two_choice(grams, lb, 14, out.keys, out.log2_slots, out.hash_mul, out.hash_mul2);
+    // global-memory variant for the verification kernel
+    if (out.exact) {
+        out.confirm_keys = out.keys;
+        out.confirm_log2 = out.log2_slots;
+        out.confirm_mul = out.hash_mul;
+        out.confirm_mul2 = out.hash_mul2;
+    } else if (!build_two_choice(grams, lb, 24, out.confirm_keys, out.confirm_log2, out.confirm_mul, out.confirm_mul2)) {
+        out.confirm_keys.clear();
+    }
 }
 
 // Fills the gram tables of `out` (exact two-choice table and bloom byte table) from the final gram list.
@@ -395,7 +409,7 @@ void finish_tables(std::vector<uint32_t>& all, bool fold, const GramHistogram* s
     out.fold_case = fold;
     out.num_grams = all.size();
     out.grams = all;
-    build_exact_table(all, out);
+    build_exact_tables(all, out);
     // bloom bitmap, one probe per gram: byte = product >> (32 - log2_bytes), bit = product & 7.  Sized so that
     // a false hit is rare next to real gram occurrences (<= 2^20 bits = 128 KiB of shared memory).
     size_t need = all.size() * 2048;

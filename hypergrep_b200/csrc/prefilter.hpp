@@ -60,6 +60,11 @@ struct Prefilter {
     int log2_slots = 0;
     uint32_t hash_mul2 = 0x85EBCA6Bu;
     std::vector<uint32_t> keys;       // 2 << log2_slots entries
+    // The same kind of table without the shared-memory size limit, kept in global memory: the verification kernel uses it
+    // to find the gram hits of a flagged chunk again, EXACTLY (a chunk flagged only by a bloom collision is dropped there).
+    std::vector<uint32_t> confirm_keys;   // 2 << confirm_log2 entries; empty if it could not be built
+    int confirm_log2 = 0;
+    uint32_t confirm_mul = 0, confirm_mul2 = 0;
     // bloom bitmap (default in the streaming kernel: one lookup per gram): with p = gram * bloom_mul,
     // byte = p >> (32 - (log2_bits - 3)), bit = p & 7
     int log2_bits = 16;

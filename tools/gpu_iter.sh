@@ -12,3 +12,4 @@ if [ "$1" = "launches" ]; then
 fi
 cat gpurun_out/iter.txt; tail -3 gpurun_out/tests.log
 for s in c1 c2 c3 lit; do tail -1 gpurun_out/prof_$s.log; done
+for n in 1000 10000; do timeout 600 python tools/profile_run.py --mib 1024 --set c5 --patterns $n --passes 3 2>&1 | tail -1; done

@@ -18,6 +18,7 @@ parser.add_argument("--mib", type=int, default=1024)
 parser.add_argument("--set", default="c2")
 parser.add_argument("--passes", type=int, default=2)
 parser.add_argument("--quiet", action="store_true")
+parser.add_argument("--patterns", type=int, default=10000, help="pattern count of the c5 set")
 args = parser.parse_args()
 lib = utils._get_hyperscanner_lib()
 plants = None
@@ -30,11 +31,22 @@ elif args.set == "lit":   # literals of >= 9 bytes only: the prefilter samples a
 else:
     patterns = synth.C2_PATTERNS
 host = torch.empty(args.mib << 20, dtype=torch.uint8).pin_memory()
-synth.fill_syslog(host.numpy(), seed=1234, plants=plants, plant_ppm=1000 if plants else 0, lib=lib)
+if args.set == "c5":   # configs[4]: long JSON-ish lines, caseless template patterns; the text is a tiled 8 MiB sample
+    import time
+    import numpy as np
+    patterns = synth.c5_patterns(args.patterns)
+    sample = np.frombuffer(synth.jsonish_bytes(8 << 20, patterns_to_plant=["session_4242 failed", "code=E31337abcd"]), dtype=np.uint8)
+    reps = -(-host.numel() // sample.size)
+    host.numpy()[:] = np.tile(sample, reps)[: host.numel()]
+    host.numpy()[-1] = 10
+    t0 = time.time()
+else:
+    synth.fill_syslog(host.numpy(), seed=1234, plants=plants, plant_ppm=1000 if plants else 0, lib=lib)
 dev = host.cuda()
 torch.cuda.synchronize()
+flags = [15] * len(patterns) if args.set == "c5" else None   # caseless
 for _ in range(args.passes):
-    rc, _, st = scan_buffer(lib, dev.data_ptr(), dev.numel(), 1, patterns, collect=False)
+    rc, _, st = scan_buffer(lib, dev.data_ptr(), dev.numel(), 1, patterns, flags=flags, collect=False)
     assert rc == 0
     print(f"set={args.set} bytes={st.bytes_scanned} lines={st.lines} matches={st.matches} candidates={st.candidates} "
           f"gpu_ms={st.gpu_ms:.3f} stream_ms={st.stream_kernel_ms:.3f} launches={st.launches} path={st.path} "
