@@ -130,6 +130,11 @@ int compile_database(const char* const* patterns, const unsigned* flags, const u
     for (unsigned i = 0; i < n; i++) raw.push_back(asts[i].get());
     if (env_size("GPUGREP_NO_PREFILTER", 0) == 0) {
         db->factors = analyse_factors(raw);
+        // which DFA group(s) a pattern's grams lead to: the verification kernel walks only those (prefilter.hpp)
+        db->factors.group_mask.assign(n, 0u);
+        for (size_t g = 0; g < db->groups.size(); g++)
+            for (int member : db->groups[g].members) db->factors.group_mask[(size_t)member] |= 1u << (g & 31);
+        for (auto& np : db->nfas) db->factors.group_mask[(size_t)np.pattern] = 0xffffffffu;
         build_prefilter(db->factors, nullptr, db->prefilter);
     } else {
         db->prefilter.note = db->factors.note = "disabled by GPUGREP_NO_PREFILTER";

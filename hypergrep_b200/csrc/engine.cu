@@ -762,6 +762,7 @@ constexpr int kEmitTile = 2048;   // candidates per emit step (and per record-of
 // positions inside a candidate chunk again: k_stream only reports "some sampled gram of this chunk MAY be in the set".
 struct ReprobeParams {
     const uint32_t* keys;   // null: walk the whole chunk.  A gram lives in keys[h1] or keys[half + h2]
+    const uint32_t* groups; // per slot of keys: the DFA groups (bit g mod 32) that can match around this gram
     uint32_t mul, mul2;     // h = (gram * mul) >> shift
     int shift;
     uint32_t half;
@@ -790,6 +791,7 @@ __global__ void __launch_bounds__(128, 16) k_verify_local(DbView db, const uint8
     bool at_line_start;
     size_t idle_from = o + 19;
     uint32_t line_bit = 1u;
+    uint32_t group_mask = 0xffffffffu;   // DFA groups to walk
     if (lookback == 0xffffffffu) {
         t = line_start_of(data, o);
         at_line_start = true;
@@ -804,17 +806,22 @@ __global__ void __launch_bounds__(128, 16) k_verify_local(DbView db, const uint8
                 for (int k = 0; k < 5; k++) w[k] |= 0x20202020u;
             }
             uint32_t hits = 0;   // bit = byte offset of a sampled gram that is in the table
+            group_mask = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 for (int sft = 0; sft < 4; sft += rp.stride) {
                     const uint32_t gram = __funnelshift_r(w[k], w[k + 1], 8 * sft);
-                    const uint32_t e1 = rp.keys[(gram * rp.mul) >> rp.shift], e2 = rp.keys[rp.half + ((gram * rp.mul2) >> rp.shift)];
-                    if (e1 == gram || e2 == gram) hits |= 1u << (4 * k + sft);
+                    const uint32_t h1 = (gram * rp.mul) >> rp.shift, h2 = rp.half + ((gram * rp.mul2) >> rp.shift);
+                    const uint32_t e1 = rp.keys[h1], e2 = rp.keys[h2];
+                    if (e1 == gram || e2 == gram) {
+                        hits |= 1u << (4 * k + sft);
+                        group_mask |= rp.groups[e1 == gram ? h1 : h2];
+                    }
                 }
                 if (rp.nodd) {
                     const uint32_t gram = __funnelshift_r(w[k], w[k + 1], 16);
                     for (int c = 0; c < rp.nodd; c++)
-                        if (gram * rp.odd_mul[c] + rp.odd_add[c] == 0u) hits |= 1u << (4 * k + 2);
+                        if (gram * rp.odd_mul[c] + rp.odd_add[c] == 0u) { hits |= 1u << (4 * k + 2); group_mask = 0xffffffffu; }
                 }
             }
             if (hits == 0) { marks[i] = 0; goto counted; }   // a bloom collision: no gram of the set here
@@ -846,7 +853,8 @@ __global__ void __launch_bounds__(128, 16) k_verify_local(DbView db, const uint8
             }
         }
     }
-    for (int g = 0; g < db.ngroups; g++) mask |= walk_local(db.groups[g], data, n, o, t, at_line_start, idle_from, line_bit);
+    for (int g = 0; g < db.ngroups; g++)
+        if ((group_mask >> (g & 31)) & 1u) mask |= walk_local(db.groups[g], data, n, o, t, at_line_start, idle_from, line_bit);
     marks[i] = mask;
     }
 counted:
@@ -1158,10 +1166,11 @@ struct DevicePrefilter {
     ProbeParams pp{};
     uint32_t lookback = 0xffffffffu;
     uint32_t* d_confirm = nullptr;   // exact gram set for the verification kernel (Prefilter::confirm_keys), or null
+    uint32_t* d_confirm_groups = nullptr;
     int confirm_log2 = 0;
     uint32_t confirm_mul = 0, confirm_mul2 = 0;
     double bloom_false_rate = 0;     // expected share of 16-byte chunks flagged by bloom collisions alone
-    ~DevicePrefilter() { if (d_table) cudaFree(d_table); if (d_confirm) cudaFree(d_confirm); }
+    ~DevicePrefilter() { if (d_table) cudaFree(d_table); if (d_confirm) cudaFree(d_confirm); if (d_confirm_groups) cudaFree(d_confirm_groups); }
 };
 
 class ScanSlot {
@@ -1344,12 +1353,14 @@ std::shared_ptr<DevicePrefilter> engine_upload_prefilter(const Prefilter& pf, st
         out->pp.amask = (uint32_t)((slots - 1) << (rshift + 2));
         src = &replicated;
     }
-    if (!pf.confirm_keys.empty()) {
+    if (!pf.confirm_keys.empty() && pf.confirm_groups.size() == pf.confirm_keys.size()) {
         out->confirm_log2 = pf.confirm_log2;
         out->confirm_mul = pf.confirm_mul;
         out->confirm_mul2 = pf.confirm_mul2;
         if (cudaMalloc((void**)&out->d_confirm, pf.confirm_keys.size() * sizeof(uint32_t)) != cudaSuccess ||
-            cudaMemcpy(out->d_confirm, pf.confirm_keys.data(), pf.confirm_keys.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaMemcpy(out->d_confirm, pf.confirm_keys.data(), pf.confirm_keys.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMalloc((void**)&out->d_confirm_groups, pf.confirm_groups.size() * sizeof(uint32_t)) != cudaSuccess ||
+            cudaMemcpy(out->d_confirm_groups, pf.confirm_groups.data(), pf.confirm_groups.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
             error = "cudaMalloc/cudaMemcpy failed for the gram confirmation table";
             return nullptr;
         }
@@ -1557,6 +1568,7 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
         ReprobeParams rp{};
         if (pf->mode == 2 && pf->d_confirm && (ddb.ngroups >= 2 || pf->bloom_false_rate > 0.005) && std::getenv("GPUGREP_NO_REPROBE") == nullptr) {
             rp.keys = pf->d_confirm;
+            rp.groups = pf->d_confirm_groups;
             rp.mul = pf->confirm_mul; rp.mul2 = pf->confirm_mul2; rp.shift = 32 - pf->confirm_log2; rp.half = 1u << pf->confirm_log2;
             rp.stride = pf->stride; rp.fold = pf->fold ? 1 : 0;
             rp.nodd = pf->nodd;

@@ -201,7 +201,7 @@ Lits analyse(const Node& n) {
     return r;
 }
 
-struct Window { const ClassString* s; size_t start; };
+struct Window { const ClassString* s; size_t start; size_t pattern; };
 
 double grams_in_window(const ClassString& s, size_t t, int stride, bool fold) {
     double total = 0;
@@ -400,16 +400,43 @@ void build_exact_tables(const std::vector<uint32_t>& grams, Prefilter& out) {
 }
 
 // Fills the gram tables of `out` (exact two-choice table and bloom byte table) from the final gram list.
-void finish_tables(std::vector<uint32_t>& all, bool fold, const GramHistogram* sample, Prefilter& out) {
-    std::sort(all.begin(), all.end());
-    all.erase(std::unique(all.begin(), all.end()), all.end());
-    // a gram equal to the empty-slot marker cannot be stored exactly; it can only be "\0\0\0\0"
-    all.erase(std::remove(all.begin(), all.end(), 0u), all.end());
+// grams of the chosen windows, each with the DFA groups of the pattern it came from
+struct GramList {
+    std::vector<std::pair<uint32_t, uint32_t>> items;   // (gram, group mask)
+    void add(const ClassString& s, size_t at, bool fold, uint32_t mask) {
+        scratch.clear();
+        expand_gram(s, at, fold, scratch);
+        for (uint32_t g : scratch) items.emplace_back(g, mask);
+    }
+    size_t size() const { return items.size(); }
+private:
+    std::vector<uint32_t> scratch;
+};
+
+uint32_t mask_of(const FactorSet& fs, size_t pattern) { return pattern < fs.group_mask.size() ? fs.group_mask[pattern] : 0xffffffffu; }
+
+void finish_tables(GramList& list, bool fold, const GramHistogram* sample, Prefilter& out) {
+    // unique grams, group masks merged
+    std::sort(list.items.begin(), list.items.end());
+    std::vector<uint32_t> all, masks;
+    for (auto& it : list.items) {
+        if (it.first == 0u) continue;   // the empty-slot marker cannot be stored exactly; it can only be "\0\0\0\0", which never occurs in a block
+        if (!all.empty() && all.back() == it.first) masks.back() |= it.second;
+        else { all.push_back(it.first); masks.push_back(it.second); }
+    }
     out.enabled = true;
     out.fold_case = fold;
     out.num_grams = all.size();
     out.grams = all;
     build_exact_tables(all, out);
+    if (!out.confirm_keys.empty()) {
+        const size_t half = (size_t)1 << out.confirm_log2;
+        out.confirm_groups.assign(out.confirm_keys.size(), 0u);
+        for (size_t k = 0; k < all.size(); k++) {
+            const size_t h1 = prefilter_hash(all[k], out.confirm_mul, out.confirm_log2), h2 = half + prefilter_hash(all[k], out.confirm_mul2, out.confirm_log2);
+            out.confirm_groups[out.confirm_keys[h1] == all[k] ? h1 : h2] |= masks[k];
+        }
+    }
     // bloom bitmap, one probe per gram: byte = product >> (32 - log2_bytes), bit = product & 7.  Sized so that
     // a false hit is rare next to real gram occurrences (<= 2^20 bits = 128 KiB of shared memory).
     size_t need = all.size() * 2048;
@@ -486,7 +513,7 @@ double odd_key_hits(const OddKey& k, bool fold, const GramHistogram& h) {
 bool build_mixed(const FactorSet& fs, const GramHistogram* sample, bool fold, Prefilter& out) {
     out = Prefilter();
     out.min_factor_len = (int)fs.min_len;
-    std::vector<uint32_t> all;
+    GramList all;
     std::vector<OddKey> odd;
     size_t lookback = 0;
     double hits = 0;
@@ -503,7 +530,7 @@ bool build_mixed(const FactorSet& fs, const GramHistogram* sample, bool fold, Pr
             }
             if (std::isinf(best)) { shorts.push_back(Short{&s, pi}); continue; }
             if (sample) hits += window_hits(s, bt, 4, fold, *sample);
-            for (int j = 0; j < 4; j++) expand_gram(s, bt + j, fold, all);
+            for (int j = 0; j < 4; j++) all.add(s, bt + j, fold, mask_of(fs, pi));
             size_t lb = fs.before[pi] == SIZE_MAX ? SIZE_MAX : fs.before[pi] + bt + 3;
             lookback = std::max(lookback, lb);
         }
@@ -526,7 +553,7 @@ bool build_mixed(const FactorSet& fs, const GramHistogram* sample, bool fold, Pr
         }
         if (std::isinf(best)) return false;
         for (int j = 0; j < 2; j++) {
-            expand_gram(s, bt + j, fold, all);
+            all.add(s, bt + j, fold, mask_of(fs, sh.pattern));
             OddKey k = odd_key_of(s, bt + j, fold);
             if (std::find(odd.begin(), odd.end(), k) == odd.end()) odd.push_back(k);
         }
@@ -578,7 +605,7 @@ static void build_uniform(const FactorSet& fs, const GramHistogram* sample, Pref
                     if (std::isinf(best)) { ok = false; break; }
                     total += best_grams;
                     if (sample) hits += (best - best_grams) / 1000.0;
-                    wins.push_back(Window{&s, bt});
+                    wins.push_back(Window{&s, bt, pi});
                     size_t lb = fs.before[pi] == SIZE_MAX ? SIZE_MAX : fs.before[pi] + bt + (size_t)stride - 1;
                     lookback = std::max(lookback, lb);
                 }
@@ -591,9 +618,9 @@ static void build_uniform(const FactorSet& fs, const GramHistogram* sample, Pref
                 for (auto& wn : wins) folded_total += grams_in_window(*wn.s, wn.start, stride, true);
                 if (total > 3.0 * folded_total && total > 2048) continue;
             }
-            std::vector<uint32_t> all;
+            GramList all;
             for (auto& wn : wins)
-                for (int j = 0; j < stride; j++) expand_gram(*wn.s, wn.start + j, fold, all);
+                for (int j = 0; j < stride; j++) all.add(*wn.s, wn.start + j, fold, mask_of(fs, wn.pattern));
             out.stride = stride;
             out.lookback = lookback > 4096 ? 0xffffffffu : (uint32_t)lookback;
             if (sample && sample->positions()) out.expected_hits_per_mib = hits * 1048576.0 / (double)sample->positions();

@@ -23,6 +23,7 @@ struct FactorSet {
     bool usable = false;                               // every pattern has a factor of >= 4 bytes
     std::vector<std::vector<ClassString>> factors;     // per pattern: alternatives
     std::vector<size_t> before;                        // per pattern: max bytes between match start and factor start (SIZE_MAX: unbounded)
+    std::vector<uint32_t> group_mask;                  // per pattern: bit (g mod 32) of the DFA group(s) the pattern is compiled into (empty: unknown)
     size_t min_len = 0;
     std::string note;
 };
@@ -63,6 +64,7 @@ struct Prefilter {
     // The same kind of table without the shared-memory size limit, kept in global memory: the verification kernel uses it
     // to find the gram hits of a flagged chunk again, EXACTLY (a chunk flagged only by a bloom collision is dropped there).
     std::vector<uint32_t> confirm_keys;   // 2 << confirm_log2 entries; empty if it could not be built
+    std::vector<uint32_t> confirm_groups; // per slot: DFA groups (bit g mod 32) whose patterns own the gram; only those are walked
     int confirm_log2 = 0;
     uint32_t confirm_mul = 0, confirm_mul2 = 0;
     // bloom bitmap (default in the streaming kernel: one lookup per gram): with p = gram * bloom_mul,
