@@ -238,3 +238,21 @@ def test_default_buffer_boundary_lines(gpu_lib, oracle_lib):
     assert parity.compare(gpu_lib, oracle_lib, data, ["foo"]) >= 8
     parity.compare(gpu_lib, oracle_lib, data, ["foo", "bar"], flags=[14, 6], ids=[1, 2])
     parity.compare(gpu_lib, oracle_lib, data, ["o{2}$", "^x+foo"])
+
+
+@pytest.mark.parametrize("switch", ["", "GPUGREP_NO_REPROBE=1", "GPUGREP_NO_MIXED_STRIDE=1", "GPUGREP_NO_TUNE=1", "GPUGREP_FILTER=exact",
+                                    "GPUGREP_MAX_DFA_STATES=300"])
+def test_every_optimisation_switch_gives_the_same_result(switch, gpu_lib, oracle_lib, monkeypatch):
+    """Each fast-path optimisation can be turned off: the result never changes.  The pattern sets carry
+    a switch-specific extra literal so that no cached database or gram table of another variant is reused.
+    GPUGREP_MAX_DFA_STATES=300 splits the sets into many DFA groups (group gating in the verification kernel)."""
+    if switch:
+        name, value = switch.split("=")
+        monkeypatch.setenv(name, value)
+    tag = "zq" + "".join(ch for ch in switch if ch.isalnum())[-12:] + "qz"
+    patterns, plants = synth.c3_patterns()
+    data = synth.syslog_bytes(2 << 20, seed=21, plants=plants + ["ERROR"], plant_ppm=20000, lib=gpu_lib)
+    assert parity.compare(gpu_lib, oracle_lib, data, patterns[:200] + [tag]) > 10                 # multi-group, large gram set
+    assert parity.compare(gpu_lib, oracle_lib, data, ["ERROR", "connection reset by peer", tag]) > 10   # mixed sampling
+    assert parity.compare(gpu_lib, oracle_lib, data, synth.C2_PATTERNS + [tag]) > 100
+    parity.compare(gpu_lib, oracle_lib, data, ["(?i)error", "Port [0-9]+", tag], flags=[14, 15, 14])
