@@ -1564,9 +1564,10 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
         unsigned vgrid = (unsigned)std::min<size_t>((s->cand_cap + 127) / 128, verify_resident);
         // Finding the hits again costs two loads per sampled gram and candidate.  It pays when bloom collisions flag a
         // noticeable share of chunks (large gram sets: those candidates are dropped without a walk) and when several DFA
-        // groups would each walk the whole chunk (measured: 32 patterns / 1 group / 415 grams 268 -> 294 us, so not there).
+        // groups would each walk the whole chunk (measured with 32 patterns / 1 group / 415 grams: no gain, so not there).
         ReprobeParams rp{};
-        if (pf->mode == 2 && pf->d_confirm && (ddb.ngroups >= 2 || pf->bloom_false_rate > 0.005) && std::getenv("GPUGREP_NO_REPROBE") == nullptr) {
+        const bool want_reprobe = ddb.ngroups >= 2 || pf->bloom_false_rate > 0.005;
+        if (pf->mode == 2 && pf->d_confirm && want_reprobe && std::getenv("GPUGREP_NO_REPROBE") == nullptr) {
             rp.keys = pf->d_confirm;
             rp.groups = pf->d_confirm_groups;
             rp.mul = pf->confirm_mul; rp.mul2 = pf->confirm_mul2; rp.shift = 32 - pf->confirm_log2; rp.half = 1u << pf->confirm_log2;
