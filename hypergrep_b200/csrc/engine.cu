@@ -123,18 +123,27 @@ __device__ __forceinline__ uint32_t any_newline16(const uint4& v) {
 }
 __device__ __forceinline__ uint32_t haszero4(uint32_t w) { return (w - 0x01010101u) & ~w & 0x80808080u; }
 
+// The two line-extent searches below run one thread per matched line, 32 different lines per warp.  Both are written as
+// "a tight loop that only skips chunks without a hit, then the exact (expensive) look at the chunk that stopped the
+// loop": the threads of a warp leave the loop at different iterations but meet again behind it, so the expensive part runs
+// once per warp with every lane active instead of once per iteration with one or two lanes.
+
 // index just past the last '\n' strictly before `pos` (0 if none): start of the line containing byte `pos`
 __device__ size_t line_start_of(const uint8_t* data, size_t pos) {
     while (pos > 0) {
-        size_t base = (pos - 1) & ~(size_t)15;
-        uint4 v = *reinterpret_cast<const uint4*>(data + base);
-        uint32_t span = (uint32_t)(pos - base);   // bytes [base, pos) are candidates, 1..16
-        if (any_newline16(v)) {
-            uint32_t m = newline_mask16(v);
-            if (span < 16) m &= (1u << span) - 1u;
-            if (m) return base + (32 - __clz(m));
+        size_t base;
+        uint4 v;
+        while (true) {   // skip whole chunks without a newline
+            base = (pos - 1) & ~(size_t)15;
+            v = *reinterpret_cast<const uint4*>(data + base);
+            if (any_newline16(v) || base == 0) break;
+            pos = base;
         }
-        pos = base;
+        const uint32_t span = (uint32_t)(pos - base);   // bytes [base, pos) are candidates, 1..16
+        uint32_t m = newline_mask16(v);
+        if (span < 16) m &= (1u << span) - 1u;
+        if (m) return base + (32 - __clz(m));
+        pos = base;   // the newlines of this chunk lie at or behind pos (first chunk only), or base == 0
     }
     return 0;
 }
@@ -147,21 +156,26 @@ __device__ size_t line_end_of(const uint8_t* data, size_t pos, size_t n, bool* h
     bool nul = false;
     size_t end = n;
     while (base < n) {
-        uint4 v = ld_chunk(data, base, n);
-        // one test for "a '\n' or a NUL may be here": with bits 1 and 3 cleared both become zero bytes (so do 0x02 and 0x08,
-        // which only cost the exact look below); bytes at or beyond n read as zero and take the same path
-        const uint32_t k = 0xf5f5f5f5u;
-        if ((haszero4(v.x & k) | haszero4(v.y & k) | haszero4(v.z & k) | haszero4(v.w & k)) != 0 || skip != 0) {
-            const uint32_t valid = (base + 16 > n ? (1u << (n - base)) - 1u : 0xffffu) & ~((1u << skip) - 1u);
-            const uint32_t m = newline_mask16(v) & valid;
-            uint32_t zm = byte_mask16(v, 0u) & valid;
-            if (m) {
-                end = base + __ffs(m);
-                zm &= (1u << __ffs(m)) - 1u;
-            }
-            if (zm) nul = true;
-            if (m) break;
+        uint4 v;
+        while (true) {
+            v = ld_chunk(data, base, n);
+            // one test for "a '\n' or a NUL may be here": with bits 1 and 3 cleared both become zero bytes (so do 0x02 and 0x08,
+            // which only cost the exact look below); bytes at or beyond n read as zero and stop the loop as well
+            const uint32_t k = 0xf5f5f5f5u;
+            if ((haszero4(v.x & k) | haszero4(v.y & k) | haszero4(v.z & k) | haszero4(v.w & k)) != 0 || skip != 0) break;
+            base += 16;
+            if (base >= n) break;
         }
+        if (base >= n) break;
+        const uint32_t valid = (base + 16 > n ? (1u << (n - base)) - 1u : 0xffffu) & ~((1u << skip) - 1u);
+        const uint32_t m = newline_mask16(v) & valid;
+        uint32_t zm = byte_mask16(v, 0u) & valid;
+        if (m) {
+            end = base + __ffs(m);
+            zm &= (1u << __ffs(m)) - 1u;
+        }
+        if (zm) nul = true;
+        if (m) break;
         skip = 0;
         base += 16;
     }
@@ -886,93 +900,116 @@ __global__ void __launch_bounds__(1024) k_tile_offsets(uint32_t* __restrict__ ti
 // marked candidate computes line extents, line numbers and the exact re-check of lines with NULs.
 // The same line can be marked by several candidate chunks; records come out ordered by line start, so the host
 // drops adjacent duplicates.
+// Records of one marked candidate chunk (see k_emit_simple); returns the number of valid records it wrote.
+__device__ uint32_t emit_candidate(const DbView& db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
+                                   const uint32_t* __restrict__ marks, const unsigned long long* __restrict__ meta,
+                                   const unsigned long long* __restrict__ prefix, size_t i, size_t at, LineRec* __restrict__ recs, size_t rec_cap,
+                                   Totals* totals) {
+    uint32_t valid = 0;
+    uint32_t mask = marks[i];
+    const size_t o = (size_t)cand[i] * 16;
+    uint4 v = ld_chunk(data, o, n);
+    uint32_t nlm = newline_mask16(v);
+    if (o + 16 > n) nlm &= (1u << (n - o)) - 1u;
+    int j = 0;
+    size_t st = 0;
+    bool first = true;
+    while (true) {
+        if (mask & (1u << j)) {
+            if (first) st = line_start_of(data, o);
+            bool has_nul = false;
+            size_t en = line_end_of(data, st, n, &has_nul);
+            bool ok = true;
+            if (first) {
+                // the line started before this chunk: an earlier candidate chunk that intersects it may have marked it
+                // already (the line is the LAST line of such a chunk); only the first marking is kept.  (A repeat still
+                // gets its extents and line number computed: its neighbours in the warp need that work anyway.)
+                for (size_t k = i; k-- > 0;) {
+                    const size_t ok_off = (size_t)cand[k] * 16;
+                    if (ok_off + 16 <= st) break;
+                    const uint32_t mk = marks[k];
+                    if (!mk) continue;
+                    uint4 pv = ld_chunk(data, ok_off, n);
+                    const uint32_t last_idx = __popc(newline_mask16(pv) & 0x7fffu);   // line starts inside that chunk
+                    if ((mk >> last_idx) & 1u) { ok = false; break; }
+                }
+            }
+            if (ok && has_nul) ok = block_matches<false>(db, data, st, en);
+            valid += ok ? 1u : 0u;
+            // line number = newlines before the line start: whole blocks from the scan, then the part of the line's own
+            // 512-byte block, counted from whichever end of the block is nearer (the block's total is in meta)
+            const size_t lb = st >> 9;
+            uint32_t line_no = newlines_before_block(prefix, meta, lb);
+            if ((st & 511) <= 256) line_no += count_newlines(data, lb << 9, st);
+            else line_no += (uint32_t)(meta[lb] >> 32) - count_newlines(data, st, min((lb + 1) << 9, n));
+            if (at < rec_cap) recs[at] = LineRec{line_no, (uint32_t)st, ok ? ((uint32_t)(en - st) | (has_nul ? kHasNulBit : 0u)) : kInvalidLen};
+            else atomicOr(&totals->flags, 4u);
+            at++;
+        }
+        if (!nlm) break;
+        int b = __ffs(nlm) - 1;
+        nlm &= nlm - 1;
+        st = o + b + 1;
+        first = false;
+        j++;
+        if ((mask >> j) == 0) break;
+    }
+    return valid;
+}
+
+// Persistent blocks walk tiles of kEmitTile candidates.  The marked candidates of a tile (about one in six) go into a
+// shared-memory queue together with their record offset (tile offset from k_tile_offsets + a block scan inside the
+// tile); the block takes them out in FULL batches of one per thread and carries the remainder over to the next tile, so
+// that the expensive per-record work runs with every thread busy instead of a last, mostly empty round per tile.
+constexpr uint32_t kEmitQueue = 4096;   // >= kEmitTile + kEmitThreads, power of two
 __global__ void __launch_bounds__(kEmitThreads) k_emit_simple(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
                                                               const uint32_t* __restrict__ marks, const uint32_t* __restrict__ tile_offsets,
                                                               const unsigned long long* __restrict__ meta, const unsigned long long* __restrict__ prefix,
                                                               const unsigned long long* meta_total, size_t cap, LineRec* __restrict__ recs, size_t rec_cap,
                                                               Totals* totals) {
-    __shared__ uint32_t s_list[kEmitTile], s_at[kEmitTile];
+    __shared__ uint32_t q_cand[kEmitQueue], q_at[kEmitQueue];
     __shared__ unsigned long long s_warp[kEmitThreads / 32], s_total;
     uint32_t valid = 0;
-    __shared__ uint32_t s_count;
+    uint32_t head = 0, queued = 0;   // the same in every thread of the block
     size_t ncand = (size_t)(*meta_total >> 32);
     if (ncand > cap) ncand = cap;
     constexpr int kPer = kEmitTile / kEmitThreads;   // consecutive candidates per thread in the compaction step
     for (size_t block_base = (size_t)blockIdx.x * kEmitTile; block_base < ncand; block_base += (size_t)gridDim.x * kEmitTile) {
-    __syncthreads();
-    if (threadIdx.x == 0) s_count = 0;
-    // record offsets: tile offset (k_tile_offsets) + exclusive scan of the records per candidate inside the tile
-    uint32_t mk[kPer];
-    uint32_t mine = 0;
+        uint32_t mk[kPer];
+        uint32_t records = 0, marked = 0;
 #pragma unroll
-    for (int j = 0; j < kPer; j++) {
-        const size_t i = block_base + (size_t)threadIdx.x * kPer + j;
-        mk[j] = i < ncand ? marks[i] : 0u;
-        mine += __popc(mk[j]);
-    }
-    uint32_t at0 = tile_offsets[block_base / kEmitTile] + (uint32_t)block_exclusive_scan(mine, s_warp, &s_total);
-#pragma unroll
-    for (int j = 0; j < kPer; j++) {
-        if (mk[j]) {
-            const uint32_t slot = atomicAdd(&s_count, 1u);
-            s_list[slot] = threadIdx.x * kPer + j;
-            s_at[slot] = at0;
-            at0 += __popc(mk[j]);
+        for (int j = 0; j < kPer; j++) {
+            const size_t i = block_base + (size_t)threadIdx.x * kPer + j;
+            mk[j] = i < ncand ? marks[i] : 0u;
+            records += __popc(mk[j]);
+            marked += mk[j] != 0u;
         }
-    }
-    __syncthreads();
-    const uint32_t todo = s_count;
-    for (uint32_t k = threadIdx.x; k < todo; k += kEmitThreads) {
-        const size_t i = block_base + s_list[k];
-        uint32_t mask = marks[i];
-        size_t at = (size_t)s_at[k];
-        const size_t o = (size_t)cand[i] * 16;
-        uint4 v = ld_chunk(data, o, n);
-        uint32_t nlm = newline_mask16(v);
-        if (o + 16 > n) nlm &= (1u << (n - o)) - 1u;
-        int j = 0;
-        size_t st = 0;
-        bool first = true;
-        while (true) {
-            if (mask & (1u << j)) {
-                if (first) st = line_start_of(data, o);
-                bool has_nul = false;
-                size_t en = line_end_of(data, st, n, &has_nul);
-                bool ok = true;
-                if (first) {
-                    // the line started before this chunk: an earlier candidate chunk that intersects it may have marked it
-                    // already (the line is the LAST line of such a chunk); only the first marking is kept
-                    for (size_t k = i; k-- > 0;) {
-                        const size_t ok_off = (size_t)cand[k] * 16;
-                        if (ok_off + 16 <= st) break;
-                        const uint32_t mk = marks[k];
-                        if (!mk) continue;
-                        uint4 pv = ld_chunk(data, ok_off, n);
-                        const uint32_t last_idx = __popc(newline_mask16(pv) & 0x7fffu);   // line starts inside that chunk
-                        if ((mk >> last_idx) & 1u) { ok = false; break; }
-                    }
-                }
-                if (ok && has_nul) ok = block_matches<false>(db, data, st, en);
-                valid += ok ? 1u : 0u;
-                // line number = newlines before the line start: whole blocks from the scan, then the part of the line's own
-                // 512-byte block, counted from whichever end of the block is nearer (the block's total is in meta)
-                const size_t lb = st >> 9;
-                uint32_t line_no = newlines_before_block(prefix, meta, lb);
-                if ((st & 511) <= 256) line_no += count_newlines(data, lb << 9, st);
-                else line_no += (uint32_t)(meta[lb] >> 32) - count_newlines(data, st, min((lb + 1) << 9, n));
-                if (at < rec_cap) recs[at] = LineRec{line_no, (uint32_t)st, ok ? ((uint32_t)(en - st) | (has_nul ? kHasNulBit : 0u)) : kInvalidLen};
-                else atomicOr(&totals->flags, 4u);
-                at++;
+        // one scan for both: queue position (marked candidates before mine) and record offset (records before mine)
+        const unsigned long long before = block_exclusive_scan(((unsigned long long)marked << 32) | records, s_warp, &s_total);
+        uint32_t slot = head + queued + (uint32_t)(before >> 32);
+        uint32_t at = tile_offsets[block_base / kEmitTile] + (uint32_t)before;
+#pragma unroll
+        for (int j = 0; j < kPer; j++) {
+            if (mk[j]) {
+                q_cand[slot & (kEmitQueue - 1)] = (uint32_t)(block_base + (size_t)threadIdx.x * kPer + j);
+                q_at[slot & (kEmitQueue - 1)] = at;
+                slot++;
+                at += __popc(mk[j]);
             }
-            if (!nlm) break;
-            int b = __ffs(nlm) - 1;
-            nlm &= nlm - 1;
-            st = o + b + 1;
-            first = false;
-            j++;
-            if ((mask >> j) == 0) break;
         }
+        queued += (uint32_t)(s_total >> 32);
+        __syncthreads();
+        while (queued >= (uint32_t)kEmitThreads) {
+            const uint32_t k = (head + threadIdx.x) & (kEmitQueue - 1);
+            valid += emit_candidate(db, data, n, cand, marks, meta, prefix, q_cand[k], q_at[k], recs, rec_cap, totals);
+            head += kEmitThreads;
+            queued -= kEmitThreads;
+        }
+        __syncthreads();   // everything taken out before the next tile overwrites queue slots / scan scratch
     }
+    if (threadIdx.x < queued) {
+        const uint32_t k = (head + threadIdx.x) & (kEmitQueue - 1);
+        valid += emit_candidate(db, data, n, cand, marks, meta, prefix, q_cand[k], q_at[k], recs, rec_cap, totals);
     }
     // unique valid records of the segment (count-only callers need nothing else)
     valid = __reduce_add_sync(0xffffffffu, valid);
