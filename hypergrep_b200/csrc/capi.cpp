@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <condition_variable>
+#include <functional>
 #include <list>
 #include <mutex>
 #include <thread>
@@ -121,8 +122,11 @@ private:
 
 constexpr size_t kSampleBytes = 512 << 10;   // head of the input used to tune the prefilter windows
 
-// Sample-tuned prefilter tables, cached per (database, device, sample fingerprint).
-std::shared_ptr<DevicePrefilter> tuned_prefilter(const std::shared_ptr<Database>& db, const uint8_t* sample, size_t len, std::string& error) {
+// Sample-tuned prefilter tables, cached per (database, device, sample fingerprint).  `sample` must hold the first
+// min(len, 64 KiB) bytes (the fingerprint); `fetch_full`, if given, returns a pointer to all `len` bytes and is only
+// called on a cache miss (device-resident inputs copy the rest of the sample only then).
+std::shared_ptr<DevicePrefilter> tuned_prefilter(const std::shared_ptr<Database>& db, const uint8_t* sample, size_t len, std::string& error,
+                                                 const std::function<const uint8_t*()>& fetch_full = nullptr) {
     if (!db->simple || !db->factors.usable) return nullptr;
     struct Entry { const Database* db; int device; uint64_t fp; std::shared_ptr<Database> keep; std::shared_ptr<DevicePrefilter> pf; };
     static std::mutex mu;
@@ -146,6 +150,8 @@ std::shared_ptr<DevicePrefilter> tuned_prefilter(const std::shared_ptr<Database>
     }
     Prefilter pf;
     if (len >= 4096 && std::getenv("GPUGREP_NO_TUNE") == nullptr) {
+        if (fetch_full) sample = fetch_full();
+        if (!sample) { error = "could not read the tuning sample"; return nullptr; }
         GramHistogram hist;
         hist.add_sample(sample, len);
         build_prefilter(db->factors, &hist, pf);
@@ -556,9 +562,15 @@ int scan_memory(const uint8_t* data, size_t size, int location, const Params& pr
     // device-resident input: all segment ends come from one small kernel instead of one synchronous copy per segment
     std::vector<size_t> dev_cuts;
     size_t dev_cut_index = 0;
-    if (on_device && size > chunk) {
-        chunk = std::min(chunk, kMaxSegmentBytes - ((size_t)16 << 20));
-        if (engine_find_cuts(data, size, chunk, dev_cuts, job.error) != 0) dev_cuts.clear();
+    std::vector<uint8_t> head;   // device-resident input: its first 64 KiB, enough for the fingerprint of the tuning sample
+    if (on_device && size) {
+        if (size > chunk) chunk = std::min(chunk, kMaxSegmentBytes - ((size_t)16 << 20));
+        head.resize(std::min<size_t>(size, 64 << 10));
+        if (slot_probe_input(slots[0], data, size, chunk, dev_cuts, head.data(), head.size(), job.error) != 0) {
+            engine_release_slot(slots[0]); engine_release_slot(slots[1]);
+            set_last_error(job.error);
+            return GPUGREP_SCAN;
+        }
     }
     size_t pos = 0;
     while (pos < size && !job.stop && rc == 0) {
@@ -587,10 +599,14 @@ int scan_memory(const uint8_t* data, size_t size, int location, const Params& pr
         if (!tuned) {
             tuned = true;
             if (on_device) {
-                sample.resize(std::min(cut, kSampleBytes));
-                if (cudaMemcpy(sample.data(), data, sample.size(), cudaMemcpyDeviceToHost) != cudaSuccess) { job.error = "cudaMemcpy of the tuning sample failed"; rc = GPUGREP_SCAN; break; }
-                job.stats.d2h_bytes += sample.size();
-                job.dpf = tuned_prefilter(job.db, sample.data(), sample.size(), job.error);
+                const size_t sample_len = std::min(cut, kSampleBytes);
+                job.stats.d2h_bytes += head.size();
+                job.dpf = tuned_prefilter(job.db, head.data(), sample_len, job.error, [&]() -> const uint8_t* {
+                    sample.resize(sample_len);
+                    if (cudaMemcpy(sample.data(), data, sample_len, cudaMemcpyDeviceToHost) != cudaSuccess) return nullptr;
+                    job.stats.d2h_bytes += sample_len;
+                    return sample.data();
+                });
             } else {
                 job.dpf = tuned_prefilter(job.db, data, cut, job.error);
             }

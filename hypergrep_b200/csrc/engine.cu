@@ -1219,7 +1219,7 @@ public:
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // 0/1: whole segment, 2/3: streaming kernel
     DevBuf d_input, d_meta, d_prefix, d_sums, d_cand, d_res, d_recoff, d_recs, d_totals;
     DevBuf d_nlpos, d_npl, d_ploff, d_plstart, d_pllen, d_flags, d_counts, d_events, d_gather, d_gidx;
-    PinBuf h_totals, h_recs, h_stage, h_gather;
+    PinBuf h_totals, h_recs, h_stage, h_gather, h_probe;
     // state of the in-flight segment
     const DeviceDb* ddb = nullptr;
     const uint8_t* data = nullptr;   // device pointer of the segment
@@ -1772,22 +1772,31 @@ int slot_collect(ScanSlot* s, SegmentResult& out, std::string& error) {
     return 0;
 }
 
-int engine_find_cuts(const uint8_t* dev_data, size_t size, size_t chunk, std::vector<size_t>& cuts, std::string& error) {
+int slot_probe_input(ScanSlot* s, const uint8_t* dev_data, size_t size, size_t chunk, std::vector<size_t>& cuts, uint8_t* head, size_t head_len,
+                     std::string& error) {
     cuts.clear();
-    if (size == 0 || chunk == 0) return 0;
-    size_t ncuts = (size + chunk - 1) / chunk;
-    unsigned long long* d = nullptr;
-    CUDA_TRY(cudaMalloc((void**)&d, ncuts * sizeof(unsigned long long)));
-    k_find_cuts<<<(unsigned)((ncuts + 63) / 64), 64>>>(dev_data, size, chunk, (size_t)4 << 20, ncuts, d);
-    std::vector<unsigned long long> h(ncuts);
-    cudaError_t e = cudaMemcpy(h.data(), d, ncuts * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-    cudaFree(d);
-    if (e != cudaSuccess) { error = std::string("k_find_cuts: ") + cudaGetErrorString(e); return 7; }
+    if (size == 0) return 0;
+    const size_t ncuts = chunk && size > chunk ? (size + chunk - 1) / chunk : 0;
+    head_len = std::min(head_len, size);
+    if (s->h_probe.reserve(ncuts * 8 + head_len + 16) != cudaSuccess || (ncuts && s->d_sums.reserve(ncuts * 8) != cudaSuccess)) {
+        error = "scratch allocation failed";
+        return 3;
+    }
+    cudaStream_t st = s->own_stream;
+    unsigned long long* h_cuts = s->h_probe.as<unsigned long long>();
+    uint8_t* h_head = s->h_probe.as<uint8_t>() + ncuts * 8;
+    if (ncuts) {
+        k_find_cuts<<<(unsigned)((ncuts + 63) / 64), 64, 0, st>>>(dev_data, size, chunk, (size_t)4 << 20, ncuts, s->d_sums.as<unsigned long long>());
+        CUDA_TRY(cudaMemcpyAsync(h_cuts, s->d_sums.p, ncuts * 8, cudaMemcpyDeviceToHost, st));
+    }
+    if (head_len) CUDA_TRY(cudaMemcpyAsync(h_head, dev_data, head_len, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (head_len) std::memcpy(head, h_head, head_len);
     size_t prev = 0;
     for (size_t j = 0; j < ncuts; j++) {
-        if (h[j] == 0 || h[j] <= prev) { cuts.clear(); return 0; }   // no newline near a boundary: caller falls back
-        cuts.push_back((size_t)h[j]);
-        prev = (size_t)h[j];
+        if (h_cuts[j] == 0 || h_cuts[j] <= prev) { cuts.clear(); break; }   // no newline near a boundary: caller falls back
+        cuts.push_back((size_t)h_cuts[j]);
+        prev = (size_t)h_cuts[j];
     }
     return 0;
 }

@@ -79,9 +79,12 @@ int slot_collect(ScanSlot* slot, SegmentResult& out, std::string& error);
 int slot_gather_lines(ScanSlot* slot, const uint32_t* starts, const uint32_t* lens, size_t count, uint8_t* out,
                       std::string& error);
 
-// Segment ends for a device-resident input: cuts[j] = offset just past the last '\n' before (j+1)*chunk (the last
-// entry is `size`).  Left empty when some boundary has no newline nearby (the caller then cuts sequentially).
-int engine_find_cuts(const uint8_t* dev_data, size_t size, size_t chunk, std::vector<size_t>& cuts, std::string& error);
+// Device-resident input, one round trip on the slot's own stream: the segment ends and the first `head_len` bytes of the
+// input (fingerprint of the prefilter sample).  cuts[j] = offset just past the last '\n' before (j+1)*chunk that keeps the
+// next segment 16-byte aligned (the last entry is `size`); left empty when the input is a single segment or some
+// boundary has no such newline nearby (the caller then cuts sequentially).
+int slot_probe_input(ScanSlot* slot, const uint8_t* dev_data, size_t size, size_t chunk, std::vector<size_t>& cuts, uint8_t* head,
+                     size_t head_len, std::string& error);
 
 constexpr size_t kMaxSegmentBytes = (size_t)3 << 30;   // offsets inside a segment are 32-bit
 

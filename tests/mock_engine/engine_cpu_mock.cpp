@@ -132,7 +132,11 @@ int slot_collect(ScanSlot* s, SegmentResult& out, std::string&) {
     return 0;
 }
 
-int engine_find_cuts(const uint8_t*, size_t, size_t, std::vector<size_t>& cuts, std::string&) { cuts.clear(); return 0; }
+int slot_probe_input(ScanSlot*, const uint8_t*, size_t, size_t, std::vector<size_t>& cuts, uint8_t*, size_t, std::string& error) {
+    cuts.clear();
+    error = "mock engine: device-resident input is not supported";
+    return 7;
+}
 
 int slot_gather_lines(ScanSlot*, const uint32_t*, const uint32_t*, size_t, uint8_t*, std::string& error) {
     error = "mock engine: gather is not supported";

@@ -49,5 +49,5 @@ for _ in range(args.passes):
     rc, _, st = scan_buffer(lib, dev.data_ptr(), dev.numel(), 1, patterns, flags=flags, collect=False)
     assert rc == 0
     print(f"set={args.set} bytes={st.bytes_scanned} lines={st.lines} matches={st.matches} candidates={st.candidates} "
-          f"gpu_ms={st.gpu_ms:.3f} stream_ms={st.stream_kernel_ms:.3f} launches={st.launches} path={st.path} "
+          f"gpu_ms={st.gpu_ms:.3f} wall_ms={st.wall_ms:.3f} stream_ms={st.stream_kernel_ms:.3f} launches={st.launches} path={st.path} "
           f"GB/s={st.bytes_scanned / st.gpu_ms / 1e6:.1f} stream_GB/s={st.bytes_scanned / st.stream_kernel_ms / 1e6:.1f}")
