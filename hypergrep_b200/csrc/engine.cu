@@ -123,49 +123,93 @@ __device__ __forceinline__ uint32_t any_newline16(const uint4& v) {
 }
 __device__ __forceinline__ uint32_t haszero4(uint32_t w) { return (w - 0x01010101u) & ~w & 0x80808080u; }
 
-// The two line-extent searches below run one thread per matched line, 32 different lines per warp.  Both are written as
+// The line-extent searches below run one thread per matched line, 32 different lines per warp.  They are written as
 // "a tight loop that only skips chunks without a hit, then the exact (expensive) look at the chunk that stopped the
 // loop": the threads of a warp leave the loop at different iterations but meet again behind it, so the expensive part runs
-// once per warp with every lane active instead of once per iteration with one or two lanes.
+// once per warp with every lane active instead of once per iteration with one or two lanes.  Each search can be bounded:
+// a line that is not settled within `bound` bytes is handed to the warp-cooperative variants further down, which read
+// 512 bytes per step (k_emit_simple: a 16 KiB JSON line is 32 steps for the warp instead of 1,000 for one thread).
+constexpr size_t kNoBound = ~(size_t)0;
 
-// index just past the last '\n' strictly before `pos` (0 if none): start of the line containing byte `pos`
-__device__ size_t line_start_of(const uint8_t* data, size_t pos) {
+// Start of the line containing byte `pos` = index just past the last '\n' strictly before `pos` (0 if none).
+// Returns true and the start in *out, or - after more than `bound` bytes without a newline - false and in *out a 16-byte
+// aligned position p <= pos with no newline in [p, pos).
+__device__ bool line_start_bounded(const uint8_t* data, size_t pos, size_t bound, size_t* out) {
+    const size_t give_up = pos > bound ? pos - bound : 0;
     while (pos > 0) {
         size_t base;
         uint4 v;
-        while (true) {   // skip whole chunks without a newline
+        while (true) {   // skip whole chunks without a newline, four per step while that many lie below (four loads in flight)
             base = (pos - 1) & ~(size_t)15;
+            if (base >= 48 && pos == base + 16) {
+                if (pos <= give_up) { *out = pos; return false; }
+                const uint4 a = *reinterpret_cast<const uint4*>(data + base), b = *reinterpret_cast<const uint4*>(data + base - 16);
+                const uint4 c = *reinterpret_cast<const uint4*>(data + base - 32), d = *reinterpret_cast<const uint4*>(data + base - 48);
+                if (any_newline16(a)) { v = a; break; }
+                if (any_newline16(b)) { v = b; base -= 16; pos = base + 16; break; }
+                if (any_newline16(c)) { v = c; base -= 32; pos = base + 16; break; }
+                if (any_newline16(d)) { v = d; base -= 48; pos = base + 16; break; }
+                pos = base - 48;
+                if (pos == 0) { base = 0; v = make_uint4(0u, 0u, 0u, 0u); break; }   // reached the start of the data: no newline before
+                continue;
+            }
             v = *reinterpret_cast<const uint4*>(data + base);
             if (any_newline16(v) || base == 0) break;
             pos = base;
         }
-        const uint32_t span = (uint32_t)(pos - base);   // bytes [base, pos) are candidates, 1..16
+        const uint32_t span = (uint32_t)(pos - base);   // bytes [base, pos) are candidates, 0..16
         uint32_t m = newline_mask16(v);
         if (span < 16) m &= (1u << span) - 1u;
-        if (m) return base + (32 - __clz(m));
+        if (m) { *out = base + (32 - __clz(m)); return true; }
         pos = base;   // the newlines of this chunk lie at or behind pos (first chunk only), or base == 0
     }
-    return 0;
+    *out = 0;
+    return true;
+}
+__device__ size_t line_start_of(const uint8_t* data, size_t pos) {
+    size_t st;
+    line_start_bounded(data, pos, kNoBound, &st);
+    return st;
 }
 
-// index just past the first '\n' at or after `pos`, or n if there is none; *has_nul is set if a NUL byte lies in
-// [pos, returned end)
-__device__ size_t line_end_of(const uint8_t* data, size_t pos, size_t n, bool* has_nul) {
+// End of the line that contains byte `pos` = index just past the first '\n' at or after `pos`, or n if there is none;
+// *has_nul is set if a NUL byte lies in [pos, end).  Returns true and the end in *out, or - after more than `bound` bytes
+// without a newline - false and in *out a 16-byte aligned position p > pos with no newline in [pos, p) (*has_nul then
+// covers [pos, p)).
+__device__ bool line_end_bounded(const uint8_t* data, size_t pos, size_t n, size_t bound, size_t* out, bool* has_nul) {
     size_t base = pos & ~(size_t)15;
+    const size_t give_up = bound == kNoBound ? kNoBound : pos + bound;
     uint32_t skip = (uint32_t)(pos - base);
     bool nul = false;
     size_t end = n;
+    bool found = true;
     while (base < n) {
         uint4 v;
-        while (true) {
-            v = ld_chunk(data, base, n);
-            // one test for "a '\n' or a NUL may be here": with bits 1 and 3 cleared both become zero bytes (so do 0x02 and 0x08,
-            // which only cost the exact look below); bytes at or beyond n read as zero and stop the loop as well
+        // one test for "a '\n' or a NUL may be here": with bits 1 and 3 cleared both become zero bytes (so do 0x02 and 0x08,
+        // which only cost the exact look below); bytes at or beyond n read as zero and stop the loop as well
+        auto maybe = [](const uint4& q) {
             const uint32_t k = 0xf5f5f5f5u;
-            if ((haszero4(v.x & k) | haszero4(v.y & k) | haszero4(v.z & k) | haszero4(v.w & k)) != 0 || skip != 0) break;
+            return (haszero4(q.x & k) | haszero4(q.y & k) | haszero4(q.z & k) | haszero4(q.w & k)) != 0;
+        };
+        while (true) {   // four chunks per step while that many lie inside the segment (four loads in flight)
+            if (skip == 0 && base + 64 <= n) {
+                if (base >= give_up) { found = false; break; }
+                const uint4 a = *reinterpret_cast<const uint4*>(data + base), b = *reinterpret_cast<const uint4*>(data + base + 16);
+                const uint4 c = *reinterpret_cast<const uint4*>(data + base + 32), d = *reinterpret_cast<const uint4*>(data + base + 48);
+                if (maybe(a)) { v = a; break; }
+                if (maybe(b)) { v = b; base += 16; break; }
+                if (maybe(c)) { v = c; base += 32; break; }
+                if (maybe(d)) { v = d; base += 48; break; }
+                base += 64;
+                if (base >= n) break;
+                continue;
+            }
+            v = ld_chunk(data, base, n);
+            if (maybe(v) || skip != 0) break;
             base += 16;
             if (base >= n) break;
         }
+        if (!found) { end = base; break; }
         if (base >= n) break;
         const uint32_t valid = (base + 16 > n ? (1u << (n - base)) - 1u : 0xffffu) & ~((1u << skip) - 1u);
         const uint32_t m = newline_mask16(v) & valid;
@@ -180,6 +224,64 @@ __device__ size_t line_end_of(const uint8_t* data, size_t pos, size_t n, bool* h
         base += 16;
     }
     if (has_nul) *has_nul = nul;
+    *out = end;
+    return found;
+}
+__device__ size_t line_end_of(const uint8_t* data, size_t pos, size_t n, bool* has_nul) {
+    size_t en;
+    line_end_bounded(data, pos, n, kNoBound, &en, has_nul);
+    return en;
+}
+
+// Warp-cooperative continuations (every lane of the warp calls them with the same arguments).
+// Last '\n' strictly before the 16-byte aligned `pos`: the index just past it, or 0.
+__device__ size_t warp_line_start(const uint8_t* data, size_t pos) {
+    const uint32_t lane = threadIdx.x & 31;
+    while (pos > 0) {
+        // lane 0 takes the chunk just below pos, lane 31 the one 512 bytes further down
+        const bool have = pos >= (size_t)16 * (lane + 1);
+        const size_t base = have ? pos - (size_t)16 * (lane + 1) : 0;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (have) v = *reinterpret_cast<const uint4*>(data + base);
+        const uint32_t hit = __ballot_sync(0xffffffffu, have && any_newline16(v) != 0);
+        if (hit) {
+            const int src = __ffs(hit) - 1;   // the nearest chunk with a newline
+            const size_t mine = base + (32 - __clz(newline_mask16(v) | 1u));   // only the value of lane `src` is used
+            return (size_t)__shfl_sync(0xffffffffu, (unsigned long long)mine, src);
+        }
+        if (pos <= 512) return 0;
+        pos -= 512;
+    }
+    return 0;
+}
+// First '\n' at or after the 16-byte aligned `pos`: the index just past it, or n; *has_nul: a NUL lies in [pos, end).
+__device__ size_t warp_line_end(const uint8_t* data, size_t pos, size_t n, bool* has_nul) {
+    const uint32_t lane = threadIdx.x & 31;
+    bool nul = false;
+    size_t end = n;
+    while (pos < n) {
+        const size_t base = pos + (size_t)16 * lane;
+        const bool have = base < n;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        uint32_t valid = 0;
+        if (have) {
+            v = ld_chunk(data, base, n);
+            valid = base + 16 > n ? (1u << (n - base)) - 1u : 0xffffu;
+        }
+        const uint32_t m = have ? newline_mask16(v) & valid : 0u;
+        const uint32_t zm = have ? byte_mask16(v, 0u) & valid : 0u;
+        const uint32_t hit = __ballot_sync(0xffffffffu, m != 0);
+        const uint32_t src = hit ? (uint32_t)__ffs(hit) - 1u : 32u;   // the first chunk with a newline
+        // NULs count in the chunks before that one, and in it before the newline
+        const bool counts = lane < src ? zm != 0 : (lane == src && (zm & ((1u << __ffs(m)) - 1u)) != 0);
+        if (__any_sync(0xffffffffu, counts)) nul = true;
+        if (hit) {
+            end = (size_t)__shfl_sync(0xffffffffu, (unsigned long long)(base + __ffs(m | 0x10000u)), (int)src);
+            break;
+        }
+        pos += 512;
+    }
+    *has_nul = nul;
     return end;
 }
 
@@ -900,25 +1002,56 @@ __global__ void __launch_bounds__(1024) k_tile_offsets(uint32_t* __restrict__ ti
 // marked candidate computes line extents, line numbers and the exact re-check of lines with NULs.
 // The same line can be marked by several candidate chunks; records come out ordered by line start, so the host
 // drops adjacent duplicates.
-// Records of one marked candidate chunk (see k_emit_simple); returns the number of valid records it wrote.
-__device__ uint32_t emit_candidate(const DbView& db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
-                                   const uint32_t* __restrict__ marks, const unsigned long long* __restrict__ meta,
-                                   const unsigned long long* __restrict__ prefix, size_t i, size_t at, LineRec* __restrict__ recs, size_t rec_cap,
-                                   Totals* totals) {
+// Records of one marked candidate chunk per lane (see k_emit_simple); returns the number of valid records the lane wrote.
+// Called by whole warps (`live` = this lane has a candidate): the lanes go through their marked lines round by round, and
+// in every round the line extents that a lane did not settle within kEmitBound bytes are finished by the whole warp.
+constexpr size_t kEmitBound = 256;
+__device__ uint32_t emit_warp(const DbView& db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
+                              const uint32_t* __restrict__ marks, const unsigned long long* __restrict__ meta,
+                              const unsigned long long* __restrict__ prefix, bool live, size_t i, size_t at, LineRec* __restrict__ recs,
+                              size_t rec_cap, Totals* totals) {
+    const uint32_t lane = threadIdx.x & 31;
     uint32_t valid = 0;
-    uint32_t mask = marks[i];
-    const size_t o = (size_t)cand[i] * 16;
-    uint4 v = ld_chunk(data, o, n);
-    uint32_t nlm = newline_mask16(v);
-    if (o + 16 > n) nlm &= (1u << (n - o)) - 1u;
-    int j = 0;
+    uint32_t mask = live ? marks[i] : 0u;
+    const size_t o = live ? (size_t)cand[i] * 16 : 0;
+    uint32_t nlm = 0;
+    if (live) {
+        nlm = newline_mask16(ld_chunk(data, o, n));
+        if (o + 16 > n) nlm &= (1u << (n - o)) - 1u;
+    }
+    // line j of the chunk starts at `st` (j = 0: somewhere before the chunk, found below); `first` = still on line 0
     size_t st = 0;
     bool first = true;
-    while (true) {
-        if (mask & (1u << j)) {
-            if (first) st = line_start_of(data, o);
-            bool has_nul = false;
-            size_t en = line_end_of(data, st, n, &has_nul);
+    while (__any_sync(0xffffffffu, mask != 0)) {
+        // skip lines of the chunk that are not marked
+        while (mask != 0 && !(mask & 1u)) {
+            if (!nlm) { mask = 0; break; }
+            st = o + __ffs(nlm);
+            nlm &= nlm - 1;
+            first = false;
+            mask >>= 1;
+        }
+        const bool work = mask != 0;
+        // ---- line start (only line 0 starts before the chunk)
+        bool settled = true;
+        if (work && first) settled = line_start_bounded(data, o, kEmitBound, &st);
+        for (uint32_t pend = __ballot_sync(0xffffffffu, work && !settled); pend; pend &= pend - 1) {
+            const int src = __ffs(pend) - 1;
+            const size_t found = warp_line_start(data, (size_t)__shfl_sync(0xffffffffu, (unsigned long long)st, src));
+            if ((int)lane == src) st = found;
+        }
+        // ---- line end
+        bool has_nul = false;
+        size_t en = 0;
+        settled = true;
+        if (work) settled = line_end_bounded(data, st, n, kEmitBound, &en, &has_nul);
+        for (uint32_t pend = __ballot_sync(0xffffffffu, work && !settled); pend; pend &= pend - 1) {
+            const int src = __ffs(pend) - 1;
+            bool more_nul = false;
+            const size_t found = warp_line_end(data, (size_t)__shfl_sync(0xffffffffu, (unsigned long long)en, src), n, &more_nul);
+            if ((int)lane == src) { en = found; has_nul |= more_nul; }
+        }
+        if (work) {
             bool ok = true;
             if (first) {
                 // the line started before this chunk: an earlier candidate chunk that intersects it may have marked it
@@ -945,14 +1078,15 @@ __device__ uint32_t emit_candidate(const DbView& db, const uint8_t* __restrict__
             if (at < rec_cap) recs[at] = LineRec{line_no, (uint32_t)st, ok ? ((uint32_t)(en - st) | (has_nul ? kHasNulBit : 0u)) : kInvalidLen};
             else atomicOr(&totals->flags, 4u);
             at++;
+            // on to the next line of the chunk
+            if (!nlm) mask = 0;
+            else {
+                st = o + __ffs(nlm);
+                nlm &= nlm - 1;
+                first = false;
+                mask >>= 1;
+            }
         }
-        if (!nlm) break;
-        int b = __ffs(nlm) - 1;
-        nlm &= nlm - 1;
-        st = o + b + 1;
-        first = false;
-        j++;
-        if ((mask >> j) == 0) break;
     }
     return valid;
 }
@@ -1001,15 +1135,16 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit_simple(DbView db, const u
         __syncthreads();
         while (queued >= (uint32_t)kEmitThreads) {
             const uint32_t k = (head + threadIdx.x) & (kEmitQueue - 1);
-            valid += emit_candidate(db, data, n, cand, marks, meta, prefix, q_cand[k], q_at[k], recs, rec_cap, totals);
+            valid += emit_warp(db, data, n, cand, marks, meta, prefix, true, q_cand[k], q_at[k], recs, rec_cap, totals);
             head += kEmitThreads;
             queued -= kEmitThreads;
         }
         __syncthreads();   // everything taken out before the next tile overwrites queue slots / scan scratch
     }
-    if (threadIdx.x < queued) {
+    if (queued) {   // whole warps, some lanes without a candidate
         const uint32_t k = (head + threadIdx.x) & (kEmitQueue - 1);
-        valid += emit_candidate(db, data, n, cand, marks, meta, prefix, q_cand[k], q_at[k], recs, rec_cap, totals);
+        const bool live = threadIdx.x < queued;
+        valid += emit_warp(db, data, n, cand, marks, meta, prefix, live, live ? q_cand[k] : 0, live ? q_at[k] : 0, recs, rec_cap, totals);
     }
     // unique valid records of the segment (count-only callers need nothing else)
     valid = __reduce_add_sync(0xffffffffu, valid);

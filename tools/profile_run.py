@@ -19,6 +19,7 @@ parser.add_argument("--set", default="c2")
 parser.add_argument("--passes", type=int, default=2)
 parser.add_argument("--quiet", action="store_true")
 parser.add_argument("--patterns", type=int, default=10000, help="pattern count of the c5 set")
+parser.add_argument("--distinct-ids", action="store_true", help="one match id per pattern (event mode, general path)")
 args = parser.parse_args()
 lib = utils._get_hyperscanner_lib()
 plants = None
@@ -46,7 +47,8 @@ dev = host.cuda()
 torch.cuda.synchronize()
 flags = [15] * len(patterns) if args.set == "c5" else None   # caseless
 for _ in range(args.passes):
-    rc, _, st = scan_buffer(lib, dev.data_ptr(), dev.numel(), 1, patterns, flags=flags, collect=False)
+    ids = list(range(len(patterns))) if args.distinct_ids else None
+    rc, _, st = scan_buffer(lib, dev.data_ptr(), dev.numel(), 1, patterns, flags=flags, ids=ids, collect=False)
     assert rc == 0
     print(f"set={args.set} bytes={st.bytes_scanned} lines={st.lines} matches={st.matches} candidates={st.candidates} "
           f"gpu_ms={st.gpu_ms:.3f} wall_ms={st.wall_ms:.3f} stream_ms={st.stream_kernel_ms:.3f} launches={st.launches} path={st.path} "
