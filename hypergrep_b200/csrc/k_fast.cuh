@@ -1,0 +1,441 @@
+// Fast-path kernels: long-line check, candidate list, local verification, record offsets, emit, segment cuts.
+// Part of the CUDA engine (engine.cu includes these files in this order; they form one translation unit).
+#pragma once
+
+namespace gpugrep {
+
+// ------------------------------------------------------------------------------------------------------------
+// FAST PATH kernels
+// ------------------------------------------------------------------------------------------------------------
+// Flags segments that may contain a line too long for the fast path: an aligned super-block of `blocks_per_super`
+// 512-byte blocks without any newline.
+__global__ void k_check_long(const unsigned long long* __restrict__ prefix, size_t nblk, size_t blocks_per_super, const unsigned long long* meta_total,
+                             Totals* totals) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t lo = j * blocks_per_super, hi = lo + blocks_per_super;
+    if (hi > nblk) return;   // partial trailing super-block cannot hide a full one
+    uint32_t a = (uint32_t)prefix[lo / kGroupBlocks];   // blocks_per_super is a multiple of kGroupBlocks
+    uint32_t b = hi < nblk ? (uint32_t)prefix[hi / kGroupBlocks] : (uint32_t)*meta_total;
+    if (a == b) atomicOr(&totals->flags, 1u);
+}
+
+// meta/prefix -> ordered list of candidate chunk indices
+__global__ void k_list_candidates(const unsigned long long* __restrict__ meta, const unsigned long long* __restrict__ prefix, size_t nblk,
+                                  uint32_t* __restrict__ cand, size_t cap, Totals* totals) {
+    const size_t ngroups = (nblk + kGroupBlocks - 1) / kGroupBlocks;
+    for (size_t grp = (size_t)blockIdx.x * blockDim.x + threadIdx.x; grp < ngroups; grp += (size_t)gridDim.x * blockDim.x) {
+        size_t at = (size_t)(prefix[grp] >> 32);
+        for (size_t g = grp * kGroupBlocks; g < nblk && g < (grp + 1) * kGroupBlocks; g++) {
+            uint32_t mask = (uint32_t)meta[g];
+            while (mask) {
+                int b = __ffs(mask) - 1;
+                mask &= mask - 1;
+                if (at < cap) cand[at] = (uint32_t)(g * 32 + b);
+                else atomicOr(&totals->flags, 2u);
+                at++;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ bool is_word_dev(uint32_t b) {
+    return (b - '0' < 10u) || ((b | 0x20u) - 'a' < 26u) || b == '_';
+}
+
+// LOCAL verification walk of one DFA group around candidate chunk [o, o+16).
+//  - starts at t (at most `lookback` bytes before the chunk, never before the line start) in the start-of-line state
+//    or in the mid-line entry state that matches the previous byte;
+//  - a NUL acts as end-of-data followed by a restart (lines with NULs are re-checked exactly by k_emit_simple);
+//  - a '\n' ends the line: the walk continues with the next line only if that line starts inside the chunk;
+//  - once past every gram hit of the chunk (idle_from: o+19, or the end of the last gram that k_verify_local found
+//    again) the walk stops as soon as the automaton is idle: a match that contains a gram hit of this chunk would
+//    still be in progress.
+// line_bit: bit of the line that contains t (bit j = j-th line intersecting the chunk).
+// Returns bit j set if the j-th line intersecting the chunk matched.
+__device__ uint32_t walk_local(const GroupDev& G, const uint8_t* __restrict__ data, size_t n, size_t o, size_t t, bool at_line_start,
+                               size_t idle_from, uint32_t line_bit) {
+    uint32_t s = 0;
+    if (!at_line_start) s = is_word_dev(data[t - 1]) ? G.mid_word : G.mid_other;
+    uint32_t mask = 0;
+    const size_t chunk_end = o + 16;
+    const uint16_t* __restrict__ flat = G.flat;
+    const uint32_t first_accept = G.first_accept, idle_end = G.idle_end;
+    if (flat) {
+        // Fast form: '\n' and NUL are ordinary columns of the table and "matched" is an absorbing state (see
+        // engine_upload), offsets are 32-bit.  The walk advances one ALIGNED WORD per step:
+        //  - a full word without a newline is four chained lookups and nothing else (no per-byte tests: a match
+        //    sticks until the line ends);
+        //  - a word with a newline, the first word of an unaligned start and the last word of the segment take the
+        //    byte-wise form below, straight-line code without inner loops (threads of a warp diverge here, so it is short).
+        // The line bit is set when the line ends in the matched state, or at the end of the walk.
+        const uint32_t end = (uint32_t)n, cend = (uint32_t)chunk_end, ifrom = (uint32_t)idle_from;
+        uint32_t pos = (uint32_t)t;
+        if (pos >= end) return G.eod_next[s] >= first_accept ? line_bit : 0u;
+        uint32_t wpos = pos & ~3u;
+        uint32_t word = *reinterpret_cast<const uint32_t*>(data + wpos);   // the buffer is padded to a multiple of 16 bytes
+        while (true) {
+            // the next word is requested before the (dependent) table lookups of this one
+            const uint32_t next_word = wpos + 4 < end ? *reinterpret_cast<const uint32_t*>(data + wpos + 4) : 0u;
+            const uint32_t x = word ^ 0x0a0a0a0au;
+            if (((x - 0x01010101u) & ~x & 0x80808080u) == 0 && pos == wpos && wpos + 4 <= end) {
+                s = flat[(s << 8) | (word & 0xffu)];
+                s = flat[(s << 8) | ((word >> 8) & 0xffu)];
+                s = flat[(s << 8) | ((word >> 16) & 0xffu)];
+                s = flat[(s << 8) | (word >> 24)];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t p = wpos + k;
+                    if (p >= pos && p < end) {
+                        const uint32_t b = (word >> (8 * k)) & 0xffu;
+                        s = flat[(s << 8) | b];
+                        if (b == '\n') {
+                            if (s >= first_accept) mask |= line_bit;
+                            if (p + 1 >= cend) return mask;   // the next line starts outside the chunk
+                            line_bit <<= 1;
+                            s = 0;
+                        }
+                    }
+                }
+            }
+            pos = wpos + 4;
+            if (s >= first_accept) {
+                if (pos >= cend) return mask | line_bit;   // matched, and no further line starts inside the chunk
+            } else if (pos >= ifrom && s < idle_end) {
+                return mask;
+            }
+            if (pos >= end) break;
+            wpos = pos;
+            word = next_word;
+        }
+        if (s >= first_accept || G.eod_next[s] >= first_accept) mask |= line_bit;
+        return mask;
+    }
+    bool done = false;
+    ByteCursor c(data, t, n);
+    while (c.pos < n) {
+        const uint32_t b = c.get();
+        if (!done) {
+            bool hit;
+            if (b == 0) {
+                hit = G.trans[s * G.stride + G.eod] >= first_accept;
+                s = 0;
+            } else {
+                s = G.trans[s * G.stride + G.cls[b]];
+                hit = s >= first_accept;
+                if (!hit && b == '\n') hit = G.trans[s * G.stride + G.eod] >= first_accept;
+            }
+            if (hit) { mask |= line_bit; done = true; }
+        }
+        c.next();
+        if (b == '\n') {
+            if (c.pos >= chunk_end || c.pos >= n) return mask;
+            line_bit <<= 1;
+            done = false;
+            s = 0;
+            continue;
+        }
+        if (c.pos >= idle_from && (done || s < idle_end)) return mask;
+        if (done && c.pos >= chunk_end) return mask;
+    }
+    if (!done && G.trans[s * G.stride + G.eod] >= first_accept) mask |= line_bit;
+    return mask;
+}
+
+constexpr int kEmitThreads = 256;
+constexpr int kEmitTile = 2048;   // candidates per emit step (and per record-offset entry): enough marked ones to keep every warp busy
+
+// The exact gram set in global memory (two-choice table, Prefilter::confirm_keys), for k_verify_local to find the hit
+// positions inside a candidate chunk again: k_stream only reports "some sampled gram of this chunk MAY be in the set".
+struct ReprobeParams {
+    const uint32_t* keys;   // null: walk the whole chunk.  A gram lives in keys[h1] or keys[half + h2]
+    const uint32_t* groups; // per slot of keys: the DFA groups (bit g mod 32) that can match around this gram
+    uint32_t mul, mul2;     // h = (gram * mul) >> shift
+    int shift;
+    uint32_t half;
+    int stride;
+    int fold;
+    int nodd;               // mixed sampling: compares at offsets 2 mod 4 (see ProbeParams)
+    uint32_t odd_mul[2], odd_add[2];
+};
+
+// One thread per candidate chunk: local verification (see walk_local); writes the bitmask of matched lines.
+// With the exact gram table at hand, the walk covers [first gram hit - lookback, end of the last gram hit] and then runs on
+// until the automaton is idle (with one hit per chunk, the usual case, a third of walking the whole chunk), and a chunk
+// that k_stream flagged only because of a bloom collision is dropped without a walk.
+__global__ void __launch_bounds__(128, 16) k_verify_local(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
+                                                          const unsigned long long* meta_total, size_t cap, uint32_t lookback, ReprobeParams rp,
+                                                          uint32_t* __restrict__ marks, uint32_t* __restrict__ tile_records) {
+    size_t ncand = (size_t)(*meta_total >> 32);
+    if (ncand > cap) ncand = cap;
+    // whole warps stay in the loop (a warp's 32 candidates are consecutive and lie in one emit tile): the records of the
+    // tile are counted with one warp reduction and one atomic
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; (i & ~(size_t)31) < ncand; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t mask = 0;
+    if (i < ncand) {
+    const size_t o = (size_t)cand[i] * 16;
+    size_t t;
+    bool at_line_start;
+    size_t idle_from = o + 19;
+    uint32_t line_bit = 1u;
+    uint32_t group_mask = 0xffffffffu;   // DFA groups to walk
+    if (lookback == 0xffffffffu) {
+        t = line_start_of(data, o);
+        at_line_start = true;
+    } else {
+        size_t hi = o;   // the walk has to start at or before hi - lookback
+        uint32_t nl_in_chunk = 0;
+        if (rp.keys) {
+            const uint4 v = ld_chunk(data, o, n);
+            uint32_t w[5] = {v.x, v.y, v.z, v.w, o + 16 < n ? ld_chunk(data, o + 16, n).x : 0u};
+            if (rp.fold) {
+#pragma unroll
+                for (int k = 0; k < 5; k++) w[k] |= 0x20202020u;
+            }
+            uint32_t hits = 0;   // bit = byte offset of a sampled gram that is in the table
+            group_mask = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                for (int sft = 0; sft < 4; sft += rp.stride) {
+                    const uint32_t gram = __funnelshift_r(w[k], w[k + 1], 8 * sft);
+                    const uint32_t h1 = (gram * rp.mul) >> rp.shift, h2 = rp.half + ((gram * rp.mul2) >> rp.shift);
+                    const uint32_t e1 = rp.keys[h1], e2 = rp.keys[h2];
+                    if (e1 == gram || e2 == gram) {
+                        hits |= 1u << (4 * k + sft);
+                        group_mask |= rp.groups[e1 == gram ? h1 : h2];
+                    }
+                }
+                if (rp.nodd) {
+                    const uint32_t gram = __funnelshift_r(w[k], w[k + 1], 16);
+                    for (int c = 0; c < rp.nodd; c++)
+                        if (gram * rp.odd_mul[c] + rp.odd_add[c] == 0u) { hits |= 1u << (4 * k + 2); group_mask = 0xffffffffu; }
+                }
+            }
+            if (hits == 0) { marks[i] = 0; goto counted; }   // a bloom collision: no gram of the set here
+            const uint32_t first = __ffs(hits) - 1, last = 31 - __clz(hits);
+            hi = o + first;
+            idle_from = o + last + 4;
+            nl_in_chunk = newline_mask16(v) & ((1u << first) - 1u);   // newlines in [o, hi)
+        }
+        // start: at most `lookback` bytes before the first hit, rounded down to a word, never before the line start
+        size_t lo = hi > lookback ? (hi - lookback) & ~(size_t)3 : 0;
+        t = lo;
+        at_line_start = lo == 0;
+        if (nl_in_chunk) {
+            const uint32_t after = 32 - __clz(nl_in_chunk);   // offset just past the last newline before the hit
+            t = o + after;
+            at_line_start = true;
+            line_bit = 1u << __popc(nl_in_chunk);
+        } else {
+            size_t p = o;   // 16-byte aligned; scan words [p-4, p) downwards for the last '\n' in [lo, o) (nothing to scan if lo >= o)
+            while (p > lo) {
+                uint32_t z = eq_mask4(*reinterpret_cast<const uint32_t*>(data + p - 4), 0x0a0a0a0au);
+                if (p - 4 < lo) z &= ~((1u << (8 * (uint32_t)(lo - (p - 4)))) - 1u);
+                if (z) {
+                    t = (p - 4) + ((31 - __clz(z)) >> 3) + 1;
+                    at_line_start = true;
+                    break;
+                }
+                p -= 4;
+            }
+        }
+    }
+    for (int g = 0; g < db.ngroups; g++)
+        if ((group_mask >> (g & 31)) & 1u) mask |= walk_local(db.groups[g], data, n, o, t, at_line_start, idle_from, line_bit);
+    marks[i] = mask;
+    }
+counted:
+    const uint32_t records = __reduce_add_sync(0xffffffffu, __popc(mask));
+    if ((threadIdx.x & 31) == 0 && records) atomicAdd(&tile_records[i / kEmitTile], records);
+    }
+}
+
+// Exclusive scan of the per-tile record counts (a few thousand entries: one block), in place; total -> *rec_total.
+__global__ void __launch_bounds__(1024) k_tile_offsets(uint32_t* __restrict__ tile_records, const unsigned long long* meta_total, size_t cap,
+                                                       unsigned long long* rec_total) {
+    __shared__ unsigned long long s_warp[32], s_total;
+    size_t ncand = (size_t)(*meta_total >> 32);
+    if (ncand > cap) ncand = cap;
+    const size_t ntiles = (ncand + kEmitTile - 1) / kEmitTile;
+    unsigned long long running = 0;
+    for (size_t base = 0; base < ntiles; base += blockDim.x) {
+        const size_t k = base + threadIdx.x;
+        const unsigned long long v = k < ntiles ? tile_records[k] : 0ull;
+        const unsigned long long ex = block_exclusive_scan(v, s_warp, &s_total);
+        if (k < ntiles) tile_records[k] = (uint32_t)(running + ex);
+        running += s_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *rec_total = running;
+}
+
+// Candidates with marked lines are first compacted per block (few candidates carry a match), then one thread per
+// marked candidate computes line extents, line numbers and the exact re-check of lines with NULs.
+// The same line can be marked by several candidate chunks; records come out ordered by line start, so the host
+// drops adjacent duplicates.
+// Records of one marked candidate chunk per lane (see k_emit_simple); returns the number of valid records the lane wrote.
+// Called by whole warps (`live` = this lane has a candidate): the lanes go through their marked lines round by round, and
+// in every round the line extents that a lane did not settle within kEmitBound bytes are finished by the whole warp.
+constexpr size_t kEmitBound = 256;
+__device__ uint32_t emit_warp(const DbView& db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
+                              const uint32_t* __restrict__ marks, const unsigned long long* __restrict__ meta,
+                              const unsigned long long* __restrict__ prefix, bool live, size_t i, size_t at, LineRec* __restrict__ recs,
+                              size_t rec_cap, Totals* totals) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t valid = 0;
+    uint32_t mask = live ? marks[i] : 0u;
+    const size_t o = live ? (size_t)cand[i] * 16 : 0;
+    uint32_t nlm = 0;
+    if (live) {
+        nlm = newline_mask16(ld_chunk(data, o, n));
+        if (o + 16 > n) nlm &= (1u << (n - o)) - 1u;
+    }
+    // line j of the chunk starts at `st` (j = 0: somewhere before the chunk, found below); `first` = still on line 0
+    size_t st = 0;
+    bool first = true;
+    while (__any_sync(0xffffffffu, mask != 0)) {
+        // skip lines of the chunk that are not marked
+        while (mask != 0 && !(mask & 1u)) {
+            if (!nlm) { mask = 0; break; }
+            st = o + __ffs(nlm);
+            nlm &= nlm - 1;
+            first = false;
+            mask >>= 1;
+        }
+        const bool work = mask != 0;
+        // ---- line start (only line 0 starts before the chunk)
+        bool settled = true;
+        if (work && first) settled = line_start_bounded(data, o, kEmitBound, &st);
+        for (uint32_t pend = __ballot_sync(0xffffffffu, work && !settled); pend; pend &= pend - 1) {
+            const int src = __ffs(pend) - 1;
+            const size_t found = warp_line_start(data, (size_t)__shfl_sync(0xffffffffu, (unsigned long long)st, src));
+            if ((int)lane == src) st = found;
+        }
+        // ---- line end
+        bool has_nul = false;
+        size_t en = 0;
+        settled = true;
+        if (work) settled = line_end_bounded(data, st, n, kEmitBound, &en, &has_nul);
+        for (uint32_t pend = __ballot_sync(0xffffffffu, work && !settled); pend; pend &= pend - 1) {
+            const int src = __ffs(pend) - 1;
+            bool more_nul = false;
+            const size_t found = warp_line_end(data, (size_t)__shfl_sync(0xffffffffu, (unsigned long long)en, src), n, &more_nul);
+            if ((int)lane == src) { en = found; has_nul |= more_nul; }
+        }
+        if (work) {
+            bool ok = true;
+            if (first) {
+                // the line started before this chunk: an earlier candidate chunk that intersects it may have marked it
+                // already (the line is the LAST line of such a chunk); only the first marking is kept.  (A repeat still
+                // gets its extents and line number computed: its neighbours in the warp need that work anyway.)
+                for (size_t k = i; k-- > 0;) {
+                    const size_t ok_off = (size_t)cand[k] * 16;
+                    if (ok_off + 16 <= st) break;
+                    const uint32_t mk = marks[k];
+                    if (!mk) continue;
+                    uint4 pv = ld_chunk(data, ok_off, n);
+                    const uint32_t last_idx = __popc(newline_mask16(pv) & 0x7fffu);   // line starts inside that chunk
+                    if ((mk >> last_idx) & 1u) { ok = false; break; }
+                }
+            }
+            if (ok && has_nul) ok = block_matches<false>(db, data, st, en);
+            valid += ok ? 1u : 0u;
+            // line number = newlines before the line start: whole blocks from the scan, then the part of the line's own
+            // 512-byte block, counted from whichever end of the block is nearer (the block's total is in meta)
+            const size_t lb = st >> 9;
+            uint32_t line_no = newlines_before_block(prefix, meta, lb);
+            if ((st & 511) <= 256) line_no += count_newlines(data, lb << 9, st);
+            else line_no += (uint32_t)(meta[lb] >> 32) - count_newlines(data, st, min((lb + 1) << 9, n));
+            if (at < rec_cap) recs[at] = LineRec{line_no, (uint32_t)st, ok ? ((uint32_t)(en - st) | (has_nul ? kHasNulBit : 0u)) : kInvalidLen};
+            else atomicOr(&totals->flags, 4u);
+            at++;
+            // on to the next line of the chunk
+            if (!nlm) mask = 0;
+            else {
+                st = o + __ffs(nlm);
+                nlm &= nlm - 1;
+                first = false;
+                mask >>= 1;
+            }
+        }
+    }
+    return valid;
+}
+
+// Persistent blocks walk tiles of kEmitTile candidates.  The marked candidates of a tile (about one in six) go into a
+// shared-memory queue together with their record offset (tile offset from k_tile_offsets + a block scan inside the
+// tile); the block takes them out in FULL batches of one per thread and carries the remainder over to the next tile, so
+// that the expensive per-record work runs with every thread busy instead of a last, mostly empty round per tile.
+constexpr uint32_t kEmitQueue = 4096;   // >= kEmitTile + kEmitThreads, power of two
+__global__ void __launch_bounds__(kEmitThreads) k_emit_simple(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
+                                                              const uint32_t* __restrict__ marks, const uint32_t* __restrict__ tile_offsets,
+                                                              const unsigned long long* __restrict__ meta, const unsigned long long* __restrict__ prefix,
+                                                              const unsigned long long* meta_total, size_t cap, LineRec* __restrict__ recs, size_t rec_cap,
+                                                              Totals* totals) {
+    __shared__ uint32_t q_cand[kEmitQueue], q_at[kEmitQueue];
+    __shared__ unsigned long long s_warp[kEmitThreads / 32], s_total;
+    uint32_t valid = 0;
+    uint32_t head = 0, queued = 0;   // the same in every thread of the block
+    size_t ncand = (size_t)(*meta_total >> 32);
+    if (ncand > cap) ncand = cap;
+    constexpr int kPer = kEmitTile / kEmitThreads;   // consecutive candidates per thread in the compaction step
+    for (size_t block_base = (size_t)blockIdx.x * kEmitTile; block_base < ncand; block_base += (size_t)gridDim.x * kEmitTile) {
+        uint32_t mk[kPer];
+        uint32_t records = 0, marked = 0;
+#pragma unroll
+        for (int j = 0; j < kPer; j++) {
+            const size_t i = block_base + (size_t)threadIdx.x * kPer + j;
+            mk[j] = i < ncand ? marks[i] : 0u;
+            records += __popc(mk[j]);
+            marked += mk[j] != 0u;
+        }
+        // one scan for both: queue position (marked candidates before mine) and record offset (records before mine)
+        const unsigned long long before = block_exclusive_scan(((unsigned long long)marked << 32) | records, s_warp, &s_total);
+        uint32_t slot = head + queued + (uint32_t)(before >> 32);
+        uint32_t at = tile_offsets[block_base / kEmitTile] + (uint32_t)before;
+#pragma unroll
+        for (int j = 0; j < kPer; j++) {
+            if (mk[j]) {
+                q_cand[slot & (kEmitQueue - 1)] = (uint32_t)(block_base + (size_t)threadIdx.x * kPer + j);
+                q_at[slot & (kEmitQueue - 1)] = at;
+                slot++;
+                at += __popc(mk[j]);
+            }
+        }
+        queued += (uint32_t)(s_total >> 32);
+        __syncthreads();
+        while (queued >= (uint32_t)kEmitThreads) {
+            const uint32_t k = (head + threadIdx.x) & (kEmitQueue - 1);
+            valid += emit_warp(db, data, n, cand, marks, meta, prefix, true, q_cand[k], q_at[k], recs, rec_cap, totals);
+            head += kEmitThreads;
+            queued -= kEmitThreads;
+        }
+        __syncthreads();   // everything taken out before the next tile overwrites queue slots / scan scratch
+    }
+    if (queued) {   // whole warps, some lanes without a candidate
+        const uint32_t k = (head + threadIdx.x) & (kEmitQueue - 1);
+        const bool live = threadIdx.x < queued;
+        valid += emit_warp(db, data, n, cand, marks, meta, prefix, live, live ? q_cand[k] : 0, live ? q_at[k] : 0, recs, rec_cap, totals);
+    }
+    // unique valid records of the segment (count-only callers need nothing else)
+    valid = __reduce_add_sync(0xffffffffu, valid);
+    if ((threadIdx.x & 31) == 0 && valid) atomicAdd(&totals->aux_total, (unsigned long long)valid);
+}
+
+// Device-resident inputs: the end of segment j is the byte after a '\n' before boundary (j+1)*chunk, chosen so that the
+// NEXT segment starts 16-byte aligned (the kernels use 16-byte loads): one line end in 16 qualifies on average.
+// One thread per boundary scans backwards (gives up after `window` bytes -> 0 = not found).
+__global__ void k_find_cuts(const uint8_t* __restrict__ data, size_t size, size_t chunk, size_t window, size_t ncuts, unsigned long long* __restrict__ cuts) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ncuts) return;
+    size_t b = (j + 1) * chunk;
+    if (b >= size) { cuts[j] = size; return; }
+    size_t lo = b > window ? b - window : 0;
+    unsigned long long found = 0;
+    for (size_t p = b; p > lo; p--) {
+        if ((p & 15) == 0 && data[p - 1] == '\n') { found = p; break; }
+    }
+    cuts[j] = found;
+}
+
+}  // namespace gpugrep
