@@ -256,3 +256,34 @@ def test_every_optimisation_switch_gives_the_same_result(switch, gpu_lib, oracle
     assert parity.compare(gpu_lib, oracle_lib, data, ["ERROR", "connection reset by peer", tag]) > 10   # mixed sampling
     assert parity.compare(gpu_lib, oracle_lib, data, synth.C2_PATTERNS + [tag]) > 100
     parity.compare(gpu_lib, oracle_lib, data, ["(?i)error", "Port [0-9]+", tag], flags=[14, 15, 14])
+
+
+def test_long_lines_with_nuls_take_the_cooperative_searches(gpu_lib, oracle_lib):
+    """Lines of 0.3-6 KiB (longer than the per-thread bound of the emit kernel, so their extents are finished by the
+    whole warp), some with NUL bytes before or after the match: the strip / cut rule (hyperscanner.c:205-217) decides
+    whether the line counts, and the has-NUL hint must survive the hand-over between the two searches."""
+    import random
+    rng = random.Random(99)
+    words = ["alpha", "bravo", "charlie", "delta", "echo", "foxtrot", "golf", "hotel", "india", "juliett"]
+    lines = []
+    for k in range(400):
+        target = rng.choice([40, 300, 900, 2500, 6000])
+        parts = []
+        size = 0
+        while size < target:
+            w = rng.choice(words) + str(rng.randint(0, 999))
+            parts.append(w)
+            size += len(w) + 1
+        if rng.random() < 0.5:
+            parts.insert(rng.randint(0, len(parts)), "needle-in-haystack")
+        text = " ".join(parts)
+        roll = rng.random()
+        if roll < 0.25:   # a NUL somewhere: a match behind it must not count, one in front of it must
+            at = rng.randint(0, len(text))
+            text = text[:at] + "\0" + text[at:]
+        elif roll < 0.35:
+            text = "\0\0" + text   # leading NULs are stripped
+        lines.append(text)
+    data = ("\n".join(lines) + "\n").encode("latin1")
+    assert parity.compare(gpu_lib, oracle_lib, data, ["needle-in-haystack"]) > 50
+    parity.compare(gpu_lib, oracle_lib, data, ["needle-in-haystack", "juliett9[0-9]{2}$", "^alpha1"])
