@@ -121,6 +121,10 @@ private:
 };
 
 constexpr size_t kSampleBytes = 512 << 10;   // head of the input used to tune the prefilter windows
+std::mutex g_plain_mu;                       // admission of plain-file scans (see scan_file)
+std::condition_variable g_plain_cv;
+int g_plain_scans = 0;
+constexpr int kMaxPlainScans = 4;
 
 // Sample-tuned prefilter tables, cached per (database, device, sample fingerprint).  `sample` must hold the first
 // min(len, 64 KiB) bytes (the fingerprint); `fetch_full`, if given, returns a pointer to all `len` bytes and is only
@@ -393,7 +397,26 @@ int scan_file(const char* path, const Params& pr, gpugrep_stats* stats_out) {
     if (!src) { set_last_error(err); return GPUGREP_GZ_OPEN; }
 
     const size_t limit = clamp_limit(pr.buffer_size);
-    size_t chunk = env_mb("GPUGREP_CHUNK_MB", 64);
+    // Segment (= pinned slot) size and admission.  Every slot costs pinned memory that has to be allocated and pinned first:
+    // a cold process scanning 16 plain files at once (multiscanner: one host thread per file) paid seconds for 45 slots of
+    // 64 MiB.  Four plain-file scans at a time already saturate the PCIe link, so the others wait their turn; compressed
+    // sources deliver ~1 GB/s per file, all run at once (the decoders are the work) and take small slots.
+    const bool plain = std::strcmp(src->kind(), "plain") == 0;
+    struct Admission {
+        bool held;
+        explicit Admission(bool gate) : held(gate) {
+            if (!held) return;
+            std::unique_lock<std::mutex> lk(g_plain_mu);
+            g_plain_cv.wait(lk, [] { return g_plain_scans < kMaxPlainScans; });
+            g_plain_scans++;
+        }
+        ~Admission() {
+            if (!held) return;
+            { std::lock_guard<std::mutex> lk(g_plain_mu); g_plain_scans--; }
+            g_plain_cv.notify_one();
+        }
+    } admission(plain);
+    size_t chunk = env_mb("GPUGREP_CHUNK_MB", plain ? 32 : 8);
     chunk = std::max(chunk, 2 * limit + 4096);
     chunk = std::min(chunk, kMaxSegmentBytes);
     constexpr int kSlots = 3;
@@ -416,6 +439,10 @@ int scan_file(const char* path, const Params& pr, gpugrep_stats* stats_out) {
     std::thread reader([&] {
         std::vector<uint8_t> carry;
         bool eof = false;
+        // the first segments are short so that the copy engine and the kernels start early (a 128 MiB file would otherwise
+        // spend a third of its time reading the first 64 MiB with the GPU idle)
+        const size_t floor_bytes = 2 * limit + 4096;
+        size_t target = std::min(chunk, std::max(floor_bytes, (size_t)8 << 20));
         while (!eof) {
             int slot;
             {
@@ -430,12 +457,13 @@ int scan_file(const char* path, const Params& pr, gpugrep_stats* stats_out) {
             size_t have = carry.size();
             size_t cut = 0;
             while (true) {
-                size_t got = src->read(buf + have, chunk - have);
+                size_t got = src->read(buf + have, target - have);
                 have += got;
                 if (got == 0) eof = true;
                 cut = cut_point(buf, have, eof, limit);
-                if (cut > 0 || eof || have == chunk) break;
+                if (cut > 0 || eof || have == target) break;
             }
+            target = std::min(chunk, target * 4);
             if (cut == 0 && !eof) cut = have;   // cannot happen (chunk >= 2*limit): defensive
             carry.assign(buf + cut, buf + have);
             std::lock_guard<std::mutex> lk(q.mu);

@@ -317,13 +317,16 @@ ScanSlot* engine_acquire_slot(std::string& error) {
     if (cudaGetDevice(&dev) != cudaSuccess) { error = "cudaGetDevice failed"; return nullptr; }
     {
         std::lock_guard<std::mutex> lk(g_mu);
-        for (size_t i = 0; i < g_free_slots.size(); i++) {
-            if (g_free_slots[i]->device == dev) {
-                ScanSlot* s = g_free_slots[i];
-                g_free_slots.erase(g_free_slots.begin() + i);
-                s->in_use = true;
-                return s;
-            }
+        // the free slot with the largest pinned buffer: a small working set of slots is reused and grown once, instead
+        // of every pooled slot being re-pinned in turn (growing a pinned buffer frees the old one, which syncs the device)
+        size_t best = g_free_slots.size();
+        for (size_t i = 0; i < g_free_slots.size(); i++)
+            if (g_free_slots[i]->device == dev && (best == g_free_slots.size() || g_free_slots[i]->h_stage.cap > g_free_slots[best]->h_stage.cap)) best = i;
+        if (best < g_free_slots.size()) {
+            ScanSlot* s = g_free_slots[best];
+            g_free_slots.erase(g_free_slots.begin() + best);
+            s->in_use = true;
+            return s;
         }
     }
     ScanSlot* s = new ScanSlot();

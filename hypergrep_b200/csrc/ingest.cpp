@@ -8,6 +8,7 @@
 
 #include <sys/stat.h>
 
+#include <atomic>
 #include <cerrno>
 #include <cstring>
 #include <mutex>
@@ -19,6 +20,10 @@ namespace {
 
 std::mutex g_zstd_mu;
 std::string g_zstd_path = "libzstd.so.1";
+
+// Helper threads of all plain-file reads of the process (multiscanner runs one scan per host thread): together they
+// never exceed the cores of the machine, so fifteen concurrent scans read with one thread each instead of 15 x 14.
+std::atomic<int> g_read_helpers{0};
 
 // raw file with a small look-ahead buffer
 class RawFile {
@@ -55,8 +60,17 @@ public:
         if (got == cap) return got;
         if (!regular_) return got + f_->read(dst + got, cap - got);
         size_t want = cap - got;
-        unsigned hw = std::thread::hardware_concurrency();
-        size_t nthreads = want >= ((size_t)8 << 20) ? std::min<size_t>(16, std::max(1u, hw > 2 ? hw - 2 : 1)) : 1;
+        // threads for this read: what is left of the process-wide budget (cores - 2, at most 16)
+        const int hw = (int)std::thread::hardware_concurrency();
+        const int budget = std::max(1, std::min(16, hw > 2 ? hw - 2 : 1));
+        int taken = 0;
+        if (want >= ((size_t)8 << 20)) {
+            int busy = g_read_helpers.load();
+            while (busy < budget && !g_read_helpers.compare_exchange_weak(busy, budget)) {}
+            taken = busy < budget ? budget - busy : 0;
+        }
+        struct GiveBack { int n; ~GiveBack() { if (n) g_read_helpers.fetch_sub(n); } } give_back{taken};
+        const size_t nthreads = (size_t)std::max(1, taken);
         if (nthreads <= 1) {
             size_t r = pread_all(dst + got, want, offset_);
             offset_ += r;

@@ -133,6 +133,9 @@ def check_compatibility(patterns: list, flags: Sequence[int] = ()) -> int:
     return lib.check_patterns(pattern_array, flags_array, ids_array, len(pattern_array))
 
 
+_GREP_BATCH = 4096   # results per callback when grep() collects lines (the reference's scan() default is 16)
+
+
 def scan(  # pylint: disable=too-many-arguments
     path: str,
     patterns: Sequence[str],
@@ -174,6 +177,46 @@ def scan(  # pylint: disable=too-many-arguments
     except KeyboardInterrupt:
         outcome["rc"] = _RC_INTERRUPTED
     return outcome["rc"]
+
+
+class _Stats(ctypes.Structure):
+    """gpugrep_stats (include/gpugrep.h)."""
+
+    _fields_ = [
+        ("bytes_scanned", ctypes.c_ulonglong), ("lines", ctypes.c_ulonglong), ("matches", ctypes.c_ulonglong),
+        ("candidates", ctypes.c_ulonglong), ("h2d_bytes", ctypes.c_ulonglong), ("d2h_bytes", ctypes.c_ulonglong),
+        ("gpu_ms", ctypes.c_double), ("stream_kernel_ms", ctypes.c_double), ("wall_ms", ctypes.c_double),
+        ("launches", ctypes.c_uint), ("stream_launches", ctypes.c_uint), ("segments", ctypes.c_uint), ("path", ctypes.c_uint),
+    ]
+
+
+def _count_matches(path: str, patterns: Sequence[str], flags: Sequence[int], max_match_count: int) -> tuple[int, int] | None:
+    """Count-only scan without a callback: the library counts on the device and copies no line back
+    (gpugrep_scan_file with on_event = NULL).  Returns None if the loaded library has no such entry point (a plain
+    libhyperscanner.so), in which case the caller counts through the callback like the reference does."""
+    lib = _get_hyperscanner_lib()
+    try:
+        entry = lib.gpugrep_scan_file
+    except AttributeError:
+        return None
+    entry.restype = ctypes.c_int
+    entry.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p,
+                      ctypes.c_int, ctypes.c_int, ctypes.c_ulonglong, ctypes.c_void_p]
+    pattern_array, flags_array, ids_array = prepare_patterns(patterns, flags=flags)
+    stats = _Stats()
+    outcome = {"rc": 0}
+
+    def _run() -> None:
+        outcome["rc"] = entry(path.encode(), pattern_array, flags_array, ids_array, len(pattern_array), None, 262140, 16,
+                              max_match_count, ctypes.byref(stats))
+
+    worker = threading.Thread(target=_run, daemon=True)   # same interruptible wait as scan()
+    worker.start()
+    try:
+        worker.join(timeout=3600)
+    except KeyboardInterrupt:
+        return 0, _RC_INTERRUPTED
+    return int(stats.matches), outcome["rc"]
 
 
 def grep(  # pylint: disable=too-many-arguments
@@ -223,11 +266,17 @@ def grep(  # pylint: disable=too-many-arguments
                 collected.append((record.line_number + 1, text))
 
     pattern_flags = _DEFAULT_FLAGS | (HS_FLAG_CASELESS if ignore_case else 0)
+    if count_only:
+        # counting needs no line copies and no Python frame per batch of 16 results
+        counted = _count_matches(file, patterns, [pattern_flags] * len(patterns), max_match_count)
+        if counted is not None:
+            return counted
     code = scan(
         file,
         patterns,
         _on_batch,
         flags=[pattern_flags] * len(patterns),
         max_match_count=max_match_count,
+        buffer_count=_GREP_BATCH,
     )
     return (counter[0] if count_only else collected), code
