@@ -123,8 +123,9 @@ private:
 constexpr size_t kSampleBytes = 512 << 10;   // head of the input used to tune the prefilter windows
 std::mutex g_plain_mu;                       // admission of plain-file scans (see scan_file)
 std::condition_variable g_plain_cv;
-int g_plain_scans = 0;
-constexpr int kMaxPlainScans = 4;
+constexpr int kMaxDevices = 64;              // power of two
+int g_plain_scans[kMaxDevices] = {};
+constexpr int kMaxPlainScans = 4;            // per device
 
 // Sample-tuned prefilter tables, cached per (database, device, sample fingerprint).  `sample` must hold the first
 // min(len, 64 KiB) bytes (the fingerprint); `fetch_full`, if given, returns a pointer to all `len` bytes and is only
@@ -402,18 +403,19 @@ int scan_file(const char* path, const Params& pr, gpugrep_stats* stats_out) {
     // 64 MiB.  Four plain-file scans at a time already saturate the PCIe link, so the others wait their turn; compressed
     // sources deliver ~1 GB/s per file, all run at once (the decoders are the work) and take small slots.
     const bool plain = std::strcmp(src->kind(), "plain") == 0;
-    struct Admission {
+    struct Admission {   // per device: files are spread round-robin over the visible GPUs
         bool held;
-        explicit Admission(bool gate) : held(gate) {
+        int device;
+        explicit Admission(bool gate) : held(gate), device(engine_current_device() & (kMaxDevices - 1)) {
             if (!held) return;
             std::unique_lock<std::mutex> lk(g_plain_mu);
-            g_plain_cv.wait(lk, [] { return g_plain_scans < kMaxPlainScans; });
-            g_plain_scans++;
+            g_plain_cv.wait(lk, [this] { return g_plain_scans[device] < kMaxPlainScans; });
+            g_plain_scans[device]++;
         }
         ~Admission() {
             if (!held) return;
-            { std::lock_guard<std::mutex> lk(g_plain_mu); g_plain_scans--; }
-            g_plain_cv.notify_one();
+            { std::lock_guard<std::mutex> lk(g_plain_mu); g_plain_scans[device]--; }
+            g_plain_cv.notify_all();
         }
     } admission(plain);
     size_t chunk = env_mb("GPUGREP_CHUNK_MB", plain ? 32 : 8);
