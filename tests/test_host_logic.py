@@ -104,3 +104,33 @@ def test_default_buffer_boundary_lines(hostmock_lib, oracle_lib):
     assert parity.compare(hostmock_lib, oracle_lib, data, ["foo"]) >= 8
     parity.compare(hostmock_lib, oracle_lib, data, ["foo", "bar"], flags=[14, 6], ids=[1, 2])
     parity.compare(hostmock_lib, oracle_lib, data, ["o{2}$", "^x+foo"])
+
+
+def test_grep_count_only_paths_agree(hostmock_lib, tmp_path, monkeypatch):
+    """grep(count_only=True) counts inside the library (gpugrep_scan_file with a NULL callback, no Python frame per batch);
+    with a library that lacks that entry point (a plain libhyperscanner.so) it counts through the callback like the
+    reference (utils.py:199-203).  Both must equal the number of collected lines, with and without max_match_count."""
+    from hypergrep_b200 import utils
+
+    text = b"".join(b"line %d %s\n" % (k, b"foobar" if k % 3 == 0 else b"nothing") for k in range(5000))
+    path = tmp_path / "count.log"
+    path.write_bytes(text)
+    monkeypatch.setattr(utils, "_get_hyperscanner_lib", lambda: hostmock_lib)
+    lines, rc = utils.grep(str(path), ["foobar", "^line 7 "])
+    assert rc == 0 and len(lines) == 1667 + 1   # line 7 is no multiple of 3
+    for limit in (0, 1, 16, 17, 1000):
+        expected = len(lines) if limit == 0 else min(limit, len(lines))
+        assert utils.grep(str(path), ["foobar", "^line 7 "], count_only=True, max_match_count=limit) == (expected, 0)
+
+    class CallbackOnly:   # what a library exporting only the reference's two symbols looks like
+        hyperscan = hostmock_lib.hyperscan
+        check_patterns = hostmock_lib.check_patterns
+
+        def __getattr__(self, name):
+            raise AttributeError(name)
+
+    monkeypatch.setattr(utils, "_get_hyperscanner_lib", CallbackOnly)
+    assert utils._count_matches(str(path), ["foobar"], [14], 0) is None
+    for limit in (0, 17):
+        expected = len(lines) if limit == 0 else limit
+        assert utils.grep(str(path), ["foobar", "^line 7 "], count_only=True, max_match_count=limit) == (expected, 0)
