@@ -269,10 +269,10 @@ __global__ void __launch_bounds__(1024) k_tile_offsets(uint32_t* __restrict__ ti
     if (threadIdx.x == 0) *rec_total = running;
 }
 
-// Candidates with marked lines are first compacted per block (few candidates carry a match), then one thread per
-// marked candidate computes line extents, line numbers and the exact re-check of lines with NULs.
-// The same line can be marked by several candidate chunks; records come out ordered by line start, so the host
-// drops adjacent duplicates.
+// Emit: candidates with marked lines are compacted per block (few candidates carry a match), then one thread per marked
+// candidate computes line extents, line numbers and the exact re-check of lines with NULs.  The same line can be marked
+// by several candidate chunks: only the first marking yields a valid record, the others are written as kInvalidLen
+// records (their slot was reserved by the record offsets) and skipped by the host.
 // Records of one marked candidate chunk per lane (see k_emit_simple); returns the number of valid records the lane wrote.
 // Called by whole warps (`live` = this lane has a candidate): the lanes go through their marked lines round by round, and
 // in every round the line extents that a lane did not settle within kEmitBound bytes are finished by the whole warp.
