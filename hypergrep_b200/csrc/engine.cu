@@ -445,7 +445,7 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
             s->data = dev_data;
         }
     }
-    s->cand_cap = n / 64 + 4096;
+    s->cand_cap = n / 32 + 4096;   // half of all 16-byte chunks; beyond that the segment falls back to the general path
     s->rec_cap = n / 48 + 4096;
     size_t nb_scan = (std::max(s->nblk, s->cand_cap) + kScanTile - 1) / kScanTile + 1;
     if (s->d_meta.reserve((s->nblk + 8) * 8) != cudaSuccess || s->d_prefix.reserve((s->nblk + 8) * 8) != cudaSuccess ||
