@@ -287,3 +287,19 @@ def test_long_lines_with_nuls_take_the_cooperative_searches(gpu_lib, oracle_lib)
     data = ("\n".join(lines) + "\n").encode("latin1")
     assert parity.compare(gpu_lib, oracle_lib, data, ["needle-in-haystack"]) > 50
     parity.compare(gpu_lib, oracle_lib, data, ["needle-in-haystack", "juliett9[0-9]{2}$", "^alpha1"])
+
+
+def test_fast_path_capacity_overflow_falls_back(gpu_lib, oracle_lib):
+    """A text in which more than half of all 16-byte chunks hold a gram of the set overflows the candidate list of the
+    fast path; a text of very short matching lines overflows its record buffer.  Both segments are redone on the
+    general path (stats.path bit 1) with identical results."""
+    from gpu_api import scan_buffer as scan
+    import torch
+
+    dense = (b"abcdabcdabcdabcd" * 40 + b"\n") * 3000 + b"tail without the gram\n"
+    short = b"abcd\n" * 200000
+    for data in (dense, short):
+        assert parity.compare(gpu_lib, oracle_lib, data, ["abcd"]) > 1000
+        dev = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+        rc, _, st = scan(gpu_lib, dev.data_ptr(), dev.numel(), 1, ["abcd"], collect=False)
+        assert rc == 0 and (st.path & 2), "expected the general-path fallback"
