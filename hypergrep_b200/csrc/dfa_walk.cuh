@@ -48,6 +48,37 @@ __device__ bool block_matches(const DbView& db, const uint8_t* data, size_t star
     for (int g = 0; g < db.ngroups; g++) {
         const GroupDev G = db.groups[g];
         uint32_t s = 0;
+        if (G.flat) {
+            // byte-indexed table with an absorbing "matched" state and the end-of-line rule folded into the '\n' column
+            // (engine_upload): one load per byte, and aligned words without '\n' / NUL take four chained loads and one test
+            const uint16_t* __restrict__ flat = G.flat;
+            const uint32_t fa = G.first_accept;
+            size_t pos = p0;
+            bool open = true;   // no '\n' / NUL seen yet: the block ends at lim and needs the end-of-data transition
+            while (pos < lim) {
+                if ((pos & 3) == 0 && pos + 4 <= lim) {
+                    const uint32_t word = *reinterpret_cast<const uint32_t*>(data + pos);
+                    if ((haszero4(word) | haszero4(word ^ 0x0a0a0a0au)) == 0) {
+                        s = flat[(s << 8) | (word & 0xffu)];
+                        s = flat[(s << 8) | ((word >> 8) & 0xffu)];
+                        s = flat[(s << 8) | ((word >> 16) & 0xffu)];
+                        s = flat[(s << 8) | (word >> 24)];
+                        pos += 4;
+                        if (s >= fa) return true;
+                        if (s == G.dead) { open = false; break; }
+                        continue;
+                    }
+                }
+                const uint32_t b = data[pos];
+                if (b == 0) break;   // end of the block: end-of-data transition below
+                s = flat[(s << 8) | b];
+                pos++;
+                if (s >= fa) return true;
+                if (b == '\n' || s == G.dead) { open = false; break; }
+            }
+            if (open && G.eod_next[s] >= fa) return true;
+            continue;
+        }
         bool dead = false;
         ByteCursor c(data, p0, lim);
         while (c.pos < lim) {
