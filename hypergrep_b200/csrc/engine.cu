@@ -514,7 +514,9 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
         // record offsets per emit tile of kEmitTile candidates: counted by the verification kernel, scanned by one block
         uint32_t* tile_records = s->d_recoff.as<uint32_t>();
         CUDA_TRY(cudaMemsetAsync(tile_records, 0, (s->cand_cap / kEmitTile + 2) * sizeof(uint32_t), st));
-        k_verify_local<<<vgrid, 128, 0, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->lookback, rp,
+        // the last sampled gram of a chunk starts at offset 16 - stride (14 with the compares of mixed sampling) and is 4 bytes long
+        const uint32_t idle_span = pf->nodd ? 18u : 20u - (uint32_t)pf->stride;
+        k_verify_local<<<vgrid, 128, 0, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->lookback, idle_span, rp,
                                               s->d_res.as<uint32_t>(), tile_records);
         k_tile_offsets<<<1, 1024, 0, st>>>(tile_records, &dT->meta_total, s->cand_cap, &dT->rec_total);
         static const unsigned emit_resident = resident_grid(k_emit_simple, kEmitThreads);

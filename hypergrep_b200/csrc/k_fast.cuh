@@ -47,7 +47,7 @@ __device__ __forceinline__ bool is_word_dev(uint32_t b) {
 //    or in the mid-line entry state that matches the previous byte;
 //  - a NUL acts as end-of-data followed by a restart (lines with NULs are re-checked exactly by k_emit_simple);
 //  - a '\n' ends the line: the walk continues with the next line only if that line starts inside the chunk;
-//  - once past every gram hit of the chunk (idle_from: o+19, or the end of the last gram that k_verify_local found
+//  - once past every gram hit of the chunk (idle_from: the end of its last sampled gram, or of the last gram that k_verify_local found
 //    again) the walk stops as soon as the automaton is idle: a match that contains a gram hit of this chunk would
 //    still be in progress.
 // line_bit: bit of the line that contains t (bit j = j-th line intersecting the chunk).
@@ -164,7 +164,8 @@ struct ReprobeParams {
 // until the automaton is idle (with one hit per chunk, the usual case, a third of walking the whole chunk), and a chunk
 // that k_stream flagged only because of a bloom collision is dropped without a walk.
 __global__ void __launch_bounds__(128, 16) k_verify_local(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
-                                                          const unsigned long long* meta_total, size_t cap, uint32_t lookback, ReprobeParams rp,
+                                                          const unsigned long long* meta_total, size_t cap, uint32_t lookback, uint32_t idle_span,
+                                                          ReprobeParams rp,
                                                           uint32_t* __restrict__ marks, uint32_t* __restrict__ tile_records) {
     size_t ncand = (size_t)(*meta_total >> 32);
     if (ncand > cap) ncand = cap;
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(128, 16) k_verify_local(DbView db, const uint8
     const size_t o = (size_t)cand[i] * 16;
     size_t t;
     bool at_line_start;
-    size_t idle_from = o + 19;
+    size_t idle_from = o + idle_span;   // end of the last sampled gram of the chunk
     uint32_t line_bit = 1u;
     uint32_t group_mask = 0xffffffffu;   // DFA groups to walk
     if (lookback == 0xffffffffu) {
