@@ -14,7 +14,7 @@ from test_host_logic import EDGE_TEXTS
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("seed", range(160))
+@pytest.mark.parametrize("seed", range(400))
 def test_random_cases_match_oracle(seed, gpu_lib, oracle_lib):
     patterns, flags, ids, buffer_size, data, buffer_count, max_match = parity.random_case(seed)
     if parity.has_all_nul_pseudo_line(data, buffer_size):
