@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <list>
+#include <future>
 #include <map>
 #include <mutex>
 
@@ -20,12 +21,17 @@ size_t env_size(const char* name, size_t dflt) {
 }
 
 // Build DFA groups for patterns[lo, hi) by recursive bisection until every group fits the state budget.
+// The two halves of a split are compiled on two threads (down to eight at once): a 10,000-pattern set is four to eight
+// groups of a few seconds each.
 bool build_groups(const std::vector<NodePtr>& asts, const std::vector<int>& idx, size_t lo, size_t hi, bool simple,
-                  size_t max_states, std::vector<DfaGroup>& out, std::vector<NfaPattern>& nfas, std::string& error) {
+                  size_t max_states, std::vector<DfaGroup>& out, std::vector<NfaPattern>& nfas, std::string& error, int depth = 0) {
     Nfa nfa;
     bool ok = true;
     for (size_t k = lo; k < hi && ok; k++) ok = nfa_add_pattern(nfa, *asts[idx[k]], (int)(k - lo), kMaxNfaInsts);
     DfaGroup g;
+    // A union DFA has about one state per distinct prefix of its patterns: with several times more NFA instructions than the
+    // state budget the attempt cannot succeed, and running it to the budget costs seconds for a 10,000-pattern set.
+    if (ok && hi - lo > 1 && nfa.prog.size() > 3 * max_states) ok = false;
     if (ok) {
         DfaBuildOptions opt;
         opt.simple = simple;
@@ -51,8 +57,26 @@ bool build_groups(const std::vector<NodePtr>& asts, const std::vector<int>& idx,
         return true;
     }
     size_t mid = lo + (hi - lo) / 2;
-    return build_groups(asts, idx, lo, mid, simple, max_states, out, nfas, error) &&
-           build_groups(asts, idx, mid, hi, simple, max_states, out, nfas, error);
+    if (depth >= 3 || hi - lo < 64)
+        return build_groups(asts, idx, lo, mid, simple, max_states, out, nfas, error, depth + 1) &&
+               build_groups(asts, idx, mid, hi, simple, max_states, out, nfas, error, depth + 1);
+    std::vector<DfaGroup> left_groups, right_groups;
+    std::vector<NfaPattern> left_nfas, right_nfas;
+    std::string left_error, right_error;
+    auto left = std::async(std::launch::async, [&] {
+        return build_groups(asts, idx, lo, mid, simple, max_states, left_groups, left_nfas, left_error, depth + 1);
+    });
+    const bool right_ok = build_groups(asts, idx, mid, hi, simple, max_states, right_groups, right_nfas, right_error, depth + 1);
+    const bool left_ok = left.get();
+    if (!left_ok || !right_ok) {
+        error = !left_ok ? left_error : right_error;
+        return false;
+    }
+    for (auto& g : left_groups) out.push_back(std::move(g));    // pattern order is kept: left half first
+    for (auto& g : right_groups) out.push_back(std::move(g));
+    for (auto& np : left_nfas) nfas.push_back(std::move(np));
+    for (auto& np : right_nfas) nfas.push_back(std::move(np));
+    return true;
 }
 
 }  // namespace
