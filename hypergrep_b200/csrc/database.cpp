@@ -21,13 +21,23 @@ size_t env_size(const char* name, size_t dflt) {
 }
 
 // Build DFA groups for patterns[lo, hi) by recursive bisection until every group fits the state budget.
-// The two halves of a split are compiled on two threads (down to eight at once): a 10,000-pattern set is four to eight
-// groups of a few seconds each.
 bool build_groups(const std::vector<NodePtr>& asts, const std::vector<int>& idx, size_t lo, size_t hi, bool simple,
                   size_t max_states, std::vector<DfaGroup>& out, std::vector<NfaPattern>& nfas, std::string& error, int depth = 0) {
     Nfa nfa;
     bool ok = true;
     for (size_t k = lo; k < hi && ok; k++) ok = nfa_add_pattern(nfa, *asts[idx[k]], (int)(k - lo), kMaxNfaInsts);
+    const size_t mid = lo + (hi - lo) / 2;
+    // A set this large may not fit one DFA: its halves are compiled on two more threads WHILE the union is attempted (three
+    // levels deep, so at most 14 helper threads); whichever result is needed is there when the attempt ends.
+    const bool speculate = depth < 3 && hi - lo >= 64 && (!ok || nfa.prog.size() * 4 > max_states);
+    std::vector<DfaGroup> left_groups, right_groups;
+    std::vector<NfaPattern> left_nfas, right_nfas;
+    std::string left_error, right_error;
+    std::future<bool> left, right;
+    if (speculate) {
+        left = std::async(std::launch::async, [&] { return build_groups(asts, idx, lo, mid, simple, max_states, left_groups, left_nfas, left_error, depth + 1); });
+        right = std::async(std::launch::async, [&] { return build_groups(asts, idx, mid, hi, simple, max_states, right_groups, right_nfas, right_error, depth + 1); });
+    }
     DfaGroup g;
     // A union DFA has about one state per distinct prefix of its patterns: with several times more NFA instructions than the
     // state budget the attempt cannot succeed, and running it to the budget costs seconds for a 10,000-pattern set.
@@ -37,6 +47,11 @@ bool build_groups(const std::vector<NodePtr>& asts, const std::vector<int>& idx,
         opt.simple = simple;
         opt.max_states = max_states;
         ok = build_dfa(nfa, opt, g.dfa);
+    }
+    bool left_ok = true, right_ok = true;
+    if (speculate) {   // the helpers use this frame's vectors: always wait for them
+        left_ok = left.get();
+        right_ok = right.get();
     }
     if (ok) {
         for (size_t k = lo; k < hi; k++) g.members.push_back(idx[k]);
@@ -56,24 +71,15 @@ bool build_groups(const std::vector<NodePtr>& asts, const std::vector<int>& idx,
         nfas.push_back(std::move(np));
         return true;
     }
-    size_t mid = lo + (hi - lo) / 2;
-    if (depth >= 3 || hi - lo < 64)
+    if (!speculate)
         return build_groups(asts, idx, lo, mid, simple, max_states, out, nfas, error, depth + 1) &&
                build_groups(asts, idx, mid, hi, simple, max_states, out, nfas, error, depth + 1);
-    std::vector<DfaGroup> left_groups, right_groups;
-    std::vector<NfaPattern> left_nfas, right_nfas;
-    std::string left_error, right_error;
-    auto left = std::async(std::launch::async, [&] {
-        return build_groups(asts, idx, lo, mid, simple, max_states, left_groups, left_nfas, left_error, depth + 1);
-    });
-    const bool right_ok = build_groups(asts, idx, mid, hi, simple, max_states, right_groups, right_nfas, right_error, depth + 1);
-    const bool left_ok = left.get();
     if (!left_ok || !right_ok) {
         error = !left_ok ? left_error : right_error;
         return false;
     }
-    for (auto& g : left_groups) out.push_back(std::move(g));    // pattern order is kept: left half first
-    for (auto& g : right_groups) out.push_back(std::move(g));
+    for (auto& grp : left_groups) out.push_back(std::move(grp));    // pattern order is kept: left half first
+    for (auto& grp : right_groups) out.push_back(std::move(grp));
     for (auto& np : left_nfas) nfas.push_back(std::move(np));
     for (auto& np : right_nfas) nfas.push_back(std::move(np));
     return true;
