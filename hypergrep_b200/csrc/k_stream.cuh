@@ -130,11 +130,27 @@ __global__ void __launch_bounds__(1024) k_stream(const uint8_t* __restrict__ dat
     const size_t nfull = n >> 9;   // blocks that lie entirely inside [0, n)
 
     // ---- main loop: groups of U full blocks, no bounds checks on the data loads
+    // The loads of the NEXT group are issued before the current group is processed (twice the bytes in flight per warp:
+    // with stride-4 sampling the kernel waits for HBM, not for its lookups).
+    uint4 ahead[U];
+    {
+        const size_t first = warp * U;
+        if (first + U <= nfull) {
+#pragma unroll
+            for (int u = 0; u < U; u++) ahead[u] = ld_stream16(data + (first << 9) + lane * 16 + u * 512);
+        }
+    }
     for (size_t g0 = warp * U; g0 + U <= nfull; g0 += nwarps * U) {
-        const uint8_t* p = data + (g0 << 9) + lane * 16;
         uint4 v[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) v[u] = ld_stream16(p + u * 512);
+        for (int u = 0; u < U; u++) v[u] = ahead[u];
+        {
+            const size_t g1 = g0 + nwarps * U;
+            if (g1 + U <= nfull) {
+#pragma unroll
+                for (int u = 0; u < U; u++) ahead[u] = ld_stream16(data + (g1 << 9) + lane * 16 + u * 512);
+            }
+        }
         uint32_t after = 0;   // first word after the group (only lane 31 needs it, for grams that straddle the end)
         if (MODE != 0 && (STRIDE < 4 || NODD > 0) && lane == 31) {
             size_t off = (g0 + U) << 9;
