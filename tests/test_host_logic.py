@@ -134,3 +134,12 @@ def test_grep_count_only_paths_agree(hostmock_lib, tmp_path, monkeypatch):
     for limit in (0, 17):
         expected = len(lines) if limit == 0 else limit
         assert utils.grep(str(path), ["foobar", "^line 7 "], count_only=True, max_match_count=limit) == (expected, 0)
+
+
+def test_multiline_circumflex_does_not_match_after_the_final_newline(hostmock_lib, oracle_lib):
+    """PCRE: a multiline ^ matches after internal newlines, not after a newline that ends the subject - and the only
+    newline of a scanned block is its last byte (found by tools/fuzz_gpu.py, seed range 50000-80000)."""
+    data = b"x\n\t xxx\t_a1AB\nyx\nx"
+    for patterns in (["x\\W^"], ["x\\W\\Z\\z^([^a]a)*?"], ["^x"], ["x\\s^", "^y"]):
+        parity.compare(hostmock_lib, oracle_lib, data, patterns, flags=[14] * len(patterns), ids=list(range(len(patterns))), buffer_size=64)
+        parity.compare(hostmock_lib, oracle_lib, data, patterns)
