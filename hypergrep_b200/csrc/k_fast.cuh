@@ -55,7 +55,12 @@ __device__ __forceinline__ bool is_word_dev(uint32_t b) {
 __device__ uint32_t walk_local(const GroupDev& G, const uint8_t* __restrict__ data, size_t n, size_t o, size_t t, bool at_line_start,
                                size_t idle_from, uint32_t line_bit) {
     uint32_t s = 0;
-    if (!at_line_start) s = is_word_dev(data[t - 1]) ? G.mid_word : G.mid_other;
+    if (!at_line_start) {
+        // the byte before the walk decides the entry state; a '\n' there means the line starts exactly at t (the caller only
+        // looks for newlines inside [t, o)), so the walk enters in the start-of-line state: ^ and \A see a line start
+        const uint32_t before = data[t - 1];
+        if (before != '\n') s = is_word_dev(before) ? G.mid_word : G.mid_other;
+    }
     uint32_t mask = 0;
     const size_t chunk_end = o + 16;
     const uint16_t* __restrict__ flat = G.flat;

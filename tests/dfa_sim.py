@@ -197,12 +197,13 @@ def fast_path_matched_line_starts(db: "CompiledDb", data: bytes) -> set:
     marked = set()
     for c in sorted(flagged):
         o = c * 16
-        lo = 0 if lookback == 0xFFFFFFFF else max(0, o - lookback)
+        lo = 0 if lookback == 0xFFFFFFFF else max(0, o - lookback) & ~3   # the kernel starts on a word boundary
         nl = data.rfind(b"\n", lo, o)
         if lookback == 0xFFFFFFFF:
             nl = data.rfind(b"\n", 0, o)
-        at_line_start = nl >= 0 or lo == 0
         t = nl + 1 if nl >= 0 else lo
+        # a '\n' right before the start of the walk: the line begins exactly at t (walk_local checks data[t - 1])
+        at_line_start = nl >= 0 or lo == 0 or data[t - 1] == 10
         line_start = data.rfind(b"\n", 0, o) + 1   # bookkeeping for the model only
         states = []
         for gi, cls, trans, acc, reports in db.groups:

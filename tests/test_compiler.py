@@ -112,3 +112,36 @@ def test_mixed_sampling_is_chosen_for_few_short_factors(gpu_lib):
     # too many short factors: plain stride 2
     many = CompiledDb(gpu_lib, ["ERROR", "WARN:", "FATAL", "PANIC", "ALERT"])
     assert many.info.prefilter_stride == 2 and not many.odd
+
+
+ANCHORED = [["^GET "], ["^abcd"], ["^foo:"], ["^.abcdefg"], [r"\AGET /index"], ["^GET ", "POST /submit"], [r"^\s*warn: disk"]]
+
+
+def anchored_alignment_text(head: bytes, body: bytes = b" /index.html HTTP/1.1 200\n") -> bytes:
+    """Lines that start with `head` at every offset 0..63 (mod 64), separated by filler lines of growing length."""
+    out = bytearray()
+    for align in range(64):
+        while len(out) % 64 != align:
+            pad = (align - len(out)) % 64
+            out += b"x" * (pad - 1) + b"\n" if pad > 1 else b"\n"
+        out += head + body
+        out += b"not at the start: " + head + b"tail\n"
+    return bytes(out)
+
+
+@pytest.mark.parametrize("patterns", ANCHORED)
+def test_fast_path_model_anchored_at_every_alignment(patterns, gpu_lib):
+    """Regression (round-1 advisor finding): a ^-anchored match whose line starts exactly where the local walk starts
+    (the '\\n' is the byte BEFORE the look-back window) must still be found, at every alignment of the line start."""
+    db = CompiledDb(gpu_lib, patterns)
+    assert db.rc == 0 and db.info.prefilter
+    heads = {"^GET ": b"GET ", "^abcd": b"abcd", "^foo:": b"foo:", "^.abcdefg": b"Zabcdefg", r"\AGET /index": b"GET",
+             r"^\s*warn: disk": b"  warn: disk"}
+    data = anchored_alignment_text(heads[patterns[0]])
+    truth, pos = set(), 0
+    for pl in split_pseudo_lines(data, 262140):
+        if db.line_reports(pl):
+            truth.add(pos)
+        pos += len(pl)
+    assert len(truth) >= 64 or patterns[0].startswith(r"\A")
+    assert fast_path_matched_line_starts(db, data) == truth

@@ -303,3 +303,22 @@ def test_fast_path_capacity_overflow_falls_back(gpu_lib, oracle_lib):
         dev = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
         rc, _, st = scan(gpu_lib, dev.data_ptr(), dev.numel(), 1, ["abcd"], collect=False)
         assert rc == 0 and (st.path & 2), "expected the general-path fallback"
+
+
+@pytest.mark.parametrize("patterns", [["^GET "], ["^abcd"], ["^foo:"], ["^.abcdefg"], [r"\AGET /index"], ["^GET ", "POST /submit"],
+                                      [r"^\s*warn: disk"], ["(?i)^get /INDEX"]])
+def test_anchored_match_at_every_line_start_alignment(patterns, gpu_lib, oracle_lib, monkeypatch):
+    """Regression (round-1 advisor finding): the local verification walk starts `lookback` bytes before the candidate chunk,
+    rounded down to a word.  A line that starts exactly there has its '\\n' one byte BEFORE the window; the walk must
+    still enter in the start-of-line state, or ^ / \\A matches are lost for about one line start in sixteen."""
+    from test_compiler import anchored_alignment_text
+
+    heads = {"^GET ": b"GET ", "^abcd": b"abcd", "^foo:": b"foo:", "^.abcdefg": b"Zabcdefg", r"\AGET /index": b"GET",
+             r"^\s*warn: disk": b"  warn: disk", "(?i)^get /INDEX": b"GET"}
+    data = anchored_alignment_text(heads[patterns[0]])
+    flags = [14] * len(patterns)
+    assert parity.compare(gpu_lib, oracle_lib, data, patterns, flags=flags) >= 64
+    # the same text behind a long filler, so that the walks do not start at offset 0 of the segment, and with tiny segments
+    assert parity.compare(gpu_lib, oracle_lib, b"filler line\n" * 1000 + data, patterns, flags=flags) >= 64
+    monkeypatch.setenv("GPUGREP_NO_REPROBE", "1")
+    assert parity.compare(gpu_lib, oracle_lib, data * 3, patterns + ["zqanchorqz"], flags=flags + [14]) >= 192
