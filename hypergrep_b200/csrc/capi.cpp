@@ -436,6 +436,8 @@ int scan_file(const char* path, const Params& pr, gpugrep_stats* stats_out) {
         return GPUGREP_SCRATCH;
     }
 
+    const bool count_only = pr.cb == nullptr && pr.max_match == 0 && job.db->simple;
+    for (ScanSlot* sl : slots) slot_set_want_records(sl, !count_only);
     SegmentQueue q;
     for (int i = 0; i < kSlots; i++) q.free_slots.push_back(i);
     std::thread reader([&] {
@@ -585,6 +587,9 @@ int scan_memory(const uint8_t* data, size_t size, int location, const Params& pr
     }
     ScanSlot* slots[2] = {engine_acquire_slot(err), engine_acquire_slot(err)};
     if (!slots[0] || !slots[1]) { engine_release_slot(slots[0]); engine_release_slot(slots[1]); set_last_error(err); return GPUGREP_SCRATCH; }
+    const bool count_only = pr.cb == nullptr && pr.max_match == 0 && job.db->simple;
+    slot_set_want_records(slots[0], !count_only);
+    slot_set_want_records(slots[1], !count_only);
     const uint8_t* seg_host[2] = {nullptr, nullptr};
     int k = 0, inflight = -1;
     bool tuned = false;
@@ -596,7 +601,7 @@ int scan_memory(const uint8_t* data, size_t size, int location, const Params& pr
     if (on_device && size) {
         if (size > chunk) chunk = std::min(chunk, kMaxSegmentBytes - ((size_t)16 << 20));
         head.resize(std::min<size_t>(size, 64 << 10));
-        if (slot_probe_input(slots[0], data, size, chunk, dev_cuts, head.data(), head.size(), job.error) != 0) {
+        if (slot_probe_input(slots[0], data, size, chunk, dev_cuts, head.data(), head.size(), pr.user_stream, job.error) != 0) {
             engine_release_slot(slots[0]); engine_release_slot(slots[1]);
             set_last_error(job.error);
             return GPUGREP_SCAN;

@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
@@ -70,9 +71,22 @@ struct PinBuf {
     ~PinBuf() { if (p) cudaFreeHost(p); }
 };
 
-int g_device = -1;
-int g_num_sms = 148;
 std::mutex g_mu;
+// SM count of the calling thread's current device (scans on different GPUs run concurrently on different host threads:
+// nothing here may depend on "the" device of the process)
+int device_sms() {
+    static int cached[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        cached[dev] = sms;   // benign race: every writer stores the same value
+    }
+    return cached[dev];
+}
+// k_verify_smem: table + class map + 32 KiB (64 bytes per thread) or 48 KiB of staged text per block must fit 227 KiB
+constexpr size_t kMaxSharedTableBytes = (size_t)176 << 10;
 
 }  // namespace
 
@@ -85,6 +99,7 @@ struct DeviceDb {
     NfaView* d_nfas = nullptr;
     int nnfa = 0;
     bool simple = false;
+    size_t smem_table_bytes = 0;   // single group with a class-compressed table (GroupDev::ctab): its size, else 0
     ~DeviceDb() { for (void* p : allocs) cudaFree(p); }
 };
 
@@ -94,7 +109,7 @@ struct DevicePrefilter {
     int table_words = 0;
     int stride = 4;
     bool fold = false;
-    int mode = 0;        // 1 exact keys, 2 bloom bitmap
+    int mode = 0;        // 1 exact keys, 2 bloom byte table, 3 bank-private blocked bloom
     int nodd = 0;        // register compares at offsets 2 mod 4 (mixed sampling; bloom mode only)
     ProbeParams pp{};
     uint32_t lookback = 0xffffffffu;
@@ -113,7 +128,7 @@ public:
     cudaStream_t copy_stream = nullptr;   // result D2H, so that it does not queue behind the next segment's kernels
     cudaEvent_t done = nullptr;           // all kernels of the segment + the totals copy have finished
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // 0/1: whole segment, 2/3: streaming kernel
-    DevBuf d_input, d_meta, d_prefix, d_sums, d_cand, d_res, d_recoff, d_recs, d_totals;
+    DevBuf d_input, d_meta, d_nlmask, d_prefix, d_sums, d_cand, d_res, d_recoff, d_recs, d_totals;
     DevBuf d_nlpos, d_npl, d_ploff, d_plstart, d_pllen, d_flags, d_counts, d_events, d_gather, d_gidx;
     PinBuf h_totals, h_recs, h_stage, h_gather, h_probe;
     // state of the in-flight segment
@@ -130,7 +145,6 @@ public:
 };
 
 int engine_select_device(int device, std::string& error) {
-    std::lock_guard<std::mutex> lk(g_mu);
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
@@ -138,17 +152,21 @@ int engine_select_device(int device, std::string& error) {
         return 7;
     }
     if (device < 0 || device >= count) device = 0;
-    CUDA_TRY(cudaSetDevice(device));
-    if (g_device != device) {
-        cudaDeviceProp prop;
-        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-        g_num_sms = prop.multiProcessorCount;
-        g_device = device;
-    }
+    CUDA_TRY(cudaSetDevice(device));   // per host thread
     return 0;
 }
 
-int engine_current_device() { return g_device; }
+int engine_current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return dev;
+}
+
+int engine_device_count() {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return count;
+}
 
 std::shared_ptr<DeviceDb> engine_upload(const std::shared_ptr<Database>& db, std::string& error) {
     static std::mutex mu;
@@ -207,6 +225,29 @@ std::shared_ptr<DeviceDb> engine_upload(const std::shared_ptr<Database>& db, std
             G.flat = (const uint16_t*)upload(flat.data(), flat.size() * sizeof(uint16_t));
             G.eod_next = (const uint16_t*)upload(eod.data(), eod.size() * sizeof(uint16_t));
             if (!G.flat || !G.eod_next) { error = "cudaMalloc/cudaMemcpy failed while uploading DFA tables"; return nullptr; }
+            // Class-compressed copy for shared memory.  Bytes of one alphabet class have identical columns in `flat`,
+            // except '\n' and NUL, whose columns carry the line rules: they get classes of their own.
+            const int ncls = d.num_classes + 2;
+            const size_t ctab_bytes = (size_t)d.num_states * ncls * 2;
+            if (db->groups.size() == 1 && ncls <= 127 && ctab_bytes <= kMaxSharedTableBytes) {
+                std::vector<uint8_t> cmap2(256);
+                std::vector<int> rep((size_t)ncls, -1);
+                for (int b = 255; b >= 0; b--) {
+                    const int c = b == 0 ? d.num_classes : (b == '\n' ? d.num_classes + 1 : d.byte_class[b]);
+                    cmap2[(size_t)b] = (uint8_t)(2 * c);
+                    rep[(size_t)c] = b;
+                }
+                std::vector<uint16_t> ctab((size_t)d.num_states * ncls + 8, 0);
+                for (int st = 0; st < d.num_states; st++)
+                    for (int c = 0; c < ncls; c++)
+                        if (rep[(size_t)c] >= 0) ctab[(size_t)st * ncls + c] = flat[(size_t)st * 256 + rep[(size_t)c]];
+                G.ctab = (const uint16_t*)upload(ctab.data(), ctab.size() * sizeof(uint16_t));
+                G.cmap2 = (const uint8_t*)upload(cmap2.data(), 256);
+                if (!G.ctab || !G.cmap2) { error = "cudaMalloc/cudaMemcpy failed while uploading DFA tables"; return nullptr; }
+                G.crow = (uint32_t)ncls * 2u;
+                G.cstates = (uint32_t)d.num_states;
+                out->smem_table_bytes = (ctab_bytes + 15) / 16 * 16;
+            }
         }
         G.stride = (uint32_t)d.stride;
         G.eod = (uint32_t)d.num_classes;
@@ -256,10 +297,17 @@ std::shared_ptr<DevicePrefilter> engine_upload_prefilter(const Prefilter& pf, st
     const std::vector<uint32_t>* src = &pf.bitmap;
     const char* want = std::getenv("GPUGREP_FILTER");
     const bool use_exact = pf.exact && pf.odd.empty() && want && std::strcmp(want, "exact") == 0;
+    const bool use_bank_private = !use_exact && pf.bp_copies > 0 && !(want && std::strcmp(want, "bloom") == 0);
     out->stride = pf.stride;
     out->fold = pf.fold_case;
-    out->mode = use_exact ? 1 : 2;
-    out->pp.mul = use_exact ? pf.hash_mul : pf.bloom_mul;
+    out->mode = use_exact ? 1 : (use_bank_private ? 3 : 2);
+    out->pp.mul = use_exact ? pf.hash_mul : (use_bank_private ? pf.bp_mul : pf.bloom_mul);
+    if (use_bank_private) {
+        out->pp.bp_words = pf.bp_words;
+        out->pp.bp_row = 4u * (uint32_t)pf.bp_copies;
+        out->pp.bp_lane_mask = (uint32_t)pf.bp_copies - 1u;
+        src = &pf.bp_table;
+    }
     out->pp.mul2 = pf.hash_mul2;
     out->pp.shift = 32 - (pf.log2_bits - 3);   // bloom: product -> byte index
     out->lookback = pf.lookback;
@@ -298,7 +346,8 @@ std::shared_ptr<DevicePrefilter> engine_upload_prefilter(const Prefilter& pf, st
             return nullptr;
         }
     }
-    out->bloom_false_rate = (double)pf.num_grams * (16.0 / pf.stride) / (double)((size_t)1 << pf.log2_bits);
+    out->bloom_false_rate = use_bank_private ? pf.bp_false_rate * (16.0 / pf.stride)
+                                             : (double)pf.num_grams * (16.0 / pf.stride) / (double)((size_t)1 << pf.log2_bits);
     out->table_words = (int)src->size();
     if (cudaMalloc((void**)&out->d_table, src->size() * sizeof(uint32_t)) != cudaSuccess ||
         cudaMemcpy(out->d_table, src->data(), src->size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -350,6 +399,8 @@ void engine_release_slot(ScanSlot* slot) {
     g_free_slots.push_back(slot);
 }
 
+void slot_set_want_records(ScanSlot* slot, bool want) { slot->want_records = want; }
+
 uint8_t* slot_host_buffer(ScanSlot* slot, size_t capacity, std::string& error) {
     if (slot->h_stage.reserve(capacity + 64) != cudaSuccess) { error = "cudaHostAlloc failed for the staging buffer"; return nullptr; }
     return slot->h_stage.as<uint8_t>();
@@ -358,13 +409,13 @@ uint8_t* slot_host_buffer(ScanSlot* slot, size_t capacity, std::string& error) {
 // Grid of a persistent (grid-stride) kernel: exactly as many blocks as can be resident at once.  A larger grid runs a
 // second, partly empty wave in which the late blocks repeat the full per-block share of the work.
 template <class Kernel>
-static unsigned resident_grid(Kernel kernel, int block, size_t smem = 0) {
+static unsigned blocks_per_sm(Kernel kernel, int block, size_t smem = 0) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess || per_sm < 1) {
         (void)cudaGetLastError();
         per_sm = 1;
     }
-    return (unsigned)(per_sm * g_num_sms);
+    return (unsigned)per_sm;
 }
 
 template <class Load>
@@ -373,8 +424,8 @@ static void launch_scan(cudaStream_t st, Load load, size_t n, unsigned long long
     size_t nb = (n + kScanTile - 1) / kScanTile;
     if (nb == 0) nb = 1;
     // persistent grid: with a device-side `limit` most tiles are empty, and empty blocks are not free to schedule
-    static const unsigned resident = resident_grid(k_scan_sums<Load>, kScanThreads);
-    unsigned grid = (unsigned)std::min<size_t>(nb, resident);
+    static const unsigned per_sm = blocks_per_sm(k_scan_sums<Load>, kScanThreads);
+    unsigned grid = (unsigned)std::min<size_t>(nb, (size_t)per_sm * device_sms());
     k_scan_sums<Load><<<grid, kScanThreads, 0, st>>>(load, n, sums, nb, limit, limit_shift);
     k_scan_top<<<1, 1024, 0, st>>>(sums, nb, total);
     k_scan_write<Load><<<grid, kScanThreads, 0, st>>>(load, n, sums, out, nb, limit, limit_shift);
@@ -383,29 +434,30 @@ static void launch_scan(cudaStream_t st, Load load, size_t n, unsigned long long
 
 template <int STRIDE, bool FOLD, int MODE, int NODD = 0>
 static cudaError_t launch_stream_t(cudaStream_t st, int grid, int block, size_t smem, const uint8_t* data, size_t n, unsigned long long* meta,
-                                   const DevicePrefilter* pf) {
+                                   uint32_t* nlmask, const DevicePrefilter* pf) {
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_stream<STRIDE, FOLD, MODE, NODD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k_stream<STRIDE, FOLD, MODE, NODD><<<grid, block, smem, st>>>(data, n, meta, pf ? pf->d_table : nullptr, pf ? pf->table_words : 0,
+    k_stream<STRIDE, FOLD, MODE, NODD><<<grid, block, smem, st>>>(data, n, meta, nlmask, pf ? pf->d_table : nullptr, pf ? pf->table_words : 0,
                                                             pf ? pf->pp : ProbeParams{});
     return cudaGetLastError();
 }
 
 template <int MODE>
 static cudaError_t launch_stream_m(cudaStream_t st, int grid, int block, size_t smem, const uint8_t* data, size_t n, unsigned long long* meta,
-                                   const DevicePrefilter* pf) {
+                                   uint32_t* nlmask, const DevicePrefilter* pf) {
     int key = pf->stride * 2 + (pf->fold ? 1 : 0);
-    if (MODE == 2 && pf->stride == 4 && pf->nodd > 0)
-        return pf->fold ? launch_stream_t<4, true, 2, 2>(st, grid, block, smem, data, n, meta, pf) : launch_stream_t<4, false, 2, 2>(st, grid, block, smem, data, n, meta, pf);
+    if (MODE >= 2 && pf->stride == 4 && pf->nodd > 0)
+        return pf->fold ? launch_stream_t<4, true, MODE, 2>(st, grid, block, smem, data, n, meta, nlmask, pf)
+                        : launch_stream_t<4, false, MODE, 2>(st, grid, block, smem, data, n, meta, nlmask, pf);
     switch (key) {
-        case 8: return launch_stream_t<4, false, MODE>(st, grid, block, smem, data, n, meta, pf);
-        case 9: return launch_stream_t<4, true, MODE>(st, grid, block, smem, data, n, meta, pf);
-        case 4: return launch_stream_t<2, false, MODE>(st, grid, block, smem, data, n, meta, pf);
-        case 5: return launch_stream_t<2, true, MODE>(st, grid, block, smem, data, n, meta, pf);
-        case 2: return launch_stream_t<1, false, MODE>(st, grid, block, smem, data, n, meta, pf);
-        default: return launch_stream_t<1, true, MODE>(st, grid, block, smem, data, n, meta, pf);
+        case 8: return launch_stream_t<4, false, MODE>(st, grid, block, smem, data, n, meta, nlmask, pf);
+        case 9: return launch_stream_t<4, true, MODE>(st, grid, block, smem, data, n, meta, nlmask, pf);
+        case 4: return launch_stream_t<2, false, MODE>(st, grid, block, smem, data, n, meta, nlmask, pf);
+        case 5: return launch_stream_t<2, true, MODE>(st, grid, block, smem, data, n, meta, nlmask, pf);
+        case 2: return launch_stream_t<1, false, MODE>(st, grid, block, smem, data, n, meta, nlmask, pf);
+        default: return launch_stream_t<1, true, MODE>(st, grid, block, smem, data, n, meta, nlmask, pf);
     }
 }
 
@@ -448,7 +500,8 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
     s->cand_cap = n / 32 + 4096;   // half of all 16-byte chunks; beyond that the segment falls back to the general path
     s->rec_cap = n / 48 + 4096;
     size_t nb_scan = (std::max(s->nblk, s->cand_cap) + kScanTile - 1) / kScanTile + 1;
-    if (s->d_meta.reserve((s->nblk + 8) * 8) != cudaSuccess || s->d_prefix.reserve((s->nblk + 8) * 8) != cudaSuccess ||
+    if (s->d_meta.reserve((s->nblk + 8) * 8) != cudaSuccess || s->d_nlmask.reserve((s->nblk + 8) * 4) != cudaSuccess ||
+        s->d_prefix.reserve((s->nblk + 8) * 8) != cudaSuccess ||
         s->d_sums.reserve(nb_scan * 8) != cudaSuccess) { error = "cudaMalloc failed for scan scratch"; return 3; }
     if (s->fast) {
         if (s->d_cand.reserve(s->cand_cap * 4) != cudaSuccess || s->d_res.reserve(s->cand_cap * sizeof(uint32_t)) != cudaSuccess ||
@@ -466,18 +519,22 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
     }
     // ---- K1 ----
     // persistent grid: enough CTAs to fill every SM, each warp strides over groups of kStreamU blocks
-    size_t smem = s->fast ? (size_t)pf->table_words * 4 + (pf->mode == 1 ? pf->pp.half_bytes : 0) : 0;
+    size_t smem = 0;
+    if (s->fast) smem = pf->mode == 3 ? (size_t)pf->pp.bp_words * pf->pp.bp_row : (size_t)pf->table_words * 4 + (pf->mode == 1 ? pf->pp.half_bytes : 0);
     int block = smem > 32 * 1024 ? 1024 : 256;
     int ctas_per_sm = smem > 100 * 1024 ? 1 : (smem > 32 * 1024 ? 2 : 6);
-    int grid = g_num_sms * ctas_per_sm;
+    int grid = device_sms() * ctas_per_sm;
     size_t groups = (s->nblk + kStreamU - 1) / kStreamU;
     size_t max_grid = (groups + (block / 32) - 1) / (block / 32);
     if ((size_t)grid > max_grid) grid = (int)std::max<size_t>(1, max_grid);
     unsigned long long* meta = s->d_meta.as<unsigned long long>();
+    uint32_t* nlmask = s->d_nlmask.as<uint32_t>();
     CUDA_TRY(cudaEventRecord(s->ev[2], st));
     cudaError_t le;
-    if (s->fast) le = pf->mode == 1 ? launch_stream_m<1>(st, grid, block, smem, s->data, n, meta, pf) : launch_stream_m<2>(st, grid, block, smem, s->data, n, meta, pf);
-    else le = launch_stream_t<4, false, 0>(st, grid, block, 0, s->data, n, meta, nullptr);
+    if (!s->fast) le = launch_stream_t<4, false, 0>(st, grid, block, 0, s->data, n, meta, nlmask, nullptr);
+    else if (pf->mode == 3) le = launch_stream_m<3>(st, grid, block, smem, s->data, n, meta, nlmask, pf);
+    else if (pf->mode == 1) le = launch_stream_m<1>(st, grid, block, smem, s->data, n, meta, nlmask, pf);
+    else le = launch_stream_m<2>(st, grid, block, smem, s->data, n, meta, nlmask, pf);
     if (le != cudaSuccess) { error = std::string("k_stream launch: ") + cudaGetErrorString(le); return 7; }
     CUDA_TRY(cudaEventRecord(s->ev[3], st));
     s->stats.launches++;
@@ -487,23 +544,22 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
     launch_scan(st, LoadMetaGroup{meta, s->nblk}, (s->nblk + kGroupBlocks - 1) / kGroupBlocks, prefix, s->d_sums.as<unsigned long long>(),
                 &dT->meta_total, s->stats);
     if (s->fast) {
+        const unsigned sms = (unsigned)device_sms();
         size_t bps = super_bytes / 512;
         size_t nsuper = s->nblk / bps;
         if (nsuper) {
             k_check_long<<<(unsigned)((nsuper + 255) / 256), 256, 0, st>>>(prefix, s->nblk, bps, &dT->meta_total, dT);
             s->stats.launches++;
         }
-        static const unsigned list_resident = resident_grid(k_list_candidates, 256);
-        k_list_candidates<<<(unsigned)std::min<size_t>((s->nblk + 255) / 256, list_resident), 256, 0, st>>>(meta, prefix, s->nblk, s->d_cand.as<uint32_t>(), s->cand_cap, dT);
+        static const unsigned list_per_sm = blocks_per_sm(k_list_candidates, 256);
+        k_list_candidates<<<(unsigned)std::min<size_t>((s->nblk + 255) / 256, (size_t)list_per_sm * sms), 256, 0, st>>>(meta, prefix, s->nblk, s->d_cand.as<uint32_t>(), s->cand_cap, dT);
         DbView view{ddb.d_groups, ddb.ngroups, ddb.d_nfas, ddb.nnfa};
-        static const unsigned verify_resident = resident_grid(k_verify_local, 128);
-        unsigned vgrid = (unsigned)std::min<size_t>((s->cand_cap + 127) / 128, verify_resident);
         // Finding the hits again costs two loads per sampled gram and candidate.  It pays when bloom collisions flag a
         // noticeable share of chunks (large gram sets: those candidates are dropped without a walk) and when several DFA
         // groups would each walk the whole chunk (measured with 32 patterns / 1 group / 415 grams: no gain, so not there).
         ReprobeParams rp{};
         const bool want_reprobe = ddb.ngroups >= 2 || pf->bloom_false_rate > 0.005;
-        if (pf->mode == 2 && pf->d_confirm && want_reprobe && std::getenv("GPUGREP_NO_REPROBE") == nullptr) {
+        if (pf->mode >= 2 && pf->d_confirm && want_reprobe && std::getenv("GPUGREP_NO_REPROBE") == nullptr) {
             rp.keys = pf->d_confirm;
             rp.groups = pf->d_confirm_groups;
             rp.mul = pf->confirm_mul; rp.mul2 = pf->confirm_mul2; rp.shift = 32 - pf->confirm_log2; rp.half = 1u << pf->confirm_log2;
@@ -516,14 +572,39 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
         CUDA_TRY(cudaMemsetAsync(tile_records, 0, (s->cand_cap / kEmitTile + 2) * sizeof(uint32_t), st));
         // the last sampled gram of a chunk starts at offset 16 - stride (14 with the compares of mixed sampling) and is 4 bytes long
         const uint32_t idle_span = pf->nodd ? 18u : 20u - (uint32_t)pf->stride;
-        k_verify_local<<<vgrid, 128, 0, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->lookback, idle_span, rp,
-                                              s->d_res.as<uint32_t>(), tile_records);
+        // Verification.  Single-group databases whose class-compressed table fits shared memory, with a look-back that the
+        // staged text window covers, take k_verify_smem; everything else the global-table kernel.
+        const char* vsel = std::getenv("GPUGREP_VERIFY");
+        const bool v1 = vsel && std::strcmp(vsel, "v1") == 0;
+        if (!v1 && ddb.smem_table_bytes && pf->lookback <= 29u) {
+            const bool wide = pf->lookback > 13u;
+            const size_t vsmem = 256 + ddb.smem_table_bytes + (size_t)(wide ? 24 : 16) * 4 * kVerifyThreads;
+            auto kernel = wide ? k_verify_smem<2, 24> : k_verify_smem<1, 16>;
+            CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
+            const unsigned per_sm = blocks_per_sm(kernel, kVerifyThreads, vsmem);
+            unsigned vgrid = (unsigned)std::min<size_t>((s->cand_cap + kVerifyThreads - 1) / kVerifyThreads, (size_t)per_sm * sms);
+            kernel<<<vgrid, kVerifyThreads, vsmem, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->lookback, idle_span, rp,
+                                                         s->d_res.as<uint32_t>(), tile_records);
+        } else {
+            static const unsigned verify_per_sm = blocks_per_sm(k_verify_local, 128);
+            unsigned vgrid = (unsigned)std::min<size_t>((s->cand_cap + 127) / 128, (size_t)verify_per_sm * sms);
+            k_verify_local<<<vgrid, 128, 0, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->lookback, idle_span, rp,
+                                                  s->d_res.as<uint32_t>(), tile_records);
+        }
         k_tile_offsets<<<1, 1024, 0, st>>>(tile_records, &dT->meta_total, s->cand_cap, &dT->rec_total);
-        static const unsigned emit_resident = resident_grid(k_emit_simple, kEmitThreads);
-        k_emit_simple<<<(unsigned)std::min<size_t>((s->cand_cap + kEmitTile - 1) / kEmitTile, emit_resident), kEmitThreads, 0, st>>>(
-            view, s->data, n, s->d_cand.as<uint32_t>(), s->d_res.as<uint32_t>(), tile_records, meta, prefix, &dT->meta_total,
-            s->cand_cap, s->d_recs.as<LineRec>(), s->rec_cap, dT);
-        s->stats.launches += 3;
+        const char* esel = std::getenv("GPUGREP_EMIT");
+        if (esel && std::strcmp(esel, "v1") == 0) {
+            static const unsigned emit_per_sm = blocks_per_sm(k_emit_simple, kEmitThreads);
+            k_emit_simple<<<(unsigned)std::min<size_t>((s->cand_cap + kEmitTile - 1) / kEmitTile, (size_t)emit_per_sm * sms), kEmitThreads, 0, st>>>(
+                view, s->data, n, s->d_cand.as<uint32_t>(), s->d_res.as<uint32_t>(), tile_records, meta, prefix, &dT->meta_total,
+                s->cand_cap, s->d_recs.as<LineRec>(), s->rec_cap, dT);
+        } else {
+            static const unsigned emit_per_sm = blocks_per_sm(k_emit_nlm, kEmitThreads);
+            k_emit_nlm<<<(unsigned)std::min<size_t>((s->cand_cap + kEmitTile - 1) / kEmitTile, (size_t)emit_per_sm * sms), kEmitThreads, 0, st>>>(
+                view, s->data, n, s->d_cand.as<uint32_t>(), s->d_res.as<uint32_t>(), tile_records, meta, prefix, nlmask, &dT->meta_total,
+                s->cand_cap, s->d_recs.as<LineRec>(), s->rec_cap, dT);
+        }
+        s->stats.launches += 4;
         CUDA_TRY(cudaEventRecord(s->ev[1], st));
     }
     CUDA_TRY(cudaMemcpyAsync(&dT->last_byte, s->data + n - 1, 1, cudaMemcpyDeviceToDevice, st));
@@ -547,7 +628,7 @@ int ScanSlot::run_general(SegmentResult& out, std::string& error) {
         k_newline_positions<<<(unsigned)((nblk * 32 + 255) / 256), 256, 0, st>>>(data, n, nblk, d_meta.as<unsigned long long>(), prefix, d_nlpos.as<uint32_t>());
         stats.launches++;
     }
-    const uint32_t limit = (uint32_t)std::max(1, buffer_size - 1);
+    const uint32_t limit = (uint32_t)std::min<long long>(std::max(1, buffer_size - 1), 1ll << 29);   // the host cuts with the same clamp (capi.cpp clamp_limit)
     size_t npl_total = nlines;
     bool split = false;
     if (nlines) {
@@ -657,7 +738,7 @@ int slot_collect(ScanSlot* s, SegmentResult& out, std::string& error) {
                 CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
                 s->stats.d2h_bytes += nrec * sizeof(LineRec);
             }
-            out.lines = s->h_recs.as<LineRec>();
+            out.lines = s->want_records ? s->h_recs.as<LineRec>() : nullptr;
             out.num_line_recs = nrec;
             done = true;
         }
@@ -674,7 +755,7 @@ int slot_collect(ScanSlot* s, SegmentResult& out, std::string& error) {
 }
 
 int slot_probe_input(ScanSlot* s, const uint8_t* dev_data, size_t size, size_t chunk, std::vector<size_t>& cuts, uint8_t* head, size_t head_len,
-                     std::string& error) {
+                     void* user_stream, std::string& error) {
     cuts.clear();
     if (size == 0) return 0;
     const size_t ncuts = chunk && size > chunk ? (size + chunk - 1) / chunk : 0;
@@ -683,7 +764,8 @@ int slot_probe_input(ScanSlot* s, const uint8_t* dev_data, size_t size, size_t c
         error = "scratch allocation failed";
         return 3;
     }
-    cudaStream_t st = s->own_stream;
+    // on the caller's stream when there is one: whatever produces the buffer there has finished before the probe reads it
+    cudaStream_t st = user_stream ? (cudaStream_t)user_stream : s->own_stream;
     unsigned long long* h_cuts = s->h_probe.as<unsigned long long>();
     uint8_t* h_head = s->h_probe.as<uint8_t>() + ncuts * 8;
     if (ncuts) {

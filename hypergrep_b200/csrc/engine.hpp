@@ -52,8 +52,9 @@ struct DevicePrefilter;   // device-resident gram table of one (sample-tuned) Pr
 class ScanSlot;    // stream + scratch + pinned result buffers for one in-flight segment
 
 // All functions return 0 or a reference return code (3 = scratch allocation, 7 = CUDA failure) and set `error`.
-int engine_select_device(int device, std::string& error);
-int engine_current_device();
+int engine_select_device(int device, std::string& error);   // cudaSetDevice for the calling host thread
+int engine_current_device();                                 // the calling thread's current device
+int engine_device_count();
 
 std::shared_ptr<DeviceDb> engine_upload(const std::shared_ptr<Database>& db, std::string& error);
 std::shared_ptr<DevicePrefilter> engine_upload_prefilter(const Prefilter& pf, std::string& error);
@@ -71,6 +72,9 @@ uint8_t* slot_host_buffer(ScanSlot* slot, size_t capacity, std::string& error);
 //  pf: gram table for the fast path, or nullptr (general path).
 int slot_submit(ScanSlot* slot, const DeviceDb& ddb, const DevicePrefilter* pf, const uint8_t* host_data, const uint8_t* dev_data, size_t n,
                 int buffer_size, void* user_stream, std::string& error);
+// Count-only callers (no callback, no match limit) need no records on the host: the record copy is skipped and
+// SegmentResult::lines stays null (num_valid_recs is still exact).  Call before slot_submit.
+void slot_set_want_records(ScanSlot* slot, bool want);
 // Wait for the segment and expose its results (valid until the next slot_submit on this slot).
 int slot_collect(ScanSlot* slot, SegmentResult& out, std::string& error);
 
@@ -83,8 +87,9 @@ int slot_gather_lines(ScanSlot* slot, const uint32_t* starts, const uint32_t* le
 // input (fingerprint of the prefilter sample).  cuts[j] = offset just past the last '\n' before (j+1)*chunk that keeps the
 // next segment 16-byte aligned (the last entry is `size`); left empty when the input is a single segment or some
 // boundary has no such newline nearby (the caller then cuts sequentially).
+// `user_stream`: the stream the caller's producer of dev_data runs on, or null; the probe is ordered behind it.
 int slot_probe_input(ScanSlot* slot, const uint8_t* dev_data, size_t size, size_t chunk, std::vector<size_t>& cuts, uint8_t* head,
-                     size_t head_len, std::string& error);
+                     size_t head_len, void* user_stream, std::string& error);
 
 constexpr size_t kMaxSegmentBytes = (size_t)3 << 30;   // offsets inside a segment are 32-bit
 

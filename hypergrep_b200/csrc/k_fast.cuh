@@ -42,80 +42,141 @@ __device__ __forceinline__ bool is_word_dev(uint32_t b) {
     return (b - '0' < 10u) || ((b | 0x20u) - 'a' < 26u) || b == '_';
 }
 
+// Transition-table accessors for the local walk.  Both present the same byte-indexed view in which '\n' and NUL are
+// ordinary columns and "matched" is one absorbing state (see engine_upload).
+struct FlatTable {   // [state][256] u16 in global memory
+    const uint16_t* __restrict__ flat;
+    __device__ __forceinline__ uint32_t step(uint32_t s, uint32_t b) const { return flat[(s << 8) | b]; }
+    __device__ __forceinline__ uint32_t step4(uint32_t s, uint32_t word) const {
+        s = flat[(s << 8) | (word & 0xffu)];
+        s = flat[(s << 8) | ((word >> 8) & 0xffu)];
+        s = flat[(s << 8) | ((word >> 16) & 0xffu)];
+        return flat[(s << 8) | (word >> 24)];
+    }
+};
+__device__ __forceinline__ uint32_t lds_u8(uint32_t shared_addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(shared_addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t shared_addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(shared_addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(shared_addr));
+    return v;
+}
+struct SharedTable {   // class-compressed [state][classes] u16 in shared memory + byte -> 2 * class map (GroupDev::ctab)
+    uint32_t tab, cls, row;   // shared-window addresses of the table and of the class map; bytes per table row
+    __device__ __forceinline__ uint32_t step(uint32_t s, uint32_t b) const { return lds_u16(tab + s * row + lds_u8(cls + b)); }
+    __device__ __forceinline__ uint32_t step4(uint32_t s, uint32_t word) const {
+        // the four class lookups do not depend on the state: they are issued first, the state chain is one multiply-add and
+        // one load per byte
+        const uint32_t c0 = lds_u8(cls + (word & 0xffu)), c1 = lds_u8(cls + ((word >> 8) & 0xffu));
+        const uint32_t c2 = lds_u8(cls + ((word >> 16) & 0xffu)), c3 = lds_u8(cls + (word >> 24));
+        s = lds_u16(tab + s * row + c0);
+        s = lds_u16(tab + s * row + c1);
+        s = lds_u16(tab + s * row + c2);
+        return lds_u16(tab + s * row + c3);
+    }
+};
+// Text accessors: aligned words of the segment.
+struct GlobalText {
+    const uint8_t* __restrict__ data;
+    __device__ __forceinline__ uint32_t word(uint32_t wpos) const { return *reinterpret_cast<const uint32_t*>(data + wpos); }
+};
+// The neighbourhood of the candidate chunk staged in shared memory (word k of the window of thread `tid` at
+// text[k * threads + tid]: whatever k the lanes of a warp are at, every lane stays in its own bank); words beyond the window
+// come from global memory.
+struct StagedText {
+    const uint8_t* __restrict__ data;
+    uint32_t base;    // shared-window address of this thread's word 0
+    uint32_t pitch;   // bytes between consecutive words of one thread (4 * threads per block)
+    uint32_t wbase;   // text offset of word 0
+    uint32_t words;
+    __device__ __forceinline__ uint32_t word(uint32_t wpos) const {
+        const uint32_t k = (wpos - wbase) >> 2;
+        return k < words ? lds_u32(base + k * pitch) : *reinterpret_cast<const uint32_t*>(data + wpos);
+    }
+};
+
 // LOCAL verification walk of one DFA group around candidate chunk [o, o+16).
 //  - starts at t (at most `lookback` bytes before the chunk, never before the line start) in the start-of-line state
 //    or in the mid-line entry state that matches the previous byte;
-//  - a NUL acts as end-of-data followed by a restart (lines with NULs are re-checked exactly by k_emit_simple);
+//  - a NUL acts as end-of-data followed by a restart (lines with NULs are re-checked exactly by the emit kernel);
 //  - a '\n' ends the line: the walk continues with the next line only if that line starts inside the chunk;
-//  - once past every gram hit of the chunk (idle_from: the end of its last sampled gram, or of the last gram that k_verify_local found
-//    again) the walk stops as soon as the automaton is idle: a match that contains a gram hit of this chunk would
-//    still be in progress.
+//  - once past every gram hit of the chunk (idle_from: the end of its last sampled gram, or of the last gram that the
+//    verification kernel found again) the walk stops as soon as the automaton is idle: a match that contains a gram hit
+//    of this chunk would still be in progress.
 // line_bit: bit of the line that contains t (bit j = j-th line intersecting the chunk).
 // Returns bit j set if the j-th line intersecting the chunk matched.
-__device__ uint32_t walk_local(const GroupDev& G, const uint8_t* __restrict__ data, size_t n, size_t o, size_t t, bool at_line_start,
-                               size_t idle_from, uint32_t line_bit) {
-    uint32_t s = 0;
-    if (!at_line_start) {
-        // the byte before the walk decides the entry state; a '\n' there means the line starts exactly at t (the caller only
-        // looks for newlines inside [t, o)), so the walk enters in the start-of-line state: ^ and \A see a line start
-        const uint32_t before = data[t - 1];
-        if (before != '\n') s = is_word_dev(before) ? G.mid_word : G.mid_other;
-    }
-    uint32_t mask = 0;
-    const size_t chunk_end = o + 16;
-    const uint16_t* __restrict__ flat = G.flat;
+// The walk advances one ALIGNED WORD per step:
+//  - a full word without a newline is four chained lookups and nothing else (no per-byte tests: a match sticks until
+//    the line ends);
+//  - a word with a newline, the first word of an unaligned start and the last word of the segment take the byte-wise
+//    form, straight-line code without inner loops (threads of a warp diverge here, so it is short).
+// The line bit is set when the line ends in the matched state, or at the end of the walk.
+template <class Table, class Text>
+__device__ __forceinline__ uint32_t walk_words(const Table& T, const Text& X, const GroupDev& G, uint32_t s, uint32_t end, uint32_t cend, uint32_t pos,
+                                               uint32_t ifrom, uint32_t line_bit) {
     const uint32_t first_accept = G.first_accept, idle_end = G.idle_end;
-    if (flat) {
-        // Fast form: '\n' and NUL are ordinary columns of the table and "matched" is an absorbing state (see
-        // engine_upload), offsets are 32-bit.  The walk advances one ALIGNED WORD per step:
-        //  - a full word without a newline is four chained lookups and nothing else (no per-byte tests: a match
-        //    sticks until the line ends);
-        //  - a word with a newline, the first word of an unaligned start and the last word of the segment take the
-        //    byte-wise form below, straight-line code without inner loops (threads of a warp diverge here, so it is short).
-        // The line bit is set when the line ends in the matched state, or at the end of the walk.
-        const uint32_t end = (uint32_t)n, cend = (uint32_t)chunk_end, ifrom = (uint32_t)idle_from;
-        uint32_t pos = (uint32_t)t;
-        if (pos >= end) return G.eod_next[s] >= first_accept ? line_bit : 0u;
-        uint32_t wpos = pos & ~3u;
-        uint32_t word = *reinterpret_cast<const uint32_t*>(data + wpos);   // the buffer is padded to a multiple of 16 bytes
-        while (true) {
-            // the next word is requested before the (dependent) table lookups of this one
-            const uint32_t next_word = wpos + 4 < end ? *reinterpret_cast<const uint32_t*>(data + wpos + 4) : 0u;
-            const uint32_t x = word ^ 0x0a0a0a0au;
-            if (((x - 0x01010101u) & ~x & 0x80808080u) == 0 && pos == wpos && wpos + 4 <= end) {
-                s = flat[(s << 8) | (word & 0xffu)];
-                s = flat[(s << 8) | ((word >> 8) & 0xffu)];
-                s = flat[(s << 8) | ((word >> 16) & 0xffu)];
-                s = flat[(s << 8) | (word >> 24)];
-            } else {
+    uint32_t mask = 0;
+    if (pos >= end) return G.eod_next[s] >= first_accept ? line_bit : 0u;
+    uint32_t wpos = pos & ~3u;
+    uint32_t word = X.word(wpos);   // the buffer is padded to a multiple of 16 bytes
+    while (true) {
+        // the next word is requested before the (dependent) table lookups of this one
+        const uint32_t next_word = wpos + 4 < end ? X.word(wpos + 4) : 0u;
+        const uint32_t x = word ^ 0x0a0a0a0au;
+        if (((x - 0x01010101u) & ~x & 0x80808080u) == 0 && pos == wpos && wpos + 4 <= end) {
+            s = T.step4(s, word);
+        } else {
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t p = wpos + k;
-                    if (p >= pos && p < end) {
-                        const uint32_t b = (word >> (8 * k)) & 0xffu;
-                        s = flat[(s << 8) | b];
-                        if (b == '\n') {
-                            if (s >= first_accept) mask |= line_bit;
-                            if (p + 1 >= cend) return mask;   // the next line starts outside the chunk
-                            line_bit <<= 1;
-                            s = 0;
-                        }
+            for (int k = 0; k < 4; k++) {
+                const uint32_t p = wpos + k;
+                if (p >= pos && p < end) {
+                    const uint32_t b = (word >> (8 * k)) & 0xffu;
+                    s = T.step(s, b);
+                    if (b == '\n') {
+                        if (s >= first_accept) mask |= line_bit;
+                        if (p + 1 >= cend) return mask;   // the next line starts outside the chunk
+                        line_bit <<= 1;
+                        s = 0;
                     }
                 }
             }
-            pos = wpos + 4;
-            if (s >= first_accept) {
-                if (pos >= cend) return mask | line_bit;   // matched, and no further line starts inside the chunk
-            } else if (pos >= ifrom && s < idle_end) {
-                return mask;
-            }
-            if (pos >= end) break;
-            wpos = pos;
-            word = next_word;
         }
-        if (s >= first_accept || G.eod_next[s] >= first_accept) mask |= line_bit;
-        return mask;
+        pos = wpos + 4;
+        if (s >= first_accept) {
+            if (pos >= cend) return mask | line_bit;   // matched, and no further line starts inside the chunk
+        } else if (pos >= ifrom && s < idle_end) {
+            return mask;
+        }
+        if (pos >= end) break;
+        wpos = pos;
+        word = next_word;
     }
+    if (s >= first_accept || G.eod_next[s] >= first_accept) mask |= line_bit;
+    return mask;
+}
+
+// entry state of a walk that starts at t: the byte before the walk decides; a '\n' there means the line starts exactly at t
+// (the callers only look for newlines inside [t, o)), so the walk enters in the start-of-line state: ^ and \A see a line start
+__device__ __forceinline__ uint32_t entry_state(const GroupDev& G, bool at_line_start, uint32_t before) {
+    if (at_line_start || before == '\n') return 0u;
+    return is_word_dev(before) ? G.mid_word : G.mid_other;
+}
+
+__device__ uint32_t walk_local(const GroupDev& G, const uint8_t* __restrict__ data, size_t n, size_t o, size_t t, bool at_line_start,
+                               size_t idle_from, uint32_t line_bit) {
+    uint32_t s = entry_state(G, at_line_start, at_line_start ? 0u : data[t - 1]);
+    uint32_t mask = 0;
+    const size_t chunk_end = o + 16;
+    const uint32_t first_accept = G.first_accept, idle_end = G.idle_end;
+    if (G.flat) return walk_words(FlatTable{G.flat}, GlobalText{data}, G, s, (uint32_t)n, (uint32_t)chunk_end, (uint32_t)t, (uint32_t)idle_from, line_bit);
     bool done = false;
     ByteCursor c(data, t, n);
     while (c.pos < n) {
@@ -253,6 +314,118 @@ __global__ void __launch_bounds__(128, 16) k_verify_local(DbView db, const uint8
 counted:
     const uint32_t records = __reduce_add_sync(0xffffffffu, __popc(mask));
     if ((threadIdx.x & 31) == 0 && records) atomicAdd(&tile_records[i / kEmitTile], records);
+    }
+}
+
+// The same verification with everything it touches per byte in shared memory (single-group databases whose
+// class-compressed table fits, GroupDev::ctab; bounded look-back):
+//  - the transition table as [state][class] u16 plus the byte -> class map: a step is one multiply-add and one shared
+//    load instead of a dependent 2-byte gather from global memory / L1 (k_verify_local was bound by exactly that);
+//  - the neighbourhood of the candidate chunk ([o - 16 PRE, o - 16 PRE + 4 WORDS), four or six 16-byte loads issued
+//    together) staged per thread, so that the walk does not wait for one global load per word.
+constexpr int kVerifyThreads = 512;
+template <int PRE, int WORDS>
+__global__ void __launch_bounds__(kVerifyThreads, 2) k_verify_smem(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
+                                                                   const unsigned long long* meta_total, size_t cap, uint32_t lookback,
+                                                                   uint32_t idle_span, ReprobeParams rp, uint32_t* __restrict__ marks,
+                                                                   uint32_t* __restrict__ tile_records) {
+    extern __shared__ __align__(16) uint32_t s_verify[];
+    const GroupDev G = db.groups[0];
+    const uint32_t table_words = (G.cstates * G.crow + 15u) / 16u * 4u;
+    {
+        const uint32_t* src_cls = reinterpret_cast<const uint32_t*>(G.cmap2);
+        const uint32_t* src_tab = reinterpret_cast<const uint32_t*>(G.ctab);
+        for (uint32_t k = threadIdx.x; k < 64u + table_words; k += blockDim.x) s_verify[k] = k < 64u ? src_cls[k] : src_tab[k - 64u];
+        __syncthreads();
+    }
+    const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_verify);
+    const SharedTable T{s_base + 256u, s_base, G.crow};
+    StagedText X{data, s_base + 256u + table_words * 4u + threadIdx.x * 4u, (uint32_t)blockDim.x * 4u, 0u, (uint32_t)WORDS};
+    const uint32_t end = (uint32_t)n;
+    size_t ncand = (size_t)(*meta_total >> 32);
+    if (ncand > cap) ncand = cap;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; (i & ~(size_t)31) < ncand; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t mask = 0;
+        if (i < ncand) {
+            const uint32_t o = cand[i] * 16u;
+            X.wbase = o >= 16u * PRE ? o - 16u * PRE : 0u;
+#pragma unroll
+            for (int c = 0; c < WORDS / 4; c++) {
+                const uint32_t off = X.wbase + 16u * c;
+                const uint4 v = off < end ? ld_chunk(data, off, n) : make_uint4(0u, 0u, 0u, 0u);
+                const uint32_t at = X.base + (4u * c) * X.pitch;
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(at), "r"(v.x));
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(at + X.pitch), "r"(v.y));
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(at + 2u * X.pitch), "r"(v.z));
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(at + 3u * X.pitch), "r"(v.w));
+            }
+            // (every thread reads back only the words it staged itself: no barrier)
+            uint32_t idle_from = o + idle_span;
+            uint32_t line_bit = 1u;
+            uint32_t hi = o;   // the walk has to start at or before hi - lookback
+            uint32_t nl_in_chunk = 0;
+            bool dropped = false;
+            if (rp.keys) {
+                uint32_t w[5] = {X.word(o), X.word(o + 4), X.word(o + 8), X.word(o + 12), o + 16 < end ? X.word(o + 16) : 0u};
+                const uint32_t nlm = movemask8(eq_mask4(w[0], 0x0a0a0a0au), eq_mask4(w[1], 0x0a0a0a0au)) |
+                                     (movemask8(eq_mask4(w[2], 0x0a0a0a0au), eq_mask4(w[3], 0x0a0a0a0au)) << 8);
+                if (rp.fold) {
+#pragma unroll
+                    for (int k = 0; k < 5; k++) w[k] |= 0x20202020u;
+                }
+                uint32_t hits = 0;   // bit = byte offset of a sampled gram that is in the table
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    for (int sft = 0; sft < 4; sft += rp.stride) {
+                        const uint32_t gram = __funnelshift_r(w[k], w[k + 1], 8 * sft);
+                        const uint32_t e1 = rp.keys[(gram * rp.mul) >> rp.shift], e2 = rp.keys[rp.half + ((gram * rp.mul2) >> rp.shift)];
+                        if (e1 == gram || e2 == gram) hits |= 1u << (4 * k + sft);
+                    }
+                    if (rp.nodd) {
+                        const uint32_t gram = __funnelshift_r(w[k], w[k + 1], 16);
+                        for (int c = 0; c < rp.nodd; c++)
+                            if (gram * rp.odd_mul[c] + rp.odd_add[c] == 0u) hits |= 1u << (4 * k + 2);
+                    }
+                }
+                if (hits == 0) {
+                    dropped = true;   // a bloom collision: no gram of the set here
+                } else {
+                    const uint32_t first = __ffs(hits) - 1, last = 31 - __clz(hits);
+                    hi = o + first;
+                    idle_from = o + last + 4;
+                    nl_in_chunk = nlm & ((1u << first) - 1u);   // newlines in [o, hi)
+                }
+            }
+            if (!dropped) {
+                // start: at most `lookback` bytes before the first hit, rounded down to a word, never before the line start
+                const uint32_t lo = hi > lookback ? (hi - lookback) & ~3u : 0u;
+                uint32_t t = lo;
+                bool at_line_start = lo == 0;
+                if (nl_in_chunk) {
+                    t = o + (32 - __clz(nl_in_chunk));   // just past the last newline before the hit
+                    at_line_start = true;
+                    line_bit = 1u << __popc(nl_in_chunk);
+                } else {
+                    uint32_t p = o;   // scan words [p-4, p) downwards for the last '\n' in [lo, o) (nothing to scan if lo >= o)
+                    while (p > lo) {
+                        uint32_t z = eq_mask4(X.word(p - 4), 0x0a0a0a0au);
+                        if (p - 4 < lo) z &= ~((1u << (8 * (lo - (p - 4)))) - 1u);
+                        if (z) {
+                            t = (p - 4) + ((31 - __clz(z)) >> 3) + 1;
+                            at_line_start = true;
+                            break;
+                        }
+                        p -= 4;
+                    }
+                }
+                uint32_t before = 0;
+                if (!at_line_start) before = t - 1 >= X.wbase ? (X.word((t - 1) & ~3u) >> (8 * ((t - 1) & 3u))) & 0xffu : data[t - 1];
+                mask = walk_words(T, X, G, entry_state(G, at_line_start, before), end, o + 16u, t, idle_from, line_bit);
+            }
+            marks[i] = mask;
+        }
+        const uint32_t records = __reduce_add_sync(0xffffffffu, __popc(mask));
+        if ((threadIdx.x & 31) == 0 && records) atomicAdd(&tile_records[i / kEmitTile], records);
     }
 }
 
@@ -424,6 +597,244 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit_simple(DbView db, const u
         valid += emit_warp(db, data, n, cand, marks, meta, prefix, live, live ? q_cand[k] : 0, live ? q_at[k] : 0, recs, rec_cap, totals);
     }
     // unique valid records of the segment (count-only callers need nothing else)
+    valid = __reduce_add_sync(0xffffffffu, valid);
+    if ((threadIdx.x & 31) == 0 && valid) atomicAdd(&totals->aux_total, (unsigned long long)valid);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Emit from the newline-chunk masks of k_stream (nlmask[block]: bit l set iff chunk l of the block holds a '\n').
+// Line start, line end and line number of a record come from a few mask words and the two text chunks that hold the
+// bounding newlines; the text of the line itself is read once, for the NUL test (hyperscanner.c:205-217 makes a line
+// with NUL bytes a different scanned block, so such lines are re-checked exactly).  k_emit_simple searched the text
+// chunk by chunk for all of this (about 2,000 instructions per record).
+// ------------------------------------------------------------------------------------------------------------
+// Index just past the last '\n' strictly before `pos` (the start of the line that contains byte pos), or 0.
+__device__ uint32_t nlm_line_start(const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ nlmask, uint32_t pos) {
+    const uint32_t c = pos >> 4;
+    uint32_t b = c >> 5;
+    uint32_t w = nlmask[b];
+    if ((pos & 15u) && ((w >> (c & 31u)) & 1u)) {
+        const uint32_t m = newline_mask16(ld_chunk(data, (size_t)c * 16, n)) & ((1u << (pos & 15u)) - 1u);
+        if (m) return c * 16u + (32u - __clz(m));
+    }
+    w &= (1u << (c & 31u)) - 1u;   // chunks of this block below c
+    while (true) {
+        if (w) {
+            const uint32_t cc = b * 32u + (31u - __clz(w));
+            const uint32_t m = newline_mask16(ld_chunk(data, (size_t)cc * 16, n));
+            return cc * 16u + (32u - __clz(m | 1u));
+        }
+        if (b == 0) return 0u;
+        if (b >= 4) {   // four mask words per step (long lines: 2 KiB of text per step)
+            const uint32_t w3 = nlmask[b - 1], w2 = nlmask[b - 2], w1 = nlmask[b - 3], w0 = nlmask[b - 4];
+            if (w3) { b -= 1; w = w3; } else if (w2) { b -= 2; w = w2; } else if (w1) { b -= 3; w = w1; } else { b -= 4; w = w0; }
+        } else {
+            b--;
+            w = nlmask[b];
+        }
+    }
+}
+// Index just past the first '\n' at or after `pos` (the end of the line that contains byte pos), or n.
+__device__ uint32_t nlm_line_end(const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ nlmask, uint32_t nblk, uint32_t pos) {
+    const uint32_t c = pos >> 4;
+    uint32_t b = c >> 5;
+    uint32_t w = nlmask[b];
+    if ((w >> (c & 31u)) & 1u) {
+        const uint32_t m = newline_mask16(ld_chunk(data, (size_t)c * 16, n)) & ~((1u << (pos & 15u)) - 1u);
+        if (m) return c * 16u + __ffs(m);
+    }
+    w &= ~((2u << (c & 31u)) - 1u);   // chunks of this block above c (c == 31: 2u << 31 == 0, the mask clears everything)
+    while (true) {
+        if (w) {
+            const uint32_t cc = b * 32u + (__ffs(w) - 1u);
+            const uint32_t m = newline_mask16(ld_chunk(data, (size_t)cc * 16, n));
+            return m ? cc * 16u + __ffs(m) : (uint32_t)n;
+        }
+        if (b + 4 < nblk) {
+            const uint32_t w0 = nlmask[b + 1], w1 = nlmask[b + 2], w2 = nlmask[b + 3], w3 = nlmask[b + 4];
+            if (w0) { b += 1; w = w0; } else if (w1) { b += 2; w = w1; } else if (w2) { b += 3; w = w2; } else { b += 4; w = w3; }
+        } else {
+            b++;
+            if (b >= nblk) return (uint32_t)n;
+            w = nlmask[b];
+        }
+    }
+}
+// Number of '\n' in [0, st), for st == 0 or st just past a newline.
+__device__ uint32_t nlm_line_number(const uint8_t* __restrict__ data, const unsigned long long* __restrict__ meta,
+                                    const unsigned long long* __restrict__ prefix, const uint32_t* __restrict__ nlmask, uint32_t st) {
+    if (st == 0) return 0u;
+    const uint32_t cq = (st - 1u) >> 4, bq = cq >> 5;
+    const uint32_t base = newlines_before_block(prefix, meta, bq);
+    const uint32_t w = nlmask[bq];
+    // every newline chunk of the block holds exactly one newline (lines of 16 bytes and more): chunks below + the one at st - 1
+    if ((uint32_t)(meta[bq] >> 32) == (uint32_t)__popc(w)) return base + __popc(w & ((1u << (cq & 31u)) - 1u)) + 1u;
+    return base + count_newlines(data, (size_t)bq << 9, st);
+}
+// NUL bytes in [from, to)?  Per-thread loop over at most `bound` bytes; returns false and sets *resume (16-byte aligned,
+// no NUL in [from, *resume)) when the range is longer.
+__device__ bool nul_scan_bounded(const uint8_t* __restrict__ data, size_t n, uint32_t from, uint32_t to, uint32_t bound, bool* has_nul, uint32_t* resume) {
+    uint32_t base = from & ~15u;
+    bool nul = false;
+    const uint32_t stop = from + bound < to ? ((from + bound) & ~15u) : to;
+    while (base < stop && !nul) {
+        // up to four chunks per step, all loads issued before the first test
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = base + 16u * k < stop ? ld_chunk(data, (size_t)base + 16u * k, n) : make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t cb = base + 16u * k;
+            if (cb < stop && (haszero4(v[k].x) | haszero4(v[k].y) | haszero4(v[k].z) | haszero4(v[k].w))) {
+                uint32_t zm = byte_mask16(v[k], 0u);
+                if (cb < from) zm &= ~((1u << (from - cb)) - 1u);
+                if (cb + 16u > to) zm &= (1u << (to - cb)) - 1u;
+                nul |= zm != 0u;
+            }
+        }
+        base += 64u;
+    }
+    *has_nul = nul;
+    if (nul || stop >= to) return true;
+    *resume = stop;
+    return false;
+}
+// Whole warp: NUL bytes in [from, to)?  from is 16-byte aligned.
+__device__ bool warp_nul_scan(const uint8_t* __restrict__ data, size_t n, uint32_t from, uint32_t to) {
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t pos = from; pos < to; pos += 512u) {
+        const uint32_t cb = pos + 16u * lane;
+        bool nul = false;
+        if (cb < to) {
+            uint32_t zm = byte_mask16(ld_chunk(data, cb, n), 0u);
+            if (cb + 16u > to) zm &= (1u << (to - cb)) - 1u;
+            nul = zm != 0u;
+        }
+        if (__any_sync(0xffffffffu, nul)) return true;
+    }
+    return false;
+}
+
+constexpr uint32_t kNulBound = 512;
+// Records of one marked candidate chunk per lane; whole warps call it (`live`: this lane has a candidate).
+__device__ uint32_t emit_lane_nlm(const DbView& db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
+                                  const uint32_t* __restrict__ marks, const unsigned long long* __restrict__ meta,
+                                  const unsigned long long* __restrict__ prefix, const uint32_t* __restrict__ nlmask, uint32_t nblk, bool live, size_t i,
+                                  size_t at, LineRec* __restrict__ recs, size_t rec_cap, Totals* totals) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t valid = 0;
+    uint32_t mask = live ? marks[i] : 0u;
+    const uint32_t o = live ? cand[i] * 16u : 0u;
+    uint32_t nlm = 0;
+    if (live && ((nlmask[o >> 9] >> ((o >> 4) & 31u)) & 1u)) nlm = newline_mask16(ld_chunk(data, o, n));
+    uint32_t st = 0;
+    bool first = true;   // still on line 0 of the chunk (the line that contains byte o)
+    while (__any_sync(0xffffffffu, mask != 0)) {
+        while (mask != 0 && !(mask & 1u)) {   // lines of the chunk that are not marked
+            if (!nlm) { mask = 0; break; }
+            st = o + __ffs(nlm);
+            nlm &= nlm - 1;
+            first = false;
+            mask >>= 1;
+        }
+        const bool work = mask != 0;
+        uint32_t en = 0, resume = 0;
+        bool has_nul = false, settled = true, ok = true;
+        if (work) {
+            if (first) st = nlm_line_start(data, n, nlmask, o);
+            en = nlm ? o + __ffs(nlm) : nlm_line_end(data, n, nlmask, nblk, o + 16u < (uint32_t)n ? o + 16u : (uint32_t)n - 1u);
+            // (nlm == 0 here means: no newline at or after st inside the chunk, so the line ends beyond it; if the chunk is
+            //  the last one, the search starts at the last byte and returns n)
+            if (first) {
+                // the line started before this chunk: an earlier candidate chunk that intersects it may have marked it
+                // already (the line is the LAST line of such a chunk); only the first marking is kept
+                for (size_t k = i; k-- > 0;) {
+                    const uint32_t ko = cand[k] * 16u;
+                    if (ko + 16u <= st) break;
+                    const uint32_t mk = marks[k];
+                    if (!mk) continue;
+                    uint32_t last_idx = 0;   // lines that start inside that chunk: newlines in its first 15 bytes
+                    if ((nlmask[ko >> 9] >> ((ko >> 4) & 31u)) & 1u) last_idx = __popc(newline_mask16(ld_chunk(data, ko, n)) & 0x7fffu);
+                    if ((mk >> last_idx) & 1u) { ok = false; break; }
+                }
+            }
+            settled = nul_scan_bounded(data, n, st, en, kNulBound, &has_nul, &resume);
+        }
+        for (uint32_t pend = __ballot_sync(0xffffffffu, work && !settled); pend; pend &= pend - 1) {
+            const int src = __ffs(pend) - 1;
+            const bool more = warp_nul_scan(data, n, __shfl_sync(0xffffffffu, resume, src), __shfl_sync(0xffffffffu, en, src));
+            if ((int)lane == src) has_nul = more;
+        }
+        if (work) {
+            if (ok && has_nul) ok = block_matches<false>(db, data, st, en);
+            valid += ok ? 1u : 0u;
+            const uint32_t line_no = nlm_line_number(data, meta, prefix, nlmask, st);
+            if (at < rec_cap) recs[at] = LineRec{line_no, st, ok ? ((en - st) | (has_nul ? kHasNulBit : 0u)) : kInvalidLen};
+            else atomicOr(&totals->flags, 4u);
+            at++;
+            if (!nlm) mask = 0;
+            else {
+                st = o + __ffs(nlm);
+                nlm &= nlm - 1;
+                first = false;
+                mask >>= 1;
+            }
+        }
+    }
+    return valid;
+}
+
+// Same tile / queue structure as k_emit_simple (persistent blocks, marked candidates queued and taken out in full batches).
+__global__ void __launch_bounds__(kEmitThreads) k_emit_nlm(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
+                                                           const uint32_t* __restrict__ marks, const uint32_t* __restrict__ tile_offsets,
+                                                           const unsigned long long* __restrict__ meta, const unsigned long long* __restrict__ prefix,
+                                                           const uint32_t* __restrict__ nlmask, const unsigned long long* meta_total, size_t cap,
+                                                           LineRec* __restrict__ recs, size_t rec_cap, Totals* totals) {
+    __shared__ uint32_t q_cand[kEmitQueue], q_at[kEmitQueue];
+    __shared__ unsigned long long s_warp[kEmitThreads / 32], s_total;
+    const uint32_t nblk = (uint32_t)((n + 511) >> 9);
+    uint32_t valid = 0;
+    uint32_t head = 0, queued = 0;   // the same in every thread of the block
+    size_t ncand = (size_t)(*meta_total >> 32);
+    if (ncand > cap) ncand = cap;
+    constexpr int kPer = kEmitTile / kEmitThreads;
+    for (size_t block_base = (size_t)blockIdx.x * kEmitTile; block_base < ncand; block_base += (size_t)gridDim.x * kEmitTile) {
+        uint32_t mk[kPer];
+        uint32_t records = 0, marked = 0;
+#pragma unroll
+        for (int j = 0; j < kPer; j++) {
+            const size_t i = block_base + (size_t)threadIdx.x * kPer + j;
+            mk[j] = i < ncand ? marks[i] : 0u;
+            records += __popc(mk[j]);
+            marked += mk[j] != 0u;
+        }
+        const unsigned long long before = block_exclusive_scan(((unsigned long long)marked << 32) | records, s_warp, &s_total);
+        uint32_t slot = head + queued + (uint32_t)(before >> 32);
+        uint32_t at = tile_offsets[block_base / kEmitTile] + (uint32_t)before;
+#pragma unroll
+        for (int j = 0; j < kPer; j++) {
+            if (mk[j]) {
+                q_cand[slot & (kEmitQueue - 1)] = (uint32_t)(block_base + (size_t)threadIdx.x * kPer + j);
+                q_at[slot & (kEmitQueue - 1)] = at;
+                slot++;
+                at += __popc(mk[j]);
+            }
+        }
+        queued += (uint32_t)(s_total >> 32);
+        __syncthreads();
+        while (queued >= (uint32_t)kEmitThreads) {
+            const uint32_t k = (head + threadIdx.x) & (kEmitQueue - 1);
+            valid += emit_lane_nlm(db, data, n, cand, marks, meta, prefix, nlmask, nblk, true, q_cand[k], q_at[k], recs, rec_cap, totals);
+            head += kEmitThreads;
+            queued -= kEmitThreads;
+        }
+        __syncthreads();
+    }
+    if (queued) {
+        const uint32_t k = (head + threadIdx.x) & (kEmitQueue - 1);
+        const bool live = threadIdx.x < queued;
+        valid += emit_lane_nlm(db, data, n, cand, marks, meta, prefix, nlmask, nblk, live, live ? q_cand[k] : 0, live ? q_at[k] : 0, recs, rec_cap, totals);
+    }
     valid = __reduce_add_sync(0xffffffffu, valid);
     if ((threadIdx.x & 31) == 0 && valid) atomicAdd(&totals->aux_total, (unsigned long long)valid);
 }

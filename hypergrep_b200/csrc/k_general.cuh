@@ -47,7 +47,7 @@ __global__ void k_count_pseudo_lines(const uint32_t* __restrict__ nlpos, size_t 
     if (i >= nlines) return;
     uint32_t st, len;
     line_extent(nlpos, nl_total, n, i, st, len);
-    npl[i] = (len + limit - 1) / limit;
+    npl[i] = len / limit + (len % limit != 0u);   // no 32-bit overflow of len + limit for huge buffer_size
     if (len > limit) atomicMax(&totals->max_line, len);
 }
 

@@ -9,8 +9,11 @@ namespace gpugrep {
 // loads in flight, newline count (SWAR + popc + warp reduce) and, when the prefilter is on, one gram-table lookup
 // per sampled 4-byte gram (shared-memory table of exact keys, or a bloom bitmap for huge gram sets).
 // Output: meta[block] = newline_count << 32 | ballot(lanes whose 16-byte chunk has a gram hit).
-// STRIDE: sample every STRIDE-th byte position (4, 2, 1).  MODE: 0 no prefilter, 1 exact keys, 2 bloom bitmap.
-// Algorithmic traffic: 1 byte read per input byte + 8 bytes written per 512.
+// STRIDE: sample every STRIDE-th byte position (4, 2, 1).  MODE: 0 no prefilter, 1 exact keys, 2 bloom byte table,
+// 3 bank-private blocked bloom (see probe_chunk).
+// Second output: nlmask[block] = ballot(lanes whose 16-byte chunk holds at least one '\n'); the emit kernel finds line
+// extents and line numbers from these words instead of searching the text again.
+// Algorithmic traffic: 1 byte read per input byte + 12 bytes written per 512.
 // ------------------------------------------------------------------------------------------------------------
 struct ProbeParams {
     uint32_t mul, mul2;   // hash multipliers (mul2: second choice of the exact table)
@@ -21,6 +24,9 @@ struct ProbeParams {
     // mixed sampling (Prefilter::odd): gram * odd_mul[k] + odd_add[k] == 0 at text offsets = 2 (mod 4).  Unused entries repeat
     // a used one.  The multipliers come from here (the parameter bank) so that the test stays ONE multiply-add on the FMA pipe.
     uint32_t odd_mul[2], odd_add[2];
+    // bank-private blocked bloom (MODE 3): the table is bp_words 32-bit words, stored bp_row / 4 times with the copies
+    // interleaved word by word; lane l only ever reads copy (l & bp_lane_mask), i.e. stays in its own bank(s).
+    uint32_t bp_words, bp_row, bp_lane_mask;
 };
 
 // Gram lookups of one 16-byte chunk.  MODE 1: two-choice table of exact 32-bit keys; the table is replicated
@@ -57,7 +63,14 @@ __device__ __forceinline__ bool probe_chunk(const uint4& v, uint32_t next, const
 #pragma unroll
         for (int s = 0; s < 4; s += STRIDE) {
             uint32_t gram = s == 0 ? w[i] : __funnelshift_r(w[i], w[i + 1], 8 * s);
-            if (MODE == 1) {
+            if (MODE == 3) {
+                // One conflict-free word load per gram, two bits of that word (a blocked bloom filter with k = 2): word =
+                // mulhi(p, words) with p = gram * mul, bits (p & 31) and ((p >> 16) & 31).  The address arithmetic is two
+                // multiply-adds (FMA pipe); the shifts by a register take their amount modulo 32 by themselves.
+                const uint32_t p = gram * pp.mul;
+                const uint32_t w32 = lds32(__umulhi(p, pp.bp_words) * pp.bp_row + c1);
+                bits |= (w32 >> (p & 31u)) & (w32 >> ((p >> 16) & 31u));
+            } else if (MODE == 1) {
                 uint32_t e1 = lds32((((gram * pp.mul) >> pp.shift) & pp.amask) | c1);
                 uint32_t e2 = lds32((((gram * pp.mul2) >> pp.shift) & pp.amask) | c2);
                 miss = __vimin3_u32(miss, e1 - gram, e2 - gram);   // differences, not XORs: ptxas can place subtractions on the FMA pipe
@@ -101,7 +114,8 @@ constexpr int kStreamU = 4;   // 512-byte blocks per warp step
 
 template <int STRIDE, bool FOLD, int MODE, int NODD>
 __global__ void __launch_bounds__(1024) k_stream(const uint8_t* __restrict__ data, size_t n, unsigned long long* __restrict__ meta,
-                                                 const uint32_t* __restrict__ table, int table_words, ProbeParams pp) {
+                                                 uint32_t* __restrict__ nlmask, const uint32_t* __restrict__ table, int table_words,
+                                                 ProbeParams pp) {
     extern __shared__ __align__(16) uint32_t s_raw[];
     // exact tables are placed at an address aligned to the size of one half (see probe_chunk); the launch reserves the slack
     uint32_t* s_tab = s_raw;
@@ -111,14 +125,19 @@ __global__ void __launch_bounds__(1024) k_stream(const uint8_t* __restrict__ dat
         s_tab = s_raw + ((aligned - saddr) >> 2);
         saddr = aligned;
     }
-    if (MODE != 0) {
+    if (MODE == 3) {
+        // every copy is the same: one global read per word, written to all copies
+        const uint32_t copies = pp.bp_row >> 2;
+        for (uint32_t i = threadIdx.x; i < pp.bp_words * copies; i += blockDim.x) s_tab[i] = table[i / copies];
+        __syncthreads();
+    } else if (MODE != 0) {
         for (int i = threadIdx.x; i < table_words; i += blockDim.x) s_tab[i] = table[i];
         __syncthreads();
     }
     constexpr int U = kStreamU;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t replica4 = (lane & ((1u << pp.rshift) - 1u)) << 2;
-    uint32_t c1 = MODE == 1 ? (saddr | replica4) : saddr, c2 = (saddr + pp.half_bytes) | replica4;
+    uint32_t c1 = MODE == 1 ? (saddr | replica4) : (MODE == 3 ? saddr + ((lane & pp.bp_lane_mask) << 2) : saddr), c2 = (saddr + pp.half_bytes) | replica4;
     asm volatile("mov.u32 %0, %0;" : "+r"(c1));   // materialise: each table address is then a single (x & amask) | c
     asm volatile("mov.u32 %0, %0;" : "+r"(c2));
     uint32_t cnl, c80;   // opaque to the optimiser so that they stay in registers (see eq_mask4_r)
@@ -157,12 +176,13 @@ __global__ void __launch_bounds__(1024) k_stream(const uint8_t* __restrict__ dat
             if (off + 4 <= n) after = *reinterpret_cast<const uint32_t*>(data + off);
             else if (off < n) after = ld_chunk(data, off, n).x;
         }
-        uint32_t cnt01, cnt23, masks[U];
+        uint32_t cnt01, cnt23, masks[U], nlm[U];
         {
             uint32_t c[U];
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 c[u] = newline_count16_fma(v[u], cnl, c80);
+                nlm[u] = __ballot_sync(0xffffffffu, c[u] != 0u);
                 uint32_t nx = 0;
                 if (MODE != 0 && (STRIDE < 4 || NODD > 0)) {
                     // first word of the next chunk: lane+1's word of this block, or (lane 31) lane 0's word of the next block
@@ -180,6 +200,7 @@ __global__ void __launch_bounds__(1024) k_stream(const uint8_t* __restrict__ dat
             uint4* out = reinterpret_cast<uint4*>(meta + g0);   // g0 is a multiple of 4: 32-byte aligned
             out[0] = make_uint4(masks[0], cnt01 & 0xffffu, masks[1], cnt01 >> 16);
             out[1] = make_uint4(masks[2], cnt23 & 0xffffu, masks[3], cnt23 >> 16);
+            *reinterpret_cast<uint4*>(nlmask + g0) = make_uint4(nlm[0], nlm[1], nlm[2], nlm[3]);
         }
     }
 
@@ -199,8 +220,9 @@ __global__ void __launch_bounds__(1024) k_stream(const uint8_t* __restrict__ dat
         bool hit = probe_chunk<STRIDE, FOLD, MODE, NODD>(v, nx, s_tab, pp, c1, c2);
         if (off >= n) hit = false;   // chunks that start at or beyond n can never be candidates
         uint32_t mask = __ballot_sync(0xffffffffu, hit);
+        uint32_t nl = __ballot_sync(0xffffffffu, cnt != 0u);
         uint32_t total = __reduce_add_sync(0xffffffffu, cnt);
-        if (lane == 0) meta[g] = ((unsigned long long)total << 32) | mask;
+        if (lane == 0) { meta[g] = ((unsigned long long)total << 32) | mask; nlmask[g] = nl; }
     }
 }
 

@@ -113,8 +113,9 @@ GPUGREP_API void gpugrep_discard_results(hyperscanner_result_t* results, int res
  * `data` is host memory. */
 GPUGREP_API size_t gpugrep_shard_begin(const void* data, size_t size, unsigned int rank, unsigned int world);
 
-/* Select the CUDA device used by subsequent calls from this thread's process (default: $GPUGREP_DEVICE,
- * else $LOCAL_RANK, else 0). */
+/* Select the CUDA device used by subsequent calls of this process; -1 restores the default, which is $GPUGREP_DEVICE,
+ * else $LOCAL_RANK, else round-robin over the visible GPUs (successive scans - one per file in multiscanner - take
+ * successive devices). */
 GPUGREP_API void gpugrep_set_device(int device);
 
 /* Path of the libzstd shared object used for .zst ingest (default "libzstd.so.1"). */

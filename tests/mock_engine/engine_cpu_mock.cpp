@@ -34,6 +34,8 @@ public:
 
 int engine_select_device(int, std::string&) { return 0; }
 int engine_current_device() { return 0; }
+int engine_device_count() { return 1; }
+void slot_set_want_records(ScanSlot*, bool) {}
 
 std::shared_ptr<DeviceDb> engine_upload(const std::shared_ptr<Database>& db, std::string&) {
     auto d = std::make_shared<DeviceDb>();
@@ -132,7 +134,7 @@ int slot_collect(ScanSlot* s, SegmentResult& out, std::string&) {
     return 0;
 }
 
-int slot_probe_input(ScanSlot*, const uint8_t*, size_t, size_t, std::vector<size_t>& cuts, uint8_t*, size_t, std::string& error) {
+int slot_probe_input(ScanSlot*, const uint8_t*, size_t, size_t, std::vector<size_t>& cuts, uint8_t*, size_t, void*, std::string& error) {
     cuts.clear();
     error = "mock engine: device-resident input is not supported";
     return 7;
