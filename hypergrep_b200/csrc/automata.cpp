@@ -175,9 +175,10 @@ struct Determinizer {
     bool assert_holds(AssertKind k, const Ctx& ctx, int look) const {
         switch (k) {
             case AssertKind::BeginBuffer: return ctx.at_start;
-            // PCRE: a multiline ^ matches at the start of the subject and after INTERNAL newlines, not after a newline that ends
-            // the subject.  The only newline of a scanned block is its last byte, so inside a block ^ is the block start.
-            case AssertKind::BeginLine: return ctx.at_start;
+            // Hyperscan: a multiline ^ holds at offset 0 and after ANY newline, also the one that ends the block (a streaming
+            // engine cannot tell that a newline is the last byte).  PCRE's default excludes that position; the oracle
+            // compiles with PCRE2_ALT_CIRCUMFLEX to agree.
+            case AssertKind::BeginLine: return ctx.at_start || ctx.prev_nl;
             case AssertKind::EndBuffer: return look == LookEod;
             case AssertKind::EndLine: return look == LookEod || look == LookNewline;
             case AssertKind::WordBoundary: return ctx.prev_word != (look == LookWord);

@@ -35,7 +35,7 @@ struct ByteSet {
 
 enum class AssertKind : uint8_t {
     BeginBuffer,   // \A, ^ without MULTILINE
-    BeginLine,     // ^ with MULTILINE: offset 0 (after '\n' would be the end of the block, where PCRE's ^ does not match)
+    BeginLine,     // ^ with MULTILINE: offset 0 or after '\n' (also the '\n' that ends the block: Hyperscan semantics)
     EndBuffer,     // \z
     EndLine,       // $ with MULTILINE: before '\n' or at end of block
     WordBoundary,  // \b

@@ -57,6 +57,10 @@ typedef void (*port_event)(port_result_t* results, int result_count);
 #define P2_NEVER_UTF 0x00001000u
 #define P2_NEVER_UCP 0x00000800u
 #define P2_NO_AUTO_CAPTURE 0x00002000u
+/* Hyperscan's multiline ^ is "start of data or after ANY newline" (a streaming-capable engine cannot know that a newline is
+   the last byte), PCRE2's default excludes a newline that ends the subject: PCRE2_ALT_CIRCUMFLEX
+   selects the Hyperscan behaviour. */
+#define P2_ALT_CIRCUMFLEX 0x00200000u
 #define P2_ANCHORED 0x80000000u
 #define P2_JIT_COMPLETE 0x00000001u
 #define P2_NOTEMPTY 0x00000004u
@@ -192,7 +196,7 @@ static void port_db_free(port_db_t* db) {
 }
 
 static uint32_t p2_options(unsigned hs_flags) {
-    uint32_t o = P2_NEVER_UTF | P2_NEVER_UCP;
+    uint32_t o = P2_NEVER_UTF | P2_NEVER_UCP | P2_ALT_CIRCUMFLEX;
     if (hs_flags & HS_FLAG_CASELESS) o |= P2_CASELESS;
     if (hs_flags & HS_FLAG_DOTALL) o |= P2_DOTALL;
     if (hs_flags & HS_FLAG_MULTILINE) o |= P2_MULTILINE;
@@ -250,7 +254,7 @@ static port_db_t* port_compile(const char* const* patterns, const unsigned* flag
             o += (size_t)sprintf(buf + o, "%s(?%s%s%s:%s)", i ? "|" : "", on, off[0] ? "-" : "", off, patterns[i]);
         }
         int err = 0; size_t eoff = 0;
-        db->merged = P2.compile((const unsigned char*)buf, o, P2_NEVER_UTF | P2_NEVER_UCP | P2_NO_AUTO_CAPTURE, &err, &eoff, NULL);
+        db->merged = P2.compile((const unsigned char*)buf, o, P2_NEVER_UTF | P2_NEVER_UCP | P2_NO_AUTO_CAPTURE | P2_ALT_CIRCUMFLEX, &err, &eoff, NULL);
         free(buf);
         if (db->merged) {
             if (P2.jit_compile(db->merged, P2_JIT_COMPLETE) != 0) { P2.code_free(db->merged); db->merged = NULL; }

@@ -6,6 +6,7 @@ import os
 import pytest
 
 import parity
+from oracle_api import scan_bytes as run_scan_bytes
 from hypergrep_b200 import synth
 
 
@@ -136,10 +137,12 @@ def test_grep_count_only_paths_agree(hostmock_lib, tmp_path, monkeypatch):
         assert utils.grep(str(path), ["foobar", "^line 7 "], count_only=True, max_match_count=limit) == (expected, 0)
 
 
-def test_multiline_circumflex_does_not_match_after_the_final_newline(hostmock_lib, oracle_lib):
-    """PCRE: a multiline ^ matches after internal newlines, not after a newline that ends the subject - and the only
-    newline of a scanned block is its last byte (found by tools/fuzz_gpu.py, seed range 50000-80000)."""
+def test_multiline_circumflex_after_the_final_newline(hostmock_lib, oracle_lib):
+    """Hyperscan's multiline ^ holds after ANY newline, also the one that ends the scanned block (SURVEY.md Appendix A); PCRE's
+    default does not, so the oracle compiles with PCRE2_ALT_CIRCUMFLEX.  `x\\W^` therefore matches the line "x\\n"."""
     data = b"x\n\t xxx\t_a1AB\nyx\nx"
+    rc, got, _ = run_scan_bytes(oracle_lib, data, ["x\\W^"])
+    assert rc == 0 and [ln for (_i, ln, _t) in got] == [0, 2]
     for patterns in (["x\\W^"], ["x\\W\\Z\\z^([^a]a)*?"], ["^x"], ["x\\s^", "^y"]):
         parity.compare(hostmock_lib, oracle_lib, data, patterns, flags=[14] * len(patterns), ids=list(range(len(patterns))), buffer_size=64)
         parity.compare(hostmock_lib, oracle_lib, data, patterns)
