@@ -109,7 +109,7 @@ struct DevicePrefilter {
     int table_words = 0;
     int stride = 4;
     bool fold = false;
-    int mode = 0;        // 1 exact keys, 2 bloom byte table, 3 bank-private blocked bloom
+    int mode = 0;        // 1 exact keys, 2 bloom byte table
     int nodd = 0;        // register compares at offsets 2 mod 4 (mixed sampling; bloom mode only)
     ProbeParams pp{};
     uint32_t lookback = 0xffffffffu;
@@ -128,7 +128,7 @@ public:
     cudaStream_t copy_stream = nullptr;   // result D2H, so that it does not queue behind the next segment's kernels
     cudaEvent_t done = nullptr;           // all kernels of the segment + the totals copy have finished
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // 0/1: whole segment, 2/3: streaming kernel
-    DevBuf d_input, d_meta, d_nlmask, d_prefix, d_sums, d_cand, d_res, d_recoff, d_recs, d_totals;
+    DevBuf d_input, d_meta, d_nlmask, d_gsum, d_prefix, d_sums, d_cand, d_res, d_recoff, d_recs, d_totals;
     DevBuf d_nlpos, d_npl, d_ploff, d_plstart, d_pllen, d_flags, d_counts, d_events, d_gather, d_gidx;
     PinBuf h_totals, h_recs, h_stage, h_gather, h_probe;
     // state of the in-flight segment
@@ -297,19 +297,13 @@ std::shared_ptr<DevicePrefilter> engine_upload_prefilter(const Prefilter& pf, st
     const std::vector<uint32_t>* src = &pf.bitmap;
     const char* want = std::getenv("GPUGREP_FILTER");
     const bool use_exact = pf.exact && pf.odd.empty() && want && std::strcmp(want, "exact") == 0;
-    const bool use_bank_private = !use_exact && pf.bp_copies > 0 && !(want && std::strcmp(want, "bloom") == 0);
     out->stride = pf.stride;
     out->fold = pf.fold_case;
-    out->mode = use_exact ? 1 : (use_bank_private ? 3 : 2);
-    out->pp.mul = use_exact ? pf.hash_mul : (use_bank_private ? pf.bp_mul : pf.bloom_mul);
-    if (use_bank_private) {
-        out->pp.bp_words = pf.bp_words;
-        out->pp.bp_row = 4u * (uint32_t)pf.bp_copies;
-        out->pp.bp_lane_mask = (uint32_t)pf.bp_copies - 1u;
-        src = &pf.bp_table;
-    }
+    out->mode = use_exact ? 1 : 2;
+    out->pp.mul = use_exact ? pf.hash_mul : pf.bloom_mul;
     out->pp.mul2 = pf.hash_mul2;
     out->pp.shift = 32 - (pf.log2_bits - 3);   // bloom: product -> byte index
+    out->pp.hi_mul = 1u << (pf.log2_bits - 3);
     out->lookback = pf.lookback;
     out->nodd = (int)std::min<size_t>(pf.odd.size(), 2);
     for (int k = 0; k < 2; k++) {
@@ -346,8 +340,7 @@ std::shared_ptr<DevicePrefilter> engine_upload_prefilter(const Prefilter& pf, st
             return nullptr;
         }
     }
-    out->bloom_false_rate = use_bank_private ? pf.bp_false_rate * (16.0 / pf.stride)
-                                             : (double)pf.num_grams * (16.0 / pf.stride) / (double)((size_t)1 << pf.log2_bits);
+    out->bloom_false_rate = (double)pf.num_grams * (16.0 / pf.stride) / (double)((size_t)1 << pf.log2_bits);
     out->table_words = (int)src->size();
     if (cudaMalloc((void**)&out->d_table, src->size() * sizeof(uint32_t)) != cudaSuccess ||
         cudaMemcpy(out->d_table, src->data(), src->size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -434,30 +427,30 @@ static void launch_scan(cudaStream_t st, Load load, size_t n, unsigned long long
 
 template <int STRIDE, bool FOLD, int MODE, int NODD = 0>
 static cudaError_t launch_stream_t(cudaStream_t st, int grid, int block, size_t smem, const uint8_t* data, size_t n, unsigned long long* meta,
-                                   uint32_t* nlmask, const DevicePrefilter* pf) {
+                                   uint32_t* nlmask, unsigned long long* gsum, const DevicePrefilter* pf) {
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_stream<STRIDE, FOLD, MODE, NODD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    k_stream<STRIDE, FOLD, MODE, NODD><<<grid, block, smem, st>>>(data, n, meta, nlmask, pf ? pf->d_table : nullptr, pf ? pf->table_words : 0,
+    k_stream<STRIDE, FOLD, MODE, NODD><<<grid, block, smem, st>>>(data, n, meta, nlmask, gsum, pf ? pf->d_table : nullptr, pf ? pf->table_words : 0,
                                                             pf ? pf->pp : ProbeParams{});
     return cudaGetLastError();
 }
 
 template <int MODE>
 static cudaError_t launch_stream_m(cudaStream_t st, int grid, int block, size_t smem, const uint8_t* data, size_t n, unsigned long long* meta,
-                                   uint32_t* nlmask, const DevicePrefilter* pf) {
+                                   uint32_t* nlmask, unsigned long long* gsum, const DevicePrefilter* pf) {
     int key = pf->stride * 2 + (pf->fold ? 1 : 0);
-    if (MODE >= 2 && pf->stride == 4 && pf->nodd > 0)
-        return pf->fold ? launch_stream_t<4, true, MODE, 2>(st, grid, block, smem, data, n, meta, nlmask, pf)
-                        : launch_stream_t<4, false, MODE, 2>(st, grid, block, smem, data, n, meta, nlmask, pf);
+    if (MODE == 2 && pf->stride == 4 && pf->nodd > 0)
+        return pf->fold ? launch_stream_t<4, true, MODE, 2>(st, grid, block, smem, data, n, meta, nlmask, gsum, pf)
+                        : launch_stream_t<4, false, MODE, 2>(st, grid, block, smem, data, n, meta, nlmask, gsum, pf);
     switch (key) {
-        case 8: return launch_stream_t<4, false, MODE>(st, grid, block, smem, data, n, meta, nlmask, pf);
-        case 9: return launch_stream_t<4, true, MODE>(st, grid, block, smem, data, n, meta, nlmask, pf);
-        case 4: return launch_stream_t<2, false, MODE>(st, grid, block, smem, data, n, meta, nlmask, pf);
-        case 5: return launch_stream_t<2, true, MODE>(st, grid, block, smem, data, n, meta, nlmask, pf);
-        case 2: return launch_stream_t<1, false, MODE>(st, grid, block, smem, data, n, meta, nlmask, pf);
-        default: return launch_stream_t<1, true, MODE>(st, grid, block, smem, data, n, meta, nlmask, pf);
+        case 8: return launch_stream_t<4, false, MODE>(st, grid, block, smem, data, n, meta, nlmask, gsum, pf);
+        case 9: return launch_stream_t<4, true, MODE>(st, grid, block, smem, data, n, meta, nlmask, gsum, pf);
+        case 4: return launch_stream_t<2, false, MODE>(st, grid, block, smem, data, n, meta, nlmask, gsum, pf);
+        case 5: return launch_stream_t<2, true, MODE>(st, grid, block, smem, data, n, meta, nlmask, gsum, pf);
+        case 2: return launch_stream_t<1, false, MODE>(st, grid, block, smem, data, n, meta, nlmask, gsum, pf);
+        default: return launch_stream_t<1, true, MODE>(st, grid, block, smem, data, n, meta, nlmask, gsum, pf);
     }
 }
 
@@ -501,6 +494,7 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
     s->rec_cap = n / 48 + 4096;
     size_t nb_scan = (std::max(s->nblk, s->cand_cap) + kScanTile - 1) / kScanTile + 1;
     if (s->d_meta.reserve((s->nblk + 8) * 8) != cudaSuccess || s->d_nlmask.reserve((s->nblk + 8) * 4) != cudaSuccess ||
+        s->d_gsum.reserve((s->nblk / kGroupBlocks + 4) * 8) != cudaSuccess ||
         s->d_prefix.reserve((s->nblk + 8) * 8) != cudaSuccess ||
         s->d_sums.reserve(nb_scan * 8) != cudaSuccess) { error = "cudaMalloc failed for scan scratch"; return 3; }
     if (s->fast) {
@@ -520,7 +514,7 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
     // ---- K1 ----
     // persistent grid: enough CTAs to fill every SM, each warp strides over groups of kStreamU blocks
     size_t smem = 0;
-    if (s->fast) smem = pf->mode == 3 ? (size_t)pf->pp.bp_words * pf->pp.bp_row : (size_t)pf->table_words * 4 + (pf->mode == 1 ? pf->pp.half_bytes : 0);
+    if (s->fast) smem = (size_t)pf->table_words * 4 + (pf->mode == 1 ? pf->pp.half_bytes : 0);
     int block = smem > 32 * 1024 ? 1024 : 256;
     int ctas_per_sm = smem > 100 * 1024 ? 1 : (smem > 32 * 1024 ? 2 : 6);
     int grid = device_sms() * ctas_per_sm;
@@ -529,20 +523,23 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
     if ((size_t)grid > max_grid) grid = (int)std::max<size_t>(1, max_grid);
     unsigned long long* meta = s->d_meta.as<unsigned long long>();
     uint32_t* nlmask = s->d_nlmask.as<uint32_t>();
+    // totals per group of four blocks, written by the streaming kernel and read by the scan; the blocks of the last,
+    // partial group add theirs with atomics into a zeroed slot
+    unsigned long long* gsum = s->d_gsum.as<unsigned long long>();
+    const size_t ngroups = (s->nblk + kGroupBlocks - 1) / kGroupBlocks;
+    CUDA_TRY(cudaMemsetAsync(gsum + (ngroups ? ngroups - 1 : 0), 0, 16, st));
     CUDA_TRY(cudaEventRecord(s->ev[2], st));
     cudaError_t le;
-    if (!s->fast) le = launch_stream_t<4, false, 0>(st, grid, block, 0, s->data, n, meta, nlmask, nullptr);
-    else if (pf->mode == 3) le = launch_stream_m<3>(st, grid, block, smem, s->data, n, meta, nlmask, pf);
-    else if (pf->mode == 1) le = launch_stream_m<1>(st, grid, block, smem, s->data, n, meta, nlmask, pf);
-    else le = launch_stream_m<2>(st, grid, block, smem, s->data, n, meta, nlmask, pf);
+    if (!s->fast) le = launch_stream_t<4, false, 0>(st, grid, block, 0, s->data, n, meta, nlmask, gsum, nullptr);
+    else if (pf->mode == 1) le = launch_stream_m<1>(st, grid, block, smem, s->data, n, meta, nlmask, gsum, pf);
+    else le = launch_stream_m<2>(st, grid, block, smem, s->data, n, meta, nlmask, gsum, pf);
     if (le != cudaSuccess) { error = std::string("k_stream launch: ") + cudaGetErrorString(le); return 7; }
     CUDA_TRY(cudaEventRecord(s->ev[3], st));
     s->stats.launches++;
     s->stats.stream_launches++;
     // ---- scan of (candidates, newlines) ----
     unsigned long long* prefix = s->d_prefix.as<unsigned long long>();
-    launch_scan(st, LoadMetaGroup{meta, s->nblk}, (s->nblk + kGroupBlocks - 1) / kGroupBlocks, prefix, s->d_sums.as<unsigned long long>(),
-                &dT->meta_total, s->stats);
+    launch_scan(st, LoadU64{gsum}, ngroups, prefix, s->d_sums.as<unsigned long long>(), &dT->meta_total, s->stats);
     if (s->fast) {
         const unsigned sms = (unsigned)device_sms();
         size_t bps = super_bytes / 512;
@@ -575,8 +572,8 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
         // Verification.  Single-group databases whose class-compressed table fits shared memory, with a look-back that the
         // staged text window covers, take k_verify_smem; everything else the global-table kernel.
         const char* vsel = std::getenv("GPUGREP_VERIFY");
-        const bool v1 = vsel && std::strcmp(vsel, "v1") == 0;
-        if (!v1 && ddb.smem_table_bytes && pf->lookback <= 29u) {
+        const bool use_smem = vsel && std::strcmp(vsel, "smem") == 0;   // measured slower than the global-table kernel (profiles/README.md)
+        if (use_smem && ddb.smem_table_bytes && pf->lookback <= 29u) {
             const bool wide = pf->lookback > 13u;
             const size_t vsmem = 256 + ddb.smem_table_bytes + (size_t)(wide ? 24 : 16) * 4 * kVerifyThreads;
             auto kernel = wide ? k_verify_smem<2, 24> : k_verify_smem<1, 16>;

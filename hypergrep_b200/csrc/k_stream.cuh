@@ -9,8 +9,7 @@ namespace gpugrep {
 // loads in flight, newline count (SWAR + popc + warp reduce) and, when the prefilter is on, one gram-table lookup
 // per sampled 4-byte gram (shared-memory table of exact keys, or a bloom bitmap for huge gram sets).
 // Output: meta[block] = newline_count << 32 | ballot(lanes whose 16-byte chunk has a gram hit).
-// STRIDE: sample every STRIDE-th byte position (4, 2, 1).  MODE: 0 no prefilter, 1 exact keys, 2 bloom byte table,
-// 3 bank-private blocked bloom (see probe_chunk).
+// STRIDE: sample every STRIDE-th byte position (4, 2, 1).  MODE: 0 no prefilter, 1 exact keys, 2 bloom byte table.
 // Second output: nlmask[block] = ballot(lanes whose 16-byte chunk holds at least one '\n'); the emit kernel finds line
 // extents and line numbers from these words instead of searching the text again.
 // Algorithmic traffic: 1 byte read per input byte + 12 bytes written per 512.
@@ -24,9 +23,7 @@ struct ProbeParams {
     // mixed sampling (Prefilter::odd): gram * odd_mul[k] + odd_add[k] == 0 at text offsets = 2 (mod 4).  Unused entries repeat
     // a used one.  The multipliers come from here (the parameter bank) so that the test stays ONE multiply-add on the FMA pipe.
     uint32_t odd_mul[2], odd_add[2];
-    // bank-private blocked bloom (MODE 3): the table is bp_words 32-bit words, stored bp_row / 4 times with the copies
-    // interleaved word by word; lane l only ever reads copy (l & bp_lane_mask), i.e. stays in its own bank(s).
-    uint32_t bp_words, bp_row, bp_lane_mask;
+    uint32_t hi_mul;      // bloom: 2^(32 - shift): the byte index is mulhi(product, hi_mul)
 };
 
 // Gram lookups of one 16-byte chunk.  MODE 1: two-choice table of exact 32-bit keys; the table is replicated
@@ -47,6 +44,9 @@ __device__ __forceinline__ uint32_t lds8(uint32_t shared_addr) {
 
 // c1 / c2: shared-window address of table half 1 / 2 (aligned to the size of a half) OR-ed with 4 * copy of this lane,
 // so that an address is formed by ONE logic op: ((product >> shift) & amask) | c.
+// The streaming kernel saturates the ALU pipe (shifts, logic ops) long before the FMA pipe (integer multiply-adds), so
+// whatever can be phrased as a multiply is: the table index of the bloom lookup is mulhi(product, 2^(32 - shift)) instead
+// of a shift (pp.hi_mul comes from the parameter bank, so ptxas cannot turn it back into one).
 template <int STRIDE, bool FOLD, int MODE, int NODD>
 __device__ __forceinline__ bool probe_chunk(const uint4& v, uint32_t next, const uint32_t* __restrict__ tab, const ProbeParams& pp, uint32_t c1,
                                             uint32_t c2) {
@@ -63,14 +63,7 @@ __device__ __forceinline__ bool probe_chunk(const uint4& v, uint32_t next, const
 #pragma unroll
         for (int s = 0; s < 4; s += STRIDE) {
             uint32_t gram = s == 0 ? w[i] : __funnelshift_r(w[i], w[i + 1], 8 * s);
-            if (MODE == 3) {
-                // One conflict-free word load per gram, two bits of that word (a blocked bloom filter with k = 2): word =
-                // mulhi(p, words) with p = gram * mul, bits (p & 31) and ((p >> 16) & 31).  The address arithmetic is two
-                // multiply-adds (FMA pipe); the shifts by a register take their amount modulo 32 by themselves.
-                const uint32_t p = gram * pp.mul;
-                const uint32_t w32 = lds32(__umulhi(p, pp.bp_words) * pp.bp_row + c1);
-                bits |= (w32 >> (p & 31u)) & (w32 >> ((p >> 16) & 31u));
-            } else if (MODE == 1) {
+            if (MODE == 1) {
                 uint32_t e1 = lds32((((gram * pp.mul) >> pp.shift) & pp.amask) | c1);
                 uint32_t e2 = lds32((((gram * pp.mul2) >> pp.shift) & pp.amask) | c2);
                 miss = __vimin3_u32(miss, e1 - gram, e2 - gram);   // differences, not XORs: ptxas can place subtractions on the FMA pipe
@@ -78,7 +71,7 @@ __device__ __forceinline__ bool probe_chunk(const uint4& v, uint32_t next, const
                 // bloom: one byte load, bit (p & 7) of it.  The byte is replicated into all four bytes of a word (one
                 // multiply on the FMA pipe) so that the wrap-around shift by p itself lands on the right bit.
                 uint32_t p = gram * pp.mul;
-                uint32_t b = lds8((p >> pp.shift) + c1);
+                uint32_t b = lds8(__umulhi(p, pp.hi_mul) + c1);
                 bits |= (b * 0x01010101u) >> (p & 31u);
             }
         }
@@ -99,10 +92,20 @@ __device__ __forceinline__ bool probe_chunk(const uint4& v, uint32_t next, const
     return MODE == 1 ? miss == 0u : (bits & 1u) != 0u;
 }
 
+// 0x80 in every byte of w equal to '\n', with the subtraction phrased as a multiply-add (FMA pipe): one = 1 and
+// neg = -0x01010101 are opaque registers (see k_stream), so ptxas keeps the IMAD.
+__device__ __forceinline__ uint32_t newline_flags4(uint32_t w, uint32_t cnl, uint32_t c80, uint32_t one, uint32_t neg) {
+    uint32_t u, t, z;
+    asm("lop3.b32 %0, %1, %2, %3, 0xBE;" : "=r"(u) : "r"(w), "r"(cnl), "r"(c80));   // (w ^ rep) | 0x80808080
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(u), "r"(one), "r"(neg));        // u - 0x01010101
+    asm("lop3.b32 %0, %1, %2, %3, 0x02;" : "=r"(z) : "r"(t), "r"(w), "r"(c80));     // ~(t | w) & 0x80808080
+    return z;
+}
 // newlines in a 16-byte chunk: four flag words (bit 7 of matching bytes) are merged into one 64-bit word with three
 // multiply-adds (FMA pipe) instead of shifts and ORs (ALU pipe, the pipe this kernel saturates first)
-__device__ __forceinline__ uint32_t newline_count16_fma(const uint4& v, uint32_t cnl, uint32_t c80) {
-    uint32_t a = eq_mask4_r(v.x, cnl, c80), b = eq_mask4_r(v.y, cnl, c80), c = eq_mask4_r(v.z, cnl, c80), d = eq_mask4_r(v.w, cnl, c80);
+__device__ __forceinline__ uint32_t newline_count16_fma(const uint4& v, uint32_t cnl, uint32_t c80, uint32_t one, uint32_t neg) {
+    uint32_t a = newline_flags4(v.x, cnl, c80, one, neg), b = newline_flags4(v.y, cnl, c80, one, neg);
+    uint32_t c = newline_flags4(v.z, cnl, c80, one, neg), d = newline_flags4(v.w, cnl, c80, one, neg);
     unsigned long long acc = a;
     asm("mad.wide.u32 %0, %1, 2, %0;" : "+l"(acc) : "r"(b));
     asm("mad.wide.u32 %0, %1, 4, %0;" : "+l"(acc) : "r"(c));
@@ -112,10 +115,60 @@ __device__ __forceinline__ uint32_t newline_count16_fma(const uint4& v, uint32_t
 
 constexpr int kStreamU = 4;   // 512-byte blocks per warp step
 
+// Per-warp constants of the streaming kernel.
+struct StreamRegs {
+    uint32_t c1, c2, cnl, c80, one, neg, lane;
+};
+
+// One warp step: four full 512-byte blocks (g0 .. g0+3) whose chunks are already in registers.
+template <int STRIDE, bool FOLD, int MODE, int NODD>
+__device__ __forceinline__ void stream_group(const uint4 (&v)[kStreamU], uint32_t g0, const uint8_t* __restrict__ data, size_t n,
+                                             unsigned long long* __restrict__ meta, uint32_t* __restrict__ nlmask, unsigned long long* __restrict__ gsum,
+                                             const uint32_t* __restrict__ s_tab, const ProbeParams& pp, const StreamRegs& r) {
+    constexpr int U = kStreamU;
+    const uint32_t lane = r.lane;
+    uint32_t after = 0;   // first word after the group (only lane 31 needs it, for grams that straddle the end)
+    if (MODE != 0 && (STRIDE < 4 || NODD > 0) && lane == 31) {
+        size_t off = (size_t)(g0 + U) << 9;
+        if (off + 4 <= n) after = *reinterpret_cast<const uint32_t*>(data + off);
+        else if (off < n) after = ld_chunk(data, off, n).x;
+    }
+    uint32_t cnt01, cnt23, masks[U], nlm[U];
+    {
+        uint32_t c[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            c[u] = newline_count16_fma(v[u], r.cnl, r.c80, r.one, r.neg);
+            nlm[u] = __ballot_sync(0xffffffffu, c[u] != 0u);
+            uint32_t nx = 0;
+            if (MODE != 0 && (STRIDE < 4 || NODD > 0)) {
+                // first word of the next chunk: lane+1's word of this block, or (lane 31) lane 0's word of the next block
+                uint32_t give = (u + 1 < U && lane == 0) ? v[u + 1 < U ? u + 1 : u].x : v[u].x;
+                nx = __shfl_sync(0xffffffffu, give, (lane + 1) & 31);
+                if (u + 1 == U && lane == 31) nx = after;
+            }
+            bool hit = probe_chunk<STRIDE, FOLD, MODE, NODD>(v[u], nx, s_tab, pp, r.c1, r.c2);
+            masks[u] = __ballot_sync(0xffffffffu, hit);
+        }
+        cnt01 = __reduce_add_sync(0xffffffffu, c[0] | (c[1] << 16));
+        cnt23 = __reduce_add_sync(0xffffffffu, c[2] | (c[3] << 16));
+    }
+    if (lane == 0) {
+        uint4* out = reinterpret_cast<uint4*>(meta + g0);   // g0 is a multiple of 4: 32-byte aligned
+        out[0] = make_uint4(masks[0], cnt01 & 0xffffu, masks[1], cnt01 >> 16);
+        out[1] = make_uint4(masks[2], cnt23 & 0xffffu, masks[3], cnt23 >> 16);
+        *reinterpret_cast<uint4*>(nlmask + g0) = make_uint4(nlm[0], nlm[1], nlm[2], nlm[3]);
+        // totals of the group (candidates << 32 | newlines): what the scan over groups reads
+        const uint32_t cands = __popc(masks[0]) + __popc(masks[1]) + __popc(masks[2]) + __popc(masks[3]);
+        const uint32_t sum = cnt01 + cnt23;
+        gsum[g0 / U] = ((unsigned long long)cands << 32) | ((sum & 0xffffu) + (sum >> 16));
+    }
+}
+
 template <int STRIDE, bool FOLD, int MODE, int NODD>
 __global__ void __launch_bounds__(1024) k_stream(const uint8_t* __restrict__ data, size_t n, unsigned long long* __restrict__ meta,
-                                                 uint32_t* __restrict__ nlmask, const uint32_t* __restrict__ table, int table_words,
-                                                 ProbeParams pp) {
+                                                 uint32_t* __restrict__ nlmask, unsigned long long* __restrict__ gsum,
+                                                 const uint32_t* __restrict__ table, int table_words, ProbeParams pp) {
     extern __shared__ __align__(16) uint32_t s_raw[];
     // exact tables are placed at an address aligned to the size of one half (see probe_chunk); the launch reserves the slack
     uint32_t* s_tab = s_raw;
@@ -125,104 +178,86 @@ __global__ void __launch_bounds__(1024) k_stream(const uint8_t* __restrict__ dat
         s_tab = s_raw + ((aligned - saddr) >> 2);
         saddr = aligned;
     }
-    if (MODE == 3) {
-        // every copy is the same: one global read per word, written to all copies
-        const uint32_t copies = pp.bp_row >> 2;
-        for (uint32_t i = threadIdx.x; i < pp.bp_words * copies; i += blockDim.x) s_tab[i] = table[i / copies];
-        __syncthreads();
-    } else if (MODE != 0) {
+    if (MODE != 0) {
         for (int i = threadIdx.x; i < table_words; i += blockDim.x) s_tab[i] = table[i];
         __syncthreads();
     }
     constexpr int U = kStreamU;
-    const uint32_t lane = threadIdx.x & 31;
+    StreamRegs r;
+    r.lane = threadIdx.x & 31;
+    const uint32_t lane = r.lane;
     const uint32_t replica4 = (lane & ((1u << pp.rshift) - 1u)) << 2;
-    uint32_t c1 = MODE == 1 ? (saddr | replica4) : (MODE == 3 ? saddr + ((lane & pp.bp_lane_mask) << 2) : saddr), c2 = (saddr + pp.half_bytes) | replica4;
-    asm volatile("mov.u32 %0, %0;" : "+r"(c1));   // materialise: each table address is then a single (x & amask) | c
-    asm volatile("mov.u32 %0, %0;" : "+r"(c2));
-    uint32_t cnl, c80;   // opaque to the optimiser so that they stay in registers (see eq_mask4_r)
-    asm volatile("mov.u32 %0, 0x0a0a0a0a;" : "=r"(cnl));
-    asm volatile("mov.u32 %0, 0x80808080;" : "=r"(c80));
-    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    const size_t nblk = (n + 511) >> 9;
-    const size_t nfull = n >> 9;   // blocks that lie entirely inside [0, n)
+    r.c1 = MODE == 1 ? (saddr | replica4) : saddr;
+    r.c2 = (saddr + pp.half_bytes) | replica4;
+    asm volatile("mov.u32 %0, %0;" : "+r"(r.c1));   // materialise: each table address is then a single (x & amask) | c
+    asm volatile("mov.u32 %0, %0;" : "+r"(r.c2));
+    // opaque to the optimiser so that they stay in registers (see eq_mask4_r, newline_flags4)
+    asm volatile("mov.u32 %0, 0x0a0a0a0a;" : "=r"(r.cnl));
+    asm volatile("mov.u32 %0, 0x80808080;" : "=r"(r.c80));
+    asm volatile("mov.u32 %0, 1;" : "=r"(r.one));
+    asm volatile("mov.u32 %0, 0xfefefeff;" : "=r"(r.neg));
+    // block indices fit 32 bits (segments are < 4 GiB): fewer registers than size_t arithmetic
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t nblk = (uint32_t)((n + 511) >> 9);
+    const uint32_t nfull = (uint32_t)(n >> 9);   // blocks that lie entirely inside [0, n)
+    const uint32_t step = nwarps * U;
 
     // ---- main loop: groups of U full blocks, no bounds checks on the data loads
     // The loads of the NEXT group are issued before the current group is processed (twice the bytes in flight per warp:
-    // with stride-4 sampling the kernel waits for HBM, not for its lookups).
-    uint4 ahead[U];
-    {
-        const size_t first = warp * U;
-        if (first + U <= nfull) {
+    // with stride-4 sampling the kernel waits for HBM, not for its lookups).  Two register buffers take turns (the loop is
+    // unrolled twice), so nothing is copied between them.
+    uint4 va[U], vb[U];
+    uint32_t g0 = warp * U;
+    const uint8_t* lane_data = data + lane * 16;
+    if (g0 + U <= nfull) {
 #pragma unroll
-            for (int u = 0; u < U; u++) ahead[u] = ld_stream16(data + (first << 9) + lane * 16 + u * 512);
-        }
+        for (int u = 0; u < U; u++) va[u] = ld_stream16(lane_data + ((size_t)g0 << 9) + u * 512);
     }
-    for (size_t g0 = warp * U; g0 + U <= nfull; g0 += nwarps * U) {
-        uint4 v[U];
+    while (g0 + U <= nfull) {
+        const uint32_t g1 = g0 + step;
+        const bool more1 = g1 + U <= nfull;
+        if (more1) {
 #pragma unroll
-        for (int u = 0; u < U; u++) v[u] = ahead[u];
-        {
-            const size_t g1 = g0 + nwarps * U;
-            if (g1 + U <= nfull) {
+            for (int u = 0; u < U; u++) vb[u] = ld_stream16(lane_data + ((size_t)g1 << 9) + u * 512);
+        }
+        stream_group<STRIDE, FOLD, MODE, NODD>(va, g0, data, n, meta, nlmask, gsum, s_tab, pp, r);
+        if (!more1) break;
+        const uint32_t g2 = g1 + step;
+        if (g2 + U <= nfull) {
 #pragma unroll
-                for (int u = 0; u < U; u++) ahead[u] = ld_stream16(data + (g1 << 9) + lane * 16 + u * 512);
-            }
+            for (int u = 0; u < U; u++) va[u] = ld_stream16(lane_data + ((size_t)g2 << 9) + u * 512);
         }
-        uint32_t after = 0;   // first word after the group (only lane 31 needs it, for grams that straddle the end)
-        if (MODE != 0 && (STRIDE < 4 || NODD > 0) && lane == 31) {
-            size_t off = (g0 + U) << 9;
-            if (off + 4 <= n) after = *reinterpret_cast<const uint32_t*>(data + off);
-            else if (off < n) after = ld_chunk(data, off, n).x;
-        }
-        uint32_t cnt01, cnt23, masks[U], nlm[U];
-        {
-            uint32_t c[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                c[u] = newline_count16_fma(v[u], cnl, c80);
-                nlm[u] = __ballot_sync(0xffffffffu, c[u] != 0u);
-                uint32_t nx = 0;
-                if (MODE != 0 && (STRIDE < 4 || NODD > 0)) {
-                    // first word of the next chunk: lane+1's word of this block, or (lane 31) lane 0's word of the next block
-                    uint32_t give = (u + 1 < U && lane == 0) ? v[u + 1 < U ? u + 1 : u].x : v[u].x;
-                    nx = __shfl_sync(0xffffffffu, give, (lane + 1) & 31);
-                    if (u + 1 == U && lane == 31) nx = after;
-                }
-                bool hit = probe_chunk<STRIDE, FOLD, MODE, NODD>(v[u], nx, s_tab, pp, c1, c2);
-                masks[u] = __ballot_sync(0xffffffffu, hit);
-            }
-            cnt01 = __reduce_add_sync(0xffffffffu, c[0] | (c[1] << 16));
-            cnt23 = __reduce_add_sync(0xffffffffu, c[2] | (c[3] << 16));
-        }
-        if (lane == 0) {
-            uint4* out = reinterpret_cast<uint4*>(meta + g0);   // g0 is a multiple of 4: 32-byte aligned
-            out[0] = make_uint4(masks[0], cnt01 & 0xffffu, masks[1], cnt01 >> 16);
-            out[1] = make_uint4(masks[2], cnt23 & 0xffffu, masks[3], cnt23 >> 16);
-            *reinterpret_cast<uint4*>(nlmask + g0) = make_uint4(nlm[0], nlm[1], nlm[2], nlm[3]);
-        }
+        stream_group<STRIDE, FOLD, MODE, NODD>(vb, g1, data, n, meta, nlmask, gsum, s_tab, pp, r);
+        g0 = g2;
     }
 
-    // ---- tail: the last (< U) full blocks and the partial block, one block per warp step, bounds-checked
-    for (size_t g = (nfull / U) * U + warp; g < nblk; g += nwarps) {
-        size_t off = (g << 9) + (size_t)lane * 16;
+    // ---- tail: the last (< U) full blocks and the partial block, one block per warp step, bounds-checked; the totals of
+    // that last, partial group are added up by its first warp
+    const uint32_t tail0 = (nfull / U) * U;
+    for (uint32_t g = tail0 + warp; g < nblk; g += nwarps) {
+        size_t off = ((size_t)g << 9) + (size_t)lane * 16;
         uint4 v = off < n ? ld_chunk(data, off, n) : make_uint4(0, 0, 0, 0);
         uint32_t nx = 0;
         if (MODE != 0 && (STRIDE < 4 || NODD > 0)) {
             nx = __shfl_down_sync(0xffffffffu, v.x, 1);
             if (lane == 31) {
-                size_t o2 = (g + 1) << 9;
+                size_t o2 = (size_t)(g + 1) << 9;
                 nx = o2 < n ? ld_chunk(data, o2, n).x : 0u;
             }
         }
-        uint32_t cnt = newline_count16_fma(v, cnl, c80);
-        bool hit = probe_chunk<STRIDE, FOLD, MODE, NODD>(v, nx, s_tab, pp, c1, c2);
+        uint32_t cnt = newline_count16_fma(v, r.cnl, r.c80, r.one, r.neg);
+        bool hit = probe_chunk<STRIDE, FOLD, MODE, NODD>(v, nx, s_tab, pp, r.c1, r.c2);
         if (off >= n) hit = false;   // chunks that start at or beyond n can never be candidates
         uint32_t mask = __ballot_sync(0xffffffffu, hit);
         uint32_t nl = __ballot_sync(0xffffffffu, cnt != 0u);
         uint32_t total = __reduce_add_sync(0xffffffffu, cnt);
-        if (lane == 0) { meta[g] = ((unsigned long long)total << 32) | mask; nlmask[g] = nl; }
+        if (lane == 0) {
+            meta[g] = ((unsigned long long)total << 32) | mask;
+            nlmask[g] = nl;
+            // the tail group has at most U blocks: their totals are accumulated with atomics into a zeroed slot
+            atomicAdd(&gsum[tail0 / U], ((unsigned long long)__popc(mask) << 32) | total);
+        }
     }
 }
 

@@ -415,66 +415,6 @@ private:
 
 uint32_t mask_of(const FactorSet& fs, size_t pattern) { return pattern < fs.group_mask.size() ? fs.group_mask[pattern] : 0xffffffffu; }
 
-// Bank-private blocked bloom (Prefilter::bp_*).  Shared memory holds 229,376 bytes of table: 32 copies of 1,792 words or 16
-// copies of 3,584 words.  The smaller table is conflict-free (one wavefront per lookup), the larger one costs two; either
-// is taken only if its false hits stay small next to the real gram occurrences of the sample.
-void build_bank_private(const std::vector<uint32_t>& all, bool fold, const GramHistogram* sample, Prefilter& out) {
-    out.bp_copies = 0;
-    out.bp_table.clear();
-    if (all.empty() || std::getenv("GPUGREP_NO_BANK_PRIVATE") != nullptr) return;
-    static const uint32_t muls[] = {0x9E3779B1u, 0x85EBCA6Bu, 0xC2B2AE35u, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u,
-                                    0x7FEB352Du, 0x846CA68Bu, 0x9E3779B9u, 0xCC9E2D51u, 0x1B873593u, 0xE6546B65u, 0x2545F491u, 0x5851F42Du};
-    double true_hits = 0, positions = 0;
-    if (sample) {
-        for (uint32_t g : all) true_hits += sample->count(g, fold);
-        positions = (double)sample->positions();
-    }
-    int forced = 0;
-    if (const char* e = std::getenv("GPUGREP_BANK_COPIES")) forced = std::atoi(e);   // experiments: 32 or 16
-    for (int copies : {32, 16}) {
-        if (forced && copies != forced) continue;
-        const uint32_t words = 229376u / (4u * (uint32_t)copies);
-        double best_false = INFINITY;
-        std::vector<uint32_t> best;
-        uint32_t best_mul = 0;
-        for (uint32_t mul : muls) {
-            std::vector<uint32_t> tab(words, 0u);
-            for (uint32_t g : all) {
-                const uint32_t p = g * mul;
-                tab[(size_t)(((uint64_t)p * words) >> 32)] |= (1u << (p & 31u)) | (1u << ((p >> 16) & 31u));
-            }
-            double false_hits = 0;
-            if (sample && positions > 0) {
-                const auto& keys = sample->keys(fold);
-                const auto& counts = sample->counts(fold);
-                for (size_t k = 0; k < keys.size(); k++) {
-                    if (!counts[k]) continue;
-                    const uint32_t p = keys[k] * mul;
-                    const uint32_t w = tab[(size_t)(((uint64_t)p * words) >> 32)];
-                    if (((w >> (p & 31u)) & (w >> ((p >> 16) & 31u)) & 1u) && !std::binary_search(all.begin(), all.end(), keys[k])) false_hits += counts[k];
-                }
-                false_hits /= positions;
-            } else {
-                // analytic: a word holds Poisson(lambda) grams of two bits each; both tested bits set by chance
-                const double lambda = (double)all.size() / words;
-                false_hits = 4.0 * (lambda + lambda * lambda) / 1024.0;
-            }
-            if (false_hits < best_false) { best_false = false_hits; best.swap(tab); best_mul = mul; }
-            if (!sample) break;
-        }
-        // acceptable: false hits are at most a quarter of the real ones, or below one lookup in 4,000
-        const double real_rate = positions > 0 ? true_hits / positions : 0.0;
-        if (forced || best_false <= std::max(0.25 * real_rate, 0.00025)) {
-            out.bp_copies = copies;
-            out.bp_words = words;
-            out.bp_mul = best_mul;
-            out.bp_table.swap(best);
-            out.bp_false_rate = best_false;
-            return;
-        }
-    }
-}
-
 void finish_tables(GramList& list, bool fold, const GramHistogram* sample, Prefilter& out) {
     // unique grams, group masks merged
     std::sort(list.items.begin(), list.items.end());
@@ -531,13 +471,11 @@ void finish_tables(GramList& list, bool fold, const GramHistogram* sample, Prefi
         if (!sample || false_hits == 0) break;
     }
     out.bitmap.swap(best_map);
-    build_bank_private(all, fold, sample, out);
 }
 
 std::string describe(const Prefilter& out, bool tuned) {
     return "stride " + std::to_string(out.stride) + (out.odd.empty() ? "" : " + " + std::to_string(out.odd.size()) + " compares at 2 mod 4") + (out.fold_case ? ", folded" : "") + ", " + std::to_string(out.num_grams) + " grams, bloom bitmap of " + std::to_string(1u << out.log2_bits) +
-           " bits, " + (out.bp_copies ? "bank-private table x" + std::to_string(out.bp_copies) + " (false hits " + std::to_string(out.bp_false_rate * 1e6) + " ppm), " : std::string()) +
-           std::to_string((int)out.expected_hits_per_mib) + " expected hits/MiB" + (out.exact ? ", exact two-choice table of 2 x " + std::to_string(1u << out.log2_slots) + " slots" : "") + (tuned ? ", sample-tuned" : "");
+           " bits, " + std::to_string((int)out.expected_hits_per_mib) + " expected hits/MiB" + (out.exact ? ", exact two-choice table of 2 x " + std::to_string(1u << out.log2_slots) + " slots" : "") + (tuned ? ", sample-tuned" : "");
 }
 
 // One register compare of the mixed scheme: the first `known` bytes of a 4-gram (little endian: the low bytes).

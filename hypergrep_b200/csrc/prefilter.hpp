@@ -73,13 +73,6 @@ struct Prefilter {
     uint32_t bloom_mul = 0x9E3779B1u;
     std::vector<uint32_t> bitmap;
     uint32_t hash_mul = 0x9E3779B1u;
-    // Bank-private blocked bloom (preferred by the streaming kernel when its false-hit rate is low enough): bp_words 32-bit
-    // words, replicated bp_copies (32 or 16) times in shared memory so that every lane reads its own bank.  A gram sets /
-    // tests two bits of ONE word: word = mulhi(p, bp_words), bits p & 31 and (p >> 16) & 31, with p = gram * bp_mul.
-    int bp_copies = 0;                // 0: not built (too many grams for a table this small)
-    uint32_t bp_words = 0, bp_mul = 0;
-    std::vector<uint32_t> bp_table;
-    double bp_false_rate = 0;         // false hits per lookup (measured on the sample, or the analytic estimate)
     std::vector<uint32_t> grams;      // the exact gram set (sorted)
     // Mixed sampling (stride == 4 only).  Factors of >= 7 bytes are found by table lookups at text offsets = 0 (mod 4).  The
     // few factors that are too short for that are ALSO compared, in registers, at offsets = 2 (mod 4): gram * mul + add == 0

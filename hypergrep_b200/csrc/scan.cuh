@@ -61,6 +61,10 @@ __device__ __forceinline__ uint32_t newlines_before_block(const unsigned long lo
     for (size_t b = blk - blk % kGroupBlocks; b < blk; b++) c += (uint32_t)(meta[b] >> 32);
     return c;
 }
+struct LoadU64 {
+    const unsigned long long* p;
+    __device__ unsigned long long operator()(size_t i) const { return p[i]; }
+};
 struct LoadU8 {
     const uint8_t* p;
     __device__ unsigned long long operator()(size_t i) const { return p[i]; }

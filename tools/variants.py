@@ -3,7 +3,7 @@
 
 Each variant sets environment switches of the engine and scans the same device-resident text with the same pattern set
 plus a variant-specific literal (so that no cached database / gram table of another variant is reused).
-    python tools/variants.py --mib 2048 --set c2 --variants new,verify_v1,emit_v1,bloom,bank16
+    python tools/variants.py --mib 2048 --set c2 --variants new,verify_smem,emit_v1,old
 """
 import argparse
 import os
@@ -22,10 +22,8 @@ VARIANTS = {
     "new": {},
     "verify_v1": {"GPUGREP_VERIFY": "v1"},
     "emit_v1": {"GPUGREP_EMIT": "v1"},
-    "old": {"GPUGREP_VERIFY": "v1", "GPUGREP_EMIT": "v1", "GPUGREP_FILTER": "bloom"},
-    "bloom": {"GPUGREP_FILTER": "bloom"},
-    "bank16": {"GPUGREP_BANK_COPIES": "16"},
-    "bank32": {"GPUGREP_BANK_COPIES": "32"},
+    "old": {"GPUGREP_VERIFY": "v1", "GPUGREP_EMIT": "v1"},
+    "verify_smem": {"GPUGREP_VERIFY": "smem"},
     "noreprobe": {"GPUGREP_NO_REPROBE": "1"},
 }
 
@@ -33,7 +31,7 @@ parser = argparse.ArgumentParser()
 parser.add_argument("--mib", type=int, default=2048)
 parser.add_argument("--set", default="c2")
 parser.add_argument("--passes", type=int, default=3)
-parser.add_argument("--variants", default="new,verify_v1,emit_v1,bloom,bank16,old")
+parser.add_argument("--variants", default="new,verify_smem,emit_v1,old")
 args = parser.parse_args()
 lib = utils._get_hyperscanner_lib()
 plants = None
