@@ -303,7 +303,6 @@ std::shared_ptr<DevicePrefilter> engine_upload_prefilter(const Prefilter& pf, st
     out->pp.mul = use_exact ? pf.hash_mul : pf.bloom_mul;
     out->pp.mul2 = pf.hash_mul2;
     out->pp.shift = 32 - (pf.log2_bits - 3);   // bloom: product -> byte index
-    out->pp.hi_mul = 1u << (pf.log2_bits - 3);
     out->lookback = pf.lookback;
     out->nodd = (int)std::min<size_t>(pf.odd.size(), 2);
     for (int k = 0; k < 2; k++) {

@@ -125,39 +125,83 @@ __device__ __forceinline__ uint32_t walk_words(const Table& T, const Text& X, co
     const uint32_t first_accept = G.first_accept, idle_end = G.idle_end;
     uint32_t mask = 0;
     if (pos >= end) return G.eod_next[s] >= first_accept ? line_bit : 0u;
-    uint32_t wpos = pos & ~3u;
-    uint32_t word = X.word(wpos);   // the buffer is padded to a multiple of 16 bytes
-    while (true) {
-        // the next word is requested before the (dependent) table lookups of this one
-        const uint32_t next_word = wpos + 4 < end ? X.word(wpos + 4) : 0u;
-        const uint32_t x = word ^ 0x0a0a0a0au;
-        if (((x - 0x01010101u) & ~x & 0x80808080u) == 0 && pos == wpos && wpos + 4 <= end) {
-            s = T.step4(s, word);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t p = wpos + k;
-                if (p >= pos && p < end) {
-                    const uint32_t b = (word >> (8 * k)) & 0xffu;
-                    s = T.step(s, b);
-                    if (b == '\n') {
-                        if (s >= first_accept) mask |= line_bit;
-                        if (p + 1 >= cend) return mask;   // the next line starts outside the chunk
-                        line_bit <<= 1;
-                        s = 0;
-                    }
+    // One byte: the table step, then - only for a '\n' - the end-of-line bookkeeping.  Returns true when the walk is over
+    // (the next line starts outside the chunk).
+    auto byte_step = [&](uint32_t b, uint32_t p) -> bool {
+        s = T.step(s, b);
+        if (b == '\n') {
+            if (s >= first_accept) mask |= line_bit;
+            if (p + 1 >= cend) return true;
+            line_bit <<= 1;
+            s = 0;
+        }
+        return false;
+    };
+    // head: up to three bytes to the next word boundary (the walk usually starts on one)
+    while ((pos & 3u) && pos < end) {
+        if (byte_step((X.word(pos & ~3u) >> (8 * (pos & 3u))) & 0xffu, pos)) return mask;
+        pos++;
+    }
+    // body: whole words.  The four table steps are the same instructions for every lane of the warp; what a newline adds
+    // sits in four short, separately guarded blocks (a warp runs one of them only if some lane has its '\n' at that very
+    // byte), instead of a second, byte-wise copy of the whole step that most warps had to execute as well.
+    if (pos + 4 <= end) {
+        uint32_t word = X.word(pos);
+        while (true) {
+            // the next word is requested before the (dependent) table lookups of this one
+            const uint32_t next_word = pos + 8 <= end ? X.word(pos + 4) : 0u;
+            const uint32_t z = eq_mask4(word, 0x0a0a0a0au);
+            if (z == 0) {
+                s = T.step4(s, word);
+            } else {
+                s = T.step(s, word & 0xffu);
+                if (z & 0x80u) {
+                    if (s >= first_accept) mask |= line_bit;
+                    if (pos + 1 >= cend) return mask;
+                    line_bit <<= 1;
+                    s = 0;
+                }
+                s = T.step(s, (word >> 8) & 0xffu);
+                if (z & 0x8000u) {
+                    if (s >= first_accept) mask |= line_bit;
+                    if (pos + 2 >= cend) return mask;
+                    line_bit <<= 1;
+                    s = 0;
+                }
+                s = T.step(s, (word >> 16) & 0xffu);
+                if (z & 0x800000u) {
+                    if (s >= first_accept) mask |= line_bit;
+                    if (pos + 3 >= cend) return mask;
+                    line_bit <<= 1;
+                    s = 0;
+                }
+                s = T.step(s, word >> 24);
+                if (z & 0x80000000u) {
+                    if (s >= first_accept) mask |= line_bit;
+                    if (pos + 4 >= cend) return mask;
+                    line_bit <<= 1;
+                    s = 0;
                 }
             }
+            pos += 4;
+            if (s >= first_accept) {
+                if (pos >= cend) return mask | line_bit;   // matched, and no further line starts inside the chunk
+            } else if (pos >= ifrom && s < idle_end) {
+                return mask;
+            }
+            if (pos + 4 > end) break;
+            word = next_word;
         }
-        pos = wpos + 4;
+    }
+    // tail: the last (partial) word of the segment
+    while (pos < end) {
+        if (byte_step((X.word(pos & ~3u) >> (8 * (pos & 3u))) & 0xffu, pos)) return mask;
+        pos++;
         if (s >= first_accept) {
-            if (pos >= cend) return mask | line_bit;   // matched, and no further line starts inside the chunk
+            if (pos >= cend) return mask | line_bit;
         } else if (pos >= ifrom && s < idle_end) {
             return mask;
         }
-        if (pos >= end) break;
-        wpos = pos;
-        word = next_word;
     }
     if (s >= first_accept || G.eod_next[s] >= first_accept) mask |= line_bit;
     return mask;

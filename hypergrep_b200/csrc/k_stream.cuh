@@ -23,7 +23,6 @@ struct ProbeParams {
     // mixed sampling (Prefilter::odd): gram * odd_mul[k] + odd_add[k] == 0 at text offsets = 2 (mod 4).  Unused entries repeat
     // a used one.  The multipliers come from here (the parameter bank) so that the test stays ONE multiply-add on the FMA pipe.
     uint32_t odd_mul[2], odd_add[2];
-    uint32_t hi_mul;      // bloom: 2^(32 - shift): the byte index is mulhi(product, hi_mul)
 };
 
 // Gram lookups of one 16-byte chunk.  MODE 1: two-choice table of exact 32-bit keys; the table is replicated
@@ -44,9 +43,8 @@ __device__ __forceinline__ uint32_t lds8(uint32_t shared_addr) {
 
 // c1 / c2: shared-window address of table half 1 / 2 (aligned to the size of a half) OR-ed with 4 * copy of this lane,
 // so that an address is formed by ONE logic op: ((product >> shift) & amask) | c.
-// The streaming kernel saturates the ALU pipe (shifts, logic ops) long before the FMA pipe (integer multiply-adds), so
-// whatever can be phrased as a multiply is: the table index of the bloom lookup is mulhi(product, 2^(32 - shift)) instead
-// of a shift (pp.hi_mul comes from the parameter bank, so ptxas cannot turn it back into one).
+// (Measured and dropped, profiles/README.md: the table index as mulhi(product, 2^k) on the FMA pipe instead of a shift -
+// IMAD.HI is the slower instruction, 0.545 -> 0.585 ms per 2 GiB.)
 template <int STRIDE, bool FOLD, int MODE, int NODD>
 __device__ __forceinline__ bool probe_chunk(const uint4& v, uint32_t next, const uint32_t* __restrict__ tab, const ProbeParams& pp, uint32_t c1,
                                             uint32_t c2) {
@@ -71,7 +69,7 @@ __device__ __forceinline__ bool probe_chunk(const uint4& v, uint32_t next, const
                 // bloom: one byte load, bit (p & 7) of it.  The byte is replicated into all four bytes of a word (one
                 // multiply on the FMA pipe) so that the wrap-around shift by p itself lands on the right bit.
                 uint32_t p = gram * pp.mul;
-                uint32_t b = lds8(__umulhi(p, pp.hi_mul) + c1);
+                uint32_t b = lds8((p >> pp.shift) + c1);
                 bits |= (b * 0x01010101u) >> (p & 31u);
             }
         }
@@ -92,20 +90,10 @@ __device__ __forceinline__ bool probe_chunk(const uint4& v, uint32_t next, const
     return MODE == 1 ? miss == 0u : (bits & 1u) != 0u;
 }
 
-// 0x80 in every byte of w equal to '\n', with the subtraction phrased as a multiply-add (FMA pipe): one = 1 and
-// neg = -0x01010101 are opaque registers (see k_stream), so ptxas keeps the IMAD.
-__device__ __forceinline__ uint32_t newline_flags4(uint32_t w, uint32_t cnl, uint32_t c80, uint32_t one, uint32_t neg) {
-    uint32_t u, t, z;
-    asm("lop3.b32 %0, %1, %2, %3, 0xBE;" : "=r"(u) : "r"(w), "r"(cnl), "r"(c80));   // (w ^ rep) | 0x80808080
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(u), "r"(one), "r"(neg));        // u - 0x01010101
-    asm("lop3.b32 %0, %1, %2, %3, 0x02;" : "=r"(z) : "r"(t), "r"(w), "r"(c80));     // ~(t | w) & 0x80808080
-    return z;
-}
 // newlines in a 16-byte chunk: four flag words (bit 7 of matching bytes) are merged into one 64-bit word with three
 // multiply-adds (FMA pipe) instead of shifts and ORs (ALU pipe, the pipe this kernel saturates first)
-__device__ __forceinline__ uint32_t newline_count16_fma(const uint4& v, uint32_t cnl, uint32_t c80, uint32_t one, uint32_t neg) {
-    uint32_t a = newline_flags4(v.x, cnl, c80, one, neg), b = newline_flags4(v.y, cnl, c80, one, neg);
-    uint32_t c = newline_flags4(v.z, cnl, c80, one, neg), d = newline_flags4(v.w, cnl, c80, one, neg);
+__device__ __forceinline__ uint32_t newline_count16_fma(const uint4& v, uint32_t cnl, uint32_t c80) {
+    uint32_t a = eq_mask4_r(v.x, cnl, c80), b = eq_mask4_r(v.y, cnl, c80), c = eq_mask4_r(v.z, cnl, c80), d = eq_mask4_r(v.w, cnl, c80);
     unsigned long long acc = a;
     asm("mad.wide.u32 %0, %1, 2, %0;" : "+l"(acc) : "r"(b));
     asm("mad.wide.u32 %0, %1, 4, %0;" : "+l"(acc) : "r"(c));
@@ -117,7 +105,7 @@ constexpr int kStreamU = 4;   // 512-byte blocks per warp step
 
 // Per-warp constants of the streaming kernel.
 struct StreamRegs {
-    uint32_t c1, c2, cnl, c80, one, neg, lane;
+    uint32_t c1, c2, cnl, c80, lane;
 };
 
 // One warp step: four full 512-byte blocks (g0 .. g0+3) whose chunks are already in registers.
@@ -138,7 +126,7 @@ __device__ __forceinline__ void stream_group(const uint4 (&v)[kStreamU], uint32_
         uint32_t c[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            c[u] = newline_count16_fma(v[u], r.cnl, r.c80, r.one, r.neg);
+            c[u] = newline_count16_fma(v[u], r.cnl, r.c80);
             nlm[u] = __ballot_sync(0xffffffffu, c[u] != 0u);
             uint32_t nx = 0;
             if (MODE != 0 && (STRIDE < 4 || NODD > 0)) {
@@ -194,8 +182,6 @@ __global__ void __launch_bounds__(1024) k_stream(const uint8_t* __restrict__ dat
     // opaque to the optimiser so that they stay in registers (see eq_mask4_r, newline_flags4)
     asm volatile("mov.u32 %0, 0x0a0a0a0a;" : "=r"(r.cnl));
     asm volatile("mov.u32 %0, 0x80808080;" : "=r"(r.c80));
-    asm volatile("mov.u32 %0, 1;" : "=r"(r.one));
-    asm volatile("mov.u32 %0, 0xfefefeff;" : "=r"(r.neg));
     // block indices fit 32 bits (segments are < 4 GiB): fewer registers than size_t arithmetic
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -205,31 +191,23 @@ __global__ void __launch_bounds__(1024) k_stream(const uint8_t* __restrict__ dat
 
     // ---- main loop: groups of U full blocks, no bounds checks on the data loads
     // The loads of the NEXT group are issued before the current group is processed (twice the bytes in flight per warp:
-    // with stride-4 sampling the kernel waits for HBM, not for its lookups).  Two register buffers take turns (the loop is
-    // unrolled twice), so nothing is copied between them.
-    uint4 va[U], vb[U];
-    uint32_t g0 = warp * U;
+    // with stride-4 sampling the kernel waits for HBM, not for its lookups).
+    uint4 ahead[U];
     const uint8_t* lane_data = data + lane * 16;
-    if (g0 + U <= nfull) {
+    if (warp * U + U <= nfull) {
 #pragma unroll
-        for (int u = 0; u < U; u++) va[u] = ld_stream16(lane_data + ((size_t)g0 << 9) + u * 512);
+        for (int u = 0; u < U; u++) ahead[u] = ld_stream16(lane_data + ((size_t)(warp * U) << 9) + u * 512);
     }
-    while (g0 + U <= nfull) {
+    for (uint32_t g0 = warp * U; g0 + U <= nfull; g0 += step) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) v[u] = ahead[u];
         const uint32_t g1 = g0 + step;
-        const bool more1 = g1 + U <= nfull;
-        if (more1) {
+        if (g1 + U <= nfull) {
 #pragma unroll
-            for (int u = 0; u < U; u++) vb[u] = ld_stream16(lane_data + ((size_t)g1 << 9) + u * 512);
+            for (int u = 0; u < U; u++) ahead[u] = ld_stream16(lane_data + ((size_t)g1 << 9) + u * 512);
         }
-        stream_group<STRIDE, FOLD, MODE, NODD>(va, g0, data, n, meta, nlmask, gsum, s_tab, pp, r);
-        if (!more1) break;
-        const uint32_t g2 = g1 + step;
-        if (g2 + U <= nfull) {
-#pragma unroll
-            for (int u = 0; u < U; u++) va[u] = ld_stream16(lane_data + ((size_t)g2 << 9) + u * 512);
-        }
-        stream_group<STRIDE, FOLD, MODE, NODD>(vb, g1, data, n, meta, nlmask, gsum, s_tab, pp, r);
-        g0 = g2;
+        stream_group<STRIDE, FOLD, MODE, NODD>(v, g0, data, n, meta, nlmask, gsum, s_tab, pp, r);
     }
 
     // ---- tail: the last (< U) full blocks and the partial block, one block per warp step, bounds-checked; the totals of
@@ -246,7 +224,7 @@ __global__ void __launch_bounds__(1024) k_stream(const uint8_t* __restrict__ dat
                 nx = o2 < n ? ld_chunk(data, o2, n).x : 0u;
             }
         }
-        uint32_t cnt = newline_count16_fma(v, r.cnl, r.c80, r.one, r.neg);
+        uint32_t cnt = newline_count16_fma(v, r.cnl, r.c80);
         bool hit = probe_chunk<STRIDE, FOLD, MODE, NODD>(v, nx, s_tab, pp, r.c1, r.c2);
         if (off >= n) hit = false;   // chunks that start at or beyond n can never be candidates
         uint32_t mask = __ballot_sync(0xffffffffu, hit);
