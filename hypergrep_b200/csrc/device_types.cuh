@@ -14,9 +14,9 @@ struct GroupDev {
     const uint16_t* flat;       // [states][256] byte-indexed transitions (local verification: one load per byte), or null
     const uint16_t* eod_next;   // [states] transition on end-of-data (with `flat`)
     // The same byte-indexed view, class-compressed for shared memory (k_verify_smem): ctab[state * (crow / 2) + class],
-    // cmap2[byte] = 2 * class ('\n' and NUL have classes of their own); null when it does not fit.
+    // cmap[byte] = class ('\n' and NUL have classes of their own); null when it does not fit.
     const uint16_t* ctab;
-    const uint8_t* cmap2;
+    const uint8_t* cmap;
     uint32_t crow, cstates;     // bytes per row of ctab, rows
     uint32_t stride, eod, first_accept, dead, accept_base, idle_end, mid_other, mid_word;
 };

@@ -85,8 +85,8 @@ int device_sms() {
     }
     return cached[dev];
 }
-// k_verify_smem: table + class map + 32 KiB (64 bytes per thread) or 48 KiB of staged text per block must fit 227 KiB
-constexpr size_t kMaxSharedTableBytes = (size_t)176 << 10;
+// k_verify_smem: table + class map per block, two blocks per SM (227 KiB of shared memory)
+constexpr size_t kMaxSharedTableBytes = (size_t)112 << 10;
 
 }  // namespace
 
@@ -229,12 +229,12 @@ std::shared_ptr<DeviceDb> engine_upload(const std::shared_ptr<Database>& db, std
             // except '\n' and NUL, whose columns carry the line rules: they get classes of their own.
             const int ncls = d.num_classes + 2;
             const size_t ctab_bytes = (size_t)d.num_states * ncls * 2;
-            if (db->groups.size() == 1 && ncls <= 127 && ctab_bytes <= kMaxSharedTableBytes) {
+            if (db->groups.size() == 1 && ncls <= 255 && ctab_bytes <= kMaxSharedTableBytes) {
                 std::vector<uint8_t> cmap2(256);
                 std::vector<int> rep((size_t)ncls, -1);
                 for (int b = 255; b >= 0; b--) {
                     const int c = b == 0 ? d.num_classes : (b == '\n' ? d.num_classes + 1 : d.byte_class[b]);
-                    cmap2[(size_t)b] = (uint8_t)(2 * c);
+                    cmap2[(size_t)b] = (uint8_t)c;
                     rep[(size_t)c] = b;
                 }
                 std::vector<uint16_t> ctab((size_t)d.num_states * ncls + 8, 0);
@@ -242,8 +242,8 @@ std::shared_ptr<DeviceDb> engine_upload(const std::shared_ptr<Database>& db, std
                     for (int c = 0; c < ncls; c++)
                         if (rep[(size_t)c] >= 0) ctab[(size_t)st * ncls + c] = flat[(size_t)st * 256 + rep[(size_t)c]];
                 G.ctab = (const uint16_t*)upload(ctab.data(), ctab.size() * sizeof(uint16_t));
-                G.cmap2 = (const uint8_t*)upload(cmap2.data(), 256);
-                if (!G.ctab || !G.cmap2) { error = "cudaMalloc/cudaMemcpy failed while uploading DFA tables"; return nullptr; }
+                G.cmap = (const uint8_t*)upload(cmap2.data(), 256);
+                if (!G.ctab || !G.cmap) { error = "cudaMalloc/cudaMemcpy failed while uploading DFA tables"; return nullptr; }
                 G.crow = (uint32_t)ncls * 2u;
                 G.cstates = (uint32_t)d.num_states;
                 out->smem_table_bytes = (ctab_bytes + 15) / 16 * 16;
@@ -571,16 +571,14 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
         // Verification.  Single-group databases whose class-compressed table fits shared memory, with a look-back that the
         // staged text window covers, take k_verify_smem; everything else the global-table kernel.
         const char* vsel = std::getenv("GPUGREP_VERIFY");
-        const bool use_smem = vsel && std::strcmp(vsel, "smem") == 0;   // measured slower than the global-table kernel (profiles/README.md)
-        if (use_smem && ddb.smem_table_bytes && pf->lookback <= 29u) {
-            const bool wide = pf->lookback > 13u;
-            const size_t vsmem = 256 + ddb.smem_table_bytes + (size_t)(wide ? 24 : 16) * 4 * kVerifyThreads;
-            auto kernel = wide ? k_verify_smem<2, 24> : k_verify_smem<1, 16>;
-            CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
-            const unsigned per_sm = blocks_per_sm(kernel, kVerifyThreads, vsmem);
-            unsigned vgrid = (unsigned)std::min<size_t>((s->cand_cap + kVerifyThreads - 1) / kVerifyThreads, (size_t)per_sm * sms);
-            kernel<<<vgrid, kVerifyThreads, vsmem, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->lookback, idle_span, rp,
-                                                         s->d_res.as<uint32_t>(), tile_records);
+        const bool v1 = vsel && std::strcmp(vsel, "v1") == 0;
+        if (!v1 && ddb.smem_table_bytes && rp.keys == nullptr && pf->lookback <= 64u) {
+            const size_t vsmem = 256 + ddb.smem_table_bytes;
+            CUDA_TRY(cudaFuncSetAttribute(k_verify_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
+            const unsigned per_sm = blocks_per_sm(k_verify_smem, kVerifySmemThreads, vsmem);
+            unsigned vgrid = (unsigned)std::min<size_t>((s->cand_cap + kVerifySmemThreads - 1) / kVerifySmemThreads, (size_t)per_sm * sms);
+            k_verify_smem<<<vgrid, kVerifySmemThreads, vsmem, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->lookback,
+                                                                    idle_span, s->d_res.as<uint32_t>(), tile_records);
         } else {
             static const unsigned verify_per_sm = blocks_per_sm(k_verify_local, 128);
             unsigned vgrid = (unsigned)std::min<size_t>((s->cand_cap + 127) / 128, (size_t)verify_per_sm * sms);

@@ -54,33 +54,19 @@ struct FlatTable {   // [state][256] u16 in global memory
         return flat[(s << 8) | (word >> 24)];
     }
 };
-__device__ __forceinline__ uint32_t lds_u8(uint32_t shared_addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(shared_addr));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds_u16(uint32_t shared_addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(shared_addr));
-    return v;
-}
-__device__ __forceinline__ uint32_t lds_u32(uint32_t shared_addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(shared_addr));
-    return v;
-}
-struct SharedTable {   // class-compressed [state][classes] u16 in shared memory + byte -> 2 * class map (GroupDev::ctab)
-    uint32_t tab, cls, row;   // shared-window addresses of the table and of the class map; bytes per table row
-    __device__ __forceinline__ uint32_t step(uint32_t s, uint32_t b) const { return lds_u16(tab + s * row + lds_u8(cls + b)); }
+struct SharedTable {   // class-compressed [state][classes] u16 in shared memory + byte -> class map (GroupDev::ctab)
+    const uint16_t* tab;
+    const uint8_t* cls;
+    uint32_t ncls;   // entries per table row
+    __device__ __forceinline__ uint32_t step(uint32_t s, uint32_t b) const { return tab[s * ncls + cls[b]]; }
     __device__ __forceinline__ uint32_t step4(uint32_t s, uint32_t word) const {
         // the four class lookups do not depend on the state: they are issued first, the state chain is one multiply-add and
         // one load per byte
-        const uint32_t c0 = lds_u8(cls + (word & 0xffu)), c1 = lds_u8(cls + ((word >> 8) & 0xffu));
-        const uint32_t c2 = lds_u8(cls + ((word >> 16) & 0xffu)), c3 = lds_u8(cls + (word >> 24));
-        s = lds_u16(tab + s * row + c0);
-        s = lds_u16(tab + s * row + c1);
-        s = lds_u16(tab + s * row + c2);
-        return lds_u16(tab + s * row + c3);
+        const uint32_t c0 = cls[word & 0xffu], c1 = cls[(word >> 8) & 0xffu], c2 = cls[(word >> 16) & 0xffu], c3 = cls[word >> 24];
+        s = tab[s * ncls + c0];
+        s = tab[s * ncls + c1];
+        s = tab[s * ncls + c2];
+        return tab[s * ncls + c3];
     }
 };
 // Text accessors: aligned words of the segment.
@@ -88,21 +74,6 @@ struct GlobalText {
     const uint8_t* __restrict__ data;
     __device__ __forceinline__ uint32_t word(uint32_t wpos) const { return *reinterpret_cast<const uint32_t*>(data + wpos); }
 };
-// The neighbourhood of the candidate chunk staged in shared memory (word k of the window of thread `tid` at
-// text[k * threads + tid]: whatever k the lanes of a warp are at, every lane stays in its own bank); words beyond the window
-// come from global memory.
-struct StagedText {
-    const uint8_t* __restrict__ data;
-    uint32_t base;    // shared-window address of this thread's word 0
-    uint32_t pitch;   // bytes between consecutive words of one thread (4 * threads per block)
-    uint32_t wbase;   // text offset of word 0
-    uint32_t words;
-    __device__ __forceinline__ uint32_t word(uint32_t wpos) const {
-        const uint32_t k = (wpos - wbase) >> 2;
-        return k < words ? lds_u32(base + k * pitch) : *reinterpret_cast<const uint32_t*>(data + wpos);
-    }
-};
-
 // LOCAL verification walk of one DFA group around candidate chunk [o, o+16).
 //  - starts at t (at most `lookback` bytes before the chunk, never before the line start) in the start-of-line state
 //    or in the mid-line entry state that matches the previous byte;
@@ -361,30 +332,27 @@ counted:
     }
 }
 
-// The same verification with everything it touches per byte in shared memory (single-group databases whose
-// class-compressed table fits, GroupDev::ctab; bounded look-back):
-//  - the transition table as [state][class] u16 plus the byte -> class map: a step is one multiply-add and one shared
-//    load instead of a dependent 2-byte gather from global memory / L1 (k_verify_local was bound by exactly that);
-//  - the neighbourhood of the candidate chunk ([o - 16 PRE, o - 16 PRE + 4 WORDS), four or six 16-byte loads issued
-//    together) staged per thread, so that the walk does not wait for one global load per word.
-constexpr int kVerifyThreads = 512;
-template <int PRE, int WORDS>
-__global__ void __launch_bounds__(kVerifyThreads, 2) k_verify_smem(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
-                                                                   const unsigned long long* meta_total, size_t cap, uint32_t lookback,
-                                                                   uint32_t idle_span, ReprobeParams rp, uint32_t* __restrict__ marks,
-                                                                   uint32_t* __restrict__ tile_records) {
+// The same verification with the transition table in shared memory (single-group databases whose class-compressed table
+// fits twice into one SM, GroupDev::ctab): [state][class] u16 plus the byte -> class map.  A step is one multiply-add and
+// one shared load (the class lookups do not depend on the state and run ahead) instead of a dependent 2-byte gather
+// from global memory through L1, which is what bounds k_verify_local.  Two blocks of 1,024 threads per SM: the same
+// 64 warps as the global-table kernel, so the text loads (still global) are hidden as well as there.
+constexpr int kVerifySmemThreads = 1024;
+__global__ void __launch_bounds__(kVerifySmemThreads, 2) k_verify_smem(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
+                                                                       const unsigned long long* meta_total, size_t cap, uint32_t lookback,
+                                                                       uint32_t idle_span, uint32_t* __restrict__ marks,
+                                                                       uint32_t* __restrict__ tile_records) {
     extern __shared__ __align__(16) uint32_t s_verify[];
     const GroupDev G = db.groups[0];
     const uint32_t table_words = (G.cstates * G.crow + 15u) / 16u * 4u;
     {
-        const uint32_t* src_cls = reinterpret_cast<const uint32_t*>(G.cmap2);
+        const uint32_t* src_cls = reinterpret_cast<const uint32_t*>(G.cmap);
         const uint32_t* src_tab = reinterpret_cast<const uint32_t*>(G.ctab);
         for (uint32_t k = threadIdx.x; k < 64u + table_words; k += blockDim.x) s_verify[k] = k < 64u ? src_cls[k] : src_tab[k - 64u];
         __syncthreads();
     }
-    const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(s_verify);
-    const SharedTable T{s_base + 256u, s_base, G.crow};
-    StagedText X{data, s_base + 256u + table_words * 4u + threadIdx.x * 4u, (uint32_t)blockDim.x * 4u, 0u, (uint32_t)WORDS};
+    const SharedTable T{reinterpret_cast<const uint16_t*>(s_verify + 64), reinterpret_cast<const uint8_t*>(s_verify), G.crow / 2u};
+    const GlobalText X{data};
     const uint32_t end = (uint32_t)n;
     size_t ncand = (size_t)(*meta_total >> 32);
     if (ncand > cap) ncand = cap;
@@ -392,80 +360,20 @@ __global__ void __launch_bounds__(kVerifyThreads, 2) k_verify_smem(DbView db, co
         uint32_t mask = 0;
         if (i < ncand) {
             const uint32_t o = cand[i] * 16u;
-            X.wbase = o >= 16u * PRE ? o - 16u * PRE : 0u;
-#pragma unroll
-            for (int c = 0; c < WORDS / 4; c++) {
-                const uint32_t off = X.wbase + 16u * c;
-                const uint4 v = off < end ? ld_chunk(data, off, n) : make_uint4(0u, 0u, 0u, 0u);
-                const uint32_t at = X.base + (4u * c) * X.pitch;
-                asm volatile("st.shared.u32 [%0], %1;" ::"r"(at), "r"(v.x));
-                asm volatile("st.shared.u32 [%0], %1;" ::"r"(at + X.pitch), "r"(v.y));
-                asm volatile("st.shared.u32 [%0], %1;" ::"r"(at + 2u * X.pitch), "r"(v.z));
-                asm volatile("st.shared.u32 [%0], %1;" ::"r"(at + 3u * X.pitch), "r"(v.w));
-            }
-            // (every thread reads back only the words it staged itself: no barrier)
-            uint32_t idle_from = o + idle_span;
-            uint32_t line_bit = 1u;
-            uint32_t hi = o;   // the walk has to start at or before hi - lookback
-            uint32_t nl_in_chunk = 0;
-            bool dropped = false;
-            if (rp.keys) {
-                uint32_t w[5] = {X.word(o), X.word(o + 4), X.word(o + 8), X.word(o + 12), o + 16 < end ? X.word(o + 16) : 0u};
-                const uint32_t nlm = movemask8(eq_mask4(w[0], 0x0a0a0a0au), eq_mask4(w[1], 0x0a0a0a0au)) |
-                                     (movemask8(eq_mask4(w[2], 0x0a0a0a0au), eq_mask4(w[3], 0x0a0a0a0au)) << 8);
-                if (rp.fold) {
-#pragma unroll
-                    for (int k = 0; k < 5; k++) w[k] |= 0x20202020u;
-                }
-                uint32_t hits = 0;   // bit = byte offset of a sampled gram that is in the table
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    for (int sft = 0; sft < 4; sft += rp.stride) {
-                        const uint32_t gram = __funnelshift_r(w[k], w[k + 1], 8 * sft);
-                        const uint32_t e1 = rp.keys[(gram * rp.mul) >> rp.shift], e2 = rp.keys[rp.half + ((gram * rp.mul2) >> rp.shift)];
-                        if (e1 == gram || e2 == gram) hits |= 1u << (4 * k + sft);
-                    }
-                    if (rp.nodd) {
-                        const uint32_t gram = __funnelshift_r(w[k], w[k + 1], 16);
-                        for (int c = 0; c < rp.nodd; c++)
-                            if (gram * rp.odd_mul[c] + rp.odd_add[c] == 0u) hits |= 1u << (4 * k + 2);
-                    }
-                }
-                if (hits == 0) {
-                    dropped = true;   // a bloom collision: no gram of the set here
-                } else {
-                    const uint32_t first = __ffs(hits) - 1, last = 31 - __clz(hits);
-                    hi = o + first;
-                    idle_from = o + last + 4;
-                    nl_in_chunk = nlm & ((1u << first) - 1u);   // newlines in [o, hi)
-                }
-            }
-            if (!dropped) {
-                // start: at most `lookback` bytes before the first hit, rounded down to a word, never before the line start
-                const uint32_t lo = hi > lookback ? (hi - lookback) & ~3u : 0u;
-                uint32_t t = lo;
-                bool at_line_start = lo == 0;
-                if (nl_in_chunk) {
-                    t = o + (32 - __clz(nl_in_chunk));   // just past the last newline before the hit
+            // start: at most `lookback` bytes before the chunk, rounded down to a word, never before the line start
+            const uint32_t lo = o > lookback ? (o - lookback) & ~3u : 0u;
+            uint32_t t = lo;
+            bool at_line_start = lo == 0;
+            for (uint32_t p = o; p > lo; p -= 4) {   // words [p-4, p) downwards: the last '\n' in [lo, o)
+                const uint32_t z = eq_mask4(X.word(p - 4), 0x0a0a0a0au);   // lo is word-aligned: the word lies inside [lo, o)
+                if (z) {
+                    t = (p - 4) + ((31 - __clz(z)) >> 3) + 1;
                     at_line_start = true;
-                    line_bit = 1u << __popc(nl_in_chunk);
-                } else {
-                    uint32_t p = o;   // scan words [p-4, p) downwards for the last '\n' in [lo, o) (nothing to scan if lo >= o)
-                    while (p > lo) {
-                        uint32_t z = eq_mask4(X.word(p - 4), 0x0a0a0a0au);
-                        if (p - 4 < lo) z &= ~((1u << (8 * (lo - (p - 4)))) - 1u);
-                        if (z) {
-                            t = (p - 4) + ((31 - __clz(z)) >> 3) + 1;
-                            at_line_start = true;
-                            break;
-                        }
-                        p -= 4;
-                    }
+                    break;
                 }
-                uint32_t before = 0;
-                if (!at_line_start) before = t - 1 >= X.wbase ? (X.word((t - 1) & ~3u) >> (8 * ((t - 1) & 3u))) & 0xffu : data[t - 1];
-                mask = walk_words(T, X, G, entry_state(G, at_line_start, before), end, o + 16u, t, idle_from, line_bit);
             }
+            const uint32_t before = at_line_start ? 0u : data[t - 1];
+            mask = walk_words(T, X, G, entry_state(G, at_line_start, before), end, o + 16u, t, o + idle_span, 1u);
             marks[i] = mask;
         }
         const uint32_t records = __reduce_add_sync(0xffffffffu, __popc(mask));
