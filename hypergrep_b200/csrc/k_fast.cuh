@@ -224,7 +224,7 @@ __device__ uint32_t walk_local(const GroupDev& G, const uint8_t* __restrict__ da
 }
 
 constexpr int kEmitThreads = 256;
-constexpr int kEmitTile = 2048;   // candidates per emit step (and per record-offset entry): enough marked ones to keep every warp busy
+constexpr int kEmitTile = 512;    // candidates per emit step (and per record-offset entry): small enough that sparse candidate lists still spread over all SMs
 
 // The exact gram set in global memory (two-choice table, Prefilter::confirm_keys), for k_verify_local to find the hit
 // positions inside a candidate chunk again: k_stream only reports "some sampled gram of this chunk MAY be in the set".
@@ -497,7 +497,7 @@ __device__ uint32_t emit_warp(const DbView& db, const uint8_t* __restrict__ data
 // shared-memory queue together with their record offset (tile offset from k_tile_offsets + a block scan inside the
 // tile); the block takes them out in FULL batches of one per thread and carries the remainder over to the next tile, so
 // that the expensive per-record work runs with every thread busy instead of a last, mostly empty round per tile.
-constexpr uint32_t kEmitQueue = 4096;   // >= kEmitTile + kEmitThreads, power of two
+constexpr uint32_t kEmitQueue = 1024;   // >= kEmitTile + kEmitThreads, power of two
 __global__ void __launch_bounds__(kEmitThreads) k_emit_simple(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
                                                               const uint32_t* __restrict__ marks, const uint32_t* __restrict__ tile_offsets,
                                                               const unsigned long long* __restrict__ meta, const unsigned long long* __restrict__ prefix,
