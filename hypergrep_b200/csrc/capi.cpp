@@ -35,8 +35,10 @@ void set_last_error(const std::string& e);
 namespace {
 
 std::atomic<int> g_device_override{-1};
+thread_local int t_device_override = -1;   // set by the shard workers of a scan that is split over several GPUs
 
 int pick_device() {
+    if (t_device_override >= 0) return t_device_override;
     int d = g_device_override.load();
     if (d >= 0) return d;
     if (const char* e = std::getenv("GPUGREP_DEVICE")) return std::atoi(e);
@@ -64,21 +66,40 @@ double now_ms() {
 // Host batcher: the result slots of hyperscanner_state_t (hyperscanner.c:64-72) and hs_callback (:83-102).
 // The reference keeps buffer_count slots of buffer_size bytes and strcpy()s every matched line into one; here the
 // lines of a batch are packed into pooled blocks (stable addresses until the batch has been delivered).
+// One result of a shard, kept until the shards before it have been delivered (scans split over several GPUs).
+struct ShardRecord {
+    unsigned id;
+    unsigned long long line;   // pseudo-line index inside the shard
+    size_t offset;             // of the delivered text in ShardResults::text (NUL-terminated there)
+};
+struct ShardResults {
+    std::vector<ShardRecord> records;
+    std::vector<char> text;
+};
+
 class Deliverer {
 public:
     Deliverer(hs_event cb, int buffer_count) : cb_(cb), cap_(std::max(1, buffer_count)) {
         if (cb_) results_.resize((size_t)cap_);
     }
+    // collecting deliverer of a shard worker: results are stored, not called back
+    explicit Deliverer(ShardResults* collect) : cb_(nullptr), cap_(1), collect_(collect) {}
     // `bytes`/`len`: the pseudo-line as it sits in the file.  The delivered text is what the reference strcpy()s:
     // leading NULs skipped, cut at the next NUL (hyperscanner.c:205-214, :92).
     void emit(unsigned id, unsigned long long line_number, const uint8_t* bytes, size_t len, bool may_have_nul = true) {
         count_++;
-        if (!cb_) return;
+        if (!cb_ && !collect_) return;
         size_t a = 0, b = len;
         if (may_have_nul) {
             while (a < len && bytes[a] == 0) a++;
             const void* z = std::memchr(bytes + a, 0, len - a);
             if (z) b = (size_t)((const uint8_t*)z - bytes);
+        }
+        if (collect_) {
+            collect_->records.push_back(ShardRecord{id, line_number, collect_->text.size()});
+            collect_->text.insert(collect_->text.end(), (const char*)bytes + a, (const char*)bytes + b);
+            collect_->text.push_back('\0');
+            return;
         }
         char* dst = place(b - a + 1);
         std::memcpy(dst, bytes + a, b - a);
@@ -98,7 +119,11 @@ public:
         used_ = 0;
     }
     unsigned long long count() const { return count_; }
-    bool wants_lines() const { return cb_ != nullptr; }
+    bool wants_lines() const { return cb_ != nullptr || collect_ != nullptr; }
+    // a stored result of a shard, already stripped: straight into the result slots
+    void emit_text(unsigned id, unsigned long long line_number, const char* text) {
+        emit(id, line_number, (const uint8_t*)text, std::strlen(text), false);
+    }
 private:
     static constexpr size_t kBlock = (size_t)1 << 20;
     char* place(size_t bytes) {
@@ -113,6 +138,7 @@ private:
     }
     hs_event cb_;
     int cap_;
+    ShardResults* collect_ = nullptr;
     int fill_ = 0;
     unsigned long long count_ = 0;
     std::vector<hyperscanner_result_t> results_;
@@ -387,14 +413,24 @@ struct SegmentQueue {
     bool abort = false;                     // consumer asked the reader to stop
 };
 
-int scan_file(const char* path, const Params& pr, gpugrep_stats* stats_out) {
+// One shard of a scan: byte range [begin, end) of a plain file; its results go to `collect` (null: count only).
+struct ShardSpec {
+    size_t begin = 0, end = 0;
+    ShardResults* collect = nullptr;
+    bool count_only = false;
+};
+
+int scan_file(const char* path, const Params& pr, gpugrep_stats* stats_out, const ShardSpec* shard = nullptr) {
     double t0 = now_ms();
-    Deliverer out(pr.cb, effective_batch(pr));
+    Deliverer own(pr.cb, effective_batch(pr));
+    Deliverer collecting(shard ? shard->collect : nullptr);
+    Deliverer counting(nullptr, 1);
+    Deliverer& out = !shard ? own : (shard->count_only ? counting : collecting);
     Job job;
     int rc = setup_job(pr, job, out);
     if (rc) { set_last_error(job.error); return rc; }
     std::string err;
-    auto src = open_byte_source(path, err);
+    auto src = shard ? open_plain_range(path, shard->begin, shard->end, err) : open_byte_source(path, err);
     if (!src) { set_last_error(err); return GPUGREP_GZ_OPEN; }
 
     const size_t limit = clamp_limit(pr.buffer_size);
@@ -436,7 +472,7 @@ int scan_file(const char* path, const Params& pr, gpugrep_stats* stats_out) {
         return GPUGREP_SCRATCH;
     }
 
-    const bool count_only = pr.cb == nullptr && pr.max_match == 0 && job.db->simple;
+    const bool count_only = !out.wants_lines() && pr.max_match == 0 && job.db->simple;
     for (ScanSlot* sl : slots) slot_set_want_records(sl, !count_only);
     SegmentQueue q;
     for (int i = 0; i < kSlots; i++) q.free_slots.push_back(i);
@@ -567,9 +603,12 @@ int device_cut(const uint8_t* dev, size_t have, bool final, size_t limit, size_t
     }
 }
 
-int scan_memory(const uint8_t* data, size_t size, int location, const Params& pr, gpugrep_stats* stats_out) {
+int scan_memory(const uint8_t* data, size_t size, int location, const Params& pr, gpugrep_stats* stats_out, const ShardSpec* shard = nullptr) {
     double t0 = now_ms();
-    Deliverer out(pr.cb, effective_batch(pr));
+    Deliverer own(pr.cb, effective_batch(pr));
+    Deliverer collecting(shard ? shard->collect : nullptr);
+    Deliverer counting(nullptr, 1);
+    Deliverer& out = !shard ? own : (shard->count_only ? counting : collecting);
     Job job;
     int rc = setup_job(pr, job, out);
     if (rc) { set_last_error(job.error); return rc; }
@@ -587,7 +626,7 @@ int scan_memory(const uint8_t* data, size_t size, int location, const Params& pr
     }
     ScanSlot* slots[2] = {engine_acquire_slot(err), engine_acquire_slot(err)};
     if (!slots[0] || !slots[1]) { engine_release_slot(slots[0]); engine_release_slot(slots[1]); set_last_error(err); return GPUGREP_SCRATCH; }
-    const bool count_only = pr.cb == nullptr && pr.max_match == 0 && job.db->simple;
+    const bool count_only = !out.wants_lines() && pr.max_match == 0 && job.db->simple;
     slot_set_want_records(slots[0], !count_only);
     slot_set_want_records(slots[1], !count_only);
     const uint8_t* seg_host[2] = {nullptr, nullptr};
@@ -677,7 +716,156 @@ int scan_memory(const uint8_t* data, size_t size, int location, const Params& pr
     return rc;
 }
 
+// ---- one input over several GPUs ----------------------------------------------------
+// $GPUGREP_DEVICES = "all" or a comma-separated list: hyperscan(path) on a plain file and gpugrep_scan_buffer on host
+// memory split the input into one newline-aligned byte range per device, scan the ranges concurrently (one host thread
+// and one pipeline per device), and merge on the calling thread: exclusive prefix sum of the shard line counts, line
+// numbers rebased, results in range order, the max_match_count rule applied to the merged sequence, callbacks batched
+// exactly as for a single device.  The only data exchanged between the shards are G line counts.
+std::vector<int> shard_devices() {
+    std::vector<int> out;
+    const char* e = std::getenv("GPUGREP_DEVICES");
+    if (!e || !*e) return out;
+    const int count = engine_device_count();
+    if (count < 1) return out;
+    if (std::strcmp(e, "all") == 0) {
+        for (int d = 0; d < count; d++) out.push_back(d);
+    } else {
+        for (const char* p = e; *p;) {
+            char* endp = nullptr;
+            long v = std::strtol(p, &endp, 10);
+            if (endp == p) break;
+            if (v >= 0 && v < count) out.push_back((int)v);
+            p = *endp == ',' ? endp + 1 : endp;
+        }
+    }
+    if (out.size() < 2) out.clear();
+    return out;
+}
+
+// below 32 MiB per shard a second device does not pay for its pipeline start ($GPUGREP_MIN_SHARD_BYTES: test hook)
+size_t min_shard_bytes() {
+    if (const char* e = std::getenv("GPUGREP_MIN_SHARD_BYTES")) {
+        if (*e) return std::max<size_t>(1, (size_t)std::strtoull(e, nullptr, 10));
+    }
+    return (size_t)32 << 20;
+}
+
+// `bounds`: G+1 newline-aligned offsets; `run(g, spec, stats)` scans shard g.
+int scan_sharded(const std::vector<int>& devices, const std::vector<size_t>& bounds, const Params& pr, gpugrep_stats* stats_out,
+                 const std::function<int(size_t, const ShardSpec&, gpugrep_stats*)>& run) {
+    const double t0 = now_ms();
+    const size_t G = bounds.size() - 1;
+    // a NULL callback without a limit only counts; everything else needs the results themselves for the ordered merge
+    const bool count_only = pr.cb == nullptr && pr.max_match == 0;
+    std::vector<ShardResults> results(G);
+    std::vector<gpugrep_stats> stats(G);
+    std::vector<int> rcs(G, 0);
+    std::vector<std::string> errors(G);
+    std::vector<std::thread> workers;
+    for (size_t g = 0; g < G; g++) {
+        workers.emplace_back([&, g] {
+            t_device_override = devices[g % devices.size()];
+            ShardSpec spec;
+            spec.begin = bounds[g];
+            spec.end = bounds[g + 1];
+            spec.collect = &results[g];
+            spec.count_only = count_only;
+            std::memset(&stats[g], 0, sizeof(gpugrep_stats));
+            rcs[g] = spec.end > spec.begin ? run(g, spec, &stats[g]) : 0;
+            if (rcs[g]) errors[g] = gpugrep_last_error();
+        });
+    }
+    for (auto& w : workers) w.join();
+    gpugrep_stats total;
+    std::memset(&total, 0, sizeof(total));
+    for (size_t g = 0; g < G; g++) {
+        if (rcs[g]) { set_last_error(errors[g]); return rcs[g]; }
+        total.bytes_scanned += stats[g].bytes_scanned; total.lines += stats[g].lines; total.candidates += stats[g].candidates;
+        total.h2d_bytes += stats[g].h2d_bytes; total.d2h_bytes += stats[g].d2h_bytes; total.gpu_ms += stats[g].gpu_ms;
+        total.stream_kernel_ms += stats[g].stream_kernel_ms; total.launches += stats[g].launches;
+        total.stream_launches += stats[g].stream_launches; total.segments += stats[g].segments; total.path |= stats[g].path;
+    }
+    // ordered merge on the calling thread
+    Deliverer out(pr.cb, effective_batch(pr));
+    unsigned long long line_base = 0;
+    bool stop = false;
+    for (size_t g = 0; g < G && !stop; g++) {
+        if (count_only) {
+            out.emit_count_only(stats[g].matches);
+        } else {
+            const auto& recs = results[g].records;
+            for (size_t i = 0; i < recs.size() && !stop;) {
+                size_t j = i;
+                for (; j < recs.size() && recs[j].line == recs[i].line; j++) {
+                    if (pr.cb) out.emit_text(recs[j].id, line_base + recs[j].line, results[g].text.data() + recs[j].offset);
+                    else out.emit_count_only(1);
+                }
+                // hyperscanner.c:222: the limit is checked after all reports of a line
+                if (pr.max_match > 0 && out.count() >= pr.max_match) stop = true;
+                i = j;
+            }
+        }
+        line_base += stats[g].lines;
+    }
+    out.flush();
+    total.matches = out.count();
+    total.wall_ms = now_ms() - t0;
+    if (stats_out) *stats_out = total;
+    set_last_error("");
+    return 0;
+}
+
+// Shard boundaries of a host buffer: k * size / G advanced to just past the next '\n'.
+std::vector<size_t> buffer_bounds(const uint8_t* data, size_t size, size_t shards) {
+    std::vector<size_t> b;
+    for (size_t g = 0; g <= shards; g++) b.push_back(gpugrep_shard_begin(data, size, (unsigned)g, (unsigned)shards));
+    return b;
+}
+
+// The same for a file, reading a window at every boundary.
+std::vector<size_t> file_bounds(const char* path, size_t size, size_t shards) {
+    std::vector<size_t> b{0};
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return {};
+    std::vector<char> window((size_t)1 << 20);
+    for (size_t g = 1; g < shards; g++) {
+        size_t pos = (size_t)(((unsigned __int128)size * g) / shards);
+        size_t found = size;
+        // the byte before pos may already be a newline
+        if (pos > 0 && fseeko(f, (off_t)(pos - 1), SEEK_SET) == 0) {
+            size_t at = pos - 1;
+            while (true) {
+                size_t got = std::fread(window.data(), 1, window.size(), f);
+                if (got == 0) break;
+                const void* nl = std::memchr(window.data(), '\n', got);
+                if (nl) { found = at + (size_t)((const char*)nl - window.data()) + 1; break; }
+                at += got;
+            }
+        }
+        b.push_back(std::max(found, b.back()));
+    }
+    std::fclose(f);
+    b.push_back(size);
+    return b;
+}
+
 }  // namespace
+
+// hyperscan(path): one device, or - plain files, $GPUGREP_DEVICES - one byte range per device.
+static int scan_path(const char* path, const Params& pr, gpugrep_stats* stats) {
+    const std::vector<int> devices = shard_devices();
+    if (!devices.empty() && pr.buffer_size >= 2) {
+        const size_t size = plain_regular_file_size(path);
+        if (size >= 2 * min_shard_bytes()) {
+            const size_t shards = std::min(devices.size(), size / min_shard_bytes());
+            const std::vector<size_t> bounds = file_bounds(path, size, shards);
+            if (bounds.size() == shards + 1)
+                return scan_sharded(devices, bounds, pr, stats, [&](size_t, const ShardSpec& spec, gpugrep_stats* st) { return scan_file(path, pr, st, &spec); });
+        }
+    }
+    return scan_file(path, pr, stats);
+}
 }  // namespace gpugrep
 
 extern "C" {
@@ -686,20 +874,30 @@ extern "C" {
 int hyperscan(char* file_name, const char* const* patterns, const unsigned int* pattern_flags, const unsigned int* pattern_ids,
               const unsigned int elements, hs_event on_event, const int buffer_size, int buffer_count, unsigned long long max_match_count) {
     gpugrep::Params pr{patterns, pattern_flags, pattern_ids, elements, on_event, buffer_size, buffer_count, max_match_count, nullptr};
-    return gpugrep::scan_file(file_name, pr, nullptr);
+    return gpugrep::scan_path(file_name, pr, nullptr);
 }
 
 int gpugrep_scan_file(const char* file_name, const char* const* patterns, const unsigned int* pattern_flags, const unsigned int* pattern_ids,
                       unsigned int elements, hs_event on_event, int buffer_size, int buffer_count, unsigned long long max_match_count,
                       gpugrep_stats* stats) {
     gpugrep::Params pr{patterns, pattern_flags, pattern_ids, elements, on_event, buffer_size, buffer_count, max_match_count, nullptr};
-    return gpugrep::scan_file(file_name, pr, stats);
+    return gpugrep::scan_path(file_name, pr, stats);
 }
 
 int gpugrep_scan_buffer(const void* data, size_t size, int location, const char* const* patterns, const unsigned int* pattern_flags,
                         const unsigned int* pattern_ids, unsigned int elements, hs_event on_event, int buffer_size, int buffer_count,
                         unsigned long long max_match_count, void* stream, gpugrep_stats* stats) {
     gpugrep::Params pr{patterns, pattern_flags, pattern_ids, elements, on_event, buffer_size, buffer_count, max_match_count, stream};
+    if (location == GPUGREP_LOC_HOST) {
+        const std::vector<int> devices = gpugrep::shard_devices();
+        if (!devices.empty() && size >= 2 * gpugrep::min_shard_bytes() && pr.buffer_size >= 2) {
+            const size_t shards = std::min(devices.size(), size / gpugrep::min_shard_bytes());
+            const std::vector<size_t> bounds = gpugrep::buffer_bounds((const uint8_t*)data, size, shards);
+            return gpugrep::scan_sharded(devices, bounds, pr, stats, [&](size_t, const gpugrep::ShardSpec& spec, gpugrep_stats* st) {
+                return gpugrep::scan_memory((const uint8_t*)data + spec.begin, spec.end - spec.begin, GPUGREP_LOC_HOST, pr, st, &spec);
+            });
+        }
+    }
     return gpugrep::scan_memory((const uint8_t*)data, size, location, pr, stats);
 }
 

@@ -50,7 +50,12 @@ class PlainSource : public ByteSource {
 public:
     PlainSource(std::unique_ptr<RawFile> f, const uint8_t* head, size_t head_len, int fd, bool regular)
         : f_(std::move(f)), head_(head, head + head_len), fd_(fd), regular_(regular), offset_(head_len) {}
+    // byte range [begin, end) of a regular file
+    PlainSource(std::unique_ptr<RawFile> f, int fd, size_t begin, size_t end)
+        : f_(std::move(f)), fd_(fd), regular_(true), offset_(begin), limit_(end) {}
     size_t read(uint8_t* dst, size_t cap) override {
+        if (limit_ != SIZE_MAX) cap = offset_ < limit_ ? std::min(cap, limit_ - offset_) : 0;
+        if (cap == 0) return 0;
         size_t got = 0;
         if (head_pos_ < head_.size()) {
             got = std::min(cap, head_.size() - head_pos_);
@@ -112,6 +117,7 @@ private:
     int fd_;
     bool regular_;
     size_t offset_;
+    size_t limit_ = SIZE_MAX;
 };
 
 // gzip members back to back; anything after the last member that is not another gzip header is ignored (zlib)
@@ -221,10 +227,13 @@ public:
                     avail_ += f_->read(in_.data() + avail_, in_.size() - avail_);
                     if (avail_ < 4) { done_ = true; break; }
                 }
+                // Between frames the reference decides like gz_look() of zstd's zlibWrapper (gzread.c): another zstd (or gzip)
+                // header continues the stream, ANYTHING else - a skippable frame included - is trailing garbage and ends the
+                // data (the wrapper's inflate() reports Z_STREAM_END at the end of every frame, so libzstd never gets to skip
+                // a skippable frame that follows one).
                 const uint8_t* p = in_.data() + pos_;
-                bool zstd_frame = p[0] == 0x28 && p[1] == 0xb5 && p[2] == 0x2f && p[3] == 0xfd;
-                bool skippable = (p[0] & 0xf0) == 0x50 && p[1] == 0x2a && p[2] == 0x4d && p[3] == 0x18;
-                if (!zstd_frame && !skippable) { done_ = true; break; }
+                const bool zstd_frame = p[0] == 0x28 && p[1] == 0xb5 && p[2] == 0x2f && p[3] == 0xfd;
+                if (!zstd_frame) { done_ = true; break; }
                 frame_done_ = false;
             }
             InBuf ib{in_.data() + pos_, avail_, 0};
@@ -274,6 +283,30 @@ std::unique_ptr<ByteSource> open_byte_source(const char* path, std::string& erro
     struct stat sb;
     bool regular = ::fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode);
     return std::make_unique<PlainSource>(std::move(raw), head, got, fd, regular);
+}
+
+std::unique_ptr<ByteSource> open_plain_range(const char* path, size_t begin, size_t end, std::string& error) {
+    int fd = ::open(path, O_RDONLY | O_CLOEXEC);
+    if (fd < 0) {
+        error = std::string("cannot open ") + path + ": " + std::strerror(errno);
+        return nullptr;
+    }
+    return std::make_unique<PlainSource>(std::make_unique<RawFile>(fd), fd, begin, end);
+}
+
+size_t plain_regular_file_size(const char* path) {
+    int fd = ::open(path, O_RDONLY | O_CLOEXEC);
+    if (fd < 0) return 0;
+    struct stat sb;
+    uint8_t head[4] = {0, 0, 0, 0};
+    size_t size = 0;
+    if (::fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode) && ::pread(fd, head, 4, 0) >= 2) {
+        const bool gz = head[0] == 0x1f && head[1] == 0x8b;
+        const bool zst = head[0] == 0x28 && head[1] == 0xb5 && head[2] == 0x2f && head[3] == 0xfd;
+        if (!gz && !zst) size = (size_t)sb.st_size;
+    }
+    ::close(fd);
+    return size;
 }
 
 }  // namespace gpugrep

@@ -21,6 +21,12 @@ public:
 // nullptr when the file cannot be opened (-> HYPERSCANNER_GZ_OPEN = 6, hyperscanner.c:192-195).
 std::unique_ptr<ByteSource> open_byte_source(const char* path, std::string& error);
 
+// Byte range [begin, end) of a plain regular file (one shard of a scan that is split over several GPUs).
+std::unique_ptr<ByteSource> open_plain_range(const char* path, size_t begin, size_t end, std::string& error);
+
+// Size of `path` if it is a plain (not gzip / zstd) regular file, else 0: only such files can be split by byte ranges.
+size_t plain_regular_file_size(const char* path);
+
 void set_zstd_library_path(const std::string& path);
 
 }  // namespace gpugrep

@@ -7,7 +7,7 @@
 #include <cstdio>
 #include <cstring>
 
-#include "../../include/gpugrep.h"
+#include "../../include/gpugrep_synth.h"
 
 namespace {
 
@@ -68,7 +68,7 @@ extern "C" {
 
 // Fills out[0, size) with complete lines (the last byte written is '\n').  Returns the number of lines.
 // plants: optional indicator strings; a line receives one with probability plant_ppm / 1e6.
-GPUGREP_API size_t gpugrep_synth_syslog(unsigned long long seed, char* out, size_t size, const char* const* plants, unsigned int nplants,
+GPUGREP_SYNTH_API size_t gpugrep_synth_syslog(unsigned long long seed, char* out, size_t size, const char* const* plants, unsigned int nplants,
                                         unsigned int plant_ppm) {
     Rng r(seed);
     Out o{out, out + size};

@@ -1,8 +1,9 @@
 """Synthetic workloads of BASELINE.json: seeded syslog-shaped text and the pattern sets.
 
 Used by bench.py, __graft_entry__.smoke() and the tests.  The text generator itself is native
-(``gpugrep_synth_syslog`` in libgpugrep.so, csrc/synth.cpp) so that 10 GiB can be produced in seconds; this module
-only holds the pattern sets and the ctypes glue.  Nothing here is on the scan path.
+(``gpugrep_synth_syslog`` in libgpugrep_synth.so, csrc/synth.cpp - a library of its own, so that a process which must
+not load the product, like ``bench.py --impl reference``, can still produce the corpus) so that 10 GiB can be produced
+in seconds; this module only holds the pattern sets and the ctypes glue.  Nothing here is on the scan path.
 """
 
 from __future__ import annotations
@@ -17,10 +18,14 @@ import numpy as np
 BLOCK_BYTES = 16 << 20  # generation granularity: block k is generated from seed + k
 
 
-def _lib() -> ctypes.CDLL:
-    from hypergrep_b200 import utils  # pylint: disable=import-outside-toplevel
+_SYNTH_LIB: ctypes.CDLL | None = None
 
-    return utils._get_hyperscanner_lib()  # pylint: disable=protected-access
+
+def _lib() -> ctypes.CDLL:
+    global _SYNTH_LIB  # pylint: disable=global-statement
+    if _SYNTH_LIB is None:
+        _SYNTH_LIB = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libgpugrep_synth.so"))
+    return _SYNTH_LIB
 
 
 def _bind(lib: ctypes.CDLL) -> ctypes.CDLL:
@@ -33,9 +38,11 @@ def _bind(lib: ctypes.CDLL) -> ctypes.CDLL:
 
 def fill_syslog(out: np.ndarray, seed: int = 1234, plants: list[str] | None = None, plant_ppm: int = 0,
                 threads: int = 0, lib: ctypes.CDLL | None = None) -> int:
-    """Fill a uint8 array with synthetic syslog text; returns the number of lines.  Deterministic in (seed, size)."""
+    """Fill a uint8 array with synthetic syslog text; returns the number of lines.  Deterministic in (seed, size).
+    `lib` is accepted for older call sites and ignored: the generator lives in libgpugrep_synth.so."""
     assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"]
-    lib = _bind(lib or _lib())
+    del lib
+    lib = _bind(_lib())
     plant_array = None
     count = 0
     if plants:

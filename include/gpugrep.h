@@ -125,12 +125,6 @@ GPUGREP_API void gpugrep_set_zstd_path(const char* path);
 GPUGREP_API const char* gpugrep_last_error(void);
 GPUGREP_API const char* gpugrep_version(void);
 
-/* Seeded synthetic syslog-shaped text for bench.py and the parity tests: fills out[0,size) with
- * complete '\n'-terminated lines (80-250 bytes, ~145 mean) and returns the line count.  `plants`: optional
- * indicator strings (each < 100 bytes), one appended to a line with probability plant_ppm / 1e6. */
-GPUGREP_API size_t gpugrep_synth_syslog(unsigned long long seed, char* out, size_t size, const char* const* plants,
-                                        unsigned int nplants, unsigned int plant_ppm);
-
 /* ---- compiled-database introspection (pattern compiler tests) ---- */
 typedef struct gpugrep_db gpugrep_db;
 

@@ -400,7 +400,8 @@ static unsigned char* zstd_slurp(const unsigned char* src, size_t n, size_t* out
         o += out.pos;
         if (is_err(r)) break; /* zlibWrapper: gzgets returns NULL on error -> loop ends */
         if (r == 0 && in.pos < in.size) {
-            /* frame finished; next must be another zstd frame, otherwise stop */
+            /* frame finished: zlibWrapper's gz_look() (gzread.c) continues only on another gzip / zstd header; anything else -
+               a skippable frame included - is trailing garbage and ends the data */
             if (in.size - in.pos < 4 || memcmp((const unsigned char*)in.src + in.pos, "\x28\xb5\x2f\xfd", 4) != 0) break;
         }
     }
@@ -523,6 +524,43 @@ int oracle_count_buffer(const char* text, size_t n, const char* const* patterns,
         st.line_number++;
     }
     *out_matches = st.match_count; *out_lines = st.line_number;
+    free(buf); free(slot.line); port_db_free(db);
+    return ret;
+}
+
+/* ---- test/bench extension: like oracle_count_buffer, and the line number of every delivered result is written to
+ * out_line_numbers[0, cap) in delivery order (bench.py compares them with the GPU's on the text it times). ---- */
+static __thread unsigned long long* g_sink = NULL;
+static __thread unsigned long long g_sink_cap = 0, g_sink_len = 0;
+static void sink_cb(port_result_t* r, int n) {
+    for (int i = 0; i < n; i++) {
+        if (g_sink_len < g_sink_cap) g_sink[g_sink_len] = r[i].line_number;
+        g_sink_len++;
+    }
+}
+int oracle_lines_buffer(const char* text, size_t n, const char* const* patterns, const unsigned int* flags, const unsigned int* ids,
+                        unsigned elements, int buffer_size, unsigned long long* out_line_numbers, unsigned long long cap,
+                        unsigned long long* out_matches, unsigned long long* out_lines) {
+    port_db_t* db = port_compile(patterns, flags, ids, elements);
+    if (!db) return PORT_DB;
+    port_state_t st; memset(&st, 0, sizeof(st));
+    port_result_t slot; slot.line = (char*)malloc((size_t)buffer_size);
+    g_sink = out_line_numbers; g_sink_cap = cap; g_sink_len = 0;
+    st.callback = sink_cb; st.result_index = -1; st.max_result_index = 0; st.results = &slot;
+    char* buf = (char*)calloc((size_t)buffer_size + 1, 1);
+    size_t pos = 0; int ret = 0;
+    while (pos < n) {
+        size_t lim = (size_t)buffer_size - 1;
+        size_t avail = n - pos < lim ? n - pos : lim;
+        const char* nl = (const char*)memchr(text + pos, '\n', avail);
+        size_t k = nl ? (size_t)(nl - (text + pos)) + 1 : avail;
+        memcpy(buf, text + pos, k); buf[k] = 0; pos += k;
+        st.line = port_strip(buf, buffer_size);
+        if ((ret = port_scan_block(db, &st, st.line, strlen(st.line))) != 0) break;
+        st.line_number++;
+    }
+    *out_matches = st.match_count; *out_lines = st.line_number;
+    g_sink = NULL;
     free(buf); free(slot.line); port_db_free(db);
     return ret;
 }

@@ -6,6 +6,7 @@
 // part of libgpugrep.so, and nothing in hypergrep_b200/ references it.  The CUDA kernels themselves are checked
 // on the GPU by the `-m gpu` tests.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -34,7 +35,11 @@ public:
 
 int engine_select_device(int, std::string&) { return 0; }
 int engine_current_device() { return 0; }
-int engine_device_count() { return 1; }
+int engine_device_count() {
+    // $GPUGREP_MOCK_DEVICES pretends several devices so that the shard / merge logic of the boundary runs on CPU
+    const char* e = std::getenv("GPUGREP_MOCK_DEVICES");
+    return e && *e ? std::max(1, std::atoi(e)) : 1;
+}
 void slot_set_want_records(ScanSlot*, bool) {}
 
 std::shared_ptr<DeviceDb> engine_upload(const std::shared_ptr<Database>& db, std::string&) {

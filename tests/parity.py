@@ -76,3 +76,38 @@ def random_case(seed: int):
 
 def gz_members(parts: list[bytes]) -> bytes:
     return b"".join(gzip.compress(p) for p in parts)
+
+
+def zstd_frame(data: bytes, level: int = 3) -> bytes:
+    """One zstd frame (system libzstd through ctypes; the image has no zstd module)."""
+    import ctypes
+
+    lib = ctypes.CDLL("libzstd.so.1")
+    lib.ZSTD_compressBound.restype = ctypes.c_size_t
+    lib.ZSTD_compressBound.argtypes = [ctypes.c_size_t]
+    lib.ZSTD_compress.restype = ctypes.c_size_t
+    lib.ZSTD_compress.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    bound = lib.ZSTD_compressBound(len(data))
+    buf = ctypes.create_string_buffer(bound)
+    size = lib.ZSTD_compress(buf, bound, data, len(data), level)
+    return buf.raw[:size]
+
+
+def zstd_skippable(payload: bytes = b"user data that is not text") -> bytes:
+    """A skippable frame: magic 0x184D2A50, little-endian length, payload."""
+    return b"\x50\x2a\x4d\x18" + len(payload).to_bytes(4, "little") + payload
+
+
+def zstd_cases(text: bytes) -> dict:
+    """Compressed layouts of `text` (which ends with a newline) and what the reference's zlibWrapper makes of them."""
+    half = text.rfind(b"\n", 0, len(text) // 2) + 1
+    a, b = text[:half], text[half:]
+    return {
+        "one_frame": zstd_frame(text),
+        "two_frames": zstd_frame(a) + zstd_frame(b),                              # read through
+        "three_frames_levels": zstd_frame(a, 1) + zstd_frame(b[: len(b) // 2], 9) + zstd_frame(b[len(b) // 2:], 3),
+        "skippable_between": zstd_frame(a) + zstd_skippable() + zstd_frame(b),   # stops after the first frame
+        "trailing_garbage": zstd_frame(a) + b"this is not zstd\n",               # garbage ignored
+        "empty_frame_then_text": zstd_frame(b"") + zstd_frame(text),
+        "truncated": zstd_frame(text)[: -7],                                      # what decodes before the error is scanned
+    }

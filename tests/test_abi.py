@@ -18,9 +18,15 @@ def _declared_symbols():
 
 def test_header_symbols_are_exported(gpu_lib):
     names = _declared_symbols()
-    assert "hyperscan" in names and "check_patterns" in names and len(names) >= 17
+    assert "hyperscan" in names and "check_patterns" in names and len(names) >= 16
     for name in names:
         assert hasattr(gpu_lib, name), f"{name} declared in include/gpugrep.h but not exported"
+
+
+def test_synth_library_is_separate(gpu_lib):
+    """The corpus generator lives in libgpugrep_synth.so (include/gpugrep_synth.h), not in the product library."""
+    synth = ctypes.CDLL(os.path.join(ROOT, "hypergrep_b200", "lib", "libgpugrep_synth.so"))
+    assert hasattr(synth, "gpugrep_synth_syslog") and not hasattr(gpu_lib, "gpugrep_synth_syslog")
 
 
 def test_result_layout_matches_reference():

@@ -70,8 +70,8 @@ def test_caseless_template_set_on_long_lines(gpu_lib, oracle_lib):
 
 
 def test_multiscanner_over_compressed_files(gpu_lib, oracle_lib, tmp_path, monkeypatch, capsys):
-    """configs[3] shape: the CLI entry (parallel_grep) over gzip + zstd + plain files, one hyperscan() job per file
-    (spread over the visible GPUs), counts checked against the oracle."""
+    """configs[3] shape: the CLI entry (parallel_grep) over gzip + zstd (one and several frames) + plain files, one
+    hyperscan() job per file (spread over the visible GPUs), counts checked against the oracle."""
     import gzip
 
     from hypergrep_b200 import multiscanner, utils
@@ -79,10 +79,14 @@ def test_multiscanner_over_compressed_files(gpu_lib, oracle_lib, tmp_path, monke
 
     monkeypatch.setattr(utils, "_get_hyperscanner_lib", lambda: gpu_lib)
     files, expected = [], []
-    for k in range(4):
+    for k in range(6):
         text = synth.syslog_bytes(1 << 20, seed=100 + k, lib=gpu_lib)
-        path = tmp_path / f"part{k}.log{'.gz' if k % 2 == 0 else ''}"
-        path.write_bytes(gzip.compress(text, 6) if k % 2 == 0 else text)
+        kind = ["gz", "plain", "zst", "gz2", "zst2", "plain"][k]
+        half = text.rfind(b"\n", 0, len(text) // 2) + 1
+        blob = {"gz": gzip.compress(text, 6), "plain": text, "zst": parity.zstd_frame(text), "gz2": parity.gz_members([text[:half], text[half:]]),
+                "zst2": parity.zstd_frame(text[:half]) + parity.zstd_frame(text[half:])}[kind]
+        path = tmp_path / f"part{k}.log{'' if kind == 'plain' else '.' + kind[:2].replace('zs', 'zst')}"
+        path.write_bytes(blob)
         files.append(str(path))
         rc, got, _ = run_scan(oracle_lib, str(path), synth.C2_PATTERNS)
         assert rc == 0
@@ -104,6 +108,14 @@ def test_compressed_inputs(gpu_lib, oracle_lib, tmp_path):
     parity.compare(gpu_lib, oracle_lib, None, ["ERROR"], path=str(garbage))
     parity.compare(gpu_lib, oracle_lib, None, ["foo"], path=str(tmp_path / "nope.txt"))
     parity.compare(gpu_lib, oracle_lib, None, ["foo"], path=str(tmp_path))
+    # zstd layouts: frames back to back are read through, a skippable frame or garbage after a frame ends the data
+    counts = {}
+    for name, blob in parity.zstd_cases(text).items():
+        path = tmp_path / f"{name}.log.zst"
+        path.write_bytes(blob)
+        counts[name] = parity.compare(gpu_lib, oracle_lib, None, synth.C2_PATTERNS, path=str(path))
+    assert counts["one_frame"] == counts["two_frames"] == counts["three_frames_levels"] == counts["empty_frame_then_text"] > 50
+    assert 0 < counts["skippable_between"] == counts["trailing_garbage"] < counts["one_frame"]
 
 
 def test_buffer_entry_points_agree_with_oracle(gpu_lib, oracle_lib):
@@ -322,3 +334,89 @@ def test_anchored_match_at_every_line_start_alignment(patterns, gpu_lib, oracle_
     assert parity.compare(gpu_lib, oracle_lib, b"filler line\n" * 1000 + data, patterns, flags=flags) >= 64
     monkeypatch.setenv("GPUGREP_NO_REPROBE", "1")
     assert parity.compare(gpu_lib, oracle_lib, data * 3, patterns + ["zqanchorqz"], flags=flags + [14]) >= 192
+
+
+def _oracle_records_threaded(oracle_lib, data: bytes, patterns, flags, threads: int):
+    """(line number, line bytes) of every oracle result over `data`, the text cut into newline-aligned shards that run
+    on `threads` host threads (the 10,000-pattern alternation costs the oracle about a second per MiB on one core)."""
+    import threading
+
+    n = len(patterns)
+    pa = (ctypes.c_char_p * n)(*[p.encode() for p in patterns])
+    fa = (ctypes.c_uint * n)(*flags)
+    ia = (ctypes.c_uint * n)(*([0] * n))
+    oracle_lib.oracle_lines_buffer.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint,
+                                               ctypes.c_int, ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_void_p, ctypes.c_void_p]
+    bounds = [0]
+    for t in range(1, threads):
+        cut = data.find(b"\n", len(data) * t // threads)
+        bounds.append(max(bounds[-1], cut + 1 if cut >= 0 else len(data)))
+    bounds.append(len(data))
+    found, counts = [None] * threads, [0] * threads
+
+    def work(t: int) -> None:
+        shard = data[bounds[t]:bounds[t + 1]]
+        cap = shard.count(b"\n") + 8
+        out = np.zeros(cap, dtype=np.uint64)
+        m, ln = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+        rc = oracle_lib.oracle_lines_buffer(shard, len(shard), pa, fa, ia, n, 262140, out.ctypes.data, cap, ctypes.byref(m), ctypes.byref(ln))
+        assert rc == 0 and m.value <= cap
+        found[t], counts[t] = out[: m.value], ln.value
+
+    pool = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    for th in pool:
+        th.start()
+    for th in pool:
+        th.join()
+    lines = data.split(b"\n")
+    records, base = [], 0
+    for t in range(threads):
+        records += [(int(v) + base, lines[int(v) + base] + b"\n") for v in found[t]]
+        base += counts[t]
+    return records
+
+
+def test_ten_thousand_caseless_patterns_full_set(gpu_lib, oracle_lib):
+    """configs[4] at its named size: ALL 10,000 caseless template patterns (many DFA groups, group gating, a candidate
+    list close to its capacity) over 64 MiB of 2-16 KiB JSON-ish lines, records compared with the oracle (every matched
+    line number and its bytes).  The oracle runs sharded over the host cores."""
+    import os
+
+    patterns = synth.c5_patterns(10000)
+    flags = [15] * len(patterns)
+    plants = ["session_10247 failed", "code=E4242abc", "REQUEST-EXPIRED-777}", "payment_555 REVOKED", "stalled xxxx31337"]
+    planted = [p for p in patterns if p.startswith("session_")][:40]
+    plants += [p.split(" ")[0] + " " + p.split("(?:")[1].split("|")[0] for p in planted]   # literal instances of real set members
+    sample = synth.jsonish_bytes(8 << 20, seed=7, patterns_to_plant=plants, plant_rate=0.3)
+    data = sample * 8   # 64 MiB: the generator is pure Python; the repeats still cross every segment / tile boundary differently
+    expected = _oracle_records_threaded(oracle_lib, data, patterns, flags, max(2, min(32, os.cpu_count() or 2)))
+    assert len(expected) > 200
+    host = np.frombuffer(data, dtype=np.uint8)
+    rc, got, st = scan_buffer(gpu_lib, host.ctypes.data, host.size, 0, patterns, flags=flags, buffer_count=4096)
+    assert rc == 0
+    assert [(ln, text) for (_i, ln, text) in got] == expected
+    assert st.lines == data.count(b"\n")
+
+
+def test_one_input_over_all_gpus(gpu_lib, oracle_lib, monkeypatch, tmp_path):
+    """$GPUGREP_DEVICES=all: one file / one host buffer split into a newline-aligned range per GPU, merged on the calling
+    thread (prefix sum of the shard line counts, ordered callbacks, max_match_count cut).  Needs two GPUs."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    monkeypatch.setenv("GPUGREP_DEVICES", "all")
+    monkeypatch.setenv("GPUGREP_MIN_SHARD_BYTES", str(1 << 20))
+    data = synth.syslog_bytes(48 << 20, seed=31)
+    assert parity.compare(gpu_lib, oracle_lib, data, synth.C2_PATTERNS) > 10000
+    parity.compare(gpu_lib, oracle_lib, data, synth.C2_PATTERNS, max_match_count=5000, buffer_count=7)
+    parity.compare(gpu_lib, oracle_lib, data[: 4 << 20], ["ERROR", "port [0-9]+", "o"], flags=[14, 14, 6], ids=[3, 1, 2])
+    # a large pinned buffer: the sharded result equals the single-device result record for record
+    size = 1 << 30
+    host = torch.empty(size, dtype=torch.uint8).pin_memory()
+    lines = synth.fill_syslog(host.numpy(), seed=1234)
+    rc, sharded, st = scan_buffer(gpu_lib, host.data_ptr(), size, 0, synth.C2_PATTERNS, buffer_count=4096)
+    assert rc == 0 and st.lines == lines and st.segments >= 2
+    monkeypatch.delenv("GPUGREP_DEVICES")
+    rc, single, st1 = scan_buffer(gpu_lib, host.data_ptr(), size, 0, synth.C2_PATTERNS, buffer_count=4096)
+    assert rc == 0 and single == sharded and st1.lines == lines

@@ -1,6 +1,7 @@
 """Host logic (capi.cpp segment cutting / batching / stop rule, ingest, pattern compiler) against the oracle, on CPU,
 through the mock engine.  The same cases run against the CUDA engine in test_gpu_parity.py."""
 
+import ctypes
 import os
 
 import pytest
@@ -146,3 +147,44 @@ def test_multiline_circumflex_after_the_final_newline(hostmock_lib, oracle_lib):
     for patterns in (["x\\W^"], ["x\\W\\Z\\z^([^a]a)*?"], ["^x"], ["x\\s^", "^y"]):
         parity.compare(hostmock_lib, oracle_lib, data, patterns, flags=[14] * len(patterns), ids=list(range(len(patterns))), buffer_size=64)
         parity.compare(hostmock_lib, oracle_lib, data, patterns)
+
+
+@pytest.mark.parametrize("devices", ["all", "0,1,2"])
+def test_one_input_over_several_devices_merges_like_one(devices, hostmock_lib, oracle_lib, monkeypatch, tmp_path):
+    """$GPUGREP_DEVICES: hyperscan(path) on a plain file and gpugrep_scan_buffer on host memory split the input into one
+    newline-aligned range per device and merge on the calling thread: same records, same line
+    numbers, same batch sizes, same max_match_count cut as one device (the mock engine pretends three devices)."""
+    from gpu_api import scan_buffer
+
+    monkeypatch.setenv("GPUGREP_MOCK_DEVICES", "3")
+    monkeypatch.setenv("GPUGREP_DEVICES", devices)
+    monkeypatch.setenv("GPUGREP_MIN_SHARD_BYTES", "100000")
+    data = synth.syslog_bytes(1 << 20, seed=77)
+    for patterns, kw in ((synth.C2_PATTERNS, {}), (synth.C2_PATTERNS, {"max_match_count": 1000, "buffer_count": 7}),
+                         (["ERROR", "port [0-9]+", "o"], {"flags": [14, 14, 6], "ids": [3, 1, 2], "max_match_count": 5000}),
+                         (["ERROR", "ssh2$"], {"buffer_size": 50}), (["no such text anywhere"], {})):
+        assert parity.compare(hostmock_lib, oracle_lib, data, patterns, **kw) >= 0
+    # host-buffer entry point, count-only and collecting
+    rc, expected, _ = run_scan_bytes(oracle_lib, data, synth.C2_PATTERNS)
+    buf = ctypes.create_string_buffer(data, len(data))
+    rc, got, stats = scan_buffer(hostmock_lib, ctypes.addressof(buf), len(data), 0, synth.C2_PATTERNS)
+    assert rc == 0 and got == expected and stats.lines == data.count(b"\n") and stats.segments >= 3
+    rc, none, stats = scan_buffer(hostmock_lib, ctypes.addressof(buf), len(data), 0, synth.C2_PATTERNS, collect=False)
+    assert rc == 0 and none is None and stats.matches == len(expected)
+    # a text without any newline cannot be split: the boundaries collapse and one shard does the work
+    blob = b"x" * 300000 + b"foo" + b"y" * 300000
+    parity.compare(hostmock_lib, oracle_lib, blob, ["foo"])
+    parity.compare(hostmock_lib, oracle_lib, b"", ["foo"])
+
+
+def test_zstd_frame_layouts(hostmock_lib, oracle_lib, tmp_path):
+    """zstd inputs (reference: gzopen/gzgets of zstd's zlibWrapper, hyperscanner.c:189-199): several frames are read
+    through; a skippable frame or garbage after a frame ends the data (gz_look() only continues on a gzip / zstd header)."""
+    text = synth.syslog_bytes(512 << 10, seed=19)
+    counts = {}
+    for name, blob in parity.zstd_cases(text).items():
+        path = tmp_path / f"{name}.log.zst"
+        path.write_bytes(blob)
+        counts[name] = parity.compare(hostmock_lib, oracle_lib, None, ["ERROR", "port [0-9]+"], path=str(path))
+    assert counts["one_frame"] == counts["two_frames"] == counts["three_frames_levels"] == counts["empty_frame_then_text"] > 50
+    assert 0 < counts["skippable_between"] == counts["trailing_garbage"] < counts["one_frame"]

@@ -1,8 +1,10 @@
 """The reference's OWN, unmodified test-suite with its loader hook redirected to another native library.
 
-Runs only where the reference checkout exists (the build container); on the GPU box /root/reference is absent and
-these tests skip.  The CPU legs pin the oracle and the host logic to every golden case the reference holds for the
-scan path; the GPU leg is the drop-in acceptance test for libgpugrep.so.
+The reference's Python layer and test module are read from /root/reference in the build container, and from the copy
+that `make -C oracle ref` (run by __graft_entry__.build()) stages under oracle/_ref/ - git-ignored, but shipped to the
+GPU box - everywhere else.  The CPU legs pin the oracle and the host logic to every golden case the reference holds
+for the scan path; the GPU leg is the drop-in acceptance test for libgpugrep.so: the reference's own unmodified
+utils.py / multiscanner.py / test_hypergrep.py on top of the new library.
 """
 
 import os
@@ -13,6 +15,8 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REFERENCE = os.environ.get("GPUGREP_REFERENCE", "/root/reference")
+if not os.path.exists(os.path.join(REFERENCE, "hypergrep", "test", "test_hypergrep.py")):
+    REFERENCE = os.path.join(ROOT, "oracle", "_ref")
 SUITE = os.path.join(REFERENCE, "hypergrep", "test", "test_hypergrep.py")
 
 needs_reference = pytest.mark.skipif(not os.path.exists(SUITE), reason="reference checkout not present")
