@@ -164,7 +164,8 @@ int compile_database(const char* const* patterns, const unsigned* flags, const u
         db->factors.group_mask.assign(n, 0u);
         for (size_t g = 0; g < db->groups.size(); g++)
             for (int member : db->groups[g].members) db->factors.group_mask[(size_t)member] |= 1u << (g & 31);
-        for (auto& np : db->nfas) db->factors.group_mask[(size_t)np.pattern] = 0xffffffffu;
+        // NFA-fallback patterns: bit 31 (shared with DFA groups 31, 63, ... - a superset, the NFA check then runs for nothing)
+        for (auto& np : db->nfas) db->factors.group_mask[(size_t)np.pattern] = 0x80000000u;
         build_prefilter(db->factors, nullptr, db->prefilter);
     } else {
         db->prefilter.note = db->factors.note = "disabled by GPUGREP_NO_PREFILTER";

@@ -103,6 +103,15 @@ __device__ bool block_matches(const DbView& db, const uint8_t* data, size_t star
     return false;
 }
 
+// simple mode, NFA-fallback patterns only: does one of them match the block [start, lim)?
+__device__ bool block_matches_nfa(const DbView& db, const uint8_t* data, size_t start, size_t lim) {
+    const size_t p0 = skip_leading_nuls(data, start, lim);
+    const size_t e = scanned_block_end(data, p0, lim);
+    for (int k = 0; k < db.nnfa; k++)
+        if (nfa_scan_block(db.nfas[k], data + p0, e - p0, [](size_t) { return true; })) return true;
+    return false;
+}
+
 // general mode: count (out == nullptr) or write the reports of the block
 __device__ uint32_t block_events(const DbView& db, const uint8_t* data, size_t start, size_t lim, uint32_t line, uint32_t pl_start,
                                  uint32_t pl_len, EventRec* out) {

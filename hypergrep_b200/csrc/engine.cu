@@ -5,7 +5,7 @@
 //   hyperscanner.c:199      hyperscanner.c:217           hyperscanner.c:83-102
 // Two paths produce identical results:
 //   FAST    (simple mode + literal prefilter + no over-long lines):
-//           k_stream -> scan -> k_check_long, k_list_candidates -> k_verify_local -> k_tile_offsets -> k_emit_simple
+//           k_stream -> scan -> k_check_long, k_list_candidates -> k_verify_smem | k_verify_local -> k_tile_offsets -> k_emit_nlm
 //   GENERAL (everything else, and the fallback when a fast-path capacity bound is hit):
 //           k_stream(no filter) -> scan -> k_newline_positions -> pseudo-line table -> k_match_pl_* -> scan -> emit
 // All byte offsets inside a segment are 32-bit (segments are < 4 GiB); line numbers are rebased on the host.
@@ -470,7 +470,9 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
         super_bytes = 2048;
         while (super_bytes * 4 <= (size_t)buffer_size && super_bytes < 65536) super_bytes *= 2;   // 2*super-1 <= buffer_size-1
     }
-    s->fast = ddb.simple && ddb.nnfa == 0 && pf != nullptr && super_bytes >= 2048 && std::getenv("GPUGREP_FORCE_GENERAL") == nullptr;
+    // (NFA-fallback patterns ride the fast path when the exact gram table is there: it tells which candidates they own)
+    s->fast = ddb.simple && pf != nullptr && super_bytes >= 2048 && std::getenv("GPUGREP_FORCE_GENERAL") == nullptr &&
+              (ddb.nnfa == 0 || (pf->mode == 2 && pf->d_confirm != nullptr && std::getenv("GPUGREP_NFA_GENERAL") == nullptr));
 
     if (host_data) {
         if (s->d_input.reserve(n + 1024) != cudaSuccess) { error = "cudaMalloc failed for the input segment"; return 3; }
@@ -554,8 +556,8 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
         // noticeable share of chunks (large gram sets: those candidates are dropped without a walk) and when several DFA
         // groups would each walk the whole chunk (measured with 32 patterns / 1 group / 415 grams: no gain, so not there).
         ReprobeParams rp{};
-        const bool want_reprobe = ddb.ngroups >= 2 || pf->bloom_false_rate > 0.005;
-        if (pf->mode >= 2 && pf->d_confirm && want_reprobe && std::getenv("GPUGREP_NO_REPROBE") == nullptr) {
+        const bool want_reprobe = ddb.ngroups >= 2 || pf->bloom_false_rate > 0.005 || ddb.nnfa > 0;
+        if (pf->mode >= 2 && pf->d_confirm && want_reprobe && (ddb.nnfa > 0 || std::getenv("GPUGREP_NO_REPROBE") == nullptr)) {
             rp.keys = pf->d_confirm;
             rp.groups = pf->d_confirm_groups;
             rp.mul = pf->confirm_mul; rp.mul2 = pf->confirm_mul2; rp.shift = 32 - pf->confirm_log2; rp.half = 1u << pf->confirm_log2;
@@ -580,24 +582,17 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
             k_verify_smem<<<vgrid, kVerifySmemThreads, vsmem, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->lookback,
                                                                     idle_span, s->d_res.as<uint32_t>(), tile_records);
         } else {
-            static const unsigned verify_per_sm = blocks_per_sm(k_verify_local, 128);
+            auto kernel = ddb.nnfa > 0 ? k_verify_local<true> : k_verify_local<false>;
+            const unsigned verify_per_sm = blocks_per_sm(kernel, 128);
             unsigned vgrid = (unsigned)std::min<size_t>((s->cand_cap + 127) / 128, (size_t)verify_per_sm * sms);
-            k_verify_local<<<vgrid, 128, 0, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->lookback, idle_span, rp,
-                                                  s->d_res.as<uint32_t>(), tile_records);
+            kernel<<<vgrid, 128, 0, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->lookback, idle_span, rp,
+                                          s->d_res.as<uint32_t>(), tile_records);
         }
         k_tile_offsets<<<1, 1024, 0, st>>>(tile_records, &dT->meta_total, s->cand_cap, &dT->rec_total);
-        const char* esel = std::getenv("GPUGREP_EMIT");
-        if (esel && std::strcmp(esel, "v1") == 0) {
-            static const unsigned emit_per_sm = blocks_per_sm(k_emit_simple, kEmitThreads);
-            k_emit_simple<<<(unsigned)std::min<size_t>((s->cand_cap + kEmitTile - 1) / kEmitTile, (size_t)emit_per_sm * sms), kEmitThreads, 0, st>>>(
-                view, s->data, n, s->d_cand.as<uint32_t>(), s->d_res.as<uint32_t>(), tile_records, meta, prefix, &dT->meta_total,
-                s->cand_cap, s->d_recs.as<LineRec>(), s->rec_cap, dT);
-        } else {
-            static const unsigned emit_per_sm = blocks_per_sm(k_emit_nlm, kEmitThreads);
-            k_emit_nlm<<<(unsigned)std::min<size_t>((s->cand_cap + kEmitTile - 1) / kEmitTile, (size_t)emit_per_sm * sms), kEmitThreads, 0, st>>>(
-                view, s->data, n, s->d_cand.as<uint32_t>(), s->d_res.as<uint32_t>(), tile_records, meta, prefix, nlmask, &dT->meta_total,
-                s->cand_cap, s->d_recs.as<LineRec>(), s->rec_cap, dT);
-        }
+        static const unsigned emit_per_sm = blocks_per_sm(k_emit_nlm, kEmitThreads);
+        k_emit_nlm<<<(unsigned)std::min<size_t>((s->cand_cap + kEmitTile - 1) / kEmitTile, (size_t)emit_per_sm * sms), kEmitThreads, 0, st>>>(
+            view, s->data, n, s->d_cand.as<uint32_t>(), s->d_res.as<uint32_t>(), tile_records, meta, prefix, nlmask, &dT->meta_total,
+            s->cand_cap, s->d_recs.as<LineRec>(), s->rec_cap, dT);
         s->stats.launches += 4;
         CUDA_TRY(cudaEventRecord(s->ev[1], st));
     }

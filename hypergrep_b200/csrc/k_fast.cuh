@@ -244,7 +244,12 @@ struct ReprobeParams {
 // With the exact gram table at hand, the walk covers [first gram hit - lookback, end of the last gram hit] and then runs on
 // until the automaton is idle (with one hit per chunk, the usual case, a third of walking the whole chunk), and a chunk
 // that k_stream flagged only because of a bloom collision is dropped without a walk.
-__global__ void __launch_bounds__(128, 16) k_verify_local(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
+// WITH_NFA: the database also holds patterns that are simulated as bit-parallel NFAs (their own DFA exceeds the state
+// budget).  Their grams carry bit 31 of the group mask; a candidate chunk with such a gram gets every line that
+// intersects it checked by the NFA simulation over the whole line (rare, and far cheaper than sending the whole segment
+// down the general path because of one such pattern).
+template <bool WITH_NFA>
+__global__ void __launch_bounds__(128, WITH_NFA ? 8 : 16) k_verify_local(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
                                                           const unsigned long long* meta_total, size_t cap, uint32_t lookback, uint32_t idle_span,
                                                           ReprobeParams rp,
                                                           uint32_t* __restrict__ marks, uint32_t* __restrict__ tile_records) {
@@ -324,6 +329,20 @@ __global__ void __launch_bounds__(128, 16) k_verify_local(DbView db, const uint8
     }
     for (int g = 0; g < db.ngroups; g++)
         if ((group_mask >> (g & 31)) & 1u) mask |= walk_local(db.groups[g], data, n, o, t, at_line_start, idle_from, line_bit);
+    if (WITH_NFA && (group_mask & 0x80000000u)) {
+        // lines that intersect the chunk: line 0 contains byte o, line j starts after the j-th newline of the chunk
+        uint32_t nlm = newline_mask16(ld_chunk(data, o, n));
+        size_t ls = line_start_of(data, o);
+        for (uint32_t bit = 1u;; bit <<= 1) {
+            bool nul = false;
+            const size_t le = line_end_of(data, ls, n, &nul);
+            if (!(mask & bit) && block_matches_nfa(db, data, ls, le)) mask |= bit;
+            if (!nlm) break;
+            ls = o + __ffs(nlm);
+            nlm &= nlm - 1;
+            if (ls >= o + 16 || ls >= n) break;   // that line starts outside the chunk
+        }
+    }
     marks[i] = mask;
     }
 counted:
@@ -400,165 +419,22 @@ __global__ void __launch_bounds__(1024) k_tile_offsets(uint32_t* __restrict__ ti
     if (threadIdx.x == 0) *rec_total = running;
 }
 
-// Emit: candidates with marked lines are compacted per block (few candidates carry a match), then one thread per marked
+// Emit.  Candidates with marked lines are compacted per block (few candidates carry a match), then one thread per marked
 // candidate computes line extents, line numbers and the exact re-check of lines with NULs.  The same line can be marked
 // by several candidate chunks: only the first marking yields a valid record, the others are written as kInvalidLen
 // records (their slot was reserved by the record offsets) and skipped by the host.
-// Records of one marked candidate chunk per lane (see k_emit_simple); returns the number of valid records the lane wrote.
-// Called by whole warps (`live` = this lane has a candidate): the lanes go through their marked lines round by round, and
-// in every round the line extents that a lane did not settle within kEmitBound bytes are finished by the whole warp.
-constexpr size_t kEmitBound = 256;
-__device__ uint32_t emit_warp(const DbView& db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
-                              const uint32_t* __restrict__ marks, const unsigned long long* __restrict__ meta,
-                              const unsigned long long* __restrict__ prefix, bool live, size_t i, size_t at, LineRec* __restrict__ recs,
-                              size_t rec_cap, Totals* totals) {
-    const uint32_t lane = threadIdx.x & 31;
-    uint32_t valid = 0;
-    uint32_t mask = live ? marks[i] : 0u;
-    const size_t o = live ? (size_t)cand[i] * 16 : 0;
-    uint32_t nlm = 0;
-    if (live) {
-        nlm = newline_mask16(ld_chunk(data, o, n));
-        if (o + 16 > n) nlm &= (1u << (n - o)) - 1u;
-    }
-    // line j of the chunk starts at `st` (j = 0: somewhere before the chunk, found below); `first` = still on line 0
-    size_t st = 0;
-    bool first = true;
-    while (__any_sync(0xffffffffu, mask != 0)) {
-        // skip lines of the chunk that are not marked
-        while (mask != 0 && !(mask & 1u)) {
-            if (!nlm) { mask = 0; break; }
-            st = o + __ffs(nlm);
-            nlm &= nlm - 1;
-            first = false;
-            mask >>= 1;
-        }
-        const bool work = mask != 0;
-        // ---- line start (only line 0 starts before the chunk)
-        bool settled = true;
-        if (work && first) settled = line_start_bounded(data, o, kEmitBound, &st);
-        for (uint32_t pend = __ballot_sync(0xffffffffu, work && !settled); pend; pend &= pend - 1) {
-            const int src = __ffs(pend) - 1;
-            const size_t found = warp_line_start(data, (size_t)__shfl_sync(0xffffffffu, (unsigned long long)st, src));
-            if ((int)lane == src) st = found;
-        }
-        // ---- line end
-        bool has_nul = false;
-        size_t en = 0;
-        settled = true;
-        if (work) settled = line_end_bounded(data, st, n, kEmitBound, &en, &has_nul);
-        for (uint32_t pend = __ballot_sync(0xffffffffu, work && !settled); pend; pend &= pend - 1) {
-            const int src = __ffs(pend) - 1;
-            bool more_nul = false;
-            const size_t found = warp_line_end(data, (size_t)__shfl_sync(0xffffffffu, (unsigned long long)en, src), n, &more_nul);
-            if ((int)lane == src) { en = found; has_nul |= more_nul; }
-        }
-        if (work) {
-            bool ok = true;
-            if (first) {
-                // the line started before this chunk: an earlier candidate chunk that intersects it may have marked it
-                // already (the line is the LAST line of such a chunk); only the first marking is kept.  (A repeat still
-                // gets its extents and line number computed: its neighbours in the warp need that work anyway.)
-                for (size_t k = i; k-- > 0;) {
-                    const size_t ok_off = (size_t)cand[k] * 16;
-                    if (ok_off + 16 <= st) break;
-                    const uint32_t mk = marks[k];
-                    if (!mk) continue;
-                    uint4 pv = ld_chunk(data, ok_off, n);
-                    const uint32_t last_idx = __popc(newline_mask16(pv) & 0x7fffu);   // line starts inside that chunk
-                    if ((mk >> last_idx) & 1u) { ok = false; break; }
-                }
-            }
-            if (ok && has_nul) ok = block_matches<false>(db, data, st, en);
-            valid += ok ? 1u : 0u;
-            // line number = newlines before the line start: whole blocks from the scan, then the part of the line's own
-            // 512-byte block, counted from whichever end of the block is nearer (the block's total is in meta)
-            const size_t lb = st >> 9;
-            uint32_t line_no = newlines_before_block(prefix, meta, lb);
-            if ((st & 511) <= 256) line_no += count_newlines(data, lb << 9, st);
-            else line_no += (uint32_t)(meta[lb] >> 32) - count_newlines(data, st, min((lb + 1) << 9, n));
-            if (at < rec_cap) recs[at] = LineRec{line_no, (uint32_t)st, ok ? ((uint32_t)(en - st) | (has_nul ? kHasNulBit : 0u)) : kInvalidLen};
-            else atomicOr(&totals->flags, 4u);
-            at++;
-            // on to the next line of the chunk
-            if (!nlm) mask = 0;
-            else {
-                st = o + __ffs(nlm);
-                nlm &= nlm - 1;
-                first = false;
-                mask >>= 1;
-            }
-        }
-    }
-    return valid;
-}
-
-// Persistent blocks walk tiles of kEmitTile candidates.  The marked candidates of a tile (about one in six) go into a
-// shared-memory queue together with their record offset (tile offset from k_tile_offsets + a block scan inside the
-// tile); the block takes them out in FULL batches of one per thread and carries the remainder over to the next tile, so
-// that the expensive per-record work runs with every thread busy instead of a last, mostly empty round per tile.
+// Persistent blocks walk tiles of kEmitTile candidates.  The marked candidates of a tile go into a shared-memory queue
+// together with their record offset (tile offset from k_tile_offsets + a block scan inside the tile); the block takes them
+// out in FULL batches of one per thread and carries the remainder over to the next tile, so that the per-record work runs
+// with every thread busy instead of a last, mostly empty round per tile.
 constexpr uint32_t kEmitQueue = 1024;   // >= kEmitTile + kEmitThreads, power of two
-__global__ void __launch_bounds__(kEmitThreads) k_emit_simple(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
-                                                              const uint32_t* __restrict__ marks, const uint32_t* __restrict__ tile_offsets,
-                                                              const unsigned long long* __restrict__ meta, const unsigned long long* __restrict__ prefix,
-                                                              const unsigned long long* meta_total, size_t cap, LineRec* __restrict__ recs, size_t rec_cap,
-                                                              Totals* totals) {
-    __shared__ uint32_t q_cand[kEmitQueue], q_at[kEmitQueue];
-    __shared__ unsigned long long s_warp[kEmitThreads / 32], s_total;
-    uint32_t valid = 0;
-    uint32_t head = 0, queued = 0;   // the same in every thread of the block
-    size_t ncand = (size_t)(*meta_total >> 32);
-    if (ncand > cap) ncand = cap;
-    constexpr int kPer = kEmitTile / kEmitThreads;   // consecutive candidates per thread in the compaction step
-    for (size_t block_base = (size_t)blockIdx.x * kEmitTile; block_base < ncand; block_base += (size_t)gridDim.x * kEmitTile) {
-        uint32_t mk[kPer];
-        uint32_t records = 0, marked = 0;
-#pragma unroll
-        for (int j = 0; j < kPer; j++) {
-            const size_t i = block_base + (size_t)threadIdx.x * kPer + j;
-            mk[j] = i < ncand ? marks[i] : 0u;
-            records += __popc(mk[j]);
-            marked += mk[j] != 0u;
-        }
-        // one scan for both: queue position (marked candidates before mine) and record offset (records before mine)
-        const unsigned long long before = block_exclusive_scan(((unsigned long long)marked << 32) | records, s_warp, &s_total);
-        uint32_t slot = head + queued + (uint32_t)(before >> 32);
-        uint32_t at = tile_offsets[block_base / kEmitTile] + (uint32_t)before;
-#pragma unroll
-        for (int j = 0; j < kPer; j++) {
-            if (mk[j]) {
-                q_cand[slot & (kEmitQueue - 1)] = (uint32_t)(block_base + (size_t)threadIdx.x * kPer + j);
-                q_at[slot & (kEmitQueue - 1)] = at;
-                slot++;
-                at += __popc(mk[j]);
-            }
-        }
-        queued += (uint32_t)(s_total >> 32);
-        __syncthreads();
-        while (queued >= (uint32_t)kEmitThreads) {
-            const uint32_t k = (head + threadIdx.x) & (kEmitQueue - 1);
-            valid += emit_warp(db, data, n, cand, marks, meta, prefix, true, q_cand[k], q_at[k], recs, rec_cap, totals);
-            head += kEmitThreads;
-            queued -= kEmitThreads;
-        }
-        __syncthreads();   // everything taken out before the next tile overwrites queue slots / scan scratch
-    }
-    if (queued) {   // whole warps, some lanes without a candidate
-        const uint32_t k = (head + threadIdx.x) & (kEmitQueue - 1);
-        const bool live = threadIdx.x < queued;
-        valid += emit_warp(db, data, n, cand, marks, meta, prefix, live, live ? q_cand[k] : 0, live ? q_at[k] : 0, recs, rec_cap, totals);
-    }
-    // unique valid records of the segment (count-only callers need nothing else)
-    valid = __reduce_add_sync(0xffffffffu, valid);
-    if ((threadIdx.x & 31) == 0 && valid) atomicAdd(&totals->aux_total, (unsigned long long)valid);
-}
 
 // ------------------------------------------------------------------------------------------------------------
 // Emit from the newline-chunk masks of k_stream (nlmask[block]: bit l set iff chunk l of the block holds a '\n').
 // Line start, line end and line number of a record come from a few mask words and the two text chunks that hold the
 // bounding newlines; the text of the line itself is read once, for the NUL test (hyperscanner.c:205-217 makes a line
-// with NUL bytes a different scanned block, so such lines are re-checked exactly).  k_emit_simple searched the text
-// chunk by chunk for all of this (about 2,000 instructions per record).
+// with NUL bytes a different scanned block, so such lines are re-checked exactly).  (Round 1 searched the text chunk by
+// chunk for all of this, about 2,000 instructions per record: 211 -> 143 us per 2 GiB of the C2 workload.)
 // ------------------------------------------------------------------------------------------------------------
 // Index just past the last '\n' strictly before `pos` (the start of the line that contains byte pos), or 0.
 __device__ uint32_t nlm_line_start(const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ nlmask, uint32_t pos) {
@@ -718,7 +594,7 @@ __device__ uint32_t emit_lane_nlm(const DbView& db, const uint8_t* __restrict__ 
             if ((int)lane == src) has_nul = more;
         }
         if (work) {
-            if (ok && has_nul) ok = block_matches<false>(db, data, st, en);
+            if (ok && has_nul) ok = block_matches<false>(db, data, st, en) || (db.nnfa > 0 && block_matches_nfa(db, data, st, en));
             valid += ok ? 1u : 0u;
             const uint32_t line_no = nlm_line_number(data, meta, prefix, nlmask, st);
             if (at < rec_cap) recs[at] = LineRec{line_no, st, ok ? ((en - st) | (has_nul ? kHasNulBit : 0u)) : kInvalidLen};
@@ -736,7 +612,6 @@ __device__ uint32_t emit_lane_nlm(const DbView& db, const uint8_t* __restrict__ 
     return valid;
 }
 
-// Same tile / queue structure as k_emit_simple (persistent blocks, marked candidates queued and taken out in full batches).
 __global__ void __launch_bounds__(kEmitThreads) k_emit_nlm(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
                                                            const uint32_t* __restrict__ marks, const uint32_t* __restrict__ tile_offsets,
                                                            const unsigned long long* __restrict__ meta, const unsigned long long* __restrict__ prefix,

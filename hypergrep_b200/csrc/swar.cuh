@@ -63,12 +63,11 @@ __device__ __forceinline__ uint32_t any_newline16(const uint4& v) {
 }
 __device__ __forceinline__ uint32_t haszero4(uint32_t w) { return (w - 0x01010101u) & ~w & 0x80808080u; }
 
-// The line-extent searches below run one thread per matched line, 32 different lines per warp.  They are written as
-// "a tight loop that only skips chunks without a hit, then the exact (expensive) look at the chunk that stopped the
-// loop": the threads of a warp leave the loop at different iterations but meet again behind it, so the expensive part runs
-// once per warp with every lane active instead of once per iteration with one or two lanes.  Each search can be bounded:
-// a line that is not settled within `bound` bytes is handed to the warp-cooperative variants further down, which read
-// 512 bytes per step (k_emit_simple: a 16 KiB JSON line is 32 steps for the warp instead of 1,000 for one thread).
+// The line-extent searches below run one thread per line, 32 different lines per warp (verification with an unbounded
+// look-back, NFA checks; the emit kernel uses the newline-chunk masks instead).  They are written as "a tight loop that
+// only skips chunks without a hit, then the exact (expensive) look at the chunk that stopped the loop": the threads of a
+// warp leave the loop at different iterations but meet again behind it, so the expensive part runs once per warp with
+// every lane active instead of once per iteration with one or two lanes.
 constexpr size_t kNoBound = ~(size_t)0;
 
 // Start of the line containing byte `pos` = index just past the last '\n' strictly before `pos` (0 if none).
@@ -171,58 +170,6 @@ __device__ size_t line_end_of(const uint8_t* data, size_t pos, size_t n, bool* h
     size_t en;
     line_end_bounded(data, pos, n, kNoBound, &en, has_nul);
     return en;
-}
-
-// Warp-cooperative continuations (every lane of the warp calls them with the same arguments).
-// Last '\n' strictly before the 16-byte aligned `pos`: the index just past it, or 0.
-__device__ size_t warp_line_start(const uint8_t* data, size_t pos) {
-    const uint32_t lane = threadIdx.x & 31;
-    while (pos > 0) {
-        // lane 0 takes the chunk just below pos, lane 31 the one 512 bytes further down
-        const bool have = pos >= (size_t)16 * (lane + 1);
-        const size_t base = have ? pos - (size_t)16 * (lane + 1) : 0;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (have) v = *reinterpret_cast<const uint4*>(data + base);
-        const uint32_t hit = __ballot_sync(0xffffffffu, have && any_newline16(v) != 0);
-        if (hit) {
-            const int src = __ffs(hit) - 1;   // the nearest chunk with a newline
-            const size_t mine = base + (32 - __clz(newline_mask16(v) | 1u));   // only the value of lane `src` is used
-            return (size_t)__shfl_sync(0xffffffffu, (unsigned long long)mine, src);
-        }
-        if (pos <= 512) return 0;
-        pos -= 512;
-    }
-    return 0;
-}
-// First '\n' at or after the 16-byte aligned `pos`: the index just past it, or n; *has_nul: a NUL lies in [pos, end).
-__device__ size_t warp_line_end(const uint8_t* data, size_t pos, size_t n, bool* has_nul) {
-    const uint32_t lane = threadIdx.x & 31;
-    bool nul = false;
-    size_t end = n;
-    while (pos < n) {
-        const size_t base = pos + (size_t)16 * lane;
-        const bool have = base < n;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        uint32_t valid = 0;
-        if (have) {
-            v = ld_chunk(data, base, n);
-            valid = base + 16 > n ? (1u << (n - base)) - 1u : 0xffffu;
-        }
-        const uint32_t m = have ? newline_mask16(v) & valid : 0u;
-        const uint32_t zm = have ? byte_mask16(v, 0u) & valid : 0u;
-        const uint32_t hit = __ballot_sync(0xffffffffu, m != 0);
-        const uint32_t src = hit ? (uint32_t)__ffs(hit) - 1u : 32u;   // the first chunk with a newline
-        // NULs count in the chunks before that one, and in it before the newline
-        const bool counts = lane < src ? zm != 0 : (lane == src && (zm & ((1u << __ffs(m)) - 1u)) != 0);
-        if (__any_sync(0xffffffffu, counts)) nul = true;
-        if (hit) {
-            end = (size_t)__shfl_sync(0xffffffffu, (unsigned long long)(base + __ffs(m | 0x10000u)), (int)src);
-            break;
-        }
-        pos += 512;
-    }
-    *has_nul = nul;
-    return end;
 }
 
 // newlines in [from, to); both ends arbitrary, to <= n.  Reads whole aligned 16-byte granules that overlap the range.

@@ -200,6 +200,40 @@ def test_nfa_fallback_for_exploding_patterns(gpu_lib, oracle_lib):
     parity.compare(gpu_lib, oracle_lib, text[: 64 << 10], patterns, flags=[14, 14, 6], ids=[1, 2, 3])
 
 
+def test_nfa_patterns_ride_the_fast_path(gpu_lib, oracle_lib, monkeypatch):
+    """A pattern whose DFA explodes but which has a literal factor (`session .{150}closed`) no longer sends the whole set down
+    the general path: its grams mark candidates like any other, and the lines of those candidates are checked by the NFA
+    simulation.  Lines with NUL bytes are re-checked with the NFA patterns as well."""
+    import random
+
+    import torch
+
+    rng = random.Random(5)
+    text = bytearray(synth.syslog_bytes(1 << 20, seed=17, lib=gpu_lib))
+    lines = bytes(text).split(b"\n")
+    out = []
+    for k, line in enumerate(lines):
+        roll = rng.random()
+        if roll < 0.02:
+            filler = bytes(rng.choice(b"abcdefghij ") for _ in range(rng.choice([149, 150, 151, 200])))
+            line = line[:40] + b" session " + filler + b"closed " + line[40:]
+        elif roll < 0.03:
+            line = line[:20] + b"\0session " + b"x" * 150 + b"closed"       # behind a NUL: must not count
+        elif roll < 0.04:
+            line = b"\0\0" + line[:30] + b" session " + b"y" * 150 + b"closed"  # leading NULs are stripped: counts
+        out.append(line)
+    data = b"\n".join(out)
+    patterns = [r"session .{150}closed", "ERROR", r"port [0-9]+"]
+    assert parity.compare(gpu_lib, oracle_lib, data, patterns) > 100
+    assert parity.compare(gpu_lib, oracle_lib, data, [r"session .{150}closed"]) > 10
+    dev = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    rc, _, st = scan_buffer(gpu_lib, dev.data_ptr(), dev.numel(), 1, patterns, collect=False)
+    assert rc == 0 and st.path == 1, "expected the fast path only"
+    monkeypatch.setenv("GPUGREP_NFA_GENERAL", "1")
+    rc, _, st2 = scan_buffer(gpu_lib, dev.data_ptr(), dev.numel(), 1, patterns, collect=False)
+    assert rc == 0 and (st2.path & 2) and st2.matches == st.matches
+
+
 def test_cli_in_fresh_processes(gpu_lib, oracle_lib, tmp_path):
     """The `hyperscanner` command line end to end, in fresh interpreters: default thread pool and --mp (fork AFTER the
     parent's compile check, which therefore must not have touched CUDA)."""
@@ -253,7 +287,7 @@ def test_default_buffer_boundary_lines(gpu_lib, oracle_lib):
 
 
 @pytest.mark.parametrize("switch", ["", "GPUGREP_NO_REPROBE=1", "GPUGREP_NO_MIXED_STRIDE=1", "GPUGREP_NO_TUNE=1", "GPUGREP_FILTER=exact",
-                                    "GPUGREP_MAX_DFA_STATES=300", "GPUGREP_VERIFY=v1", "GPUGREP_EMIT=v1", "GPUGREP_VERIFY=v1"])
+                                    "GPUGREP_MAX_DFA_STATES=300", "GPUGREP_VERIFY=v1", "GPUGREP_NFA_GENERAL=1"])
 def test_every_optimisation_switch_gives_the_same_result(switch, gpu_lib, oracle_lib, monkeypatch):
     """Each fast-path optimisation can be turned off: the result never changes.  The pattern sets carry
     a switch-specific extra literal so that no cached database or gram table of another variant is reused.

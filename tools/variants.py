@@ -21,8 +21,6 @@ from hypergrep_b200 import synth, utils  # noqa: E402
 VARIANTS = {
     "new": {},
     "verify_v1": {"GPUGREP_VERIFY": "v1"},
-    "emit_v1": {"GPUGREP_EMIT": "v1"},
-    "old": {"GPUGREP_VERIFY": "v1", "GPUGREP_EMIT": "v1"},
     "verify_v1": {"GPUGREP_VERIFY": "v1"},
     "noreprobe": {"GPUGREP_NO_REPROBE": "1"},
 }
@@ -31,7 +29,7 @@ parser = argparse.ArgumentParser()
 parser.add_argument("--mib", type=int, default=2048)
 parser.add_argument("--set", default="c2")
 parser.add_argument("--passes", type=int, default=3)
-parser.add_argument("--variants", default="new,verify_v1,emit_v1,old")
+parser.add_argument("--variants", default="new,verify_v1")
 args = parser.parse_args()
 lib = utils._get_hyperscanner_lib()
 plants = None
