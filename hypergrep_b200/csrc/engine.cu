@@ -589,8 +589,9 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
                                           s->d_res.as<uint32_t>(), tile_records);
         }
         k_tile_offsets<<<1, 1024, 0, st>>>(tile_records, &dT->meta_total, s->cand_cap, &dT->rec_total);
-        static const unsigned emit_per_sm = blocks_per_sm(k_emit_nlm, kEmitThreads);
-        k_emit_nlm<<<(unsigned)std::min<size_t>((s->cand_cap + kEmitTile - 1) / kEmitTile, (size_t)emit_per_sm * sms), kEmitThreads, 0, st>>>(
+        auto emit_kernel = ddb.nnfa > 0 ? k_emit_nlm<true> : k_emit_nlm<false>;
+        const unsigned emit_per_sm = blocks_per_sm(emit_kernel, kEmitThreads);
+        emit_kernel<<<(unsigned)std::min<size_t>((s->cand_cap + kEmitTile - 1) / kEmitTile, (size_t)emit_per_sm * sms), kEmitThreads, 0, st>>>(
             view, s->data, n, s->d_cand.as<uint32_t>(), s->d_res.as<uint32_t>(), tile_records, meta, prefix, nlmask, &dT->meta_total,
             s->cand_cap, s->d_recs.as<LineRec>(), s->rec_cap, dT);
         s->stats.launches += 4;

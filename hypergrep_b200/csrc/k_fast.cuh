@@ -545,6 +545,7 @@ __device__ bool warp_nul_scan(const uint8_t* __restrict__ data, size_t n, uint32
 
 constexpr uint32_t kNulBound = 512;
 // Records of one marked candidate chunk per lane; whole warps call it (`live`: this lane has a candidate).
+template <bool WITH_NFA>
 __device__ uint32_t emit_lane_nlm(const DbView& db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
                                   const uint32_t* __restrict__ marks, const unsigned long long* __restrict__ meta,
                                   const unsigned long long* __restrict__ prefix, const uint32_t* __restrict__ nlmask, uint32_t nblk, bool live, size_t i,
@@ -594,7 +595,7 @@ __device__ uint32_t emit_lane_nlm(const DbView& db, const uint8_t* __restrict__ 
             if ((int)lane == src) has_nul = more;
         }
         if (work) {
-            if (ok && has_nul) ok = block_matches<false>(db, data, st, en) || (db.nnfa > 0 && block_matches_nfa(db, data, st, en));
+            if (ok && has_nul) ok = block_matches<false>(db, data, st, en) || (WITH_NFA && block_matches_nfa(db, data, st, en));
             valid += ok ? 1u : 0u;
             const uint32_t line_no = nlm_line_number(data, meta, prefix, nlmask, st);
             if (at < rec_cap) recs[at] = LineRec{line_no, st, ok ? ((en - st) | (has_nul ? kHasNulBit : 0u)) : kInvalidLen};
@@ -612,6 +613,7 @@ __device__ uint32_t emit_lane_nlm(const DbView& db, const uint8_t* __restrict__ 
     return valid;
 }
 
+template <bool WITH_NFA>   // the database holds NFA-fallback patterns: lines with NUL bytes are re-checked with them too (1 KiB of local memory)
 __global__ void __launch_bounds__(kEmitThreads) k_emit_nlm(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
                                                            const uint32_t* __restrict__ marks, const uint32_t* __restrict__ tile_offsets,
                                                            const unsigned long long* __restrict__ meta, const unsigned long long* __restrict__ prefix,
@@ -651,7 +653,7 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit_nlm(DbView db, const uint
         __syncthreads();
         while (queued >= (uint32_t)kEmitThreads) {
             const uint32_t k = (head + threadIdx.x) & (kEmitQueue - 1);
-            valid += emit_lane_nlm(db, data, n, cand, marks, meta, prefix, nlmask, nblk, true, q_cand[k], q_at[k], recs, rec_cap, totals);
+            valid += emit_lane_nlm<WITH_NFA>(db, data, n, cand, marks, meta, prefix, nlmask, nblk, true, q_cand[k], q_at[k], recs, rec_cap, totals);
             head += kEmitThreads;
             queued -= kEmitThreads;
         }
@@ -660,7 +662,7 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit_nlm(DbView db, const uint
     if (queued) {
         const uint32_t k = (head + threadIdx.x) & (kEmitQueue - 1);
         const bool live = threadIdx.x < queued;
-        valid += emit_lane_nlm(db, data, n, cand, marks, meta, prefix, nlmask, nblk, live, live ? q_cand[k] : 0, live ? q_at[k] : 0, recs, rec_cap, totals);
+        valid += emit_lane_nlm<WITH_NFA>(db, data, n, cand, marks, meta, prefix, nlmask, nblk, live, live ? q_cand[k] : 0, live ? q_at[k] : 0, recs, rec_cap, totals);
     }
     valid = __reduce_add_sync(0xffffffffu, valid);
     if ((threadIdx.x & 31) == 0 && valid) atomicAdd(&totals->aux_total, (unsigned long long)valid);
