@@ -115,10 +115,20 @@ struct DevicePrefilter {
     uint32_t lookback = 0xffffffffu;
     uint32_t* d_confirm = nullptr;   // exact gram set for the verification kernel (Prefilter::confirm_keys), or null
     uint32_t* d_confirm_groups = nullptr;
+    uint32_t* d_confirm_ext = nullptr;            // Prefilter::confirm_ext, or null
+    unsigned long long* d_ext_keys = nullptr;
+    int ext_log2 = 0;
+    unsigned long long ext_mul = 0, ext_mul2 = 0;
     int confirm_log2 = 0;
     uint32_t confirm_mul = 0, confirm_mul2 = 0;
     double bloom_false_rate = 0;     // expected share of 16-byte chunks flagged by bloom collisions alone
-    ~DevicePrefilter() { if (d_table) cudaFree(d_table); if (d_confirm) cudaFree(d_confirm); if (d_confirm_groups) cudaFree(d_confirm_groups); }
+    ~DevicePrefilter() {
+        if (d_table) cudaFree(d_table);
+        if (d_confirm) cudaFree(d_confirm);
+        if (d_confirm_groups) cudaFree(d_confirm_groups);
+        if (d_confirm_ext) cudaFree(d_confirm_ext);
+        if (d_ext_keys) cudaFree(d_ext_keys);
+    }
 };
 
 class ScanSlot {
@@ -337,6 +347,18 @@ std::shared_ptr<DevicePrefilter> engine_upload_prefilter(const Prefilter& pf, st
             cudaMemcpy(out->d_confirm_groups, pf.confirm_groups.data(), pf.confirm_groups.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
             error = "cudaMalloc/cudaMemcpy failed for the gram confirmation table";
             return nullptr;
+        }
+        if (pf.confirm_ext.size() == pf.confirm_keys.size() && !pf.ext_keys.empty()) {
+            out->ext_log2 = pf.ext_log2;
+            out->ext_mul = pf.ext_mul;
+            out->ext_mul2 = pf.ext_mul2;
+            if (cudaMalloc((void**)&out->d_confirm_ext, pf.confirm_ext.size() * sizeof(uint32_t)) != cudaSuccess ||
+                cudaMemcpy(out->d_confirm_ext, pf.confirm_ext.data(), pf.confirm_ext.size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess ||
+                cudaMalloc((void**)&out->d_ext_keys, pf.ext_keys.size() * sizeof(uint64_t)) != cudaSuccess ||
+                cudaMemcpy(out->d_ext_keys, pf.ext_keys.data(), pf.ext_keys.size() * sizeof(uint64_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+                error = "cudaMalloc/cudaMemcpy failed for the extended confirmation table";
+                return nullptr;
+            }
         }
     }
     out->bloom_false_rate = (double)pf.num_grams * (16.0 / pf.stride) / (double)((size_t)1 << pf.log2_bits);
@@ -564,6 +586,11 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
             rp.stride = pf->stride; rp.fold = pf->fold ? 1 : 0;
             rp.nodd = pf->nodd;
             for (int k = 0; k < 2; k++) { rp.odd_mul[k] = pf->pp.odd_mul[k]; rp.odd_add[k] = pf->pp.odd_add[k]; }
+            if (pf->d_confirm_ext && pf->d_ext_keys) {
+                rp.ext_info = pf->d_confirm_ext;
+                rp.ext_keys = pf->d_ext_keys;
+                rp.ext_mul = pf->ext_mul; rp.ext_mul2 = pf->ext_mul2; rp.ext_shift = 64 - pf->ext_log2; rp.ext_half = 1u << pf->ext_log2;
+            }
         }
         // record offsets per emit tile of kEmitTile candidates: counted by the verification kernel, scanned by one block
         uint32_t* tile_records = s->d_recoff.as<uint32_t>();

@@ -238,7 +238,44 @@ struct ReprobeParams {
     int fold;
     int nodd;               // mixed sampling: compares at offsets 2 mod 4 (see ProbeParams)
     uint32_t odd_mul[2], odd_add[2];
+    // extended confirmation (Prefilter::confirm_ext): per slot of keys the variants (bytes in front of the gram, 6 or 8
+    // bytes in all); the text around the hit has to be in ext_keys (two-choice table of 64-bit keys) as well
+    const uint32_t* ext_info;   // null: off
+    const unsigned long long* ext_keys;
+    unsigned long long ext_mul, ext_mul2;
+    int ext_shift;
+    uint32_t ext_half;
 };
+
+// 8 text bytes from an arbitrary offset (little endian); pos + 8 <= n
+__device__ __forceinline__ unsigned long long load64_unaligned(const uint8_t* __restrict__ data, size_t pos, size_t n) {
+    if (pos + 16 <= n) {
+        const unsigned long long* p = reinterpret_cast<const unsigned long long*>(data + (pos & ~(size_t)7));
+        const unsigned long long lo = p[0], hi = p[1];
+        const uint32_t sh = 8u * (uint32_t)(pos & 7);
+        return sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
+    }
+    unsigned long long v = 0;
+    for (int k = 0; k < 8; k++) v |= (unsigned long long)data[pos + k] << (8 * k);
+    return v;
+}
+
+// Is the text around a gram hit at `q` one of the exact stretches the gram stands for?  info: Prefilter::confirm_ext.
+__device__ bool ext_confirmed(const ReprobeParams& rp, const uint8_t* __restrict__ data, size_t n, size_t q, uint32_t info) {
+    for (; info; info >>= 5) {
+        const uint32_t before = info & 7u, len = (info & 8u) ? 8u : 6u;
+        if (q < before || q - before + len > n) continue;   // a real occurrence lies inside the segment
+        const size_t pos = q - before;
+        unsigned long long v = pos + 8 <= n ? load64_unaligned(data, pos, n) : 0ull;
+        if (pos + 8 > n) for (uint32_t k = 0; k < len; k++) v |= (unsigned long long)data[pos + k] << (8 * k);
+        if (rp.fold) v |= 0x2020202020202020ull;
+        if (len == 6u) v = (v & 0x0000ffffffffffffull) | 0xA5A5000000000000ull;
+        const unsigned long long e1 = rp.ext_keys[(uint32_t)((v * rp.ext_mul) >> rp.ext_shift)];
+        const unsigned long long e2 = rp.ext_keys[rp.ext_half + (uint32_t)((v * rp.ext_mul2) >> rp.ext_shift)];
+        if (e1 == v || e2 == v) return true;
+    }
+    return false;
+}
 
 // One thread per candidate chunk: local verification (see walk_local); writes the bitmask of matched lines.
 // With the exact gram table at hand, the walk covers [first gram hit - lookback, end of the last gram hit] and then runs on
@@ -288,8 +325,12 @@ __global__ void __launch_bounds__(128, WITH_NFA ? 8 : 16) k_verify_local(DbView 
                     const uint32_t h1 = (gram * rp.mul) >> rp.shift, h2 = rp.half + ((gram * rp.mul2) >> rp.shift);
                     const uint32_t e1 = rp.keys[h1], e2 = rp.keys[h2];
                     if (e1 == gram || e2 == gram) {
-                        hits |= 1u << (4 * k + sft);
-                        group_mask |= rp.groups[e1 == gram ? h1 : h2];
+                        const uint32_t slot = e1 == gram ? h1 : h2;
+                        const uint32_t info = rp.ext_info ? rp.ext_info[slot] : 0u;
+                        if (info == 0u || ext_confirmed(rp, data, n, o + 4 * k + sft, info)) {
+                            hits |= 1u << (4 * k + sft);
+                            group_mask |= rp.groups[slot];
+                        }
                     }
                 }
                 if (rp.nodd) {

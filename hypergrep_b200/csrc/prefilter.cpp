@@ -401,28 +401,120 @@ void build_exact_tables(const std::vector<uint32_t>& grams, Prefilter& out) {
 
 // Fills the gram tables of `out` (exact two-choice table and bloom byte table) from the final gram list.
 // grams of the chosen windows, each with the DFA groups of the pattern it came from
+// Exact bytes around a gram instance (see Prefilter::confirm_ext): `before` bytes in front of the gram, 6 or 8 in all.
+struct GramExt {
+    uint8_t before = 0, len = 0;   // len == 0: no extension (a class position is too close, or the factor is too short)
+    uint64_t key = 0;
+};
+constexpr uint64_t kExt6Tag = 0xA5A5000000000000ull;
+
+GramExt extension_of(const ClassString& s, size_t at, bool fold) {
+    auto single = [&](size_t i, unsigned& value) {
+        ByteSet eff = effective(s[i], fold);
+        if (eff.count() != 1) return false;
+        for (unsigned v = 0; v < 256; v++) if (eff.test(v)) value = v;
+        return true;
+    };
+    for (size_t len : {(size_t)8, (size_t)6}) {
+        for (size_t before = 0; before + 4 <= len; before++) {   // as much as possible behind the gram first
+            if (before > at || at - before + len > s.size()) continue;
+            uint64_t key = 0;
+            bool ok = true;
+            for (size_t i = 0; i < len && ok; i++) {
+                unsigned v = 0;
+                ok = single(at - before + i, v);
+                key |= (uint64_t)v << (8 * i);
+            }
+            if (!ok) continue;
+            GramExt e;
+            e.before = (uint8_t)before;
+            e.len = (uint8_t)len;
+            e.key = len == 8 ? key : (key | kExt6Tag);
+            return e;
+        }
+    }
+    return GramExt();
+}
+
 struct GramList {
-    std::vector<std::pair<uint32_t, uint32_t>> items;   // (gram, group mask)
+    struct Item { uint32_t gram, mask; GramExt ext; };
+    std::vector<Item> items;   // (gram, group mask, exact bytes around this instance)
     void add(const ClassString& s, size_t at, bool fold, uint32_t mask) {
         scratch.clear();
         expand_gram(s, at, fold, scratch);
-        for (uint32_t g : scratch) items.emplace_back(g, mask);
+        const GramExt ext = scratch.size() == 1 ? extension_of(s, at, fold) : GramExt();
+        for (uint32_t g : scratch) items.push_back(Item{g, mask, ext});
     }
     size_t size() const { return items.size(); }
 private:
     std::vector<uint32_t> scratch;
 };
 
+// two-choice table of 64-bit keys (same scheme as build_two_choice)
+bool build_two_choice64(const std::vector<uint64_t>& keys_in, std::vector<uint64_t>& out_keys, int& out_lb, uint64_t& out_m1, uint64_t& out_m2) {
+    static const uint64_t muls[] = {0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0xD6E8FEB86659FD93ull, 0xFF51AFD7ED558CCDull,
+                                    0xC4CEB9FE1A85EC53ull, 0x94D049BB133111EBull, 0xBF58476D1CE4E5B9ull, 0x2545F4914F6CDD1Dull};
+    int lb = 4;
+    while (lb < 26 && ((size_t)2 << lb) * 2 < keys_in.size() * 5) lb++;
+    for (; lb <= 26; lb++) {
+        const size_t slots = (size_t)1 << lb;
+        for (int a = 0; a + 1 < 8; a += 2) {
+            const uint64_t m1 = muls[a], m2 = muls[a + 1];
+            std::vector<uint64_t> keys(2 * slots, 0);
+            bool ok = true;
+            for (uint64_t k : keys_in) {
+                uint64_t cur = k;
+                int side = 0, kicks = 0;
+                while (true) {
+                    size_t at = side == 0 ? (size_t)((cur * m1) >> (64 - lb)) : slots + (size_t)((cur * m2) >> (64 - lb));
+                    if (keys[at] == 0) { keys[at] = cur; break; }
+                    if (kicks == 0 && side == 0) {
+                        size_t alt = slots + (size_t)((cur * m2) >> (64 - lb));
+                        if (keys[alt] == 0) { keys[alt] = cur; break; }
+                    }
+                    std::swap(cur, keys[at]);
+                    side ^= 1;
+                    if (++kicks > 200) { ok = false; break; }
+                }
+                if (!ok) break;
+            }
+            if (ok) { out_keys.swap(keys); out_lb = lb; out_m1 = m1; out_m2 = m2; return true; }
+        }
+    }
+    return false;
+}
+
 uint32_t mask_of(const FactorSet& fs, size_t pattern) { return pattern < fs.group_mask.size() ? fs.group_mask[pattern] : 0xffffffffu; }
 
 void finish_tables(GramList& list, bool fold, const GramHistogram* sample, Prefilter& out) {
     // unique grams, group masks merged
-    std::sort(list.items.begin(), list.items.end());
-    std::vector<uint32_t> all, masks;
-    for (auto& it : list.items) {
-        if (it.first == 0u) continue;   // the empty-slot marker cannot be stored exactly; it can only be "\0\0\0\0", which never occurs in a block
-        if (!all.empty() && all.back() == it.first) masks.back() |= it.second;
-        else { all.push_back(it.first); masks.push_back(it.second); }
+    std::sort(list.items.begin(), list.items.end(), [](const GramList::Item& a, const GramList::Item& b) { return a.gram < b.gram; });
+    std::vector<uint32_t> all, masks, exts;   // exts: confirm_ext encoding per unique gram (0 = accepted as it is)
+    std::vector<uint64_t> ext_keys;
+    for (size_t i = 0; i < list.items.size();) {
+        size_t j = i;
+        uint32_t mask = 0;
+        bool confirmable = true;
+        std::vector<std::pair<uint8_t, uint8_t>> variants;
+        for (; j < list.items.size() && list.items[j].gram == list.items[i].gram; j++) {
+            mask |= list.items[j].mask;
+            const GramExt& e = list.items[j].ext;
+            if (e.len == 0) { confirmable = false; continue; }
+            auto v = std::make_pair(e.before, e.len);
+            if (std::find(variants.begin(), variants.end(), v) == variants.end()) variants.push_back(v);
+        }
+        if (list.items[i].gram != 0u) {   // the empty-slot marker cannot be stored exactly; it can only be "\0\0\0\0", which never occurs in a block
+            uint32_t enc = 0;
+            if (confirmable && !variants.empty() && variants.size() <= 3) {
+                for (size_t v = 0; v < variants.size(); v++)
+                    enc |= (16u | (variants[v].second == 8 ? 8u : 0u) | variants[v].first) << (5 * v);
+                for (size_t k = i; k < j; k++) ext_keys.push_back(list.items[k].ext.key);
+            }
+            all.push_back(list.items[i].gram);
+            masks.push_back(mask);
+            exts.push_back(enc);
+        }
+        i = j;
     }
     out.enabled = true;
     out.fold_case = fold;
@@ -435,6 +527,19 @@ void finish_tables(GramList& list, bool fold, const GramHistogram* sample, Prefi
         for (size_t k = 0; k < all.size(); k++) {
             const size_t h1 = prefilter_hash(all[k], out.confirm_mul, out.confirm_log2), h2 = half + prefilter_hash(all[k], out.confirm_mul2, out.confirm_log2);
             out.confirm_groups[out.confirm_keys[h1] == all[k] ? h1 : h2] |= masks[k];
+        }
+        // extended confirmation (Prefilter::confirm_ext): only when the second table can be built
+        std::sort(ext_keys.begin(), ext_keys.end());
+        ext_keys.erase(std::unique(ext_keys.begin(), ext_keys.end()), ext_keys.end());
+        out.confirm_ext.clear();
+        out.ext_keys.clear();
+        if (!ext_keys.empty() && std::getenv("GPUGREP_NO_EXT_CONFIRM") == nullptr &&
+            build_two_choice64(ext_keys, out.ext_keys, out.ext_log2, out.ext_mul, out.ext_mul2)) {
+            out.confirm_ext.assign(out.confirm_keys.size(), 0u);
+            for (size_t k = 0; k < all.size(); k++) {
+                const size_t h1 = prefilter_hash(all[k], out.confirm_mul, out.confirm_log2), h2 = half + prefilter_hash(all[k], out.confirm_mul2, out.confirm_log2);
+                out.confirm_ext[out.confirm_keys[h1] == all[k] ? h1 : h2] = exts[k];
+            }
         }
     }
     // bloom bitmap, one probe per gram: byte = product >> (32 - log2_bytes), bit = product & 7.  Sized so that

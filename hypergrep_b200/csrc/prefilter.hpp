@@ -67,6 +67,15 @@ struct Prefilter {
     std::vector<uint32_t> confirm_groups; // per slot: DFA groups (bit g mod 32) whose patterns own the gram; only those are walked
     int confirm_log2 = 0;
     uint32_t confirm_mul = 0, confirm_mul2 = 0;
+    // Extended confirmation.  A 4-byte gram of digits ("1234") occurs all over numeric text although the factor it stands for
+    // ("12345\"") does not: where the factor is exact (single-valued bytes) around the gram, the verification kernel also
+    // compares 6 or 8 bytes of text around the hit with a second exact table before it walks any automaton.
+    // confirm_ext[slot of confirm_keys]: 0 = the gram is accepted as it is; else up to three variants of 5 bits each:
+    // bits 0-2 = bytes in front of the gram (0..4), bit 3 = 8-byte key (else 6), bit 4 = variant present.
+    std::vector<uint32_t> confirm_ext;
+    std::vector<uint64_t> ext_keys;       // two-choice table, 2 << ext_log2 entries, 0 = empty; 6-byte keys carry 0xA5A5 on top
+    int ext_log2 = 0;
+    uint64_t ext_mul = 0, ext_mul2 = 0;
     // bloom bitmap (default in the streaming kernel: one lookup per gram): with p = gram * bloom_mul,
     // byte = p >> (32 - (log2_bits - 3)), bit = p & 7
     int log2_bits = 16;
