@@ -139,7 +139,7 @@ public:
     cudaEvent_t done = nullptr;           // all kernels of the segment + the totals copy have finished
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // 0/1: whole segment, 2/3: streaming kernel
     DevBuf d_input, d_meta, d_nlmask, d_gsum, d_prefix, d_sums, d_cand, d_res, d_recoff, d_recs, d_totals;
-    DevBuf d_nlpos, d_npl, d_ploff, d_plstart, d_pllen, d_flags, d_counts, d_events, d_gather, d_gidx;
+    DevBuf d_nlpos, d_npl, d_ploff, d_plstart, d_pllen, d_flags, d_counts, d_events, d_gather, d_gidx, d_hitinfo;
     PinBuf h_totals, h_recs, h_stage, h_gather, h_probe;
     // state of the in-flight segment
     const DeviceDb* ddb = nullptr;
@@ -599,9 +599,22 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
         const uint32_t idle_span = pf->nodd ? 18u : 20u - (uint32_t)pf->stride;
         // Verification.  Single-group databases whose class-compressed table fits shared memory, with a look-back that the
         // staged text window covers, take k_verify_smem; everything else the global-table kernel.
+        // Confirmation of the candidates (which grams really hit, which DFA groups they lead to) in a kernel of its own:
+        // the bloom table again from shared memory, exact tables only for what passes it.
+        const unsigned long long* hitinfo = nullptr;
+        if (rp.keys) {
+            if (s->d_hitinfo.reserve(s->cand_cap * 8) != cudaSuccess) { error = "cudaMalloc failed for candidate scratch"; return 3; }
+            const size_t csmem = (size_t)pf->table_words * 4;
+            CUDA_TRY(cudaFuncSetAttribute(k_confirm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+            const unsigned cgrid = (unsigned)std::min<size_t>((s->cand_cap + kConfirmThreads - 1) / kConfirmThreads, sms);
+            k_confirm<<<cgrid, kConfirmThreads, csmem, st>>>(s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->d_table, pf->table_words,
+                                                             pf->pp, rp, s->d_hitinfo.as<unsigned long long>());
+            hitinfo = s->d_hitinfo.as<unsigned long long>();
+            s->stats.launches++;
+        }
         const char* vsel = std::getenv("GPUGREP_VERIFY");
         const bool v1 = vsel && std::strcmp(vsel, "v1") == 0;
-        if (!v1 && ddb.smem_table_bytes && rp.keys == nullptr && pf->lookback <= 64u) {
+        if (!v1 && ddb.smem_table_bytes && hitinfo == nullptr && pf->lookback <= 64u) {
             const size_t vsmem = 256 + ddb.smem_table_bytes;
             CUDA_TRY(cudaFuncSetAttribute(k_verify_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
             const unsigned per_sm = blocks_per_sm(k_verify_smem, kVerifySmemThreads, vsmem);
@@ -612,7 +625,7 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
             auto kernel = ddb.nnfa > 0 ? k_verify_local<true> : k_verify_local<false>;
             const unsigned verify_per_sm = blocks_per_sm(kernel, 128);
             unsigned vgrid = (unsigned)std::min<size_t>((s->cand_cap + 127) / 128, (size_t)verify_per_sm * sms);
-            kernel<<<vgrid, 128, 0, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->lookback, idle_span, rp,
+            kernel<<<vgrid, 128, 0, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->lookback, idle_span, hitinfo,
                                           s->d_res.as<uint32_t>(), tile_records);
         }
         k_tile_offsets<<<1, 1024, 0, st>>>(tile_records, &dT->meta_total, s->cand_cap, &dT->rec_total);

@@ -226,7 +226,7 @@ __device__ uint32_t walk_local(const GroupDev& G, const uint8_t* __restrict__ da
 constexpr int kEmitThreads = 256;
 constexpr int kEmitTile = 512;    // candidates per emit step (and per record-offset entry): small enough that sparse candidate lists still spread over all SMs
 
-// The exact gram set in global memory (two-choice table, Prefilter::confirm_keys), for k_verify_local to find the hit
+// The exact gram set in global memory (two-choice table, Prefilter::confirm_keys), for k_confirm to find the hit
 // positions inside a candidate chunk again: k_stream only reports "some sampled gram of this chunk MAY be in the set".
 struct ReprobeParams {
     const uint32_t* keys;   // null: walk the whole chunk.  A gram lives in keys[h1] or keys[half + h2]
@@ -277,10 +277,79 @@ __device__ bool ext_confirmed(const ReprobeParams& rp, const uint8_t* __restrict
     return false;
 }
 
+// Confirmation of candidate chunks (databases with several DFA groups, large gram sets, NFA-fallback patterns): which
+// sampled grams of the chunk are REALLY in the set, and which DFA groups do they lead to?  k_stream only said "some gram
+// of this chunk may be".  One thread per candidate:
+//  1. the bloom byte table again, from shared memory like in k_stream (8 cheap lookups);
+//  2. for the few positions that pass: the exact two-choice gram table in global memory, and - where the factor around
+//     the gram is exact - 6 or 8 bytes of text against a second exact table (digit grams like "1234" are everywhere in
+//     numeric text, the factor "12345\"" they stand for is not);
+//  3. result per candidate: hit offsets (bit = byte offset in the chunk) << 32 | DFA group mask; 0 = dropped.
+// The verification kernel then walks only what is left (for the 10,000-pattern set: one candidate in a few hundred).
+// Doing this inside the verification kernel (round 1) cost two scattered global loads per sampled gram and candidate.
+constexpr int kConfirmThreads = 1024;
+__global__ void __launch_bounds__(kConfirmThreads, 1) k_confirm(const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
+                                                                const unsigned long long* meta_total, size_t cap, const uint32_t* __restrict__ table,
+                                                                int table_words, ProbeParams pp, ReprobeParams rp,
+                                                                unsigned long long* __restrict__ hitinfo) {
+    extern __shared__ __align__(16) uint32_t s_bloom[];
+    for (int k = threadIdx.x; k < table_words; k += blockDim.x) s_bloom[k] = table[k];
+    __syncthreads();
+    const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_bloom);
+    size_t ncand = (size_t)(*meta_total >> 32);
+    if (ncand > cap) ncand = cap;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncand; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t o = (size_t)cand[i] * 16;
+        const uint4 v = ld_chunk(data, o, n);
+        uint32_t w[5] = {v.x, v.y, v.z, v.w, o + 16 < n ? ld_chunk(data, o + 16, n).x : 0u};
+        if (rp.fold) {
+#pragma unroll
+            for (int k = 0; k < 5; k++) w[k] |= 0x20202020u;
+        }
+        uint32_t maybe = 0;   // bit = byte offset of a sampled gram that passes the bloom table
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+#pragma unroll
+            for (int sft = 0; sft < 4; sft++) {
+                if (sft % rp.stride) continue;
+                const uint32_t gram = sft == 0 ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * sft);
+                const uint32_t p = gram * pp.mul;
+                maybe |= ((s_bytes[p >> pp.shift] >> (p & 7u)) & 1u) << (4 * k + sft);
+            }
+        }
+        uint32_t hits = 0, group_mask = 0;
+        while (maybe) {
+            const uint32_t at = __ffs(maybe) - 1;
+            maybe &= maybe - 1;
+            const uint32_t k = at >> 2, sft = at & 3u;
+            const uint32_t gram = __funnelshift_r(w[k], w[k + 1], 8 * sft);
+            const uint32_t h1 = (gram * rp.mul) >> rp.shift, h2 = rp.half + ((gram * rp.mul2) >> rp.shift);
+            const uint32_t e1 = rp.keys[h1], e2 = rp.keys[h2];
+            if (e1 == gram || e2 == gram) {
+                const uint32_t slot = e1 == gram ? h1 : h2;
+                const uint32_t info = rp.ext_info ? rp.ext_info[slot] : 0u;
+                if (info == 0u || ext_confirmed(rp, data, n, o + at, info)) {
+                    hits |= 1u << at;
+                    group_mask |= rp.groups[slot];
+                }
+            }
+        }
+        if (rp.nodd) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t gram = __funnelshift_r(w[k], w[k + 1], 16);
+                for (int c = 0; c < rp.nodd; c++)
+                    if (gram * rp.odd_mul[c] + rp.odd_add[c] == 0u) { hits |= 1u << (4 * k + 2); group_mask = 0xffffffffu; }
+            }
+        }
+        hitinfo[i] = hits ? ((unsigned long long)hits << 32) | group_mask : 0ull;
+    }
+}
+
 // One thread per candidate chunk: local verification (see walk_local); writes the bitmask of matched lines.
-// With the exact gram table at hand, the walk covers [first gram hit - lookback, end of the last gram hit] and then runs on
-// until the automaton is idle (with one hit per chunk, the usual case, a third of walking the whole chunk), and a chunk
-// that k_stream flagged only because of a bloom collision is dropped without a walk.
+// With the result of k_confirm at hand (hitinfo), the walk covers [first gram hit - lookback, end of the last gram hit] and
+// then runs on until the automaton is idle, only the DFA groups that own the grams are walked, and a chunk without a
+// confirmed gram is dropped without a walk.
 // WITH_NFA: the database also holds patterns that are simulated as bit-parallel NFAs (their own DFA exceeds the state
 // budget).  Their grams carry bit 31 of the group mask; a candidate chunk with such a gram gets every line that
 // intersects it checked by the NFA simulation over the whole line (rare, and far cheaper than sending the whole segment
@@ -288,7 +357,7 @@ __device__ bool ext_confirmed(const ReprobeParams& rp, const uint8_t* __restrict
 template <bool WITH_NFA>
 __global__ void __launch_bounds__(128, WITH_NFA ? 8 : 16) k_verify_local(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
                                                           const unsigned long long* meta_total, size_t cap, uint32_t lookback, uint32_t idle_span,
-                                                          ReprobeParams rp,
+                                                          const unsigned long long* __restrict__ hitinfo,
                                                           uint32_t* __restrict__ marks, uint32_t* __restrict__ tile_records) {
     size_t ncand = (size_t)(*meta_total >> 32);
     if (ncand > cap) ncand = cap;
@@ -309,41 +378,15 @@ __global__ void __launch_bounds__(128, WITH_NFA ? 8 : 16) k_verify_local(DbView 
     } else {
         size_t hi = o;   // the walk has to start at or before hi - lookback
         uint32_t nl_in_chunk = 0;
-        if (rp.keys) {
-            const uint4 v = ld_chunk(data, o, n);
-            uint32_t w[5] = {v.x, v.y, v.z, v.w, o + 16 < n ? ld_chunk(data, o + 16, n).x : 0u};
-            if (rp.fold) {
-#pragma unroll
-                for (int k = 0; k < 5; k++) w[k] |= 0x20202020u;
-            }
-            uint32_t hits = 0;   // bit = byte offset of a sampled gram that is in the table
-            group_mask = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                for (int sft = 0; sft < 4; sft += rp.stride) {
-                    const uint32_t gram = __funnelshift_r(w[k], w[k + 1], 8 * sft);
-                    const uint32_t h1 = (gram * rp.mul) >> rp.shift, h2 = rp.half + ((gram * rp.mul2) >> rp.shift);
-                    const uint32_t e1 = rp.keys[h1], e2 = rp.keys[h2];
-                    if (e1 == gram || e2 == gram) {
-                        const uint32_t slot = e1 == gram ? h1 : h2;
-                        const uint32_t info = rp.ext_info ? rp.ext_info[slot] : 0u;
-                        if (info == 0u || ext_confirmed(rp, data, n, o + 4 * k + sft, info)) {
-                            hits |= 1u << (4 * k + sft);
-                            group_mask |= rp.groups[slot];
-                        }
-                    }
-                }
-                if (rp.nodd) {
-                    const uint32_t gram = __funnelshift_r(w[k], w[k + 1], 16);
-                    for (int c = 0; c < rp.nodd; c++)
-                        if (gram * rp.odd_mul[c] + rp.odd_add[c] == 0u) { hits |= 1u << (4 * k + 2); group_mask = 0xffffffffu; }
-                }
-            }
-            if (hits == 0) { marks[i] = 0; goto counted; }   // a bloom collision: no gram of the set here
+        if (hitinfo) {
+            const unsigned long long info = hitinfo[i];
+            const uint32_t hits = (uint32_t)(info >> 32);
+            if (hits == 0) { marks[i] = 0; goto counted; }   // k_confirm found no gram of the set in this chunk
+            group_mask = (uint32_t)info;
             const uint32_t first = __ffs(hits) - 1, last = 31 - __clz(hits);
             hi = o + first;
             idle_from = o + last + 4;
-            nl_in_chunk = newline_mask16(v) & ((1u << first) - 1u);   // newlines in [o, hi)
+            nl_in_chunk = newline_mask16(ld_chunk(data, o, n)) & ((1u << first) - 1u);   // newlines in [o, hi)
         }
         // start: at most `lookback` bytes before the first hit, rounded down to a word, never before the line start
         size_t lo = hi > lookback ? (hi - lookback) & ~(size_t)3 : 0;
@@ -668,7 +711,14 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit_nlm(DbView db, const uint
     size_t ncand = (size_t)(*meta_total >> 32);
     if (ncand > cap) ncand = cap;
     constexpr int kPer = kEmitTile / kEmitThreads;
+    const size_t ntiles = (ncand + kEmitTile - 1) / kEmitTile;
     for (size_t block_base = (size_t)blockIdx.x * kEmitTile; block_base < ncand; block_base += (size_t)gridDim.x * kEmitTile) {
+        {
+            // a tile without any record (sparse matches among many candidates): nothing to queue, not even its marks are read
+            const size_t tile = block_base / kEmitTile;
+            const uint32_t next = tile + 1 < ntiles ? tile_offsets[tile + 1] : (uint32_t)totals->rec_total;
+            if (next == tile_offsets[tile]) continue;
+        }
         uint32_t mk[kPer];
         uint32_t records = 0, marked = 0;
 #pragma unroll

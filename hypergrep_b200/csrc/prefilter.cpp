@@ -580,7 +580,8 @@ void finish_tables(GramList& list, bool fold, const GramHistogram* sample, Prefi
 
 std::string describe(const Prefilter& out, bool tuned) {
     return "stride " + std::to_string(out.stride) + (out.odd.empty() ? "" : " + " + std::to_string(out.odd.size()) + " compares at 2 mod 4") + (out.fold_case ? ", folded" : "") + ", " + std::to_string(out.num_grams) + " grams, bloom bitmap of " + std::to_string(1u << out.log2_bits) +
-           " bits, " + std::to_string((int)out.expected_hits_per_mib) + " expected hits/MiB" + (out.exact ? ", exact two-choice table of 2 x " + std::to_string(1u << out.log2_slots) + " slots" : "") + (tuned ? ", sample-tuned" : "");
+           " bits, " + std::to_string((int)out.expected_hits_per_mib) + " expected hits/MiB" +
+           (out.confirm_ext.empty() ? std::string() : ", " + std::to_string(std::count_if(out.confirm_ext.begin(), out.confirm_ext.end(), [](uint32_t e) { return e != 0; })) + " grams with extended confirmation") + (out.exact ? ", exact two-choice table of 2 x " + std::to_string(1u << out.log2_slots) + " slots" : "") + (tuned ? ", sample-tuned" : "");
 }
 
 // One register compare of the mixed scheme: the first `known` bytes of a 4-gram (little endian: the low bytes).
