@@ -268,7 +268,7 @@ __device__ bool ext_confirmed(const ReprobeParams& rp, const uint8_t* __restrict
         const size_t pos = q - before;
         unsigned long long v = pos + 8 <= n ? load64_unaligned(data, pos, n) : 0ull;
         if (pos + 8 > n) for (uint32_t k = 0; k < len; k++) v |= (unsigned long long)data[pos + k] << (8 * k);
-        if (rp.fold) v |= 0x2020202020202020ull;
+        v |= 0x2020202020202020ull;   // the extended keys are folded on every byte (prefilter.cpp extension_of)
         if (len == 6u) v = (v & 0x0000ffffffffffffull) | 0xA5A5000000000000ull;
         const unsigned long long e1 = rp.ext_keys[(uint32_t)((v * rp.ext_mul) >> rp.ext_shift)];
         const unsigned long long e2 = rp.ext_keys[rp.ext_half + (uint32_t)((v * rp.ext_mul2) >> rp.ext_shift)];
@@ -505,8 +505,7 @@ __global__ void __launch_bounds__(1024) k_tile_offsets(uint32_t* __restrict__ ti
 
 // Emit.  Candidates with marked lines are compacted per block (few candidates carry a match), then one thread per marked
 // candidate computes line extents, line numbers and the exact re-check of lines with NULs.  The same line can be marked
-// by several candidate chunks: only the first marking yields a valid record, the others are written as kInvalidLen
-// records (their slot was reserved by the record offsets) and skipped by the host.
+// by several candidate chunks: every marking yields a record here, k_dedupe_records invalidates the repeats.
 // Persistent blocks walk tiles of kEmitTile candidates.  The marked candidates of a tile go into a shared-memory queue
 // together with their record offset (tile offset from k_tile_offsets + a block scan inside the tile); the block takes them
 // out in FULL batches of one per thread and carries the remainder over to the next tile, so that the per-record work runs
@@ -611,16 +610,26 @@ __device__ bool nul_scan_bounded(const uint8_t* __restrict__ data, size_t n, uin
     *resume = stop;
     return false;
 }
-// Whole warp: NUL bytes in [from, to)?  from is 16-byte aligned.
+// Whole warp: NUL bytes in [from, to)?  from is 16-byte aligned.  2 KiB per step (four loads per lane in flight: the
+// lines are read from DRAM, so the steps of a 16 KiB line cost a round trip each).
 __device__ bool warp_nul_scan(const uint8_t* __restrict__ data, size_t n, uint32_t from, uint32_t to) {
     const uint32_t lane = threadIdx.x & 31;
-    for (uint32_t pos = from; pos < to; pos += 512u) {
-        const uint32_t cb = pos + 16u * lane;
+    for (uint32_t pos = from; pos < to; pos += 2048u) {
+        uint4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t cb = pos + 512u * j + 16u * lane;
+            v[j] = cb < to ? ld_chunk(data, cb, n) : make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+        }
         bool nul = false;
-        if (cb < to) {
-            uint32_t zm = byte_mask16(ld_chunk(data, cb, n), 0u);
-            if (cb + 16u > to) zm &= (1u << (to - cb)) - 1u;
-            nul = zm != 0u;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t cb = pos + 512u * j + 16u * lane;
+            if (cb < to) {
+                uint32_t zm = byte_mask16(v[j], 0u);
+                if (cb + 16u > to) zm &= (1u << (to - cb)) - 1u;
+                nul |= zm != 0u;
+            }
         }
         if (__any_sync(0xffffffffu, nul)) return true;
     }
@@ -658,19 +667,6 @@ __device__ uint32_t emit_lane_nlm(const DbView& db, const uint8_t* __restrict__ 
             en = nlm ? o + __ffs(nlm) : nlm_line_end(data, n, nlmask, nblk, o + 16u < (uint32_t)n ? o + 16u : (uint32_t)n - 1u);
             // (nlm == 0 here means: no newline at or after st inside the chunk, so the line ends beyond it; if the chunk is
             //  the last one, the search starts at the last byte and returns n)
-            if (first) {
-                // the line started before this chunk: an earlier candidate chunk that intersects it may have marked it
-                // already (the line is the LAST line of such a chunk); only the first marking is kept
-                for (size_t k = i; k-- > 0;) {
-                    const uint32_t ko = cand[k] * 16u;
-                    if (ko + 16u <= st) break;
-                    const uint32_t mk = marks[k];
-                    if (!mk) continue;
-                    uint32_t last_idx = 0;   // lines that start inside that chunk: newlines in its first 15 bytes
-                    if ((nlmask[ko >> 9] >> ((ko >> 4) & 31u)) & 1u) last_idx = __popc(newline_mask16(ld_chunk(data, ko, n)) & 0x7fffu);
-                    if ((mk >> last_idx) & 1u) { ok = false; break; }
-                }
-            }
             settled = nul_scan_bounded(data, n, st, en, kNulBound, &has_nul, &resume);
         }
         for (uint32_t pend = __ballot_sync(0xffffffffu, work && !settled); pend; pend &= pend - 1) {
@@ -754,6 +750,23 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit_nlm(DbView db, const uint
         const uint32_t k = (head + threadIdx.x) & (kEmitQueue - 1);
         const bool live = threadIdx.x < queued;
         valid += emit_lane_nlm<WITH_NFA>(db, data, n, cand, marks, meta, prefix, nlmask, nblk, live, live ? q_cand[k] : 0, live ? q_at[k] : 0, recs, rec_cap, totals);
+    }
+    (void)valid;   // the unique valid records are counted by k_dedupe_records
+}
+
+// The same line can be marked by several candidate chunks that intersect it.  Their records are ADJACENT in the record
+// array (records follow candidate order, and every candidate between two chunks of one line lies on that line too), so a
+// repeat is a record with the start offset of its predecessor: it is marked kInvalidLen here (the host skips those), and
+// the valid records - what a count-only caller needs - are counted.  (Round 1 looked back over the earlier candidates of
+// the line inside the emit kernel: with a fifth of all chunks being candidates and 8 KiB lines that was a walk over
+// ~100 candidates per record.)
+__global__ void __launch_bounds__(256) k_dedupe_records(LineRec* __restrict__ recs, size_t rec_cap, Totals* totals) {
+    size_t nrec = (size_t)totals->rec_total;
+    if (nrec > rec_cap) nrec = rec_cap;
+    uint32_t valid = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nrec; i += (size_t)gridDim.x * blockDim.x) {
+        if (i > 0 && recs[i].start == recs[i - 1].start) recs[i].len = kInvalidLen;
+        else if (recs[i].len != kInvalidLen) valid++;
     }
     valid = __reduce_add_sync(0xffffffffu, valid);
     if ((threadIdx.x & 31) == 0 && valid) atomicAdd(&totals->aux_total, (unsigned long long)valid);

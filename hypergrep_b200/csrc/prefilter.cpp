@@ -408,11 +408,20 @@ struct GramExt {
 };
 constexpr uint64_t kExt6Tag = 0xA5A5000000000000ull;
 
-GramExt extension_of(const ClassString& s, size_t at, bool fold) {
+// The extended keys are compared case-folded on EVERY byte (text | 0x20, whatever the gram table does): a caseless letter
+// {x, X} is then as good as an exact byte, and so is any other position whose bytes agree once bit 5 is set.  The filter
+// stays a superset filter: folding can only make more text pass.
+GramExt extension_of(const ClassString& s, size_t at) {
     auto single = [&](size_t i, unsigned& value) {
-        ByteSet eff = effective(s[i], fold);
-        if (eff.count() != 1) return false;
-        for (unsigned v = 0; v < 256; v++) if (eff.test(v)) value = v;
+        int seen = -1;
+        for (unsigned v = 0; v < 256; v++) {
+            if (!s[i].test(v)) continue;
+            const int f = (int)(v | 0x20u);
+            if (seen >= 0 && seen != f) return false;
+            seen = f;
+        }
+        if (seen < 0) return false;
+        value = (unsigned)seen;
         return true;
     };
     for (size_t len : {(size_t)8, (size_t)6}) {
@@ -442,7 +451,7 @@ struct GramList {
     void add(const ClassString& s, size_t at, bool fold, uint32_t mask) {
         scratch.clear();
         expand_gram(s, at, fold, scratch);
-        const GramExt ext = scratch.size() == 1 ? extension_of(s, at, fold) : GramExt();
+        const GramExt ext = extension_of(s, at);   // the same for every case variant of the gram
         for (uint32_t g : scratch) items.push_back(Item{g, mask, ext});
     }
     size_t size() const { return items.size(); }
