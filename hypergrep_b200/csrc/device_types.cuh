@@ -38,7 +38,7 @@ struct Totals {
     unsigned int flags;              // bit0: a 64 KiB super-block without newline; bit1: candidate overflow; bit2: record overflow
     unsigned int last_byte;
     unsigned int max_line;           // general path: longest line
-    unsigned int pad;
+    unsigned int survivors;          // fast path: candidates that k_confirm kept (length of the survivor list)
 };
 
 #define CUDA_TRY(expr)                                                                      \

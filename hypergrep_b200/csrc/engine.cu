@@ -139,7 +139,7 @@ public:
     cudaEvent_t done = nullptr;           // all kernels of the segment + the totals copy have finished
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // 0/1: whole segment, 2/3: streaming kernel
     DevBuf d_input, d_meta, d_nlmask, d_gsum, d_prefix, d_sums, d_cand, d_res, d_recoff, d_recs, d_totals;
-    DevBuf d_nlpos, d_npl, d_ploff, d_plstart, d_pllen, d_flags, d_counts, d_events, d_gather, d_gidx, d_hitinfo;
+    DevBuf d_nlpos, d_npl, d_ploff, d_plstart, d_pllen, d_flags, d_counts, d_events, d_gather, d_gidx, d_hitinfo, d_survivors;
     PinBuf h_totals, h_recs, h_stage, h_gather, h_probe;
     // state of the in-flight segment
     const DeviceDb* ddb = nullptr;
@@ -602,14 +602,19 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
         // Confirmation of the candidates (which grams really hit, which DFA groups they lead to) in a kernel of its own:
         // the bloom table again from shared memory, exact tables only for what passes it.
         const unsigned long long* hitinfo = nullptr;
+        const uint32_t* survivors = nullptr;
         if (rp.keys) {
-            if (s->d_hitinfo.reserve(s->cand_cap * 8) != cudaSuccess) { error = "cudaMalloc failed for candidate scratch"; return 3; }
+            if (s->d_hitinfo.reserve(s->cand_cap * 8) != cudaSuccess || s->d_survivors.reserve(s->cand_cap * 4) != cudaSuccess) {
+                error = "cudaMalloc failed for candidate scratch"; return 3;
+            }
             const size_t csmem = (size_t)pf->table_words * 4;
             CUDA_TRY(cudaFuncSetAttribute(k_confirm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
             const unsigned cgrid = (unsigned)std::min<size_t>((s->cand_cap + kConfirmThreads - 1) / kConfirmThreads, sms);
             k_confirm<<<cgrid, kConfirmThreads, csmem, st>>>(s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->d_table, pf->table_words,
-                                                             pf->pp, rp, s->d_hitinfo.as<unsigned long long>());
+                                                             pf->pp, rp, s->d_hitinfo.as<unsigned long long>(), s->d_res.as<uint32_t>(),
+                                                             s->d_survivors.as<uint32_t>(), dT);
             hitinfo = s->d_hitinfo.as<unsigned long long>();
+            survivors = s->d_survivors.as<uint32_t>();
             s->stats.launches++;
         }
         const char* vsel = std::getenv("GPUGREP_VERIFY");
@@ -626,7 +631,7 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
             const unsigned verify_per_sm = blocks_per_sm(kernel, 128);
             unsigned vgrid = (unsigned)std::min<size_t>((s->cand_cap + 127) / 128, (size_t)verify_per_sm * sms);
             kernel<<<vgrid, 128, 0, st>>>(view, s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->lookback, idle_span, hitinfo,
-                                          s->d_res.as<uint32_t>(), tile_records);
+                                          survivors, dT, s->d_res.as<uint32_t>(), tile_records);
         }
         k_tile_offsets<<<1, 1024, 0, st>>>(tile_records, &dT->meta_total, s->cand_cap, &dT->rec_total);
         auto emit_kernel = ddb.nnfa > 0 ? k_emit_nlm<true> : k_emit_nlm<false>;

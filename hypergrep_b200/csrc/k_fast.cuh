@@ -291,22 +291,40 @@ constexpr int kConfirmThreads = 1024;
 __global__ void __launch_bounds__(kConfirmThreads, 1) k_confirm(const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
                                                                 const unsigned long long* meta_total, size_t cap, const uint32_t* __restrict__ table,
                                                                 int table_words, ProbeParams pp, ReprobeParams rp,
-                                                                unsigned long long* __restrict__ hitinfo) {
+                                                                unsigned long long* __restrict__ hitinfo, uint32_t* __restrict__ marks,
+                                                                uint32_t* __restrict__ survivors, Totals* totals) {
     extern __shared__ __align__(16) uint32_t s_bloom[];
     for (int k = threadIdx.x; k < table_words; k += blockDim.x) s_bloom[k] = table[k];
     __syncthreads();
     const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_bloom);
     size_t ncand = (size_t)(*meta_total >> 32);
     if (ncand > cap) ncand = cap;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncand; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t o = (size_t)cand[i] * 16;
-        const uint4 v = ld_chunk(data, o, n);
-        uint32_t w[5] = {v.x, v.y, v.z, v.w, o + 16 < n ? ld_chunk(data, o + 16, n).x : 0u};
+    // The text of a candidate comes from DRAM (the segment was streamed long ago): the chunk of the NEXT candidate of this
+    // thread is requested before the current one is looked at.
+    const size_t step = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t o_next = i < ncand ? (size_t)cand[i] * 16 : 0;
+    uint4 v_next = ld_chunk(data, o_next, n);
+    uint32_t x_next = o_next + 16 < n ? *reinterpret_cast<const uint32_t*>(data + o_next + 16) : 0u;
+    for (; (i & ~(size_t)31) < ncand; i += step) {
+        const bool live = i < ncand;
+        const size_t o = o_next;
+        const uint4 v = v_next;
+        uint32_t w[5] = {v.x, v.y, v.z, v.w, x_next};
+        if (o + 20 > n) w[4] = o + 16 < n ? ld_chunk(data, o + 16, n).x : 0u;   // the last words of the segment: bytes beyond n read as zero
+        if (i + step < ncand) {
+            o_next = (size_t)cand[i + step] * 16;
+            v_next = ld_chunk(data, o_next, n);
+            x_next = o_next + 16 < n ? *reinterpret_cast<const uint32_t*>(data + o_next + 16) : 0u;
+        } else {
+            o_next = 0;
+        }
         if (rp.fold) {
 #pragma unroll
             for (int k = 0; k < 5; k++) w[k] |= 0x20202020u;
         }
         uint32_t maybe = 0;   // bit = byte offset of a sampled gram that passes the bloom table
+        if (live) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
 #pragma unroll
@@ -316,6 +334,7 @@ __global__ void __launch_bounds__(kConfirmThreads, 1) k_confirm(const uint8_t* _
                 const uint32_t p = gram * pp.mul;
                 maybe |= ((s_bytes[p >> pp.shift] >> (p & 7u)) & 1u) << (4 * k + sft);
             }
+        }
         }
         uint32_t hits = 0, group_mask = 0;
         while (maybe) {
@@ -334,7 +353,7 @@ __global__ void __launch_bounds__(kConfirmThreads, 1) k_confirm(const uint8_t* _
                 }
             }
         }
-        if (rp.nodd) {
+        if (rp.nodd && live) {
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const uint32_t gram = __funnelshift_r(w[k], w[k + 1], 16);
@@ -342,7 +361,21 @@ __global__ void __launch_bounds__(kConfirmThreads, 1) k_confirm(const uint8_t* _
                     if (gram * rp.odd_mul[c] + rp.odd_add[c] == 0u) { hits |= 1u << (4 * k + 2); group_mask = 0xffffffffu; }
             }
         }
-        hitinfo[i] = hits ? ((unsigned long long)hits << 32) | group_mask : 0ull;
+        // The candidates that are left go into a compact list (in no particular order: the verification kernel writes its
+        // result by candidate index): few survive for large sets, and a warp of the verification kernel should be full.
+        const bool keep = live && hits != 0u;
+        if (live) {
+            hitinfo[i] = keep ? ((unsigned long long)hits << 32) | group_mask : 0ull;
+            if (!keep) marks[i] = 0u;
+        }
+        const uint32_t alive = __ballot_sync(0xffffffffu, keep);
+        if (alive) {
+            const uint32_t lane = threadIdx.x & 31;
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&totals->survivors, (unsigned int)__popc(alive));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) survivors[base + __popc(alive & ((1u << lane) - 1u))] = (uint32_t)i;
+        }
     }
 }
 
@@ -358,14 +391,19 @@ template <bool WITH_NFA>
 __global__ void __launch_bounds__(128, WITH_NFA ? 8 : 16) k_verify_local(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
                                                           const unsigned long long* meta_total, size_t cap, uint32_t lookback, uint32_t idle_span,
                                                           const unsigned long long* __restrict__ hitinfo,
+                                                          const uint32_t* __restrict__ survivors, const Totals* totals,
                                                           uint32_t* __restrict__ marks, uint32_t* __restrict__ tile_records) {
     size_t ncand = (size_t)(*meta_total >> 32);
     if (ncand > cap) ncand = cap;
-    // whole warps stay in the loop (a warp's 32 candidates are consecutive and lie in one emit tile): the records of the
-    // tile are counted with one warp reduction and one atomic
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; (i & ~(size_t)31) < ncand; i += (size_t)gridDim.x * blockDim.x) {
+    // with a survivor list (k_confirm) the kernel walks that list, in whatever order it has: results go by candidate index
+    const size_t count = survivors ? (size_t)totals->survivors : ncand;
+    // whole warps stay in the loop (without a survivor list a warp's 32 candidates are consecutive and lie in one emit
+    // tile: the records of the tile are counted with one warp reduction and one atomic)
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; (j & ~(size_t)31) < count; j += (size_t)gridDim.x * blockDim.x) {
     uint32_t mask = 0;
-    if (i < ncand) {
+    size_t i = j;
+    if (j < count) {
+    if (survivors) i = survivors[j];
     const size_t o = (size_t)cand[i] * 16;
     size_t t;
     bool at_line_start;
@@ -430,8 +468,12 @@ __global__ void __launch_bounds__(128, WITH_NFA ? 8 : 16) k_verify_local(DbView 
     marks[i] = mask;
     }
 counted:
-    const uint32_t records = __reduce_add_sync(0xffffffffu, __popc(mask));
-    if ((threadIdx.x & 31) == 0 && records) atomicAdd(&tile_records[i / kEmitTile], records);
+    if (survivors) {
+        if (mask) atomicAdd(&tile_records[i / kEmitTile], (uint32_t)__popc(mask));
+    } else {
+        const uint32_t records = __reduce_add_sync(0xffffffffu, __popc(mask));
+        if ((threadIdx.x & 31) == 0 && records) atomicAdd(&tile_records[i / kEmitTile], records);
+    }
     }
 }
 
@@ -747,8 +789,12 @@ __global__ void __launch_bounds__(kEmitThreads) k_emit_nlm(DbView db, const uint
         __syncthreads();
     }
     if (queued) {
-        const uint32_t k = (head + threadIdx.x) & (kEmitQueue - 1);
-        const bool live = threadIdx.x < queued;
+        // the remainder is dealt out across the warps (entry j -> lane j / 8 of warp j % 8), not to the first warps only: the
+        // long-line searches of one warp run one after the other
+        constexpr uint32_t kWarps = kEmitThreads / 32;
+        const uint32_t j = (threadIdx.x >> 5) + kWarps * (threadIdx.x & 31);
+        const uint32_t k = (head + j) & (kEmitQueue - 1);
+        const bool live = j < queued;
         valid += emit_lane_nlm<WITH_NFA>(db, data, n, cand, marks, meta, prefix, nlmask, nblk, live, live ? q_cand[k] : 0, live ? q_at[k] : 0, recs, rec_cap, totals);
     }
     (void)valid;   // the unique valid records are counted by k_dedupe_records
