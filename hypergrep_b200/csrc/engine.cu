@@ -122,6 +122,7 @@ struct DevicePrefilter {
     int confirm_log2 = 0;
     uint32_t confirm_mul = 0, confirm_mul2 = 0;
     double bloom_false_rate = 0;     // expected share of 16-byte chunks flagged by bloom collisions alone
+    double expected_hits_per_mib = -1;   // gram hits per MiB of the tuning sample (-1: no sample)
     ~DevicePrefilter() {
         if (d_table) cudaFree(d_table);
         if (d_confirm) cudaFree(d_confirm);
@@ -362,6 +363,7 @@ std::shared_ptr<DevicePrefilter> engine_upload_prefilter(const Prefilter& pf, st
         }
     }
     out->bloom_false_rate = (double)pf.num_grams * (16.0 / pf.stride) / (double)((size_t)1 << pf.log2_bits);
+    out->expected_hits_per_mib = pf.expected_hits_per_mib;
     out->table_words = (int)src->size();
     if (cudaMalloc((void**)&out->d_table, src->size() * sizeof(uint32_t)) != cudaSuccess ||
         cudaMemcpy(out->d_table, src->data(), src->size() * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -608,11 +610,22 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
                 error = "cudaMalloc failed for candidate scratch"; return 3;
             }
             const size_t csmem = (size_t)pf->table_words * 4;
-            CUDA_TRY(cudaFuncSetAttribute(k_confirm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-            const unsigned cgrid = (unsigned)std::min<size_t>((s->cand_cap + kConfirmThreads - 1) / kConfirmThreads, sms);
-            k_confirm<<<cgrid, kConfirmThreads, csmem, st>>>(s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->d_table, pf->table_words,
-                                                             pf->pp, rp, s->d_hitinfo.as<unsigned long long>(), s->d_res.as<uint32_t>(),
-                                                             s->d_survivors.as<uint32_t>(), dT);
+            // dense candidate sets (more than ~6 % of the chunks expected): stream the text again instead of gathering chunks
+            const char* csel = std::getenv("GPUGREP_CONFIRM");
+            const bool dense = csel ? std::strcmp(csel, "dense") == 0 : pf->expected_hits_per_mib > 4000.0;
+            if (dense) {
+                CUDA_TRY(cudaFuncSetAttribute(k_confirm_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+                const unsigned cgrid = (unsigned)std::min<size_t>((s->nblk * 32 + kConfirmThreads - 1) / kConfirmThreads, sms);
+                k_confirm_dense<<<cgrid, kConfirmThreads, csmem, st>>>(s->data, n, meta, prefix, s->cand_cap, pf->d_table, pf->table_words, pf->pp, rp,
+                                                                       s->d_hitinfo.as<unsigned long long>(), s->d_res.as<uint32_t>(),
+                                                                       s->d_survivors.as<uint32_t>(), dT);
+            } else {
+                CUDA_TRY(cudaFuncSetAttribute(k_confirm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+                const unsigned cgrid = (unsigned)std::min<size_t>((s->cand_cap + kConfirmThreads - 1) / kConfirmThreads, sms);
+                k_confirm<<<cgrid, kConfirmThreads, csmem, st>>>(s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->d_table, pf->table_words,
+                                                                 pf->pp, rp, s->d_hitinfo.as<unsigned long long>(), s->d_res.as<uint32_t>(),
+                                                                 s->d_survivors.as<uint32_t>(), dT);
+            }
             hitinfo = s->d_hitinfo.as<unsigned long long>();
             survivors = s->d_survivors.as<uint32_t>();
             s->stats.launches++;
