@@ -610,22 +610,11 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
                 error = "cudaMalloc failed for candidate scratch"; return 3;
             }
             const size_t csmem = (size_t)pf->table_words * 4;
-            // dense candidate sets (more than ~6 % of the chunks expected): stream the text again instead of gathering chunks
-            const char* csel = std::getenv("GPUGREP_CONFIRM");
-            const bool dense = csel ? std::strcmp(csel, "dense") == 0 : pf->expected_hits_per_mib > 4000.0;
-            if (dense) {
-                CUDA_TRY(cudaFuncSetAttribute(k_confirm_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-                const unsigned cgrid = (unsigned)std::min<size_t>((s->nblk * 32 + kConfirmThreads - 1) / kConfirmThreads, sms);
-                k_confirm_dense<<<cgrid, kConfirmThreads, csmem, st>>>(s->data, n, meta, prefix, s->cand_cap, pf->d_table, pf->table_words, pf->pp, rp,
-                                                                       s->d_hitinfo.as<unsigned long long>(), s->d_res.as<uint32_t>(),
-                                                                       s->d_survivors.as<uint32_t>(), dT);
-            } else {
-                CUDA_TRY(cudaFuncSetAttribute(k_confirm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-                const unsigned cgrid = (unsigned)std::min<size_t>((s->cand_cap + kConfirmThreads - 1) / kConfirmThreads, sms);
-                k_confirm<<<cgrid, kConfirmThreads, csmem, st>>>(s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->d_table, pf->table_words,
-                                                                 pf->pp, rp, s->d_hitinfo.as<unsigned long long>(), s->d_res.as<uint32_t>(),
-                                                                 s->d_survivors.as<uint32_t>(), dT);
-            }
+            CUDA_TRY(cudaFuncSetAttribute(k_confirm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+            const unsigned cgrid = (unsigned)std::min<size_t>((s->cand_cap + kConfirmThreads - 1) / kConfirmThreads, sms);
+            k_confirm<<<cgrid, kConfirmThreads, csmem, st>>>(s->data, n, s->d_cand.as<uint32_t>(), &dT->meta_total, s->cand_cap, pf->d_table, pf->table_words,
+                                                             pf->pp, rp, s->d_hitinfo.as<unsigned long long>(), s->d_res.as<uint32_t>(),
+                                                             s->d_survivors.as<uint32_t>(), dT);
             hitinfo = s->d_hitinfo.as<unsigned long long>();
             survivors = s->d_survivors.as<uint32_t>();
             s->stats.launches++;

@@ -287,6 +287,9 @@ __device__ bool ext_confirmed(const ReprobeParams& rp, const uint8_t* __restrict
 //  3. result per candidate: hit offsets (bit = byte offset in the chunk) << 32 | DFA group mask; 0 = dropped.
 // The verification kernel then walks only what is left (for the 10,000-pattern set: one candidate in a few hundred).
 // Doing this inside the verification kernel (round 1) cost two scattered global loads per sampled gram and candidate.
+// (Tried and dropped: a variant that streams the whole text again, one warp per 512-byte block with the candidate lanes
+// doing this work - no gather from DRAM, but only a fifth of the lanes are busy in the expensive part: 1.66 -> 3.07 ms
+// per GiB for the 10,000-pattern set.  Packing 32 candidates into a warp is what makes this kernel affordable.)
 constexpr int kConfirmThreads = 1024;
 __global__ void __launch_bounds__(kConfirmThreads, 1) k_confirm(const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
                                                                 const unsigned long long* meta_total, size_t cap, const uint32_t* __restrict__ table,
@@ -375,96 +378,6 @@ __global__ void __launch_bounds__(kConfirmThreads, 1) k_confirm(const uint8_t* _
             if (lane == 0) base = atomicAdd(&totals->survivors, (unsigned int)__popc(alive));
             base = __shfl_sync(0xffffffffu, base, 0);
             if (keep) survivors[base + __popc(alive & ((1u << lane) - 1u))] = (uint32_t)i;
-        }
-    }
-}
-
-// The same confirmation for DENSE candidate sets (a fifth of all chunks for the 10,000-pattern set over numeric text):
-// gathering 16-byte chunks by candidate index then runs into the random-access rate of HBM (one 64-byte burst per
-// candidate, ~1.6 TB/s effective), while streaming the whole text once more, coalesced, costs a fraction of that.
-// One warp per 512-byte block, lane = chunk; candidate lanes (meta bits) do the work of k_confirm, their candidate index
-// is the prefix of the block plus the rank of their bit.
-__global__ void __launch_bounds__(kConfirmThreads, 1) k_confirm_dense(const uint8_t* __restrict__ data, size_t n, const unsigned long long* __restrict__ meta,
-                                                                      const unsigned long long* __restrict__ prefix, size_t cap,
-                                                                      const uint32_t* __restrict__ table, int table_words, ProbeParams pp, ReprobeParams rp,
-                                                                      unsigned long long* __restrict__ hitinfo, uint32_t* __restrict__ marks,
-                                                                      uint32_t* __restrict__ survivors, Totals* totals) {
-    extern __shared__ __align__(16) uint32_t s_bloom[];
-    for (int k = threadIdx.x; k < table_words; k += blockDim.x) s_bloom[k] = table[k];
-    __syncthreads();
-    const uint8_t* s_bytes = reinterpret_cast<const uint8_t*>(s_bloom);
-    const uint32_t lane = threadIdx.x & 31;
-    const size_t nblk = (n + 511) >> 9;
-    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    for (size_t b = warp; b < nblk; b += nwarps) {
-        const uint32_t cmask = (uint32_t)meta[b];
-        if (cmask == 0u) continue;   // (warp-uniform)
-        // candidates before this block: group prefix + the earlier blocks of the group
-        size_t base = (size_t)(prefix[b / kGroupBlocks] >> 32);
-        for (size_t e = b - b % kGroupBlocks; e < b; e++) base += __popc((uint32_t)meta[e]);
-        const size_t off = (b << 9) + (size_t)lane * 16;
-        const uint4 v = off < n ? ld_chunk(data, off, n) : make_uint4(0u, 0u, 0u, 0u);
-        uint32_t nx = __shfl_down_sync(0xffffffffu, v.x, 1);   // first word of the next chunk
-        if (lane == 31) {
-            const size_t o2 = (b + 1) << 9;
-            nx = o2 < n ? ld_chunk(data, o2, n).x : 0u;
-        }
-        const bool live = (cmask >> lane) & 1u;
-        const size_t i = base + __popc(cmask & ((1u << lane) - 1u));
-        uint32_t w[5] = {v.x, v.y, v.z, v.w, nx};
-        if (rp.fold) {
-#pragma unroll
-            for (int k = 0; k < 5; k++) w[k] |= 0x20202020u;
-        }
-        uint32_t maybe = 0;
-        if (live && i < cap) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-#pragma unroll
-                for (int sft = 0; sft < 4; sft++) {
-                    if (sft % rp.stride) continue;
-                    const uint32_t gram = sft == 0 ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * sft);
-                    const uint32_t p = gram * pp.mul;
-                    maybe |= ((s_bytes[p >> pp.shift] >> (p & 7u)) & 1u) << (4 * k + sft);
-                }
-            }
-        }
-        uint32_t hits = 0, group_mask = 0;
-        while (maybe) {
-            const uint32_t at = __ffs(maybe) - 1;
-            maybe &= maybe - 1;
-            const uint32_t k = at >> 2, sft = at & 3u;
-            const uint32_t gram = __funnelshift_r(w[k], w[k + 1], 8 * sft);
-            const uint32_t h1 = (gram * rp.mul) >> rp.shift, h2 = rp.half + ((gram * rp.mul2) >> rp.shift);
-            const uint32_t e1 = rp.keys[h1], e2 = rp.keys[h2];
-            if (e1 == gram || e2 == gram) {
-                const uint32_t slot = e1 == gram ? h1 : h2;
-                const uint32_t info = rp.ext_info ? rp.ext_info[slot] : 0u;
-                if (info == 0u || ext_confirmed(rp, data, n, off + at, info)) {
-                    hits |= 1u << at;
-                    group_mask |= rp.groups[slot];
-                }
-            }
-        }
-        if (rp.nodd && live && i < cap) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t gram = __funnelshift_r(w[k], w[k + 1], 16);
-                for (int c = 0; c < rp.nodd; c++)
-                    if (gram * rp.odd_mul[c] + rp.odd_add[c] == 0u) { hits |= 1u << (4 * k + 2); group_mask = 0xffffffffu; }
-            }
-        }
-        const bool keep = live && i < cap && hits != 0u;
-        if (live && i < cap) {
-            hitinfo[i] = keep ? ((unsigned long long)hits << 32) | group_mask : 0ull;
-            if (!keep) marks[i] = 0u;
-        }
-        const uint32_t alive = __ballot_sync(0xffffffffu, keep);
-        if (alive) {
-            uint32_t at = 0;
-            if (lane == 0) at = atomicAdd(&totals->survivors, (unsigned int)__popc(alive));
-            at = __shfl_sync(0xffffffffu, at, 0);
-            if (keep) survivors[at + __popc(alive & ((1u << lane) - 1u))] = (uint32_t)i;
         }
     }
 }

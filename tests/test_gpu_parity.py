@@ -287,7 +287,7 @@ def test_default_buffer_boundary_lines(gpu_lib, oracle_lib):
 
 
 @pytest.mark.parametrize("switch", ["", "GPUGREP_NO_REPROBE=1", "GPUGREP_NO_MIXED_STRIDE=1", "GPUGREP_NO_TUNE=1", "GPUGREP_FILTER=exact",
-                                    "GPUGREP_MAX_DFA_STATES=300", "GPUGREP_VERIFY=v1", "GPUGREP_NFA_GENERAL=1", "GPUGREP_NO_EXT_CONFIRM=1", "GPUGREP_CONFIRM=dense", "GPUGREP_CONFIRM=sparse"])
+                                    "GPUGREP_MAX_DFA_STATES=300", "GPUGREP_VERIFY=v1", "GPUGREP_NFA_GENERAL=1", "GPUGREP_NO_EXT_CONFIRM=1"])
 def test_every_optimisation_switch_gives_the_same_result(switch, gpu_lib, oracle_lib, monkeypatch):
     """Each fast-path optimisation can be turned off: the result never changes.  The pattern sets carry
     a switch-specific extra literal so that no cached database or gram table of another variant is reused.
