@@ -8,6 +8,7 @@
 // boundaries, two segments are kept in flight (read/H2D of k+1 overlaps kernels and delivery of k), and the
 // matched-line records that come back are turned into callbacks on the calling thread, in file order.
 #include <cuda_runtime.h>
+#include <sys/stat.h>
 
 #include <algorithm>
 #include <atomic>
@@ -37,18 +38,38 @@ namespace {
 std::atomic<int> g_device_override{-1};
 thread_local int t_device_override = -1;   // set by the shard workers of a scan that is split over several GPUs
 
-int pick_device() {
+// Outstanding bytes per device (files being scanned): a new scan goes to the least loaded GPU, so that one large file
+// next to many small ones does not leave the other devices idle (placement by size).
+constexpr int kMaxLoadDevices = 64;
+std::atomic<unsigned long long> g_device_load[kMaxLoadDevices];
+
+// `charged`: set when the choice was made by load (the caller gives the weight back through release_device).
+int pick_device(unsigned long long weight, bool* charged) {
+    *charged = false;
     if (t_device_override >= 0) return t_device_override;
     int d = g_device_override.load();
     if (d >= 0) return d;
     if (const char* e = std::getenv("GPUGREP_DEVICE")) return std::atoi(e);
     if (const char* e = std::getenv("LOCAL_RANK")) return std::atoi(e);
-    // no explicit choice: spread successive scans (one per file in multiscanner) over all visible GPUs
-    static std::atomic<unsigned> next{0};
-    int count = 0;
-    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 1) return 0;
-    return (int)(next.fetch_add(1) % (unsigned)count);
+    // no explicit choice: spread the scans (one per file in multiscanner) over all visible GPUs
+    const int count = std::min(engine_device_count(), kMaxLoadDevices);
+    if (count <= 1) return 0;
+    static std::mutex mu;
+    static unsigned next = 0;
+    std::lock_guard<std::mutex> lk(mu);
+    int best = 0;
+    unsigned long long best_load = ~0ull;
+    for (int k = 0; k < count; k++) {   // ties go round-robin
+        const int dev = (int)((next + (unsigned)k) % (unsigned)count);
+        const unsigned long long load = g_device_load[dev].load();
+        if (load < best_load) { best_load = load; best = dev; }
+    }
+    next = (unsigned)best + 1;
+    g_device_load[best].fetch_add(weight + 1);
+    *charged = true;
+    return best;
 }
+void release_device(int device, unsigned long long weight) { g_device_load[device].fetch_sub(weight + 1); }
 
 size_t env_mb(const char* name, size_t dflt_mb) {
     if (const char* b = std::getenv("GPUGREP_CHUNK_BYTES")) {   // test hook: tiny segments exercise the cut logic
@@ -198,6 +219,10 @@ std::shared_ptr<DevicePrefilter> tuned_prefilter(const std::shared_ptr<Database>
 }
 
 struct Job {
+    int device = 0;
+    unsigned long long device_weight = 0;
+    bool device_charged = false;
+    ~Job() { if (device_charged) release_device(device, device_weight); }
     std::shared_ptr<Database> db;
     std::shared_ptr<DeviceDb> ddb;
     std::shared_ptr<DevicePrefilter> dpf;   // null: general path
@@ -210,6 +235,30 @@ struct Job {
     std::string error;
     // flattened accept-set lookup for general mode
     std::vector<uint32_t> report_begin_flat;
+    // Drift of the text: the prefilter windows were chosen against the head of the input.  When a segment flags far more
+    // chunks than that sample promised, the windows are chosen again against a sample that also holds text of the
+    // drifting region (the filter is a superset filter: results do not change, only the number of candidates does).
+    std::vector<uint8_t> tune_head;   // head of the input the current table was tuned on (at most 256 KiB)
+    int retunes = 0;
+    bool drifted(const SegmentResult& r, size_t segment_bytes) const {
+        if (!dpf || retunes >= 3 || segment_bytes < ((size_t)1 << 20) || !(r.stats.path & 1)) return false;
+        if (std::getenv("GPUGREP_NO_RETUNE") != nullptr) return false;
+        const double expected = prefilter_expected_hits(dpf.get());
+        if (expected < 0) return false;
+        const double seen = (double)r.stats.candidates / ((double)segment_bytes / 1048576.0);
+        return seen > 2.0 * std::max(expected, 500.0) + 1000.0;
+    }
+    // `region`: host bytes of the drifting text (a few hundred KiB are used)
+    void retune(const uint8_t* region, size_t len) {
+        std::vector<uint8_t> sample(tune_head);
+        const size_t take = std::min<size_t>(len, kSampleBytes - std::min(kSampleBytes / 2, sample.size()));
+        sample.resize(std::min(sample.size(), kSampleBytes / 2));
+        sample.insert(sample.end(), region, region + take);
+        std::string err;
+        auto fresh = tuned_prefilter(db, sample.data(), sample.size(), err);
+        if (fresh) dpf = fresh;
+        retunes++;
+    }
 
     void prepare() {
         for (auto& rb : db->report_begin) {
@@ -367,7 +416,7 @@ size_t cut_point(const uint8_t* p, size_t have, bool final, size_t limit) {
     return cut;
 }
 
-int setup_job(const Params& pr, Job& job, Deliverer& out) {
+int setup_job(const Params& pr, Job& job, Deliverer& out, unsigned long long weight = 0) {
     int rc = 0;
     job.db = cached_database(pr.patterns, pr.flags, pr.ids, pr.elements, rc, job.error);
     if (!job.db) {
@@ -375,7 +424,9 @@ int setup_job(const Params& pr, Job& job, Deliverer& out) {
         return GPUGREP_DB;
     }
     if (pr.buffer_size < 2) { job.error = "buffer_size must be at least 2"; return GPUGREP_SCAN; }
-    if (engine_select_device(pick_device(), job.error) != 0) {
+    job.device_weight = weight;
+    job.device = pick_device(weight, &job.device_charged);
+    if (engine_select_device(job.device, job.error) != 0) {
         std::fprintf(stderr, "ERROR: Unable to allocate scratch space. Exiting. (%s)\n", job.error.c_str());
         return GPUGREP_SCRATCH;
     }
@@ -427,7 +478,12 @@ int scan_file(const char* path, const Params& pr, gpugrep_stats* stats_out, cons
     Deliverer counting(nullptr, 1);
     Deliverer& out = !shard ? own : (shard->count_only ? counting : collecting);
     Job job;
-    int rc = setup_job(pr, job, out);
+    unsigned long long weight = 0;   // bytes on disk: the scan goes to the least loaded device
+    {
+        struct stat sb;
+        if (::stat(path, &sb) == 0 && S_ISREG(sb.st_mode)) weight = shard ? shard->end - shard->begin : (unsigned long long)sb.st_size;
+    }
+    int rc = setup_job(pr, job, out, weight);
     if (rc) { set_last_error(job.error); return rc; }
     std::string err;
     auto src = shard ? open_plain_range(path, shard->begin, shard->end, err) : open_byte_source(path, err);
@@ -522,6 +578,7 @@ int scan_file(const char* path, const Params& pr, gpugrep_stats* stats_out, cons
         q.cv.notify_all();
     };
     int inflight = -1;
+    size_t inflight_len = 0;
     bool tuned = false;
     while (!job.stop && rc == 0) {
         int slot = -1;
@@ -535,16 +592,22 @@ int scan_file(const char* path, const Params& pr, gpugrep_stats* stats_out, cons
             q.ready.erase(q.ready.begin());
         }
         job.stats.bytes_scanned += len;
-        if (!tuned) { job.dpf = tuned_prefilter(job.db, bufs[slot], len, job.error); tuned = true; }
+        if (!tuned) {
+            job.dpf = tuned_prefilter(job.db, bufs[slot], len, job.error);
+            job.tune_head.assign(bufs[slot], bufs[slot] + std::min(len, kSampleBytes / 2));
+            tuned = true;
+        }
         rc = slot_submit(slots[slot], *job.ddb, job.dpf.get(), bufs[slot], nullptr, len, pr.buffer_size, nullptr, job.error);
         if (rc) { release(slot); break; }
         if (inflight >= 0) {
             SegmentResult res;
             rc = slot_collect(slots[inflight], res, job.error);
             if (rc == 0) rc = job.deliver(res, bufs[inflight], slots[inflight]);
+            if (rc == 0 && job.drifted(res, inflight_len)) job.retune(bufs[inflight] + inflight_len / 2, inflight_len - inflight_len / 2);
             release(inflight);
         }
         inflight = slot;
+        inflight_len = len;
     }
     if (inflight >= 0) {
         SegmentResult res;
@@ -610,7 +673,7 @@ int scan_memory(const uint8_t* data, size_t size, int location, const Params& pr
     Deliverer counting(nullptr, 1);
     Deliverer& out = !shard ? own : (shard->count_only ? counting : collecting);
     Job job;
-    int rc = setup_job(pr, job, out);
+    int rc = setup_job(pr, job, out, size);
     if (rc) { set_last_error(job.error); return rc; }
     std::string err;
     const size_t limit = clamp_limit(pr.buffer_size);
@@ -630,6 +693,8 @@ int scan_memory(const uint8_t* data, size_t size, int location, const Params& pr
     slot_set_want_records(slots[0], !count_only);
     slot_set_want_records(slots[1], !count_only);
     const uint8_t* seg_host[2] = {nullptr, nullptr};
+    const uint8_t* seg_dev[2] = {nullptr, nullptr};
+    size_t seg_len[2] = {0, 0};
     int k = 0, inflight = -1;
     bool tuned = false;
     std::vector<uint8_t> sample;
@@ -675,6 +740,7 @@ int scan_memory(const uint8_t* data, size_t size, int location, const Params& pr
             if (on_device) {
                 const size_t sample_len = std::min(cut, kSampleBytes);
                 job.stats.d2h_bytes += head.size();
+                job.tune_head.assign(head.begin(), head.begin() + std::min(head.size(), kSampleBytes / 2));
                 job.dpf = tuned_prefilter(job.db, head.data(), sample_len, job.error, [&]() -> const uint8_t* {
                     sample.resize(sample_len);
                     if (cudaMemcpy(sample.data(), data, sample_len, cudaMemcpyDeviceToHost) != cudaSuccess) return nullptr;
@@ -683,6 +749,7 @@ int scan_memory(const uint8_t* data, size_t size, int location, const Params& pr
                 });
             } else {
                 job.dpf = tuned_prefilter(job.db, data, cut, job.error);
+                job.tune_head.assign(data, data + std::min(cut, kSampleBytes / 2));
             }
         }
         rc = slot_submit(slots[k], *job.ddb, job.dpf.get(), host_src, on_device ? data + pos : nullptr, cut, pr.buffer_size, pr.user_stream, job.error);
@@ -694,9 +761,24 @@ int scan_memory(const uint8_t* data, size_t size, int location, const Params& pr
             SegmentResult res;
             rc = slot_collect(slots[inflight], res, job.error);
             if (rc == 0) rc = job.deliver(res, seg_host[inflight], slots[inflight]);
+            if (rc == 0 && job.drifted(res, seg_len[inflight])) {
+                // sample of the drifting region: host bytes as they are, device-resident text through one small copy
+                const size_t half = seg_len[inflight] / 2, span = std::min(seg_len[inflight] - half, kSampleBytes / 2);
+                if (seg_host[inflight]) {
+                    job.retune(seg_host[inflight] + half, span);
+                } else {
+                    std::vector<uint8_t> region(span);
+                    if (cudaMemcpy(region.data(), seg_dev[inflight] + half, span, cudaMemcpyDeviceToHost) == cudaSuccess) {
+                        job.stats.d2h_bytes += span;
+                        job.retune(region.data(), span);
+                    }
+                }
+            }
             inflight = -1;
         }
         inflight = k;
+        seg_len[k] = cut;
+        seg_dev[k] = on_device ? data + (pos - cut) : nullptr;
         k ^= 1;
     }
     if (inflight >= 0) {

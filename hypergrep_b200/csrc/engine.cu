@@ -373,6 +373,8 @@ std::shared_ptr<DevicePrefilter> engine_upload_prefilter(const Prefilter& pf, st
     return out;
 }
 
+double prefilter_expected_hits(const DevicePrefilter* pf) { return pf ? pf->expected_hits_per_mib : -1.0; }
+
 namespace {
 std::vector<ScanSlot*> g_free_slots;
 }

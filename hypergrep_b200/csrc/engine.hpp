@@ -58,6 +58,8 @@ int engine_device_count();
 
 std::shared_ptr<DeviceDb> engine_upload(const std::shared_ptr<Database>& db, std::string& error);
 std::shared_ptr<DevicePrefilter> engine_upload_prefilter(const Prefilter& pf, std::string& error);
+// Gram hits per MiB that the tuning sample promised for this table (-1: built without a sample).
+double prefilter_expected_hits(const DevicePrefilter* pf);
 
 ScanSlot* engine_acquire_slot(std::string& error);   // pooled per device; never returns a slot in use
 void engine_release_slot(ScanSlot* slot);

@@ -52,6 +52,8 @@ std::shared_ptr<DevicePrefilter> engine_upload_prefilter(const Prefilter& pf, st
     return pf.enabled ? std::make_shared<DevicePrefilter>() : nullptr;
 }
 
+double prefilter_expected_hits(const DevicePrefilter*) { return -1.0; }
+
 ScanSlot* engine_acquire_slot(std::string&) { return new ScanSlot(); }
 void engine_release_slot(ScanSlot* s) { delete s; }
 

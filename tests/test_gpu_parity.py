@@ -454,3 +454,25 @@ def test_one_input_over_all_gpus(gpu_lib, oracle_lib, monkeypatch, tmp_path):
     monkeypatch.delenv("GPUGREP_DEVICES")
     rc, single, st1 = scan_buffer(gpu_lib, host.data_ptr(), size, 0, synth.C2_PATTERNS, buffer_count=4096)
     assert rc == 0 and single == sharded and st1.lines == lines
+
+
+def test_text_drift_retunes_the_prefilter(gpu_lib, oracle_lib, monkeypatch):
+    """The prefilter windows are tuned on the head of the input.  When the text changes character later on (syslog lines
+    first, long JSON-ish lines full of numbers after that), the segments of the second half flag far more chunks than the
+    sample promised; the windows are then chosen again with text of the drifting region.  Results never change (the filter
+    is a superset filter) - the candidate count does."""
+    import torch
+
+    monkeypatch.setenv("GPUGREP_CHUNK_MB", "4")
+    first = synth.syslog_bytes(16 << 20, seed=41)
+    second = synth.jsonish_bytes(4 << 20, seed=43, patterns_to_plant=["port 4242", "Failed password for"], plant_rate=0.2) * 4
+    data = first + second
+    patterns = synth.C2_PATTERNS + [r"\d{5}\"", r"[a-z]{4}\d{3}"]   # digit-heavy factors: harmless in syslog text, everywhere in the JSON
+    assert parity.compare(gpu_lib, oracle_lib, data, patterns) > 1000
+    host = torch.frombuffer(bytearray(data), dtype=torch.uint8).pin_memory()
+    rc, _, tuned = scan_buffer(gpu_lib, host.data_ptr(), host.numel(), 0, patterns, collect=False)
+    monkeypatch.setenv("GPUGREP_NO_RETUNE", "1")
+    rc2, _, fixed = scan_buffer(gpu_lib, host.data_ptr(), host.numel(), 0, patterns + ["zqnoretuneqz"], collect=False)
+    assert rc == 0 and rc2 == 0 and tuned.matches == fixed.matches
+    print(f"candidates with re-tuning {tuned.candidates}, without {fixed.candidates}")
+    assert tuned.candidates <= fixed.candidates
