@@ -190,6 +190,15 @@ std::shared_ptr<DevicePrefilter> tuned_prefilter(const std::shared_ptr<Database>
         std::memcpy(&w, sample + i, 8);
         fp = (fp ^ w) * 1099511628211ull;
     }
+    // a sample that is fully at hand (no fetch_full) is also told apart by its tail: a re-tuning sample shares its head
+    // with the one it replaces
+    if (!fetch_full && len > ((size_t)64 << 10)) {
+        for (size_t i = len - ((size_t)64 << 10); i + 8 <= len; i += 8) {
+            uint64_t w;
+            std::memcpy(&w, sample + i, 8);
+            fp = (fp ^ w) * 1099511628211ull;
+        }
+    }
     const int device = engine_current_device();
     {
         std::lock_guard<std::mutex> lk(mu);

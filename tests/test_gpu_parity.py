@@ -458,21 +458,30 @@ def test_one_input_over_all_gpus(gpu_lib, oracle_lib, monkeypatch, tmp_path):
 
 def test_text_drift_retunes_the_prefilter(gpu_lib, oracle_lib, monkeypatch):
     """The prefilter windows are tuned on the head of the input.  When the text changes character later on (syslog lines
-    first, long JSON-ish lines full of numbers after that), the segments of the second half flag far more chunks than the
-    sample promised; the windows are then chosen again with text of the drifting region.  Results never change (the filter
-    is a superset filter) - the candidate count does."""
+    first, then access-log lines in which `zqxjk=` is on every line), the segments of the second half flag far more
+    chunks than the sample promised; the windows are then chosen again with text of the drifting region (`500 w` instead
+    of `zqxj`).  Results never change (the filter is a superset filter) - the candidate count does."""
+    import random
+
     import torch
 
     monkeypatch.setenv("GPUGREP_CHUNK_MB", "4")
     first = synth.syslog_bytes(16 << 20, seed=41)
-    second = synth.jsonish_bytes(4 << 20, seed=43, patterns_to_plant=["port 4242", "Failed password for"], plant_rate=0.2) * 4
-    data = first + second
-    patterns = synth.C2_PATTERNS + [r"\d{5}\"", r"[a-z]{4}\d{3}"]   # digit-heavy factors: harmless in syslog text, everywhere in the JSON
+    rng = random.Random(43)
+    lines = []
+    size = 0
+    while size < (16 << 20):
+        code = 500 if rng.random() < 0.01 else rng.choice([200, 200, 200, 204, 301, 404])
+        line = f"ts={rng.randint(1_600_000_000, 1_800_000_000)} zqxjk={code} {'wvfgh' if code == 500 else 'gateway'} unavailable bytes={rng.randint(0, 99999)} path=/api/v{rng.randint(1, 3)}/items/{rng.randint(0, 10 ** 6)}\n"
+        lines.append(line)
+        size += len(line)
+    data = first + "".join(lines).encode()
+    patterns = synth.C2_PATTERNS + ["zqxjk=500 wvfgh"]   # no window of it occurs in the syslog half: the tuner cannot know that `zqxjk=` will be on every line later
     assert parity.compare(gpu_lib, oracle_lib, data, patterns) > 1000
     host = torch.frombuffer(bytearray(data), dtype=torch.uint8).pin_memory()
     rc, _, tuned = scan_buffer(gpu_lib, host.data_ptr(), host.numel(), 0, patterns, collect=False)
     monkeypatch.setenv("GPUGREP_NO_RETUNE", "1")
-    rc2, _, fixed = scan_buffer(gpu_lib, host.data_ptr(), host.numel(), 0, patterns + ["zqnoretuneqz"], collect=False)
-    assert rc == 0 and rc2 == 0 and tuned.matches == fixed.matches
+    rc2, _, fixed = scan_buffer(gpu_lib, host.data_ptr(), host.numel(), 0, patterns, collect=False)
+    assert rc == 0 and rc2 == 0 and tuned.matches == fixed.matches and tuned.path == 1
     print(f"candidates with re-tuning {tuned.candidates}, without {fixed.candidates}")
-    assert tuned.candidates <= fixed.candidates
+    assert tuned.candidates < fixed.candidates
