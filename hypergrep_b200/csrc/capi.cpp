@@ -720,6 +720,64 @@ int scan_memory(const uint8_t* data, size_t size, int location, const Params& pr
             return GPUGREP_SCAN;
         }
     }
+    // Collect segment `idx` and deliver its results.  A large segment in which the fast path hit one of its bounds (a line
+    // too long for it, a candidate / record overflow) is not sent down the general path as a whole: the same bytes are
+    // scanned again in 64 MiB pieces on this slot, one after the other, and only the piece with the problem pays for it.
+    constexpr size_t kSplitAbove = (size_t)128 << 20, kSplitPiece = (size_t)64 << 20;
+    auto finish = [&](int idx) -> int {
+        SegmentResult res;
+        int r = slot_collect(slots[idx], res, job.error, kSplitAbove);
+        if (r == kSplitSegment) {
+            const uint8_t* base_host = seg_host[idx];
+            const uint8_t* base_dev = seg_dev[idx];
+            const size_t len = seg_len[idx];
+            job.stats.split_segments++;
+            for (size_t p = 0; p < len && !job.stop;) {
+                const size_t have = std::min(kSplitPiece, len - p);
+                const bool last = p + have == len;
+                size_t cut = 0;
+                if (on_device) {
+                    r = device_cut(base_dev + p, have, last, limit, cut, job.error);
+                    if (r) return r;
+                } else {
+                    cut = cut_point(base_host + p, have, last, limit);
+                }
+                if (cut == 0) cut = have;
+                const uint8_t* host_src = nullptr;
+                if (!on_device) {
+                    host_src = base_host + p;
+                    if (!pinned) {
+                        uint8_t* stage = slot_host_buffer(slots[idx], std::max(chunk, kSplitPiece), job.error);
+                        if (!stage) return GPUGREP_SCRATCH;
+                        std::memcpy(stage, base_host + p, cut);
+                        host_src = stage;
+                    }
+                }
+                r = slot_submit(slots[idx], *job.ddb, job.dpf.get(), host_src, on_device ? base_dev + p : nullptr, cut, pr.buffer_size, pr.user_stream, job.error);
+                if (r) return r;
+                r = slot_collect(slots[idx], res, job.error);
+                if (r == 0) r = job.deliver(res, on_device ? nullptr : base_host + p, slots[idx]);
+                if (r) return r;
+                p += cut;
+            }
+            return 0;
+        }
+        if (r == 0) r = job.deliver(res, seg_host[idx], slots[idx]);
+        if (r == 0 && job.drifted(res, seg_len[idx])) {
+            // sample of the drifting region: host bytes as they are, device-resident text through one small copy
+            const size_t half = seg_len[idx] / 2, span = std::min(seg_len[idx] - half, kSampleBytes / 2);
+            if (seg_host[idx]) {
+                job.retune(seg_host[idx] + half, span);
+            } else {
+                std::vector<uint8_t> region(span);
+                if (cudaMemcpy(region.data(), seg_dev[idx] + half, span, cudaMemcpyDeviceToHost) == cudaSuccess) {
+                    job.stats.d2h_bytes += span;
+                    job.retune(region.data(), span);
+                }
+            }
+        }
+        return r;
+    };
     size_t pos = 0;
     while (pos < size && !job.stop && rc == 0) {
         size_t have = std::min(chunk, size - pos);
@@ -767,22 +825,7 @@ int scan_memory(const uint8_t* data, size_t size, int location, const Params& pr
         job.stats.bytes_scanned += cut;
         pos += cut;
         if (inflight >= 0) {
-            SegmentResult res;
-            rc = slot_collect(slots[inflight], res, job.error);
-            if (rc == 0) rc = job.deliver(res, seg_host[inflight], slots[inflight]);
-            if (rc == 0 && job.drifted(res, seg_len[inflight])) {
-                // sample of the drifting region: host bytes as they are, device-resident text through one small copy
-                const size_t half = seg_len[inflight] / 2, span = std::min(seg_len[inflight] - half, kSampleBytes / 2);
-                if (seg_host[inflight]) {
-                    job.retune(seg_host[inflight] + half, span);
-                } else {
-                    std::vector<uint8_t> region(span);
-                    if (cudaMemcpy(region.data(), seg_dev[inflight] + half, span, cudaMemcpyDeviceToHost) == cudaSuccess) {
-                        job.stats.d2h_bytes += span;
-                        job.retune(region.data(), span);
-                    }
-                }
-            }
+            rc = finish(inflight);
             inflight = -1;
         }
         inflight = k;
@@ -791,10 +834,8 @@ int scan_memory(const uint8_t* data, size_t size, int location, const Params& pr
         k ^= 1;
     }
     if (inflight >= 0) {
-        SegmentResult res;
-        int rc2 = slot_collect(slots[inflight], res, job.error);
+        int rc2 = finish(inflight);   // always drain the GPU
         if (rc == 0) rc = rc2;
-        if (rc == 0) rc = job.deliver(res, seg_host[inflight], slots[inflight]);
     }
     out.flush();
     engine_release_slot(slots[0]);

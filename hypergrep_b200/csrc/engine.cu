@@ -755,7 +755,7 @@ int ScanSlot::run_general(SegmentResult& out, std::string& error) {
     return 0;
 }
 
-int slot_collect(ScanSlot* s, SegmentResult& out, std::string& error) {
+int slot_collect(ScanSlot* s, SegmentResult& out, std::string& error, size_t split_above) {
     cudaStream_t st = s->stream;
     out = SegmentResult();
     // wait for THIS segment only: the stream may already hold the next segment's kernels
@@ -784,6 +784,7 @@ int slot_collect(ScanSlot* s, SegmentResult& out, std::string& error) {
         }
     }
     if (!done) {
+        if (s->fast && split_above && s->n > split_above) { out.stats = s->stats; return kSplitSegment; }
         int rc = s->run_general(out, error);
         if (rc) return rc;
     }

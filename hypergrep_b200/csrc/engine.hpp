@@ -78,7 +78,12 @@ int slot_submit(ScanSlot* slot, const DeviceDb& ddb, const DevicePrefilter* pf, 
 // SegmentResult::lines stays null (num_valid_recs is still exact).  Call before slot_submit.
 void slot_set_want_records(ScanSlot* slot, bool want);
 // Wait for the segment and expose its results (valid until the next slot_submit on this slot).
-int slot_collect(ScanSlot* slot, SegmentResult& out, std::string& error);
+// Returns kSplitSegment (and no results) when the fast path hit one of its capacity bounds - a line too long for it, a
+// candidate or record overflow - in a segment of more than `split_above` bytes: the caller then scans the same bytes again
+// in smaller segments, so that only the piece with the problem takes the (much slower) general path.  split_above == 0:
+// never ask, take the general path for the whole segment.
+constexpr int kSplitSegment = -2;
+int slot_collect(ScanSlot* slot, SegmentResult& out, std::string& error, size_t split_above = 0);
 
 // Copy the bytes of matched lines to the host when the input lives only on the device (device-resident scans
 // with a callback).  `recs` are LineRec-like (start,len) pairs already on the host; out must hold sum(len)+count.

@@ -87,6 +87,8 @@ typedef struct gpugrep_stats {
     unsigned int stream_launches;      /* of which: launches of the streaming kernel                       */
     unsigned int segments;             /* device segments processed                                        */
     unsigned int path;                 /* bit 0: prefilter fast path used; bit 1: general line-table path used */
+    unsigned int split_segments;       /* large segments that hit a fast-path bound and were scanned again in 64 MiB pieces */
+    unsigned int reserved;
 } gpugrep_stats;
 
 #define GPUGREP_LOC_HOST 0   /* data is host memory (pinned memory is copied directly, pageable is staged) */

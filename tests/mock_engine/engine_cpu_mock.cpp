@@ -117,7 +117,7 @@ static void walk(const Database& db, const uint8_t* p, size_t len, uint32_t line
     }
 }
 
-int slot_collect(ScanSlot* s, SegmentResult& out, std::string&) {
+int slot_collect(ScanSlot* s, SegmentResult& out, std::string&, size_t) {
     out = SegmentResult();
     s->recs.clear(); s->events.clear();
     const Database& db = *s->ddb->db;
