@@ -488,7 +488,7 @@ def test_text_drift_retunes_the_prefilter(gpu_lib, oracle_lib, monkeypatch):
 
 
 def test_long_line_costs_one_piece_not_the_segment(gpu_lib):
-    """A line too long for the fast path (no newline within 64 KiB) used to send its whole device-resident segment - up to
+    """A line too long for the fast path (an aligned 64 KiB without a newline) used to send its whole device-resident segment - up to
     2 GiB - down the general path.  Now the segment is scanned again in 64 MiB pieces and only the piece that holds the
     line takes the general path; the result is the same as ever."""
     import torch
@@ -500,14 +500,15 @@ def test_long_line_costs_one_piece_not_the_segment(gpu_lib):
     start = 100 << 20
     while view[start - 1] != 10:
         start += 1
-    view[start:start + (100 << 10)] = ord("x")   # one line of more than 100 KiB
+    view[start:start + (300 << 10)] = ord("x")   # one line of more than 300 KiB: longer than the gzgets buffer, it is split into pseudo-lines
     dev = host.cuda()
     torch.cuda.synchronize()
     rc, _, st = scan_buffer(gpu_lib, dev.data_ptr(), size, 1, synth.C1_PATTERNS, collect=False)
     assert rc == 0
     e = np.flatnonzero(view[:-4] == ord("E"))
     occurrences = int(np.count_nonzero((view[e + 1] == ord("R")) & (view[e + 2] == ord("R")) & (view[e + 3] == ord("O")) & (view[e + 4] == ord("R"))))
-    assert st.matches == occurrences and st.lines == int(np.count_nonzero(view == 10))
+    # (the long line is two pseudo-lines: 262,139 bytes, then the rest)
+    assert st.matches == occurrences and st.lines == int(np.count_nonzero(view == 10)) + 1
     assert st.split_segments == 1 and st.path == 3, (st.split_segments, st.path)
     # records too (line numbers and bytes), against the same scan from host memory in small segments
     rc, dev_records, _ = scan_buffer(gpu_lib, dev.data_ptr(), size, 1, synth.C1_PATTERNS, buffer_count=4096)
