@@ -42,7 +42,7 @@ elif args.set == "lit":
 else:
     patterns = list(synth.C2_PATTERNS)
 host = torch.empty(args.mib << 20, dtype=torch.uint8).pin_memory()
-synth.fill_syslog(host.numpy(), seed=1234, plants=plants, plant_ppm=1000 if plants else 0, lib=lib)
+synth.fill_syslog(host.numpy(), seed=int(os.environ.get("GPUGREP_TEXT_SEED", "1234")), plants=plants, plant_ppm=1000 if plants else 0, lib=lib)
 dev = host.cuda()
 torch.cuda.synchronize()
 SWITCHES = sorted({k for v in VARIANTS.values() for k in v})
