@@ -609,12 +609,16 @@ def extra_configs(lib, scan, host, dev, size: int, stream) -> dict:  # pylint: d
         for k in range(passes):
             if k == passes - 1:
                 begin.record(stream)
+            t0 = time.perf_counter()
             st = scan(ptr, nbytes, 1, None, pats)
+            if os.environ.get("GPUGREP_BENCH_TRACE"):
+                print(f"trace pass {k}: wall {1e3 * (time.perf_counter() - t0):.3f} ms, gpu {st.gpu_ms:.3f} ms, stream {st.stream_kernel_ms:.3f} ms, launches {st.launches}", file=sys.stderr)
         end.record(stream)
         torch.cuda.synchronize()
         ms = begin.elapsed_time(end)
-        return {"value": nbytes / ms / 1e6, "unit": "GB/s", "bytes": nbytes, "matches": int(st.matches), "ms": ms, "kernel_ms": st.gpu_ms,
-                "candidates_per_gib": st.candidates / (nbytes / (1 << 30)), "path": int(st.path), "launches": int(st.launches)}
+        return {"value": nbytes / ms / 1e6, "unit": "GB/s", "bytes": nbytes, "matches": int(st.matches), "ms": ms, "kernel_ms": st.gpu_ms, "stream_kernel_ms": st.stream_kernel_ms,
+                "candidates_per_gib": st.candidates / (nbytes / (1 << 30)), "path": int(st.path), "launches": int(st.launches),
+                "segments": int(st.segments), "split_segments": int(st.split_segments)}
 
     out["configs[0] 'ERROR' (1 literal)"] = timed(dev.data_ptr(), part, marshal(synth.C1_PATTERNS))
     c3, plants = synth.c3_patterns()

@@ -384,11 +384,14 @@ ScanSlot* engine_acquire_slot(std::string& error) {
     if (cudaGetDevice(&dev) != cudaSuccess) { error = "cudaGetDevice failed"; return nullptr; }
     {
         std::lock_guard<std::mutex> lk(g_mu);
-        // the free slot with the largest pinned buffer: a small working set of slots is reused and grown once, instead
-        // of every pooled slot being re-pinned in turn (growing a pinned buffer frees the old one, which syncs the device)
+        // The free slot that owns the most memory (pinned staging + device scratch), the most recently released one among
+        // equals: a small working set of slots is reused and grown once, instead of every pooled slot being re-pinned or
+        // re-allocated in turn (growing a buffer frees the old one, which synchronises the device - with a dozen pooled
+        // slots of equal staging size the scratch of a 2 GiB device-resident scan was re-allocated for several calls in a row).
+        auto weight = [](const ScanSlot* sl) { return sl->h_stage.cap + sl->d_input.cap + sl->d_cand.cap + sl->d_hitinfo.cap + sl->d_recs.cap; };
         size_t best = g_free_slots.size();
         for (size_t i = 0; i < g_free_slots.size(); i++)
-            if (g_free_slots[i]->device == dev && (best == g_free_slots.size() || g_free_slots[i]->h_stage.cap > g_free_slots[best]->h_stage.cap)) best = i;
+            if (g_free_slots[i]->device == dev && (best == g_free_slots.size() || weight(g_free_slots[i]) >= weight(g_free_slots[best]))) best = i;
         if (best < g_free_slots.size()) {
             ScanSlot* s = g_free_slots[best];
             g_free_slots.erase(g_free_slots.begin() + best);
@@ -527,6 +530,12 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
     if (s->fast) {
         if (s->d_cand.reserve(s->cand_cap * 4) != cudaSuccess || s->d_res.reserve(s->cand_cap * sizeof(uint32_t)) != cudaSuccess ||
             s->d_recoff.reserve((s->cand_cap / kEmitTile + 2) * sizeof(uint32_t)) != cudaSuccess || s->d_recs.reserve(s->rec_cap * sizeof(LineRec)) != cudaSuccess) {
+            error = "cudaMalloc failed for candidate scratch"; return 3;
+        }
+        // (confirmation scratch too, although only multi-group / large sets use it: an allocation in the middle of the launch
+        //  sequence would stall the stream)
+        if ((ddb.ngroups >= 2 || ddb.nnfa > 0 || pf->bloom_false_rate > 0.005) &&
+            (s->d_hitinfo.reserve(s->cand_cap * 8) != cudaSuccess || s->d_survivors.reserve(s->cand_cap * 4) != cudaSuccess)) {
             error = "cudaMalloc failed for candidate scratch"; return 3;
         }
     }
