@@ -178,7 +178,7 @@ constexpr int kMaxPlainScans = 4;            // per device
 // min(len, 64 KiB) bytes (the fingerprint); `fetch_full`, if given, returns a pointer to all `len` bytes and is only
 // called on a cache miss (device-resident inputs copy the rest of the sample only then).
 std::shared_ptr<DevicePrefilter> tuned_prefilter(const std::shared_ptr<Database>& db, const uint8_t* sample, size_t len, std::string& error,
-                                                 const std::function<const uint8_t*()>& fetch_full = nullptr) {
+                                                 const std::function<const uint8_t*()>& fetch_full = nullptr, bool reuse_sibling = false) {
     if (!db->simple || !db->factors.usable) return nullptr;
     struct Entry { const Database* db; int device; uint64_t fp; std::shared_ptr<Database> keep; std::shared_ptr<DevicePrefilter> pf; };
     static std::mutex mu;
@@ -207,6 +207,14 @@ std::shared_ptr<DevicePrefilter> tuned_prefilter(const std::shared_ptr<Database>
                 cache.splice(cache.begin(), cache, it);
                 return cache.front().pf;
             }
+        }
+        // Another input of the same scan (multiscanner: many files, one pattern set): the table that was tuned on a
+        // sibling file is taken as it is - building the gram histogram of every file's head costs milliseconds per file,
+        // more than scanning a small file does.  If this text is different after all, the first segments flag more chunks
+        // than the sample promised and the windows are chosen again (Job::drifted / retune).
+        if (reuse_sibling && std::getenv("GPUGREP_NO_TUNE") == nullptr) {
+            for (auto it = cache.begin(); it != cache.end(); ++it)
+                if (it->db == db.get() && it->device == device && prefilter_expected_hits(it->pf.get()) >= 0) return it->pf;
         }
     }
     Prefilter pf;
@@ -602,7 +610,7 @@ int scan_file(const char* path, const Params& pr, gpugrep_stats* stats_out, cons
         }
         job.stats.bytes_scanned += len;
         if (!tuned) {
-            job.dpf = tuned_prefilter(job.db, bufs[slot], len, job.error);
+            job.dpf = tuned_prefilter(job.db, bufs[slot], len, job.error, nullptr, /*reuse_sibling=*/true);
             job.tune_head.assign(bufs[slot], bufs[slot] + std::min(len, kSampleBytes / 2));
             tuned = true;
         }
