@@ -704,7 +704,7 @@ int scan_memory(const uint8_t* data, size_t size, int location, const Params& pr
         if (cudaPointerGetAttributes(&attr, data) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
         else cudaGetLastError();
     }
-    ScanSlot* slots[2] = {engine_acquire_slot(err), engine_acquire_slot(err)};
+    ScanSlot* slots[2] = {engine_acquire_slot(err, location != GPUGREP_LOC_DEVICE), engine_acquire_slot(err, location != GPUGREP_LOC_DEVICE)};
     if (!slots[0] || !slots[1]) { engine_release_slot(slots[0]); engine_release_slot(slots[1]); set_last_error(err); return GPUGREP_SCRATCH; }
     const bool count_only = !out.wants_lines() && pr.max_match == 0 && job.db->simple;
     slot_set_want_records(slots[0], !count_only);

@@ -379,16 +379,19 @@ namespace {
 std::vector<ScanSlot*> g_free_slots;
 }
 
-ScanSlot* engine_acquire_slot(std::string& error) {
+ScanSlot* engine_acquire_slot(std::string& error, bool for_host_input) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { error = "cudaGetDevice failed"; return nullptr; }
     {
         std::lock_guard<std::mutex> lk(g_mu);
-        // The free slot that owns the most memory (pinned staging + device scratch), the most recently released one among
-        // equals: a small working set of slots is reused and grown once, instead of every pooled slot being re-pinned or
-        // re-allocated in turn (growing a buffer frees the old one, which synchronises the device - with a dozen pooled
-        // slots of equal staging size the scratch of a 2 GiB device-resident scan was re-allocated for several calls in a row).
-        auto weight = [](const ScanSlot* sl) { return sl->h_stage.cap + sl->d_input.cap + sl->d_cand.cap + sl->d_hitinfo.cap + sl->d_recs.cap; };
+        // The free slot that already owns what this scan needs - the largest pinned staging buffer for host inputs (pinning
+        // 32 MiB costs milliseconds), the most device scratch for device-resident inputs - and the most recently released
+        // one among equals: a small working set of slots is reused and grown once, instead of every pooled slot being
+        // re-pinned or re-allocated in turn (growing a buffer frees the old one, which synchronises the device).
+        auto weight = [for_host_input](const ScanSlot* sl) {
+            const size_t device_scratch = sl->d_input.cap + sl->d_cand.cap + sl->d_hitinfo.cap + sl->d_recs.cap;
+            return for_host_input ? std::make_pair(sl->h_stage.cap, device_scratch) : std::make_pair(device_scratch, sl->h_stage.cap);
+        };
         size_t best = g_free_slots.size();
         for (size_t i = 0; i < g_free_slots.size(); i++)
             if (g_free_slots[i]->device == dev && (best == g_free_slots.size() || weight(g_free_slots[i]) >= weight(g_free_slots[best]))) best = i;

@@ -61,7 +61,9 @@ std::shared_ptr<DevicePrefilter> engine_upload_prefilter(const Prefilter& pf, st
 // Gram hits per MiB that the tuning sample promised for this table (-1: built without a sample).
 double prefilter_expected_hits(const DevicePrefilter* pf);
 
-ScanSlot* engine_acquire_slot(std::string& error);   // pooled per device; never returns a slot in use
+// Pooled per device; never returns a slot in use.  `for_host_input`: the caller will stage host bytes through the slot's pinned
+// buffer (the slot with the largest pinned buffer is preferred: pinning is slow); else the one with the most device scratch.
+ScanSlot* engine_acquire_slot(std::string& error, bool for_host_input = true);
 void engine_release_slot(ScanSlot* slot);
 
 // Pinned staging buffer of the slot (grow-only); used by host ingest to read file bytes into.

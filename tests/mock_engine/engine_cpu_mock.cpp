@@ -54,7 +54,7 @@ std::shared_ptr<DevicePrefilter> engine_upload_prefilter(const Prefilter& pf, st
 
 double prefilter_expected_hits(const DevicePrefilter*) { return -1.0; }
 
-ScanSlot* engine_acquire_slot(std::string&) { return new ScanSlot(); }
+ScanSlot* engine_acquire_slot(std::string&, bool) { return new ScanSlot(); }
 void engine_release_slot(ScanSlot* s) { delete s; }
 
 uint8_t* slot_host_buffer(ScanSlot* s, size_t capacity, std::string&) {
