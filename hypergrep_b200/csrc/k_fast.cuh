@@ -46,28 +46,19 @@ __device__ __forceinline__ bool is_word_dev(uint32_t b) {
 // ordinary columns and "matched" is one absorbing state (see engine_upload).
 struct FlatTable {   // [state][256] u16 in global memory
     const uint16_t* __restrict__ flat;
+    __device__ __forceinline__ uint32_t cls_of(uint32_t b) const { return b; }   // the table is byte-indexed
+    __device__ __forceinline__ uint32_t next(uint32_t s, uint32_t c) const { return flat[(s << 8) | c]; }
     __device__ __forceinline__ uint32_t step(uint32_t s, uint32_t b) const { return flat[(s << 8) | b]; }
-    __device__ __forceinline__ uint32_t step4(uint32_t s, uint32_t word) const {
-        s = flat[(s << 8) | (word & 0xffu)];
-        s = flat[(s << 8) | ((word >> 8) & 0xffu)];
-        s = flat[(s << 8) | ((word >> 16) & 0xffu)];
-        return flat[(s << 8) | (word >> 24)];
-    }
 };
 struct SharedTable {   // class-compressed [state][classes] u16 in shared memory + byte -> class map (GroupDev::ctab)
     const uint16_t* tab;
     const uint8_t* cls;
     uint32_t ncls;   // entries per table row
+    // the class lookups do not depend on the state: the walk issues the four of a word first, the state chain is then one
+    // multiply-add and one load per byte
+    __device__ __forceinline__ uint32_t cls_of(uint32_t b) const { return cls[b]; }
+    __device__ __forceinline__ uint32_t next(uint32_t s, uint32_t c) const { return tab[s * ncls + c]; }
     __device__ __forceinline__ uint32_t step(uint32_t s, uint32_t b) const { return tab[s * ncls + cls[b]]; }
-    __device__ __forceinline__ uint32_t step4(uint32_t s, uint32_t word) const {
-        // the four class lookups do not depend on the state: they are issued first, the state chain is one multiply-add and
-        // one load per byte
-        const uint32_t c0 = cls[word & 0xffu], c1 = cls[(word >> 8) & 0xffu], c2 = cls[(word >> 16) & 0xffu], c3 = cls[word >> 24];
-        s = tab[s * ncls + c0];
-        s = tab[s * ncls + c1];
-        s = tab[s * ncls + c2];
-        return tab[s * ncls + c3];
-    }
 };
 // Text accessors: aligned words of the segment.
 struct GlobalText {
@@ -96,77 +87,59 @@ __device__ __forceinline__ uint32_t walk_words(const Table& T, const Text& X, co
     const uint32_t first_accept = G.first_accept, idle_end = G.idle_end;
     uint32_t mask = 0;
     if (pos >= end) return G.eod_next[s] >= first_accept ? line_bit : 0u;
-    // One byte: the table step, then - only for a '\n' - the end-of-line bookkeeping.  Returns true when the walk is over
-    // (the next line starts outside the chunk).
-    auto byte_step = [&](uint32_t b, uint32_t p) -> bool {
+    // Whole words.  Every lane of the warp runs the SAME four table steps per word; what a newline adds sits in four
+    // short guarded blocks (a warp enters one only if some lane has its '\n' at that very byte), and a walk that starts
+    // inside its first word (it begins right behind a newline) skips the leading bytes of that word by predicate.  An
+    // earlier form took a byte-wise copy of the step for words with a newline and a byte loop for the unaligned start: most
+    // warps had to execute those as well, with one or two lanes busy (ncu: 13 of 32 lanes, issue slots 72 % used).
+    uint32_t wpos = pos & ~3u;
+    if (wpos + 4 <= end) {
+        uint32_t skip = pos & 3u;   // bytes of the first word that lie in front of the start
+        uint32_t word = X.word(wpos);
+        bool over = false;   // the walk ended at a newline whose successor line starts outside the chunk
+        while (true) {
+            // the next word is requested before the (dependent) table lookups of this one
+            const uint32_t next_word = wpos + 8 <= end ? X.word(wpos + 4) : 0u;
+            const uint32_t z = eq_mask4(word, 0x0a0a0a0au);
+            const uint32_t c0 = T.cls_of(word & 0xffu), c1 = T.cls_of((word >> 8) & 0xffu), c2 = T.cls_of((word >> 16) & 0xffu), c3 = T.cls_of(word >> 24);
+#define GPUGREP_WALK_BYTE(K, C, ZBIT)                                   \
+            if (skip <= (K)) {                                          \
+                s = T.next(s, (C));                                     \
+                if (z & (ZBIT)) {                                       \
+                    if (s >= first_accept) mask |= line_bit;            \
+                    if (wpos + (K) + 1 >= cend) { over = true; break; } \
+                    line_bit <<= 1;                                     \
+                    s = 0;                                              \
+                }                                                       \
+            }
+            GPUGREP_WALK_BYTE(0u, c0, 0x80u)
+            GPUGREP_WALK_BYTE(1u, c1, 0x8000u)
+            GPUGREP_WALK_BYTE(2u, c2, 0x800000u)
+            GPUGREP_WALK_BYTE(3u, c3, 0x80000000u)
+#undef GPUGREP_WALK_BYTE
+            skip = 0;
+            wpos += 4;
+            if (s >= first_accept) {
+                if (wpos >= cend) return mask | line_bit;   // matched, and no further line starts inside the chunk
+            } else if (wpos >= ifrom && s < idle_end) {
+                return mask;
+            }
+            if (wpos + 4 > end) break;
+            word = next_word;
+        }
+        if (over) return mask;
+        pos = wpos;
+    }
+    // tail: the last (partial) word of the segment, byte by byte
+    while (pos < end) {
+        const uint32_t b = (X.word(pos & ~3u) >> (8 * (pos & 3u))) & 0xffu;
         s = T.step(s, b);
         if (b == '\n') {
             if (s >= first_accept) mask |= line_bit;
-            if (p + 1 >= cend) return true;
+            if (pos + 1 >= cend) return mask;
             line_bit <<= 1;
             s = 0;
         }
-        return false;
-    };
-    // head: up to three bytes to the next word boundary (the walk usually starts on one)
-    while ((pos & 3u) && pos < end) {
-        if (byte_step((X.word(pos & ~3u) >> (8 * (pos & 3u))) & 0xffu, pos)) return mask;
-        pos++;
-    }
-    // body: whole words.  The four table steps are the same instructions for every lane of the warp; what a newline adds
-    // sits in four short, separately guarded blocks (a warp runs one of them only if some lane has its '\n' at that very
-    // byte), instead of a second, byte-wise copy of the whole step that most warps had to execute as well.
-    if (pos + 4 <= end) {
-        uint32_t word = X.word(pos);
-        while (true) {
-            // the next word is requested before the (dependent) table lookups of this one
-            const uint32_t next_word = pos + 8 <= end ? X.word(pos + 4) : 0u;
-            const uint32_t z = eq_mask4(word, 0x0a0a0a0au);
-            if (z == 0) {
-                s = T.step4(s, word);
-            } else {
-                s = T.step(s, word & 0xffu);
-                if (z & 0x80u) {
-                    if (s >= first_accept) mask |= line_bit;
-                    if (pos + 1 >= cend) return mask;
-                    line_bit <<= 1;
-                    s = 0;
-                }
-                s = T.step(s, (word >> 8) & 0xffu);
-                if (z & 0x8000u) {
-                    if (s >= first_accept) mask |= line_bit;
-                    if (pos + 2 >= cend) return mask;
-                    line_bit <<= 1;
-                    s = 0;
-                }
-                s = T.step(s, (word >> 16) & 0xffu);
-                if (z & 0x800000u) {
-                    if (s >= first_accept) mask |= line_bit;
-                    if (pos + 3 >= cend) return mask;
-                    line_bit <<= 1;
-                    s = 0;
-                }
-                s = T.step(s, word >> 24);
-                if (z & 0x80000000u) {
-                    if (s >= first_accept) mask |= line_bit;
-                    if (pos + 4 >= cend) return mask;
-                    line_bit <<= 1;
-                    s = 0;
-                }
-            }
-            pos += 4;
-            if (s >= first_accept) {
-                if (pos >= cend) return mask | line_bit;   // matched, and no further line starts inside the chunk
-            } else if (pos >= ifrom && s < idle_end) {
-                return mask;
-            }
-            if (pos + 4 > end) break;
-            word = next_word;
-        }
-    }
-    // tail: the last (partial) word of the segment
-    while (pos < end) {
-        if (byte_step((X.word(pos & ~3u) >> (8 * (pos & 3u))) & 0xffu, pos)) return mask;
         pos++;
         if (s >= first_accept) {
             if (pos >= cend) return mask | line_bit;
