@@ -5,7 +5,7 @@
 //   hyperscanner.c:199      hyperscanner.c:217           hyperscanner.c:83-102
 // Two paths produce identical results:
 //   FAST    (simple mode + literal prefilter + no over-long lines):
-//           k_stream -> scan -> k_check_long, k_list_candidates -> k_verify_smem | k_verify_local -> k_tile_offsets -> k_emit_nlm
+//           k_stream -> scan -> k_list_candidates [-> k_confirm] -> k_verify_smem | k_verify_local -> k_tile_offsets -> k_emit_nlm -> k_dedupe_records
 //   GENERAL (everything else, and the fallback when a fast-path capacity bound is hit):
 //           k_stream(no filter) -> scan -> k_newline_positions -> pseudo-line table -> k_match_pl_* -> scan -> emit
 // All byte offsets inside a segment are 32-bit (segments are < 4 GiB); line numbers are rebased on the host.
@@ -581,14 +581,10 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
     launch_scan(st, LoadU64{gsum}, ngroups, prefix, s->d_sums.as<unsigned long long>(), &dT->meta_total, s->stats);
     if (s->fast) {
         const unsigned sms = (unsigned)device_sms();
-        size_t bps = super_bytes / 512;
-        size_t nsuper = s->nblk / bps;
-        if (nsuper) {
-            k_check_long<<<(unsigned)((nsuper + 255) / 256), 256, 0, st>>>(prefix, s->nblk, bps, &dT->meta_total, dT);
-            s->stats.launches++;
-        }
+        const size_t bps = super_bytes / 512;
         static const unsigned list_per_sm = blocks_per_sm(k_list_candidates, 256);
-        k_list_candidates<<<(unsigned)std::min<size_t>((s->nblk + 255) / 256, (size_t)list_per_sm * sms), 256, 0, st>>>(meta, prefix, s->nblk, s->d_cand.as<uint32_t>(), s->cand_cap, dT);
+        k_list_candidates<<<(unsigned)std::min<size_t>((s->nblk + 255) / 256, (size_t)list_per_sm * sms), 256, 0, st>>>(meta, prefix, s->nblk, bps, &dT->meta_total,
+                                                                                                                    s->d_cand.as<uint32_t>(), s->cand_cap, dT);
         DbView view{ddb.d_groups, ddb.ngroups, ddb.d_nfas, ddb.nnfa};
         // Finding the hits again costs two loads per sampled gram and candidate.  It pays when bloom collisions flag a
         // noticeable share of chunks (large gram sets: those candidates are dropped without a walk) and when several DFA
@@ -656,7 +652,7 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
             view, s->data, n, s->d_cand.as<uint32_t>(), s->d_res.as<uint32_t>(), tile_records, meta, prefix, nlmask, &dT->meta_total,
             s->cand_cap, s->d_recs.as<LineRec>(), s->rec_cap, dT);
         k_dedupe_records<<<(unsigned)std::min<size_t>((s->rec_cap + 255) / 256, (size_t)sms * 4), 256, 0, st>>>(s->d_recs.as<LineRec>(), s->rec_cap, dT);
-        s->stats.launches += 5;
+        s->stats.launches += 5;   // list, verify, tile offsets, emit, dedupe
         CUDA_TRY(cudaEventRecord(s->ev[1], st));
     }
     CUDA_TRY(cudaMemcpyAsync(&dT->last_byte, s->data + n - 1, 1, cudaMemcpyDeviceToDevice, st));

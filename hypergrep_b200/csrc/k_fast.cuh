@@ -7,25 +7,24 @@ namespace gpugrep {
 // ------------------------------------------------------------------------------------------------------------
 // FAST PATH kernels
 // ------------------------------------------------------------------------------------------------------------
-// Flags segments that may contain a line too long for the fast path: an aligned super-block of `blocks_per_super`
-// 512-byte blocks without any newline.
-__global__ void k_check_long(const unsigned long long* __restrict__ prefix, size_t nblk, size_t blocks_per_super, const unsigned long long* meta_total,
-                             Totals* totals) {
-    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t lo = j * blocks_per_super, hi = lo + blocks_per_super;
-    if (hi > nblk) return;   // partial trailing super-block cannot hide a full one
-    uint32_t a = (uint32_t)prefix[lo / kGroupBlocks];   // blocks_per_super is a multiple of kGroupBlocks
-    uint32_t b = hi < nblk ? (uint32_t)prefix[hi / kGroupBlocks] : (uint32_t)*meta_total;
-    if (a == b) atomicOr(&totals->flags, 1u);
-}
-
-// meta/prefix -> ordered list of candidate chunk indices
+// meta/prefix -> ordered list of candidate chunk indices.  Along the way: flags segments that may contain a line too long
+// for the fast path - an aligned super-block of `blocks_per_super` 512-byte blocks (a multiple of kGroupBlocks; 0: no
+// check) without any newline.
 __global__ void k_list_candidates(const unsigned long long* __restrict__ meta, const unsigned long long* __restrict__ prefix, size_t nblk,
-                                  uint32_t* __restrict__ cand, size_t cap, Totals* totals) {
+                                  size_t blocks_per_super, const unsigned long long* meta_total, uint32_t* __restrict__ cand, size_t cap,
+                                  Totals* totals) {
     const size_t ngroups = (nblk + kGroupBlocks - 1) / kGroupBlocks;
     for (size_t grp = (size_t)blockIdx.x * blockDim.x + threadIdx.x; grp < ngroups; grp += (size_t)gridDim.x * blockDim.x) {
-        size_t at = (size_t)(prefix[grp] >> 32);
-        for (size_t g = grp * kGroupBlocks; g < nblk && g < (grp + 1) * kGroupBlocks; g++) {
+        const unsigned long long before = prefix[grp];
+        const size_t first = grp * kGroupBlocks;
+        if (blocks_per_super && first % blocks_per_super == 0 && first + blocks_per_super <= nblk) {
+            // (a partial trailing super-block cannot hide a full one)
+            const size_t hi = first + blocks_per_super;
+            const uint32_t b = hi < nblk ? (uint32_t)prefix[hi / kGroupBlocks] : (uint32_t)*meta_total;
+            if ((uint32_t)before == b) atomicOr(&totals->flags, 1u);
+        }
+        size_t at = (size_t)(before >> 32);
+        for (size_t g = first; g < nblk && g < first + kGroupBlocks; g++) {
             uint32_t mask = (uint32_t)meta[g];
             while (mask) {
                 int b = __ffs(mask) - 1;
@@ -502,23 +501,25 @@ __global__ void __launch_bounds__(kVerifySmemThreads, 2) k_verify_smem(DbView db
     }
 }
 
-// Exclusive scan of the per-tile record counts (a few thousand entries: one block), in place; total -> *rec_total.
+// Exclusive scan of the per-tile record counts (some thousand entries: one block, every thread takes a run of consecutive
+// tiles so that one block-wide scan does it), in place; total -> *rec_total.
 __global__ void __launch_bounds__(1024) k_tile_offsets(uint32_t* __restrict__ tile_records, const unsigned long long* meta_total, size_t cap,
                                                        unsigned long long* rec_total) {
     __shared__ unsigned long long s_warp[32], s_total;
     size_t ncand = (size_t)(*meta_total >> 32);
     if (ncand > cap) ncand = cap;
     const size_t ntiles = (ncand + kEmitTile - 1) / kEmitTile;
-    unsigned long long running = 0;
-    for (size_t base = 0; base < ntiles; base += blockDim.x) {
-        const size_t k = base + threadIdx.x;
-        const unsigned long long v = k < ntiles ? tile_records[k] : 0ull;
-        const unsigned long long ex = block_exclusive_scan(v, s_warp, &s_total);
-        if (k < ntiles) tile_records[k] = (uint32_t)(running + ex);
-        running += s_total;
-        __syncthreads();
+    const size_t per = (ntiles + blockDim.x - 1) / blockDim.x;
+    const size_t lo = min(ntiles, (size_t)threadIdx.x * per), hi = min(ntiles, lo + per);
+    unsigned long long sum = 0;
+    for (size_t k = lo; k < hi; k++) sum += tile_records[k];
+    unsigned long long run = block_exclusive_scan(sum, s_warp, &s_total);
+    for (size_t k = lo; k < hi; k++) {
+        const uint32_t v = tile_records[k];
+        tile_records[k] = (uint32_t)run;
+        run += v;
     }
-    if (threadIdx.x == 0) *rec_total = running;
+    if (threadIdx.x == 0) *rec_total = s_total;
 }
 
 // Emit.  Candidates with marked lines are compacted per block (few candidates carry a match), then one thread per marked
