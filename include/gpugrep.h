@@ -92,7 +92,10 @@ typedef struct gpugrep_stats {
 } gpugrep_stats;
 
 #define GPUGREP_LOC_HOST 0   /* data is host memory (pinned memory is copied directly, pageable is staged) */
-#define GPUGREP_LOC_DEVICE 1 /* data is a device pointer on the current device                            */
+#define GPUGREP_LOC_DEVICE 1 /* data is a device pointer on the current device; the kernels read it in aligned 16-byte  \
+                                granules, so the allocation must be readable up to the next multiple of 16 bytes behind \
+                                data + size (true for any cudaMalloc / framework allocation: their granularity is >= 256  \
+                                bytes); a pointer that is not 16-byte aligned is staged once, device to device          */
 
 /* Scan a memory buffer holding the (decompressed) file contents; same pattern, batching and callback
  * semantics as hyperscan().  on_event may be NULL: matches are then only counted (no line bytes are copied).
