@@ -713,7 +713,7 @@ __device__ uint32_t emit_lane_nlm(const DbView& db, const uint8_t* __restrict__ 
 }
 
 template <bool WITH_NFA>   // the database holds NFA-fallback patterns: lines with NUL bytes are re-checked with them too (1 KiB of local memory)
-__global__ void __launch_bounds__(kEmitThreads) k_emit_nlm(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
+__global__ void __launch_bounds__(kEmitThreads, 6) k_emit_nlm(DbView db, const uint8_t* __restrict__ data, size_t n, const uint32_t* __restrict__ cand,
                                                            const uint32_t* __restrict__ marks, const uint32_t* __restrict__ tile_offsets,
                                                            const unsigned long long* __restrict__ meta, const unsigned long long* __restrict__ prefix,
                                                            const uint32_t* __restrict__ nlmask, const unsigned long long* meta_total, size_t cap,
