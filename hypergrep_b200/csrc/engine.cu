@@ -27,6 +27,7 @@
 // device code, in dependency order
 #include "device_types.cuh"
 #include "swar.cuh"
+#include "confirm.cuh"
 #include "k_stream.cuh"
 #include "scan.cuh"
 #include "dfa_walk.cuh"
@@ -550,6 +551,26 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
         CUDA_TRY(cudaEventRecord(s->done, st));
         return 0;
     }
+    ReprobeParams rp{};
+    if (s->fast) {
+        // Finding the hits again costs two loads per sampled gram and candidate.  It pays when bloom collisions flag a
+        // noticeable share of chunks (large gram sets: those candidates are dropped without a walk) and when several DFA
+        // groups would each walk the whole chunk (measured with 32 patterns / 1 group / 415 grams: no gain, so not there).
+        const bool want_reprobe = ddb.ngroups >= 2 || pf->bloom_false_rate > 0.005 || ddb.nnfa > 0;
+        if (pf->mode >= 2 && pf->d_confirm && want_reprobe && (ddb.nnfa > 0 || std::getenv("GPUGREP_NO_REPROBE") == nullptr)) {
+            rp.keys = pf->d_confirm;
+            rp.groups = pf->d_confirm_groups;
+            rp.mul = pf->confirm_mul; rp.mul2 = pf->confirm_mul2; rp.shift = 32 - pf->confirm_log2; rp.half = 1u << pf->confirm_log2;
+            rp.stride = pf->stride; rp.fold = pf->fold ? 1 : 0;
+            rp.nodd = pf->nodd;
+            for (int k = 0; k < 2; k++) { rp.odd_mul[k] = pf->pp.odd_mul[k]; rp.odd_add[k] = pf->pp.odd_add[k]; }
+            if (pf->d_confirm_ext && pf->d_ext_keys) {
+                rp.ext_info = pf->d_confirm_ext;
+                rp.ext_keys = pf->d_ext_keys;
+                rp.ext_mul = pf->ext_mul; rp.ext_mul2 = pf->ext_mul2; rp.ext_shift = 64 - pf->ext_log2; rp.ext_half = 1u << pf->ext_log2;
+            }
+        }
+    }
     // ---- K1 ----
     // persistent grid: enough CTAs to fill every SM, each warp strides over groups of kStreamU blocks
     size_t smem = 0;
@@ -586,24 +607,6 @@ int slot_submit(ScanSlot* s, const DeviceDb& ddb, const DevicePrefilter* pf, con
         k_list_candidates<<<(unsigned)std::min<size_t>((s->nblk + 255) / 256, (size_t)list_per_sm * sms), 256, 0, st>>>(meta, prefix, s->nblk, bps, &dT->meta_total,
                                                                                                                     s->d_cand.as<uint32_t>(), s->cand_cap, dT);
         DbView view{ddb.d_groups, ddb.ngroups, ddb.d_nfas, ddb.nnfa};
-        // Finding the hits again costs two loads per sampled gram and candidate.  It pays when bloom collisions flag a
-        // noticeable share of chunks (large gram sets: those candidates are dropped without a walk) and when several DFA
-        // groups would each walk the whole chunk (measured with 32 patterns / 1 group / 415 grams: no gain, so not there).
-        ReprobeParams rp{};
-        const bool want_reprobe = ddb.ngroups >= 2 || pf->bloom_false_rate > 0.005 || ddb.nnfa > 0;
-        if (pf->mode >= 2 && pf->d_confirm && want_reprobe && (ddb.nnfa > 0 || std::getenv("GPUGREP_NO_REPROBE") == nullptr)) {
-            rp.keys = pf->d_confirm;
-            rp.groups = pf->d_confirm_groups;
-            rp.mul = pf->confirm_mul; rp.mul2 = pf->confirm_mul2; rp.shift = 32 - pf->confirm_log2; rp.half = 1u << pf->confirm_log2;
-            rp.stride = pf->stride; rp.fold = pf->fold ? 1 : 0;
-            rp.nodd = pf->nodd;
-            for (int k = 0; k < 2; k++) { rp.odd_mul[k] = pf->pp.odd_mul[k]; rp.odd_add[k] = pf->pp.odd_add[k]; }
-            if (pf->d_confirm_ext && pf->d_ext_keys) {
-                rp.ext_info = pf->d_confirm_ext;
-                rp.ext_keys = pf->d_ext_keys;
-                rp.ext_mul = pf->ext_mul; rp.ext_mul2 = pf->ext_mul2; rp.ext_shift = 64 - pf->ext_log2; rp.ext_half = 1u << pf->ext_log2;
-            }
-        }
         // record offsets per emit tile of kEmitTile candidates: counted by the verification kernel, scanned by one block
         uint32_t* tile_records = s->d_recoff.as<uint32_t>();
         CUDA_TRY(cudaMemsetAsync(tile_records, 0, (s->cand_cap / kEmitTile + 2) * sizeof(uint32_t), st));

@@ -198,57 +198,6 @@ __device__ uint32_t walk_local(const GroupDev& G, const uint8_t* __restrict__ da
 constexpr int kEmitThreads = 256;
 constexpr int kEmitTile = 512;    // candidates per emit step (and per record-offset entry): small enough that sparse candidate lists still spread over all SMs
 
-// The exact gram set in global memory (two-choice table, Prefilter::confirm_keys), for k_confirm to find the hit
-// positions inside a candidate chunk again: k_stream only reports "some sampled gram of this chunk MAY be in the set".
-struct ReprobeParams {
-    const uint32_t* keys;   // null: walk the whole chunk.  A gram lives in keys[h1] or keys[half + h2]
-    const uint32_t* groups; // per slot of keys: the DFA groups (bit g mod 32) that can match around this gram
-    uint32_t mul, mul2;     // h = (gram * mul) >> shift
-    int shift;
-    uint32_t half;
-    int stride;
-    int fold;
-    int nodd;               // mixed sampling: compares at offsets 2 mod 4 (see ProbeParams)
-    uint32_t odd_mul[2], odd_add[2];
-    // extended confirmation (Prefilter::confirm_ext): per slot of keys the variants (bytes in front of the gram, 6 or 8
-    // bytes in all); the text around the hit has to be in ext_keys (two-choice table of 64-bit keys) as well
-    const uint32_t* ext_info;   // null: off
-    const unsigned long long* ext_keys;
-    unsigned long long ext_mul, ext_mul2;
-    int ext_shift;
-    uint32_t ext_half;
-};
-
-// 8 text bytes from an arbitrary offset (little endian); pos + 8 <= n
-__device__ __forceinline__ unsigned long long load64_unaligned(const uint8_t* __restrict__ data, size_t pos, size_t n) {
-    if (pos + 16 <= n) {
-        const unsigned long long* p = reinterpret_cast<const unsigned long long*>(data + (pos & ~(size_t)7));
-        const unsigned long long lo = p[0], hi = p[1];
-        const uint32_t sh = 8u * (uint32_t)(pos & 7);
-        return sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
-    }
-    unsigned long long v = 0;
-    for (int k = 0; k < 8; k++) v |= (unsigned long long)data[pos + k] << (8 * k);
-    return v;
-}
-
-// Is the text around a gram hit at `q` one of the exact stretches the gram stands for?  info: Prefilter::confirm_ext.
-__device__ bool ext_confirmed(const ReprobeParams& rp, const uint8_t* __restrict__ data, size_t n, size_t q, uint32_t info) {
-    for (; info; info >>= 5) {
-        const uint32_t before = info & 7u, len = (info & 8u) ? 8u : 6u;
-        if (q < before || q - before + len > n) continue;   // a real occurrence lies inside the segment
-        const size_t pos = q - before;
-        unsigned long long v = pos + 8 <= n ? load64_unaligned(data, pos, n) : 0ull;
-        if (pos + 8 > n) for (uint32_t k = 0; k < len; k++) v |= (unsigned long long)data[pos + k] << (8 * k);
-        v |= 0x2020202020202020ull;   // the extended keys are folded on every byte (prefilter.cpp extension_of)
-        if (len == 6u) v = (v & 0x0000ffffffffffffull) | 0xA5A5000000000000ull;
-        const unsigned long long e1 = rp.ext_keys[(uint32_t)((v * rp.ext_mul) >> rp.ext_shift)];
-        const unsigned long long e2 = rp.ext_keys[rp.ext_half + (uint32_t)((v * rp.ext_mul2) >> rp.ext_shift)];
-        if (e1 == v || e2 == v) return true;
-    }
-    return false;
-}
-
 // Confirmation of candidate chunks (databases with several DFA groups, large gram sets, NFA-fallback patterns): which
 // sampled grams of the chunk are REALLY in the set, and which DFA groups do they lead to?  k_stream only said "some gram
 // of this chunk may be".  One thread per candidate:
@@ -298,44 +247,8 @@ __global__ void __launch_bounds__(kConfirmThreads, 1) k_confirm(const uint8_t* _
 #pragma unroll
             for (int k = 0; k < 5; k++) w[k] |= 0x20202020u;
         }
-        uint32_t maybe = 0;   // bit = byte offset of a sampled gram that passes the bloom table
-        if (live) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-#pragma unroll
-            for (int sft = 0; sft < 4; sft++) {
-                if (sft % rp.stride) continue;
-                const uint32_t gram = sft == 0 ? w[k] : __funnelshift_r(w[k], w[k + 1], 8 * sft);
-                const uint32_t p = gram * pp.mul;
-                maybe |= ((s_bytes[p >> pp.shift] >> (p & 7u)) & 1u) << (4 * k + sft);
-            }
-        }
-        }
         uint32_t hits = 0, group_mask = 0;
-        while (maybe) {
-            const uint32_t at = __ffs(maybe) - 1;
-            maybe &= maybe - 1;
-            const uint32_t k = at >> 2, sft = at & 3u;
-            const uint32_t gram = __funnelshift_r(w[k], w[k + 1], 8 * sft);
-            const uint32_t h1 = (gram * rp.mul) >> rp.shift, h2 = rp.half + ((gram * rp.mul2) >> rp.shift);
-            const uint32_t e1 = rp.keys[h1], e2 = rp.keys[h2];
-            if (e1 == gram || e2 == gram) {
-                const uint32_t slot = e1 == gram ? h1 : h2;
-                const uint32_t info = rp.ext_info ? rp.ext_info[slot] : 0u;
-                if (info == 0u || ext_confirmed(rp, data, n, o + at, info)) {
-                    hits |= 1u << at;
-                    group_mask |= rp.groups[slot];
-                }
-            }
-        }
-        if (rp.nodd && live) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t gram = __funnelshift_r(w[k], w[k + 1], 16);
-                for (int c = 0; c < rp.nodd; c++)
-                    if (gram * rp.odd_mul[c] + rp.odd_add[c] == 0u) { hits |= 1u << (4 * k + 2); group_mask = 0xffffffffu; }
-            }
-        }
+        if (live) confirm_chunk(w, o, s_bytes, pp, rp, data, n, hits, group_mask);
         // The candidates that are left go into a compact list (in no particular order: the verification kernel writes its
         // result by candidate index): few survive for large sets, and a warp of the verification kernel should be full.
         const bool keep = live && hits != 0u;

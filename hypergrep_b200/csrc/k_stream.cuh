@@ -14,17 +14,6 @@ namespace gpugrep {
 // extents and line numbers from these words instead of searching the text again.
 // Algorithmic traffic: 1 byte read per input byte + 12 bytes written per 512.
 // ------------------------------------------------------------------------------------------------------------
-struct ProbeParams {
-    uint32_t mul, mul2;   // hash multipliers (mul2: second choice of the exact table)
-    int shift;            // bloom: 32 - log2(bits).  exact: shift that turns the product into a BYTE offset (see below)
-    uint32_t amask;       // exact: keeps the slot bits of the byte offset, clears the replica / word bits
-    uint32_t half_bytes;  // exact: byte offset of the second half of the table
-    int rshift;           // exact: log2 of the replication factor (copies interleaved across banks)
-    // mixed sampling (Prefilter::odd): gram * odd_mul[k] + odd_add[k] == 0 at text offsets = 2 (mod 4).  Unused entries repeat
-    // a used one.  The multipliers come from here (the parameter bank) so that the test stays ONE multiply-add on the FMA pipe.
-    uint32_t odd_mul[2], odd_add[2];
-};
-
 // Gram lookups of one 16-byte chunk.  MODE 1: two-choice table of exact 32-bit keys; the table is replicated
 // 2^rshift times with the copies interleaved word by word, and a lane only ever reads copy (lane mod 2^rshift):
 // with 32 copies every lane stays in its own shared-memory bank and the loads are conflict-free.
@@ -109,6 +98,9 @@ struct StreamRegs {
 };
 
 // One warp step: four full 512-byte blocks (g0 .. g0+3) whose chunks are already in registers.
+// (Tried and dropped, profiles/README.md: a CONFIRM variant in which a lane whose chunk passes the bloom table confirms it
+// right here with the exact tables of confirm.cuh - for the 10,000-pattern set this kernel went from 0.31 to 2.5 ms per GiB:
+// the warp runs the confirmation code, global lookups and all, in nearly every chunk step with a handful of lanes busy.)
 template <int STRIDE, bool FOLD, int MODE, int NODD>
 __device__ __forceinline__ void stream_group(const uint4 (&v)[kStreamU], uint32_t g0, const uint8_t* __restrict__ data, size_t n,
                                              unsigned long long* __restrict__ meta, uint32_t* __restrict__ nlmask, unsigned long long* __restrict__ gsum,
