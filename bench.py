@@ -702,6 +702,54 @@ def file_leg(view, multiscanner) -> dict:
                             "rc": int(code), "output_tail": sink.getvalue().strip().splitlines()[-1:]}
             for p in paths:
                 os.unlink(p)
+
+        # ONE compressed file of 256 MiB of text: a single member / frame (what `gzip` and `zstd` write: one decode thread,
+        # like the reference's gzgets() stream) against many members / frames (bgzip, pzstd, concatenated rotations: decoded
+        # by helper threads ahead of the reader, hypergrep_b200/csrc/ingest_members.cpp).
+        text = b"".join(chunks[:4])
+        cores = os.cpu_count() or 2
+        single: dict = {"bytes": len(text), "decode_threads_many": 1 + max(0, min(16, cores - 2))}
+
+        def pieces(step: int) -> list:
+            out, at = [], 0
+            while at < len(text):
+                end = text.find(b"\n", min(len(text) - 1, at + step)) + 1 or len(text)
+                out.append(text[at:end])
+                at = end
+            return out
+
+        def zstd_frame(data: bytes) -> bytes:
+            bound = zstd.ZSTD_compressBound(len(data))
+            buf = ctypes.create_string_buffer(bound)
+            return buf.raw[:zstd.ZSTD_compress(buf, bound, data, len(data), 3)]
+
+        layouts = {
+            "zstd_one_frame": (".zst", zstd_frame, [text]),
+            "zstd_frames_8MiB": (".zst", zstd_frame, pieces(8 << 20)),
+            "gzip_one_member": (".gz", lambda d: gzip.compress(d, 1), [text]),
+            "gzip_members_1MiB": (".gz", lambda d: gzip.compress(d, 1), pieces(1 << 20)),
+        }
+        for name, (suffix, pack, parts) in layouts.items():
+            path = os.path.join(tmp, "single.log" + suffix)
+            with ThreadPoolExecutor(max_workers=max(1, min(16, cores - 1))) as pool:
+                blob = b"".join(pool.map(pack, parts))
+            with open(path, "wb") as handle:
+                handle.write(blob)
+            best, counts = None, set()
+            for _ in range(2):
+                sink = io.StringIO()
+                t0 = time.perf_counter()
+                with contextlib.redirect_stdout(sink):
+                    code = multiscanner.parallel_grep([path], synth.C2_PATTERNS, count_results=True)
+                elapsed = time.perf_counter() - t0
+                best = elapsed if best is None else min(best, elapsed)
+                counts.add(sink.getvalue().strip())
+            single[name] = {"value": len(text) / best / 1e9, "unit": "GB/s of text", "seconds": best, "members": len(parts),
+                            "compression_ratio": len(text) / len(blob), "rc": int(code), "output": sorted(counts)}
+            os.unlink(path)
+        # the same text must give the same count in every layout
+        single["counts_agree"] = len({tuple(o.split(":")[-1] for o in single[n]["output"]) for n in layouts}) == 1
+        result["single_file"] = single
     return result
 
 

@@ -1055,6 +1055,34 @@ size_t gpugrep_shard_begin(const void* data, size_t size, unsigned int rank, uns
 // without a Python frame per batch.
 void gpugrep_discard_results(hyperscanner_result_t* results, int result_count) { (void)results; (void)result_count; }
 
+// The host ingest alone (no GPU work): what the scan of `file_name` would read, as a byte count and an FNV-1a hash.
+int gpugrep_ingest_probe(const char* file_name, unsigned long long* text_bytes, unsigned long long* text_hash) {
+    std::string error;
+    auto src = gpugrep::open_byte_source(file_name, error);
+    if (!src) {
+        gpugrep::set_last_error(error);
+        return 6;
+    }
+    std::vector<uint8_t> buf((size_t)8 << 20);
+    unsigned long long total = 0, hash = 1469598103934665603ull;
+    for (;;) {
+        const size_t got = src->read(buf.data(), buf.size());
+        if (got == 0) break;
+        // (eight bytes at a time: the hash must not be what limits the measurement)
+        size_t i = 0;
+        for (; i + 8 <= got; i += 8) {
+            unsigned long long w;
+            std::memcpy(&w, buf.data() + i, 8);
+            hash = (hash ^ w) * 1099511628211ull;
+        }
+        for (; i < got; i++) hash = (hash ^ buf[i]) * 1099511628211ull;
+        total += got;
+    }
+    if (text_bytes) *text_bytes = total;
+    if (text_hash) *text_hash = hash;
+    return 0;
+}
+
 void gpugrep_set_device(int device) { gpugrep::g_device_override.store(device); }
 void gpugrep_set_zstd_path(const char* path) { if (path) gpugrep::set_zstd_library_path(path); }
 

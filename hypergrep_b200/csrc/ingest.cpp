@@ -1,5 +1,6 @@
 // Host ingest implementations.  See ingest.hpp.
 #include "ingest.hpp"
+#include "ingest_codecs.hpp"
 
 #include <dlfcn.h>
 #include <fcntl.h>
@@ -120,68 +121,12 @@ private:
     size_t limit_ = SIZE_MAX;
 };
 
-// gzip members back to back; anything after the last member that is not another gzip header is ignored (zlib)
-class GzipSource : public ByteSource {
-public:
-    GzipSource(std::unique_ptr<RawFile> f, const uint8_t* head, size_t head_len) : f_(std::move(f)), in_(1 << 20) {
-        std::memcpy(in_.data(), head, head_len);
-        avail_ = head_len;
-        std::memset(&zs_, 0, sizeof(zs_));
-        ok_ = inflateInit2(&zs_, 15 + 16) == Z_OK;   // gzip wrapper
-    }
-    ~GzipSource() override { if (ok_) inflateEnd(&zs_); }
-    size_t read(uint8_t* dst, size_t cap) override {
-        if (!ok_ || done_) return 0;
-        size_t produced = 0;
-        while (produced < cap) {
-            if (avail_ == 0) {
-                pos_ = 0;
-                avail_ = f_->read(in_.data(), in_.size());
-                if (avail_ == 0) { done_ = true; break; }
-            }
-            if (need_header_check_) {
-                // between members: another gzip header continues the stream, anything else is trailing garbage
-                if (avail_ < 2) {
-                    // pull more so that two bytes can be inspected
-                    std::memmove(in_.data(), in_.data() + pos_, avail_);
-                    pos_ = 0;
-                    size_t more = f_->read(in_.data() + avail_, in_.size() - avail_);
-                    avail_ += more;
-                    if (avail_ < 2) { done_ = true; break; }
-                }
-                if (!(in_[pos_] == 0x1f && in_[pos_ + 1] == 0x8b)) { done_ = true; break; }
-                inflateReset(&zs_);
-                need_header_check_ = false;
-            }
-            zs_.next_in = in_.data() + pos_;
-            zs_.avail_in = (uInt)std::min<size_t>(avail_, 1u << 30);
-            zs_.next_out = dst + produced;
-            zs_.avail_out = (uInt)std::min<size_t>(cap - produced, 1u << 30);
-            uInt in_before = zs_.avail_in, out_before = zs_.avail_out;
-            int rc = inflate(&zs_, Z_NO_FLUSH);
-            size_t used = in_before - zs_.avail_in;
-            pos_ += used; avail_ -= used;
-            produced += out_before - zs_.avail_out;
-            if (rc == Z_STREAM_END) { need_header_check_ = true; continue; }
-            if (rc != Z_OK && rc != Z_BUF_ERROR) { done_ = true; break; }   // corrupt data: stop, keep what was decoded
-            if (rc == Z_BUF_ERROR && used == 0 && out_before == zs_.avail_out && avail_ > 0) { done_ = true; break; }
-        }
-        return produced;
-    }
-    const char* kind() const override { return "gzip"; }
-private:
-    std::unique_ptr<RawFile> f_;
-    std::vector<uint8_t> in_;
-    size_t pos_ = 0, avail_ = 0;
-    z_stream zs_;
-    bool ok_ = false, done_ = false, need_header_check_ = false;
-};
-
-// zstd through dlopen (the image ships libzstd.so.1 without headers); frames back to back
+// zstd through dlopen (the image ships libzstd.so.1 without headers)
 struct ZstdApi {
     void* handle = nullptr;
     void* (*create)() = nullptr;
     size_t (*free_ds)(void*) = nullptr;
+    size_t (*init_ds)(void*) = nullptr;
     size_t (*decompress)(void*, void*, void*) = nullptr;
     unsigned (*is_error)(size_t) = nullptr;
     bool load() {
@@ -192,71 +137,128 @@ struct ZstdApi {
         if (!h) return false;
         create = (void* (*)())dlsym(h, "ZSTD_createDStream");
         free_ds = (size_t (*)(void*))dlsym(h, "ZSTD_freeDStream");
+        init_ds = (size_t (*)(void*))dlsym(h, "ZSTD_initDStream");
         decompress = (size_t (*)(void*, void*, void*))dlsym(h, "ZSTD_decompressStream");
         is_error = (unsigned (*)(size_t))dlsym(h, "ZSTD_isError");
-        if (!create || !free_ds || !decompress || !is_error) return false;
+        if (!create || !free_ds || !init_ds || !decompress || !is_error) return false;
         handle = h;
         return true;
     }
 };
 ZstdApi g_zstd;
 
-class ZstdSource : public ByteSource {
+class GzipCodec : public MemberCodec {
+public:
+    GzipCodec() {
+        std::memset(&zs_, 0, sizeof(zs_));
+        ok_ = inflateInit2(&zs_, 15 + 16) == Z_OK;   // gzip wrapper
+    }
+    ~GzipCodec() override { if (ok_) inflateEnd(&zs_); }
+    bool ok() const override { return ok_; }
+    void reset() override { inflateReset(&zs_); }
+    Step step(const uint8_t* in, size_t in_len, size_t& in_pos, uint8_t* out, size_t out_cap, size_t& out_pos) override {
+        zs_.next_in = const_cast<Bytef*>(in + in_pos);
+        zs_.avail_in = (uInt)std::min<size_t>(in_len - in_pos, 1u << 30);
+        zs_.next_out = out + out_pos;
+        zs_.avail_out = (uInt)std::min<size_t>(out_cap - out_pos, 1u << 30);
+        const uInt in_before = zs_.avail_in, out_before = zs_.avail_out;
+        const int rc = inflate(&zs_, Z_NO_FLUSH);
+        const size_t used = in_before - zs_.avail_in, made = out_before - zs_.avail_out;
+        in_pos += used;
+        out_pos += made;
+        if (rc == Z_STREAM_END) return MemberEnd;
+        if (rc != Z_OK && rc != Z_BUF_ERROR) return Failed;   // corrupt data: stop, keep what was decoded
+        if (rc == Z_BUF_ERROR && used == 0 && made == 0 && in_pos < in_len) return Failed;
+        return More;
+    }
+private:
+    z_stream zs_;
+    bool ok_ = false;
+};
+
+class ZstdCodec : public MemberCodec {
     struct InBuf { const void* src; size_t size; size_t pos; };
     struct OutBuf { void* dst; size_t size; size_t pos; };
 public:
-    ZstdSource(std::unique_ptr<RawFile> f, const uint8_t* head, size_t head_len) : f_(std::move(f)), in_(1 << 20) {
+    ZstdCodec() : ds_(g_zstd.create()) {}
+    ~ZstdCodec() override { if (ds_) g_zstd.free_ds(ds_); }
+    bool ok() const override { return ds_ != nullptr; }
+    void reset() override { g_zstd.init_ds(ds_); }
+    Step step(const uint8_t* in, size_t in_len, size_t& in_pos, uint8_t* out, size_t out_cap, size_t& out_pos) override {
+        InBuf ib{in + in_pos, in_len - in_pos, 0};
+        OutBuf ob{out + out_pos, out_cap - out_pos, 0};
+        const size_t rc = g_zstd.decompress(ds_, &ob, &ib);
+        in_pos += ib.pos;
+        out_pos += ob.pos;
+        if (g_zstd.is_error(rc)) return Failed;
+        if (rc == 0) return MemberEnd;
+        if (ib.pos == 0 && ob.pos == 0 && in_pos < in_len && out_pos < out_cap) return Failed;
+        return More;
+    }
+private:
+    void* ds_;
+};
+
+// Members / frames back to back, decoded by the calling thread.
+class SequentialMemberSource : public ByteSource {
+public:
+    SequentialMemberSource(Packing kind, std::unique_ptr<RawFile> f, const uint8_t* head, size_t head_len)
+        : kind_(kind), f_(std::move(f)), in_(1 << 20), codec_(make_member_codec(kind)) {
         std::memcpy(in_.data(), head, head_len);
         avail_ = head_len;
-        ds_ = g_zstd.create();
     }
-    ~ZstdSource() override { if (ds_) g_zstd.free_ds(ds_); }
     size_t read(uint8_t* dst, size_t cap) override {
-        if (!ds_ || done_) return 0;
+        if (!codec_ || !codec_->ok() || done_) return 0;
         size_t produced = 0;
         while (produced < cap) {
-            if (avail_ == 0) {
+            if (avail_ == 0 && !eof_) {
                 pos_ = 0;
                 avail_ = f_->read(in_.data(), in_.size());
-                if (avail_ == 0) { done_ = true; break; }
+                eof_ = avail_ == 0;
             }
-            if (frame_done_) {
-                if (avail_ < 4) {
+            if (between_) {
+                const size_t need = member_header_bytes(kind_);
+                if (avail_ < need && !eof_) {
+                    // pull more so that the header bytes can be inspected
                     std::memmove(in_.data(), in_.data() + pos_, avail_);
                     pos_ = 0;
                     avail_ += f_->read(in_.data() + avail_, in_.size() - avail_);
-                    if (avail_ < 4) { done_ = true; break; }
                 }
-                // Between frames the reference decides like gz_look() of zstd's zlibWrapper (gzread.c): another zstd (or gzip)
-                // header continues the stream, ANYTHING else - a skippable frame included - is trailing garbage and ends the
-                // data (the wrapper's inflate() reports Z_STREAM_END at the end of every frame, so libzstd never gets to skip
-                // a skippable frame that follows one).
-                const uint8_t* p = in_.data() + pos_;
-                const bool zstd_frame = p[0] == 0x28 && p[1] == 0xb5 && p[2] == 0x2f && p[3] == 0xfd;
-                if (!zstd_frame) { done_ = true; break; }
-                frame_done_ = false;
+                if (avail_ < need || !member_continues(kind_, in_.data() + pos_)) { done_ = true; break; }
+                codec_->reset();
+                between_ = false;
             }
-            InBuf ib{in_.data() + pos_, avail_, 0};
-            OutBuf ob{dst + produced, cap - produced, 0};
-            size_t rc = g_zstd.decompress(ds_, &ob, &ib);
-            pos_ += ib.pos; avail_ -= ib.pos;
-            produced += ob.pos;
-            if (g_zstd.is_error(rc)) { done_ = true; break; }
-            if (rc == 0) frame_done_ = true;
-            if (ib.pos == 0 && ob.pos == 0 && rc != 0 && avail_ > 0 && produced < cap) { done_ = true; break; }
+            // (at the end of the file the decoder may still hold text that did not fit the previous destination: it is
+            // called with no input until nothing comes out any more)
+            size_t used = 0, made = 0;
+            const MemberCodec::Step st = codec_->step(in_.data() + pos_, avail_, used, dst + produced, cap - produced, made);
+            pos_ += used; avail_ -= used;
+            produced += made;
+            if (st == MemberCodec::MemberEnd) { between_ = true; continue; }
+            if (st == MemberCodec::Failed) { done_ = true; break; }
+            if (eof_ && avail_ == 0 && made == 0) { done_ = true; break; }   // truncated member
         }
         return produced;
     }
-    const char* kind() const override { return "zstd"; }
+    const char* kind() const override { return kind_ == Packing::Gzip ? "gzip" : "zstd"; }
 private:
+    Packing kind_;
     std::unique_ptr<RawFile> f_;
     std::vector<uint8_t> in_;
     size_t pos_ = 0, avail_ = 0;
-    void* ds_ = nullptr;
-    bool done_ = false, frame_done_ = false;
+    std::unique_ptr<MemberCodec> codec_;
+    bool done_ = false, between_ = false, eof_ = false;
 };
 
 }  // namespace
+
+bool zstd_available() { return g_zstd.load(); }
+
+std::unique_ptr<MemberCodec> make_member_codec(Packing kind) {
+    if (kind == Packing::Gzip) return std::make_unique<GzipCodec>();
+    if (!g_zstd.load()) return nullptr;
+    return std::make_unique<ZstdCodec>();
+}
 
 void set_zstd_library_path(const std::string& path) {
     std::lock_guard<std::mutex> lk(g_zstd_mu);
@@ -272,13 +274,17 @@ std::unique_ptr<ByteSource> open_byte_source(const char* path, std::string& erro
     auto raw = std::make_unique<RawFile>(fd);
     uint8_t head[4];
     size_t got = raw->read(head, sizeof(head));
-    if (got >= 2 && head[0] == 0x1f && head[1] == 0x8b) return std::make_unique<GzipSource>(std::move(raw), head, got);
-    if (got == 4 && head[0] == 0x28 && head[1] == 0xb5 && head[2] == 0x2f && head[3] == 0xfd) {
-        if (!g_zstd.load()) {
-            error = "zstd input but libzstd could not be loaded";
-            return nullptr;
-        }
-        return std::make_unique<ZstdSource>(std::move(raw), head, got);
+    const bool gz = got >= 2 && head[0] == 0x1f && head[1] == 0x8b;
+    const bool zst = got == 4 && head[0] == 0x28 && head[1] == 0xb5 && head[2] == 0x2f && head[3] == 0xfd;
+    if (zst && !g_zstd.load()) {
+        error = "zstd input but libzstd could not be loaded";
+        return nullptr;
+    }
+    if (gz || zst) {
+        const Packing kind = gz ? Packing::Gzip : Packing::Zstd;
+        // regular files with several members / frames: decoded by several threads (ingest_members.cpp)
+        if (auto parallel = open_parallel_members(kind, fd)) return parallel;
+        return std::make_unique<SequentialMemberSource>(kind, std::move(raw), head, got);
     }
     struct stat sb;
     bool regular = ::fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode);

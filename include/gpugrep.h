@@ -126,6 +126,12 @@ GPUGREP_API void gpugrep_set_device(int device);
 /* Path of the libzstd shared object used for .zst ingest (default "libzstd.so.1"). */
 GPUGREP_API void gpugrep_set_zstd_path(const char* path);
 
+/* The host ingest alone - no GPU work: reads `file_name` the way hyperscan() would (plain, gzip members, zstd frames;
+ * several decode threads for files of many members, GPUGREP_DECODE_THREADS=n to set their number, 0/1 for one thread)
+ * and returns the number of text bytes and a hash of them.  For measuring the ingest (reference: gzopen()/gzgets(),
+ * hyperscanner.c:189-199) and for checking the multi-threaded decode against the one-thread decode.  Returns 0 or 6. */
+GPUGREP_API int gpugrep_ingest_probe(const char* file_name, unsigned long long* text_bytes, unsigned long long* text_hash);
+
 /* Human-readable reason of the last failure on this thread ("" if none). */
 GPUGREP_API const char* gpugrep_last_error(void);
 GPUGREP_API const char* gpugrep_version(void);

@@ -111,3 +111,49 @@ def zstd_cases(text: bytes) -> dict:
         "empty_frame_then_text": zstd_frame(b"") + zstd_frame(text),
         "truncated": zstd_frame(text)[: -7],                                      # what decodes before the error is scanned
     }
+
+
+def member_layout_cases(kind: str, text: bytes, seed: int = 5) -> dict:
+    """Files of MANY gzip members / zstd frames (what bgzip, pzstd or `cat a.gz b.gz` write), with the situations the
+    multi-threaded decode (ingest_members.cpp) has to get right: bytes inside a member that look like a member header,
+    empty members, one large member among small ones, garbage, a corrupt and a truncated member.  Every layout is read by
+    the reference through ONE gzgets() stream (hyperscanner.c:189-199): that is what the oracle does."""
+    rng = random.Random(seed)
+    magic = b"\x1f\x8b\x08\x00\x00\x00\x00\x00\x00\x03" if kind == "gzip" else b"\x28\xb5\x2f\xfd\x04\x58\x01\x00\x00"
+
+    def pack(data: bytes, level: int | None = None) -> bytes:
+        if kind == "gzip":
+            return gzip.compress(data, compresslevel=6 if level is None else level)
+        return zstd_frame(data, 3 if level is None else level)
+
+    def stored(data: bytes) -> bytes:
+        """A member whose payload is kept verbatim, so that header look-alikes inside `data` appear in the file."""
+        if kind == "gzip":
+            return gzip.compress(data, compresslevel=0)
+        return zstd_frame(data, -5) if False else zstd_frame(data, 1)
+
+    lines = text.splitlines(keepends=True)
+    pieces, at = [], 0
+    while at < len(lines):
+        step = rng.choice([1, 7, 40, 200, 900])
+        pieces.append(b"".join(lines[at:at + step]))
+        at += step
+    many = b"".join(pack(p, rng.choice([1, 6, 9]) if kind == "gzip" else rng.choice([1, 3, 9])) for p in pieces)
+    # incompressible lines that contain member headers: the bytes show up verbatim inside the member
+    noise = b"".join(magic + rng.randbytes(rng.randint(30, 200)).replace(b"\n", b" ").replace(b"\0", b" ") + b" ERROR port 77\n" for _ in range(300))
+    third = len(pieces) // 3
+    head, mid, tail = b"".join(pieces[:third]), b"".join(pieces[third:2 * third]), b"".join(pieces[2 * third:])
+    small = lambda blob: b"".join(pack(q) for q in [blob[i:i + 20000] for i in range(0, len(blob), 20000)])   # cuts inside lines are fine
+    corrupt = bytearray(small(head) + pack(mid) + small(tail))
+    hit = len(small(head)) + len(pack(mid)) // 2
+    corrupt[hit:hit + 8] = bytes(b ^ 0x5a for b in corrupt[hit:hit + 8])
+    return {
+        "many_members": many,
+        "header_lookalikes": small(head) + stored(noise) + small(noise) + stored(noise + mid) + small(tail),
+        "empty_members": pack(b"") + small(head) + pack(b"") + pack(b"") + small(mid + tail) + pack(b""),
+        "large_member_among_small": small(head) + pack(mid + noise + mid) + small(tail),
+        "garbage_after_members": small(head) + b"\n no member here \n" + small(tail),
+        "garbage_that_starts_like_a_member": small(head) + magic[:2] + b"\xff\xff not a member" + small(tail),
+        "corrupt_member": bytes(corrupt),
+        "truncated_last_member": (small(head) + pack(mid))[:-9],
+    }

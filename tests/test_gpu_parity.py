@@ -118,6 +118,38 @@ def test_compressed_inputs(gpu_lib, oracle_lib, tmp_path):
     assert 0 < counts["skippable_between"] == counts["trailing_garbage"] < counts["one_frame"]
 
 
+@pytest.mark.parametrize("kind", ["gzip", "zstd"])
+def test_many_members_decoded_by_several_threads(kind, gpu_lib, oracle_lib, tmp_path, monkeypatch):
+    """one file of many gzip members / zstd frames decoded by helper threads from speculative starts
+    (ingest_members.cpp).  Every layout gives the records of the reference's single gzgets() stream (hyperscanner.c:189-199)."""
+    import gzip
+
+    text = synth.syslog_bytes(2 << 20, seed=31, lib=gpu_lib)
+    suffix = ".log.gz" if kind == "gzip" else ".log.zst"
+    monkeypatch.setenv("GPUGREP_DECODE_MIN_BYTES", "0")
+    for name, blob in parity.member_layout_cases(kind, text).items():
+        path = tmp_path / f"{name}{suffix}"
+        path.write_bytes(blob)
+        counts = set()
+        for threads, spacing in (("0", "1048576"), ("6", "2000"), ("3", "50000")):
+            monkeypatch.setenv("GPUGREP_DECODE_THREADS", threads)
+            monkeypatch.setenv("GPUGREP_DECODE_SPACING", spacing)
+            counts.add(parity.compare(gpu_lib, oracle_lib, None, synth.C2_PATTERNS, path=str(path)))
+        assert len(counts) == 1 and counts.pop() > 0, (kind, name)
+    # a file above the size threshold with the defaults of the machine: 40 MiB of text in 2 MiB members
+    for name in ("GPUGREP_DECODE_MIN_BYTES", "GPUGREP_DECODE_THREADS", "GPUGREP_DECODE_SPACING"):
+        monkeypatch.delenv(name)
+    big = synth.syslog_bytes(40 << 20, seed=37, lib=gpu_lib)
+    cuts = [0]
+    while cuts[-1] < len(big):
+        cuts.append(big.find(b"\n", min(len(big) - 1, cuts[-1] + (2 << 20))) + 1 or len(big))
+    pack = (lambda d: gzip.compress(d, 1)) if kind == "gzip" else parity.zstd_frame
+    path = tmp_path / f"big{suffix}"
+    path.write_bytes(b"".join(pack(big[a:b]) for a, b in zip(cuts, cuts[1:])))
+    assert path.stat().st_size > (4 << 20)
+    assert parity.compare(gpu_lib, oracle_lib, None, synth.C2_PATTERNS, path=str(path)) > 1000
+
+
 def test_buffer_entry_points_agree_with_oracle(gpu_lib, oracle_lib):
     """gpugrep_scan_buffer from pageable host memory, pinned host memory and device memory == oracle."""
     import torch

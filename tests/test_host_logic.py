@@ -188,3 +188,51 @@ def test_zstd_frame_layouts(hostmock_lib, oracle_lib, tmp_path):
         counts[name] = parity.compare(hostmock_lib, oracle_lib, None, ["ERROR", "port [0-9]+"], path=str(path))
     assert counts["one_frame"] == counts["two_frames"] == counts["three_frames_levels"] == counts["empty_frame_then_text"] > 50
     assert 0 < counts["skippable_between"] == counts["trailing_garbage"] < counts["one_frame"]
+
+
+@pytest.mark.parametrize("kind", ["gzip", "zstd"])
+def test_many_members_decoded_by_several_threads(hostmock_lib, oracle_lib, tmp_path, monkeypatch, kind):
+    """One file of many gzip members / zstd frames, decoded ahead of the reader by helper threads from speculative
+    starts (ingest_members.cpp): the records equal those of the reference's single gzgets() stream (hyperscanner.c:189-199)
+    in every layout, and those of the one-thread decode of the library itself."""
+    text = synth.syslog_bytes(1 << 20, seed=23)
+    patterns = ["ERROR", "port [0-9]+"]
+    suffix = ".log.gz" if kind == "gzip" else ".log.zst"
+    for name, blob in parity.member_layout_cases(kind, text).items():
+        path = tmp_path / f"{name}{suffix}"
+        path.write_bytes(blob)
+        monkeypatch.setenv("GPUGREP_DECODE_THREADS", "0")
+        one = parity.compare(hostmock_lib, oracle_lib, None, patterns, path=str(path))
+        for spacing, chain in (("512", "20000"), ("4096", "200000"), ("100000", "1")):
+            monkeypatch.setenv("GPUGREP_DECODE_THREADS", "4")
+            monkeypatch.setenv("GPUGREP_DECODE_MIN_BYTES", "0")
+            monkeypatch.setenv("GPUGREP_DECODE_SPACING", spacing)
+            monkeypatch.setenv("GPUGREP_DECODE_CHAIN", chain)
+            many = parity.compare(hostmock_lib, oracle_lib, None, patterns, path=str(path))
+            assert many == one, (kind, name, spacing)
+        assert one > 0, (kind, name)
+
+
+def test_ingest_probe_same_text_with_any_thread_count(hostmock_lib, tmp_path, monkeypatch):
+    """gpugrep_ingest_probe (the ingest alone): byte count and hash of the text do not depend on the decode threads,
+    and equal Python's own decode."""
+    import gzip
+
+    text = synth.syslog_bytes(3 << 20, seed=29)
+    files = {"t.log": text, "t.log.gz": parity.member_layout_cases("gzip", text)["many_members"],
+             "t.log.zst": parity.member_layout_cases("zstd", text)["many_members"], "one.log.gz": gzip.compress(text, 1)}
+    hostmock_lib.gpugrep_ingest_probe.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]
+    monkeypatch.setenv("GPUGREP_DECODE_MIN_BYTES", "0")
+    monkeypatch.setenv("GPUGREP_DECODE_SPACING", "3000")
+    seen = set()
+    for name, blob in files.items():
+        path = tmp_path / name
+        path.write_bytes(blob)
+        for threads in ("0", "2", "5"):
+            monkeypatch.setenv("GPUGREP_DECODE_THREADS", threads)
+            size, digest = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+            assert hostmock_lib.gpugrep_ingest_probe(str(path).encode(), ctypes.byref(size), ctypes.byref(digest)) == 0
+            assert size.value == len(text)
+            seen.add(digest.value)
+    assert len(seen) == 1
+    assert hostmock_lib.gpugrep_ingest_probe(str(tmp_path / "missing").encode(), None, None) == 6
