@@ -721,7 +721,8 @@ def file_leg(view, multiscanner) -> dict:
         def zstd_frame(data: bytes) -> bytes:
             bound = zstd.ZSTD_compressBound(len(data))
             buf = ctypes.create_string_buffer(bound)
-            return buf.raw[:zstd.ZSTD_compress(buf, bound, data, len(data), 3)]
+            written = zstd.ZSTD_compress(buf, bound, data, len(data), 3)
+            return buf.raw[:written]
 
         layouts = {
             "zstd_one_frame": (".zst", zstd_frame, [text]),
