@@ -98,6 +98,13 @@ struct ShardResults {
     std::vector<char> text;
 };
 
+// Sink of gpugrep_match_ends(): (line, id, end) records instead of lines.
+struct EndsSink {
+    gpugrep_match_end* out;
+    size_t capacity;
+    size_t count = 0;
+};
+
 class Deliverer {
 public:
     Deliverer(hs_event cb, int buffer_count) : cb_(cb), cap_(std::max(1, buffer_count)) {
@@ -133,6 +140,13 @@ public:
         if (fill_ == cap_) flush();
     }
     void emit_count_only(unsigned long long n) { count_ += n; }
+    void set_ends(EndsSink* sink) { ends_ = sink; }
+    bool wants_ends() const { return ends_ != nullptr; }
+    void emit_end(unsigned id, unsigned long long line_number, unsigned end) {
+        count_++;
+        if (ends_->count < ends_->capacity) ends_->out[ends_->count] = gpugrep_match_end{line_number, id, end};
+        ends_->count++;
+    }
     void flush() {
         if (cb_ && fill_ > 0) cb_(results_.data(), fill_);
         fill_ = 0;
@@ -160,6 +174,7 @@ private:
     hs_event cb_;
     int cap_;
     ShardResults* collect_ = nullptr;
+    EndsSink* ends_ = nullptr;
     int fill_ = 0;
     unsigned long long count_ = 0;
     std::vector<hyperscanner_result_t> results_;
@@ -399,7 +414,8 @@ struct Job {
                     if (std::find(fired.begin(), fired.end(), evs[k].id) != fired.end()) continue;
                     fired.push_back(evs[k].id);
                 }
-                if (out->wants_lines()) out->emit(evs[k].id, line_base + e0.line, bytes, e0.len);
+                if (out->wants_ends()) out->emit_end(evs[k].id, line_base + e0.line, evs[k].end);
+                else if (out->wants_lines()) out->emit(evs[k].id, line_base + e0.line, bytes, e0.len);
                 else out->emit_count_only(1);
             }
             // hyperscanner.c:222: the limit is checked after all reports of the line
@@ -420,6 +436,7 @@ struct Params {
     int buffer_count;
     unsigned long long max_match;
     void* user_stream;
+    EndsSink* ends = nullptr;   // gpugrep_match_ends(): end offsets instead of lines
 };
 
 // Largest prefix of [p, p+have) that ends on a pseudo-line boundary; 0 if none exists yet.
@@ -686,6 +703,7 @@ int device_cut(const uint8_t* dev, size_t have, bool final, size_t limit, size_t
 int scan_memory(const uint8_t* data, size_t size, int location, const Params& pr, gpugrep_stats* stats_out, const ShardSpec* shard = nullptr) {
     double t0 = now_ms();
     Deliverer own(pr.cb, effective_batch(pr));
+    own.set_ends(pr.ends);
     Deliverer collecting(shard ? shard->collect : nullptr);
     Deliverer counting(nullptr, 1);
     Deliverer& out = !shard ? own : (shard->count_only ? counting : collecting);
@@ -1039,6 +1057,19 @@ int gpugrep_scan_buffer(const void* data, size_t size, int location, const char*
         }
     }
     return gpugrep::scan_memory((const uint8_t*)data, size, location, pr, stats);
+}
+
+int gpugrep_match_ends(const void* data, size_t size, int location, const char* const* patterns, const unsigned int* pattern_flags,
+                       const unsigned int* pattern_ids, unsigned int elements, int buffer_size, gpugrep_match_end* out, size_t capacity,
+                       size_t* count, gpugrep_stats* stats) {
+    // every end is wanted: without SINGLEMATCH the set is scanned on the general path, whose records carry the offsets
+    std::vector<unsigned> flags(elements);
+    for (unsigned i = 0; i < elements; i++) flags[i] = (pattern_flags ? pattern_flags[i] : 0u) & ~8u;
+    gpugrep::EndsSink sink{out, out ? capacity : 0};
+    gpugrep::Params pr{patterns, flags.data(), pattern_ids, elements, nullptr, buffer_size, 1, 0, nullptr, &sink};
+    const int rc = gpugrep::scan_memory((const uint8_t*)data, size, location, pr, stats);
+    if (count) *count = sink.count;
+    return rc;
 }
 
 size_t gpugrep_shard_begin(const void* data, size_t size, unsigned int rank, unsigned int world) {

@@ -1,5 +1,6 @@
 // C ABI: check_patterns() and the compiled-database introspection entry points of include/gpugrep.h.
 // Host only: nothing here touches CUDA, so it is safe to call before fork().
+#include <cctype>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -7,10 +8,95 @@
 
 #include "../../include/gpugrep.h"
 #include "database.hpp"
+#include "regex.hpp"
 
 namespace gpugrep {
 thread_local std::string g_last_error;
 void set_last_error(const std::string& e) { g_last_error = e; }
+}  // namespace gpugrep
+
+namespace gpugrep {
+namespace {
+
+// Width of every match, or -1 when it varies.
+int fixed_width(const Node& n) {
+    switch (n.kind) {
+        case NodeKind::Empty: return 0;
+        case NodeKind::Assert: return 0;
+        case NodeKind::Set: return 1;
+        case NodeKind::Concat: {
+            int total = 0;
+            for (const NodePtr& k : n.kids) {
+                const int w = fixed_width(*k);
+                if (w < 0) return -1;
+                total += w;
+            }
+            return total;
+        }
+        case NodeKind::Alt: {
+            int width = -2;
+            for (const NodePtr& k : n.kids) {
+                const int w = fixed_width(*k);
+                if (w < 0 || (width != -2 && w != width)) return -1;
+                width = w;
+            }
+            return width == -2 ? 0 : width;
+        }
+        case NodeKind::Repeat: {
+            const int w = n.kids.empty() ? 0 : fixed_width(*n.kids[0]);
+            if (w < 0 || n.min != n.max || n.max < 0) return -1;
+            return w * n.min;
+        }
+    }
+    return -1;
+}
+
+// Conservative lexical screen: only syntax that Python's re (str pattern, no flags, ASCII text) and this compiler read
+// the same way.  Everything else keeps the reference's re.finditer() path.
+bool same_meaning_in_python(const std::string& p) {
+    bool in_class = false;
+    for (size_t i = 0; i < p.size(); i++) {
+        const unsigned char c = (unsigned char)p[i];
+        if (c < 0x20 || c > 0x7e) return false;
+        if (c == '\\') {
+            if (i + 1 >= p.size()) return false;
+            const unsigned char e = (unsigned char)p[++i];
+            if (e == 'x') {   // exactly two hex digits in Python
+                if (i + 2 >= p.size() || !std::isxdigit((unsigned char)p[i + 1]) || !std::isxdigit((unsigned char)p[i + 2])) return false;
+                i += 2;
+                continue;
+            }
+            if (std::isalnum(e)) {
+                if (in_class ? std::strchr("dDwWntrf", e) == nullptr : std::strchr("dDwWbBAntrf", e) == nullptr) return false;
+            }
+            continue;
+        }
+        if (in_class) {
+            if (c == '[') return false;                  // POSIX classes / nested sets
+            if (c == ']' && !(p[i - 1] == '[' || (p[i - 1] == '^' && i >= 2 && p[i - 2] == '['))) in_class = false;
+            continue;
+        }
+        switch (c) {
+            case '[': in_class = true; break;
+            case '*': case '+': return false;
+            case '?': if (i < 1 || p[i - 1] != '(') return false; if (i + 1 >= p.size() || p[i + 1] != ':') return false; break;   // only (?:
+            case '{': {   // only {digits}
+                size_t j = i + 1;
+                while (j < p.size() && std::isdigit((unsigned char)p[j])) j++;
+                if (j == i + 1 || j >= p.size() || p[j] != '}') return false;
+                if (j + 1 < p.size() && (p[j + 1] == '?' || p[j + 1] == '+' || p[j + 1] == '{')) return false;
+                i = j;
+                break;
+            }
+            case '}': return false;
+            case '$': return false;   // end-or-final-newline consumes the newline in the automaton
+            default: break;
+        }
+    }
+    return !in_class;
+}
+
+}  // namespace
 }  // namespace gpugrep
 
 struct gpugrep_db {
@@ -31,6 +117,16 @@ int check_patterns(const char* const* patterns, const unsigned int* pattern_flag
     }
     gpugrep::set_last_error("");
     return 0;
+}
+
+int gpugrep_span_width(const char* pattern) {
+    if (!pattern) return -1;
+    const std::string text(pattern);
+    if (!gpugrep::same_meaning_in_python(text)) return -1;
+    gpugrep::ParseResult parsed = gpugrep::parse_regex(text, 0);
+    if (!parsed.root) return -1;
+    const int width = gpugrep::fixed_width(*parsed.root);
+    return width > 0 ? width : -1;
 }
 
 const char* gpugrep_last_error(void) { return gpugrep::g_last_error.c_str(); }

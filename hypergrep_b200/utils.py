@@ -252,19 +252,29 @@ def grep(  # pylint: disable=too-many-arguments
     if code:
         return (0 if count_only else collected), code
 
+    # `-o`: spans from the engine's match END offsets where that is exact (patterns of one fixed width whose syntax means the
+    # same in Python's re; ASCII lines), re.finditer() as in the reference (utils.py:205-212) for everything else.
+    widths = _span_widths(patterns) if only_matching else None
+    groups: list[list[tuple[int, str]]] = []      # one entry per record, in record order
+    deferred: list[tuple[int, int, bytes]] = []   # (index into groups, pattern id, line bytes)
+
     def _on_batch(matches: ctypes.Array, count: int) -> None:
         if count_only:
             counter[0] += count
             return
         for position in range(count):
             record = matches[position]
-            text = record.line.decode(errors=errors)
+            raw = record.line
             if only_matching:
                 # Same quirk as the reference (utils.py:205-212): record.id is the user id, not the pattern index.
-                for part in python_patterns[record.id].finditer(text):
-                    collected.append((record.line_number + 1, f"{part.group()}\n"))
+                if widths is not None and widths[record.id] > 0 and raw.isascii() and raw.endswith(b"\n"):
+                    deferred.append((len(groups), record.id, raw))
+                    groups.append([(record.line_number + 1, "")])
+                    continue
+                text = raw.decode(errors=errors)
+                groups.append([(record.line_number + 1, f"{part.group()}\n") for part in python_patterns[record.id].finditer(text)])
             else:
-                collected.append((record.line_number + 1, text))
+                collected.append((record.line_number + 1, raw.decode(errors=errors)))
 
     pattern_flags = _DEFAULT_FLAGS | (HS_FLAG_CASELESS if ignore_case else 0)
     if count_only:
@@ -280,4 +290,76 @@ def grep(  # pylint: disable=too-many-arguments
         max_match_count=max_match_count,
         buffer_count=_GREP_BATCH,
     )
+    if only_matching:
+        _fill_spans(groups, deferred, patterns, widths, python_patterns, errors)
+        collected = [entry for group in groups for entry in group]
     return (counter[0] if count_only else collected), code
+
+
+class _MatchEnd(ctypes.Structure):
+    """gpugrep_match_end (include/gpugrep.h)."""
+
+    _fields_ = [("line_number", ctypes.c_ulonglong), ("id", ctypes.c_uint), ("end", ctypes.c_uint)]
+
+
+def _span_widths(patterns: Sequence[str]) -> list[int] | None:
+    """Fixed match width per pattern (-1: use re.finditer), or None if the loaded library cannot report match ends
+    (a plain libhyperscanner.so)."""
+    lib = _get_hyperscanner_lib()
+    try:
+        width = lib.gpugrep_span_width
+        lib.gpugrep_match_ends  # pylint: disable=pointless-statement
+    except AttributeError:
+        return None
+    width.restype = ctypes.c_int
+    width.argtypes = [ctypes.c_char_p]
+    return [width(pattern.encode()) for pattern in patterns]
+
+
+def _fill_spans(groups: list, deferred: list, patterns: Sequence[str], widths: list[int] | None, python_patterns: list,
+                errors: str) -> None:
+    """the spans of the deferred records from ONE scan of their lines that reports every match
+    end (gpugrep_match_ends, patterns compiled without flags like the reference's re.compile(pattern)).  A pattern of
+    fixed width w matches [end - w, end); finditer()'s left-to-right, non-overlapping choice is a greedy pass over the
+    ends.  Any failure falls back to re.finditer() for those records."""
+    if not deferred:
+        return
+    lib = _get_hyperscanner_lib()
+    entry = lib.gpugrep_match_ends
+    entry.restype = ctypes.c_int
+    entry.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint,
+                      ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), ctypes.c_void_p]
+    text = b"".join(raw for _, _, raw in deferred)
+    # (ids = pattern indices here: the reference indexes its compiled patterns with the id of the record)
+    pattern_array, flags_array, ids_array = prepare_patterns(patterns, flags=[0] * len(patterns), ids=list(range(len(patterns))))
+    capacity = 4 * len(deferred) + 1024
+    found = ctypes.c_size_t(0)
+    ends = None
+    for _ in range(2):
+        ends = (_MatchEnd * capacity)()
+        code = entry(text, len(text), 0, pattern_array, flags_array, ids_array, len(pattern_array), 262140, ends, capacity,
+                     ctypes.byref(found), None)
+        if code != 0:
+            ends = None
+            break
+        if found.value <= capacity:
+            break
+        capacity, ends = found.value, None
+    per_line: dict[int, list[int]] = {}
+    if ends is not None:
+        wanted = [pattern_id for _, pattern_id, _ in deferred]
+        for k in range(found.value):
+            item = ends[k]
+            if item.id == wanted[item.line_number]:
+                per_line.setdefault(item.line_number, []).append(item.end)
+    for line, (slot, pattern_id, raw) in enumerate(deferred):
+        number = groups[slot][0][0]
+        if ends is None:
+            parts = [part.group() for part in python_patterns[pattern_id].finditer(raw.decode(errors=errors))]
+        else:
+            width, last, parts = widths[pattern_id], 0, []
+            for end in per_line.get(line, ()):   # ascending
+                if end - width >= last:
+                    parts.append(raw[end - width:end].decode(errors=errors))
+                    last = end
+        groups[slot] = [(number, f"{part}\n") for part in parts]

@@ -110,6 +110,31 @@ GPUGREP_API int gpugrep_scan_file(const char* file_name, const char* const* patt
                       const unsigned int* pattern_ids, unsigned int elements, hs_event on_event, int buffer_size,
                       int buffer_count, unsigned long long max_match_count, gpugrep_stats* stats);
 
+/* ---- match END offsets (spans for `grep -o`) --------------------------------------------
+ * The reference gets the spans of `-o` by re-running Python's re.finditer() over every matched line (utils.py:205-212);
+ * Hyperscan itself reports (id, end offset) per match and the reference drops the offset (hyperscanner.c:83-102).
+ * gpugrep_match_ends() keeps it: one record per (pseudo-line, pattern id, end offset) at which a match of that pattern
+ * ends, in hs_scan order (by line, then end offset, then id).  `end` counts bytes from the start of the scanned block,
+ * i.e. of the text hyperscan() would deliver as `line` (leading NULs skipped).  HS_FLAG_SINGLEMATCH is ignored here
+ * (every end is reported).  At most `capacity` records are stored; *count is the number found, so a caller that gets
+ * *count > capacity repeats the call with a larger array.  Returns 0 or a code of hyperscan(). */
+typedef struct gpugrep_match_end {
+    unsigned long long line_number; /* 0-based pseudo-line index inside `data` */
+    unsigned int id;                /* pattern id                              */
+    unsigned int end;               /* offset just behind the match            */
+} gpugrep_match_end;
+
+GPUGREP_API int gpugrep_match_ends(const void* data, size_t size, int location, const char* const* patterns,
+                       const unsigned int* pattern_flags, const unsigned int* pattern_ids, unsigned int elements,
+                       int buffer_size, gpugrep_match_end* out, size_t capacity, size_t* count, gpugrep_stats* stats);
+
+/* Width in bytes of every match of `pattern` compiled WITHOUT flags (what the reference's re.compile(pattern) does for
+ * `-o`), or -1 if matches can differ in width, can be empty, or the pattern uses syntax whose meaning differs between
+ * Python's re and this compiler (then the caller keeps using re.finditer()).  For a fixed width w the span of a match
+ * that ends at e is [e - w, e), and finditer()'s non-overlapping left-to-right selection is a greedy pass over the
+ * sorted ends.  Host only (no CUDA). */
+GPUGREP_API int gpugrep_span_width(const char* pattern);
+
 /* An hs_event that discards its batch (benchmarks: full delivery path without a Python frame per batch). */
 GPUGREP_API void gpugrep_discard_results(hyperscanner_result_t* results, int result_count);
 

@@ -157,3 +157,27 @@ def member_layout_cases(kind: str, text: bytes, seed: int = 5) -> dict:
         "corrupt_member": bytes(corrupt),
         "truncated_last_member": (small(head) + pack(mid))[:-9],
     }
+
+
+ONLY_MATCHING_FIXED = ["ERROR", "port [0-9]{4}", "[a-f0-9]{8}", "(?:GET|PUT) /", r"user=\w\w\w", "a.c", r"\bsshd\b", "^Oct", "aa",
+                       "(ab|cd)e", "x{3}", r"\d\d:\d\d", "[^ ]{5} ", r"\.\.", r"\x41B", "[]x]y", r"\Afoo", "(a|b)(c|d)", r"\Bo\B", r"\bA"]
+ONLY_MATCHING_OTHER = ["ERR.*", "a+", "foo|barbaz", "(?i)error", "end$", r"\s\s", "colou?r", "x{2,3}", "[[:alpha:]]x", "^", r"\w+@"]
+
+
+def only_matching_text(seed: int = 3) -> bytes:
+    """Lines that exercise `grep -o`: overlapping candidates, several patterns on one line, lines that are not ASCII, a
+    line with NULs, a last line without newline."""
+    rng = random.Random(seed)
+    words = ["ERROR", "error", "port 8080", "port 80", "deadbeef", "0123abcd", "GET /index", "PUT /x", "user=bob", "user=al", "abc", "axc",
+             "sshd", "xsshd", "Oct 12", "aaaaa", "aa", "abe", "cde", "xxxxxxx", "12:34:56", "hello world ", "....", "AB", "]y", "foo", "ac", "bd",
+             "colour", "color", "end", "tab\there", "caf\u00e9".encode().decode("latin-1"), "A"]
+    lines = []
+    for _ in range(1500):
+        line = " ".join(rng.choice(words) for _ in range(rng.randint(1, 9)))
+        lines.append(line.encode("latin-1") + b"\n")
+    lines.insert(7, b"aaaaaaaaa ERROR aaaa\n")
+    lines.insert(11, b"foo ERROR port 1234 with \xff\xfe bytes ERROR\n")
+    lines.insert(13, b"\0\0ERROR after nuls ERROR\0 hidden ERROR\n")
+    lines.insert(17, b"Oct 12 Oct 13 ERRORERROR\n")
+    lines.append(b"ERROR last line without newline aa")
+    return b"".join(lines)

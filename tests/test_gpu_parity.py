@@ -9,7 +9,7 @@ import parity
 from gpu_api import scan_buffer
 from hypergrep_b200 import synth
 from oracle_api import scan_bytes
-from test_host_logic import EDGE_TEXTS
+from test_host_logic import EDGE_TEXTS, check_only_matching
 
 pytestmark = pytest.mark.gpu
 
@@ -546,3 +546,9 @@ def test_long_line_costs_one_piece_not_the_segment(gpu_lib):
     rc, dev_records, _ = scan_buffer(gpu_lib, dev.data_ptr(), size, 1, synth.C1_PATTERNS, buffer_count=4096)
     rc2, host_records, st2 = scan_buffer(gpu_lib, host.data_ptr(), size, 0, synth.C1_PATTERNS, buffer_count=4096)
     assert rc == 0 and rc2 == 0 and dev_records == host_records and st2.split_segments == 0
+
+
+def test_only_matching_spans_from_match_ends(gpu_lib, tmp_path, monkeypatch):
+    """`grep -o` spans from the device's match END offsets (gpugrep_match_ends) == re.finditer over every
+    matched line (reference utils.py:205-212), for fixed-width patterns; everything else keeps the reference's way."""
+    check_only_matching(gpu_lib, tmp_path, monkeypatch)

@@ -236,3 +236,74 @@ def test_ingest_probe_same_text_with_any_thread_count(hostmock_lib, tmp_path, mo
             seen.add(digest.value)
     assert len(seen) == 1
     assert hostmock_lib.gpugrep_ingest_probe(str(tmp_path / "missing").encode(), None, None) == 6
+
+
+def check_only_matching(lib, tmp_path, monkeypatch):
+    """grep(only_matching=True) with spans from the engine's match ends == the reference's algorithm (re.finditer over
+    every matched line, utils.py:205-212), record for record."""
+    from hypergrep_b200 import utils
+
+    monkeypatch.setattr(utils, "_get_hyperscanner_lib", lambda: lib)
+    path = tmp_path / "only.log"
+    path.write_bytes(parity.only_matching_text())
+    widths = utils._span_widths(parity.ONLY_MATCHING_FIXED + parity.ONLY_MATCHING_OTHER)
+    assert all(w > 0 for w in widths[:len(parity.ONLY_MATCHING_FIXED)]), widths
+    assert all(w == -1 for w in widths[len(parity.ONLY_MATCHING_FIXED):]), widths
+    used = []
+    original = utils._fill_spans
+
+    def counting(groups, deferred, *rest):
+        used.append(len(deferred))
+        return original(groups, deferred, *rest)
+
+    sets = [[p] for p in parity.ONLY_MATCHING_FIXED] + [parity.ONLY_MATCHING_FIXED, parity.ONLY_MATCHING_FIXED[:4] + parity.ONLY_MATCHING_OTHER[:3],
+                                                     parity.ONLY_MATCHING_OTHER[:3]]
+    for patterns in sets:
+        for ignore_case in (False, True):
+            monkeypatch.setattr(utils, "_fill_spans", counting)
+            got = utils.grep(str(path), patterns, only_matching=True, ignore_case=ignore_case)
+            with monkeypatch.context() as plain:   # the reference's way: no widths, finditer for every record
+                plain.setattr(utils, "_span_widths", lambda _patterns: None)
+                expected = utils.grep(str(path), patterns, only_matching=True, ignore_case=ignore_case)
+            assert got == expected, (patterns, ignore_case)
+    assert sum(used) > 3000   # most records did take the engine's ends
+    # random fixed-width patterns over random text
+    import random
+
+    rng = random.Random(11)
+    atoms = ["a", "b", "ab", "[ab]", ".", "[^a]", "(a|b)", "(?:ab|ba)", "a{2}", "[a-c]{3}", r"\w", r"\d", r"\bb", "c"]
+    for round_number in range(40):
+        patterns = ["".join(rng.choice(atoms) for _ in range(rng.randint(1, 4))) for _ in range(rng.randint(1, 3))]
+        text = b"".join(bytes(rng.choice(b"abc1 ") for _ in range(rng.randint(0, 30))) + b"\n" for _ in range(200))
+        path.write_bytes(text)
+        got = utils.grep(str(path), patterns, only_matching=True)
+        with monkeypatch.context() as plain:
+            plain.setattr(utils, "_span_widths", lambda _patterns: None)
+            expected = utils.grep(str(path), patterns, only_matching=True)
+        assert got == expected, (round_number, patterns)
+
+
+def test_only_matching_spans_from_match_ends(hostmock_lib, tmp_path, monkeypatch):
+    check_only_matching(hostmock_lib, tmp_path, monkeypatch)
+
+
+def test_match_ends_entry_point(hostmock_lib):
+    """gpugrep_match_ends: (line, id, end) for every match end, hs_scan order, SINGLEMATCH ignored, capacity respected."""
+    from hypergrep_b200 import utils
+
+    text = b"abcabc x\n\nzzabc\nno match here\nbcbc"
+    patterns, flags, ids = utils.prepare_patterns(["abc", "bc", "c x"], flags=[8, 0, 0], ids=[5, 6, 7])
+    entry = hostmock_lib.gpugrep_match_ends
+    entry.restype = ctypes.c_int
+    entry.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint,
+                      ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), ctypes.c_void_p]
+    expected = [(0, 5, 3), (0, 6, 3), (0, 5, 6), (0, 6, 6), (0, 7, 8), (2, 5, 5), (2, 6, 5), (4, 6, 2), (4, 6, 4)]
+    for capacity in (64, 4, 0):
+        out = (utils._MatchEnd * max(1, capacity))()
+        found = ctypes.c_size_t()
+        assert entry(text, len(text), 0, patterns, flags, ids, 3, 262140, out, capacity, ctypes.byref(found), None) == 0
+        assert found.value == len(expected)
+        got = [(out[k].line_number, out[k].id, out[k].end) for k in range(min(capacity, found.value))]
+        assert got == expected[:capacity]
+    bad, bad_flags, bad_ids = utils.prepare_patterns(["(unclosed"], flags=[0], ids=[0])
+    assert entry(text, len(text), 0, bad, bad_flags, bad_ids, 1, 262140, None, 0, None, None) == 4
