@@ -57,6 +57,10 @@ typedef void (*port_event)(port_result_t* results, int result_count);
 #define P2_NEVER_UTF 0x00001000u
 #define P2_NEVER_UCP 0x00000800u
 #define P2_NO_AUTO_CAPTURE 0x00002000u
+/* Without this PCRE2 turns a trailing `\w+` into the possessive `\w++`, and pcre2_dfa_match() then reports only the
+   longest match from a start offset; Hyperscan reports EVERY end offset of a non-SINGLEMATCH expression (pcre2api:
+   "PCRE2_NO_AUTO_POSSESS ... may also be needed if you want all matches from pcre2_dfa_match()"). */
+#define P2_NO_AUTO_POSSESS 0x00004000u
 /* Hyperscan's multiline ^ is "start of data or after ANY newline" (a streaming-capable engine cannot know that a newline is
    the last byte), PCRE2's default excludes a newline that ends the subject: PCRE2_ALT_CIRCUMFLEX
    selects the Hyperscan behaviour. */
@@ -196,7 +200,7 @@ static void port_db_free(port_db_t* db) {
 }
 
 static uint32_t p2_options(unsigned hs_flags) {
-    uint32_t o = P2_NEVER_UTF | P2_NEVER_UCP | P2_ALT_CIRCUMFLEX;
+    uint32_t o = P2_NEVER_UTF | P2_NEVER_UCP | P2_ALT_CIRCUMFLEX | P2_NO_AUTO_POSSESS;
     if (hs_flags & HS_FLAG_CASELESS) o |= P2_CASELESS;
     if (hs_flags & HS_FLAG_DOTALL) o |= P2_DOTALL;
     if (hs_flags & HS_FLAG_MULTILINE) o |= P2_MULTILINE;

@@ -552,3 +552,18 @@ def test_only_matching_spans_from_match_ends(gpu_lib, tmp_path, monkeypatch):
     """`grep -o` spans from the device's match END offsets (gpugrep_match_ends) == re.finditer over every
     matched line (reference utils.py:205-212), for fixed-width patterns; everything else keeps the reference's way."""
     check_only_matching(gpu_lib, tmp_path, monkeypatch)
+
+
+def test_device_text_reads_stay_inside_the_buffer():
+    """Memory safety of caller-owned device text (GPUGREP_LOC_DEVICE, include/gpugrep.h): the kernels read nothing before
+    `data` and nothing past data + round_up(size, 16).  compute-sanitizer is closed on the GPU pool, so the text is placed
+    flush against UNMAPPED virtual pages (cuMemMap) and every kernel path is run over it in a subprocess: a stray read
+    is an illegal-address fault there (tests/guarded_device_scan.py)."""
+    import os
+    import subprocess
+    import sys
+
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "guarded_device_scan.py")
+    done = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=900, check=False)
+    assert done.returncode == 0, done.stdout[-2000:] + done.stderr[-2000:]
+    assert "guarded scans ok" in done.stdout

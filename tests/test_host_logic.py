@@ -307,3 +307,17 @@ def test_match_ends_entry_point(hostmock_lib):
         assert got == expected[:capacity]
     bad, bad_flags, bad_ids = utils.prepare_patterns(["(unclosed"], flags=[0], ids=[0])
     assert entry(text, len(text), 0, bad, bad_flags, bad_ids, 1, 262140, None, 0, None, None) == 4
+
+
+def test_every_end_of_a_trailing_repeat_is_reported(hostmock_lib, oracle_lib):
+    """Without HS_FLAG_SINGLEMATCH Hyperscan reports EVERY end offset: `user=\\w+` over "user=bob" ends at 6, 7 and 8 - three
+    reports, three callbacks with the same line (hyperscanner.c:83-102 copies the line per report).  (The oracle needs
+    PCRE2_NO_AUTO_POSSESS for this: PCRE2 otherwise makes the trailing repeat possessive and its DFA matcher returns the
+    longest match only - found by tests/guarded_device_scan.py in round 2.)"""
+    text = b"user=bob and user=al\nnothing here\nport 8080 user=x\n12345\n"
+    patterns, flags, ids = ["user=\\w+", "[0-9]+", "port [0-9]+"], [6, 6, 14], [1, 2, 3]
+    count = parity.compare(hostmock_lib, oracle_lib, text, patterns, flags=flags, ids=ids)
+    # line 0: 3 + 2 ends of user=..; line 2: port (once, SINGLEMATCH), 4 digit ends, 1 user= end; line 3: 5 digit ends
+    assert count == 5 + (1 + 4 + 1) + 5
+    rc, got, _ = run_scan_bytes(hostmock_lib, text, patterns, flags=flags, ids=ids)
+    assert rc == 0 and [r[0] for r in got if r[1] == 0] == [1, 1, 1, 1, 1]
