@@ -54,6 +54,13 @@ def main() -> int:
     assert driver.cuMemcpyDtoH(probe, lo - 16, 16)[0] != driver.CUresult.CUDA_SUCCESS
 
     syslog = synth.syslog_bytes(6 << 20, seed=41)
+    if "--negative" in sys.argv:
+        # control: a text that claims 64 bytes more than are mapped must fault (otherwise the guard proves nothing)
+        n = 1 << 20
+        ok(driver.cuMemcpyHtoD(hi - n, syslog[:n], n))
+        rc, _, _ = scan_buffer(lib, hi - n, n + 64, 1, synth.C2_PATTERNS, collect=False)
+        print(f"negative control: rc={rc} {lib.gpugrep_last_error()}")
+        return 0 if rc == 7 else 1
     long_lines = synth.jsonish_bytes(3 << 20, patterns_to_plant=["session_4242 failed"])
     c3, plants = synth.c3_patterns()
     planted = synth.syslog_bytes(4 << 20, seed=43, plants=plants, plant_ppm=2000)
