@@ -288,6 +288,8 @@ std::unique_ptr<ByteSource> open_byte_source(const char* path, std::string& erro
     }
     struct stat sb;
     bool regular = ::fstat(fd, &sb) == 0 && S_ISREG(sb.st_mode);
+    // one front-to-back pass: ask the kernel for aggressive read-ahead (a hint; ignored by tmpfs)
+    if (regular) ::posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
     return std::make_unique<PlainSource>(std::move(raw), head, got, fd, regular);
 }
 
@@ -297,6 +299,7 @@ std::unique_ptr<ByteSource> open_plain_range(const char* path, size_t begin, siz
         error = std::string("cannot open ") + path + ": " + std::strerror(errno);
         return nullptr;
     }
+    ::posix_fadvise(fd, (off_t)begin, (off_t)(end - begin), POSIX_FADV_SEQUENTIAL);
     return std::make_unique<PlainSource>(std::make_unique<RawFile>(fd), fd, begin, end);
 }
 
