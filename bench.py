@@ -49,7 +49,7 @@ def parse_args() -> argparse.Namespace:
     parser.add_argument("--gib", type=float, default=float(os.environ.get("GPUGREP_BENCH_GIB", "10")))
     parser.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the cpu_baseline sample")
     parser.add_argument("--strong", action="store_true", help="one text of --gib GiB split over the ranks, merged and checked")
-    parser.add_argument("--no-extras", action="store_true", help="skip the extra configs / Python-level legs (N=1 only anyway)")
+    parser.add_argument("--no-extras", action="store_true", help="skip the extra configs / Python-level legs")
     return parser.parse_args()
 
 
@@ -455,6 +455,31 @@ def main() -> None:  # pylint: disable=too-many-locals,too-many-statements,too-m
     avg_launch_ms = stream_ms / max(1, stream_launches)
     achieved = kernel_bytes / (avg_launch_ms / 1e3) / 1e9 if avg_launch_ms > 0 else 0.0
 
+    # ---- the other BASELINE configurations on N GPUs: every rank scans its own copy of the text (weak scaling, like the
+    # headline), time = max over ranks.  One gather at the end, also when a rank failed, so that no rank waits for another.
+    multi_extra = None
+    if world > 1 and not args.no_extras and not args.strong:
+        local = torch.full((len(DEVICE_LEGS), 3), float("nan"), dtype=torch.float64)
+        try:
+            legs = device_legs(lib, scan, host, dev, size, stream)
+            for k, name in enumerate(DEVICE_LEGS):
+                local[k] = torch.tensor([legs[name]["ms"], legs[name]["bytes"], legs[name]["matches"]], dtype=torch.float64)
+        except Exception as error:  # pylint: disable=broad-except
+            print(f"rank {rank}: extra legs failed: {error}", file=sys.stderr)
+        gathered = [torch.empty_like(local, device=dev.device) for _ in range(world)]
+        dist.all_gather(gathered, local.to(dev.device))
+        if rank == 0:
+            stacked = torch.stack([g.cpu() for g in gathered])   # [rank][leg][ms, bytes, matches]
+            multi_extra = {}
+            for k, name in enumerate(DEVICE_LEGS):
+                ms, nbytes, matches = stacked[:, k, 0], stacked[:, k, 1], stacked[:, k, 2]
+                if bool(torch.isnan(ms).any()):
+                    multi_extra[name] = {"value": None, "failed_ranks": [int(r) for r in torch.nonzero(torch.isnan(ms)).flatten()]}
+                    continue
+                multi_extra[name] = {"value": float(nbytes.sum() / ms.max() / 1e6), "unit": "GB/s", "n_gpus": world, "bytes_per_gpu": int(nbytes[0]),
+                                     "ms_max_over_ranks": float(ms.max()), "ms_min_over_ranks": float(ms.min()),
+                                     "matches": int(matches.sum())}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -481,6 +506,8 @@ def main() -> None:  # pylint: disable=too-many-locals,too-many-statements,too-m
     }
     if merge is not None:
         line["merge_check"] = merge
+    if multi_extra is not None:
+        line["extra"] = multi_extra
     # DRAM traffic of the roofline kernel from the committed ncu capture (profiles/), scaled to this run's launch size
     for name in ("r2_k_stream_traffic.json", "r1_k_stream_traffic.json"):
         try:
@@ -590,12 +617,12 @@ def main() -> None:  # pylint: disable=too-many-locals,too-many-statements,too-m
         dist.destroy_process_group()
 
 
-def extra_configs(lib, scan, host, dev, size: int, stream) -> dict:  # pylint: disable=too-many-locals
-    """Device-resident throughput of BASELINE configs[0], [2] and [4], and the configs[3] file leg, on one GPU."""
+def device_legs(lib, scan, host, dev, size: int, stream) -> dict:  # pylint: disable=too-many-locals
+    """Device-resident throughput of BASELINE configs[0], [2] and [4] on this rank's GPU."""
     import numpy as np  # pylint: disable=import-outside-toplevel
     import torch  # pylint: disable=import-outside-toplevel
 
-    from hypergrep_b200 import multiscanner, synth  # pylint: disable=import-outside-toplevel
+    from hypergrep_b200 import synth  # pylint: disable=import-outside-toplevel
 
     out: dict = {}
     part = min(size, 2 << 30)
@@ -636,6 +663,18 @@ def extra_configs(lib, scan, host, dev, size: int, stream) -> dict:  # pylint: d
     tiled_dev = tiled.cuda()
     out["configs[4] 10,000 caseless patterns, 2-16 KiB lines"] = timed(tiled_dev.data_ptr(), long_size, marshal(c5, [15] * len(c5)), passes=2)
     del tiled_dev, tiled
+    return out
+
+
+DEVICE_LEGS = ["configs[0] 'ERROR' (1 literal)", "configs[2] 1,000 IOC patterns", "configs[4] 10,000 caseless patterns, 2-16 KiB lines"]
+
+
+def extra_configs(lib, scan, host, dev, size: int, stream) -> dict:
+    """The other BASELINE configurations: device-resident C1 / C3 / C5 (device_legs) and the C4 file legs."""
+    import hypergrep_b200.multiscanner as multiscanner  # pylint: disable=import-outside-toplevel
+
+    out = device_legs(lib, scan, host, dev, size, stream)
+    view = host.numpy()
     # configs[3] shape: files (plain / gzip -6 / zstd -3) through the reference-facing CLI entry, one job per file
     try:
         out["configs[3] files through multiscanner.parallel_grep"] = file_leg(view, multiscanner)
