@@ -293,6 +293,7 @@ struct Job {
     }
 
     void prepare() {
+        if (db->simple) return;   // the flat report ranges are only read when events are expanded to ids
         for (auto& rb : db->report_begin) {
             // every group's list ends with a sentinel; keep [begin, next begin) pairs addressable by flat index
             for (size_t k = 0; k + 1 < rb.size(); k++) { report_begin_flat.push_back(rb[k]); report_end_flat.push_back(rb[k + 1]); }

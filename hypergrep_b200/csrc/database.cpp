@@ -178,15 +178,15 @@ std::shared_ptr<Database> cached_database(const char* const* patterns, const uns
                                           unsigned n, int& rc, std::string& error) {
     static std::mutex mu;
     static std::list<std::shared_ptr<Database>> cache;   // most recent first
+    // (built for every scan call: 10,000 patterns are 300 KB of key, so no per-pattern formatting or allocation here)
     std::string key;
+    key.reserve((size_t)n * 48 + 64);
     for (unsigned i = 0; i < n; i++) {
         if (!patterns || !patterns[i]) break;
         key.append(patterns[i]);
+        const unsigned tail[2] = {flags ? flags[i] : 0u, ids ? ids[i] : 0u};
         key.push_back('\0');
-        key.append(std::to_string(flags ? flags[i] : 0));
-        key.push_back(',');
-        key.append(std::to_string(ids ? ids[i] : 0));
-        key.push_back('\0');
+        key.append(reinterpret_cast<const char*>(tail), sizeof(tail));
     }
     key.append(std::getenv("GPUGREP_NO_PREFILTER") ? "np" : "");
     if (const char* b = std::getenv("GPUGREP_MAX_DFA_STATES")) key.append(b);
