@@ -736,7 +736,7 @@ def file_leg(view, multiscanner) -> dict:
                 paths = list(pool.map(lambda k, kind=kind: write(kind, k), range(files)))
             compressed = sum(os.path.getsize(p) for p in paths)
             best = None
-            for _ in range(2):
+            for _ in range(5 if kind == "plain" else 2):   # (eight scans at once warm their pinned slots up over the first runs)
                 sink = io.StringIO()
                 t0 = time.perf_counter()
                 with contextlib.redirect_stdout(sink):
