@@ -617,7 +617,7 @@ def main() -> None:  # pylint: disable=too-many-locals,too-many-statements,too-m
         dist.destroy_process_group()
 
 
-def device_legs(lib, scan, host, dev, size: int, stream, reuse_host: bool = False) -> dict:  # pylint: disable=too-many-locals
+def device_legs(lib, scan, host, dev, size: int, stream, reuse_host: bool = False, oracle=None) -> dict:  # pylint: disable=too-many-locals
     """Device-resident throughput of BASELINE configs[0], [2] and [4] on this rank's GPU.  `reuse_host`: the pinned text of
     the headline run is no longer needed (multi-rank runs) and serves as the staging buffer, so that eight ranks do not pin
     another 3 GiB each."""
@@ -649,12 +649,40 @@ def device_legs(lib, scan, host, dev, size: int, stream, reuse_host: bool = Fals
                 "candidates_per_gib": st.candidates / (nbytes / (1 << 30)), "path": int(st.path), "launches": int(st.launches),
                 "segments": int(st.segments), "split_segments": int(st.split_segments)}
 
-    out["configs[0] 'ERROR' (1 literal)"] = timed(dev.data_ptr(), part, marshal(synth.C1_PATTERNS))
+    def parity(text_view, text_ptr: int, nbytes: int, pat_list, flags, marshaled, sample_bytes: int) -> dict:
+        """Matched line numbers of a prefix of the leg's text: library (host path, records delivered) against the oracle on all
+        host cores.  The device-resident pass that was timed counts the same text (its `matches` are for the whole of it)."""
+        sample = min(nbytes, sample_bytes)
+        while sample > 1 and text_view[sample - 1] != 10:
+            sample -= 1
+        threads = os.cpu_count() or 1
+        secs, cpu_matches, cpu_lines = oracle_scan(oracle, text_view, sample, pat_list, threads, True, flags)
+        collector = LineCollector()
+        scan(text_ptr, sample, 0, ctypes.cast(collector.func, ctypes.c_void_p), marshaled)
+        gpu_lines = collector.lines()
+        same = bool(gpu_lines.size == cpu_lines.size and np.array_equal(gpu_lines, cpu_lines))
+        if not same:
+            print(f"PARITY FAILURE in an extra leg: {gpu_lines.size} lines, oracle {cpu_lines.size}", file=sys.stderr)
+        return {"checked": True, "identical": same, "parity_checked_bytes": int(sample), "matched_lines": int(cpu_matches),
+                "gpu_matched_lines": int(gpu_lines.size), "oracle_seconds": secs, "oracle_threads": threads}
+
+    def with_parity(result: dict, *args) -> dict:
+        if oracle is not None:
+            try:
+                result["parity"] = parity(*args)
+            except Exception as error:  # pylint: disable=broad-except
+                result["parity"] = {"checked": False, "error": str(error)}
+        return result
+
+    c1 = marshal(synth.C1_PATTERNS)
+    out["configs[0] 'ERROR' (1 literal)"] = with_parity(timed(dev.data_ptr(), part, c1), view, host.data_ptr(), part, synth.C1_PATTERNS, None, c1, part)
     c3, plants = synth.c3_patterns()
     planted = host[:part] if reuse_host else torch.empty(part, dtype=torch.uint8).pin_memory()
     synth.fill_syslog(planted.numpy(), seed=4321, plants=plants, plant_ppm=1000)
     planted_dev = planted.cuda()
-    out["configs[2] 1,000 IOC patterns"] = timed(planted_dev.data_ptr(), part, marshal(c3))
+    c3m = marshal(c3)
+    out["configs[2] 1,000 IOC patterns"] = with_parity(timed(planted_dev.data_ptr(), part, c3m), planted.numpy(), planted.data_ptr(), part, c3, None, c3m,
+                                                        512 << 20)
     del planted_dev, planted
     # configs[4]: caseless template patterns over long JSON-ish lines (an 8 MiB generated sample, tiled to 1 GiB)
     c5 = synth.c5_patterns(10000)
@@ -667,7 +695,9 @@ def device_legs(lib, scan, host, dev, size: int, stream, reuse_host: bool = Fals
         tiled = torch.from_numpy(np.tile(sample, -(-long_size // sample.size))[:long_size].copy())
     tiled[-1] = 10
     tiled_dev = tiled.cuda()
-    out["configs[4] 10,000 caseless patterns, 2-16 KiB lines"] = timed(tiled_dev.data_ptr(), long_size, marshal(c5, [15] * len(c5)), passes=2)
+    c5m = marshal(c5, [15] * len(c5))
+    out["configs[4] 10,000 caseless patterns, 2-16 KiB lines"] = with_parity(timed(tiled_dev.data_ptr(), long_size, c5m, passes=2), tiled.numpy(),
+                                                                              tiled.data_ptr(), long_size, c5, [15] * len(c5), c5m, 24 << 20)
     del tiled_dev, tiled
     return out
 
@@ -679,7 +709,12 @@ def extra_configs(lib, scan, host, dev, size: int, stream) -> dict:
     """The other BASELINE configurations: device-resident C1 / C3 / C5 (device_legs) and the C4 file legs."""
     import hypergrep_b200.multiscanner as multiscanner  # pylint: disable=import-outside-toplevel
 
-    out = device_legs(lib, scan, host, dev, size, stream)
+    oracle = None
+    try:
+        oracle = load_oracle()
+    except Exception:  # pylint: disable=broad-except
+        pass
+    out = device_legs(lib, scan, host, dev, size, stream, oracle=oracle)
     view = host.numpy()
     # configs[3] shape: files (plain / gzip -6 / zstd -3) through the reference-facing CLI entry, one job per file
     try:
