@@ -321,3 +321,56 @@ def test_every_end_of_a_trailing_repeat_is_reported(hostmock_lib, oracle_lib):
     assert count == 5 + (1 + 4 + 1) + 5
     rc, got, _ = run_scan_bytes(hostmock_lib, text, patterns, flags=flags, ids=ids)
     assert rc == 0 and [r[0] for r in got if r[1] == 0] == [1, 1, 1, 1, 1]
+
+
+@pytest.mark.parametrize("kind", ["gzip", "zstd"])
+def test_random_member_layouts_decode_like_one_stream(hostmock_lib, tmp_path, monkeypatch, kind):
+    """Differential test of the multi-threaded member decode (ingest_members.cpp) against the one-thread decode of the same
+    library: random member sizes (empty ones included), stored members whose payload contains header look-alikes, and
+    random damage - a flipped byte, a truncation, garbage between members - under random start spacings, hand-over
+    sizes and thread counts.  Byte count and hash of the delivered text must be identical."""
+    import gzip
+    import random
+
+    hostmock_lib.gpugrep_ingest_probe.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_ulonglong), ctypes.POINTER(ctypes.c_ulonglong)]
+    rng = random.Random(1234 if kind == "gzip" else 4321)
+    text = synth.syslog_bytes(1 << 20, seed=47)
+    magic = b"\x1f\x8b\x08\x00\x00\x00\x00\x00\x00\x03" if kind == "gzip" else b"\x28\xb5\x2f\xfd\x04\x58\x01\x00\x00"
+    pack = (lambda d, lvl: gzip.compress(d, lvl)) if kind == "gzip" else (lambda d, lvl: parity.zstd_frame(d, max(1, lvl)))
+    path = tmp_path / ("r.log.gz" if kind == "gzip" else "r.log.zst")
+
+    def probe():
+        size, digest = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+        assert hostmock_lib.gpugrep_ingest_probe(str(path).encode(), ctypes.byref(size), ctypes.byref(digest)) == 0
+        return size.value, digest.value
+
+    for case in range(40):
+        members, at = [], 0
+        while at < len(text) and len(members) < 60:
+            step = rng.choice([0, 1, 300, 5000, 40000, 200000])
+            piece = text[at:at + step]
+            at += step
+            if rng.random() < 0.15:   # incompressible payload with member headers inside
+                piece = b"".join(magic + rng.randbytes(50) for _ in range(40)) + piece
+                members.append(pack(piece, 0 if kind == "gzip" else 1))
+            else:
+                members.append(pack(piece, rng.choice([1, 6, 9])))
+        blob = bytearray(b"".join(members))
+        damage = rng.choice(["none", "none", "flip", "truncate", "garbage", "garbage_magic"])
+        if damage == "flip" and len(blob) > 100:
+            spot = rng.randrange(20, len(blob) - 1)
+            blob[spot] ^= 0x55
+        elif damage == "truncate" and len(blob) > 100:
+            del blob[rng.randrange(10, len(blob)):]
+        elif damage in ("garbage", "garbage_magic") and len(members) > 2:
+            cut = len(b"".join(members[:rng.randrange(1, len(members))]))
+            blob[cut:cut] = (magic[:2] if damage == "garbage_magic" else b"") + rng.randbytes(rng.randrange(1, 40))
+        path.write_bytes(bytes(blob))
+        monkeypatch.setenv("GPUGREP_DECODE_THREADS", "0")
+        expected = probe()
+        for _ in range(2):
+            monkeypatch.setenv("GPUGREP_DECODE_THREADS", str(rng.choice([2, 3, 5, 9])))
+            monkeypatch.setenv("GPUGREP_DECODE_MIN_BYTES", "0")
+            monkeypatch.setenv("GPUGREP_DECODE_SPACING", str(rng.choice([64, 1000, 20000, 300000])))
+            monkeypatch.setenv("GPUGREP_DECODE_CHAIN", str(rng.choice([1, 5000, 100000, 16 << 20])))
+            assert probe() == expected, (kind, case, damage)
