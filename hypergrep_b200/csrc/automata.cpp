@@ -223,6 +223,7 @@ struct Determinizer {
 }  // namespace
 
 static void minimise(Dfa& d, const std::vector<char>& idle);
+static std::vector<uint8_t> nfa_longest_paths(const Nfa& nfa);
 
 bool build_nfa_tables(const Nfa& nfa, NfaTables& out) {
     DfaBuildOptions opt;
@@ -419,8 +420,43 @@ bool build_dfa(const Nfa& nfa, const DfaBuildOptions& opt, Dfa& out) {
     out.idle_end = 0;
     std::vector<char> idle(kernels.size(), 0);
     for (size_t k = 0; k < kernels.size(); k++) idle[k] = kernels[k].empty() && out.accept_of[k] == 0;
+    // depth: bytes consumed on the longest NFA path to any item of the kernel (terminal kernels: nothing in progress)
+    const std::vector<uint8_t> longest = nfa_longest_paths(nfa);
+    out.depth.assign(kernels.size(), 0);
+    for (size_t k = 0; k < kernels.size(); k++)
+        for (int pc : kernels[k])
+            if (pc >= 0) out.depth[k] = std::max(out.depth[k], longest[(size_t)pc]);
     minimise(out, idle);
     return true;
+}
+
+// Longest path, in consumed bytes, from a pattern start to every instruction; 255 = unbounded (reachable through a loop).
+static std::vector<uint8_t> nfa_longest_paths(const Nfa& nfa) {
+    const size_t n = nfa.prog.size();
+    std::vector<uint8_t> len(n, 0);
+    std::vector<char> reached(n, 0), queued(n, 0);
+    std::vector<int> work;
+    for (int st : nfa.starts)
+        if (st >= 0 && (size_t)st < n && !reached[(size_t)st]) { reached[(size_t)st] = 1; queued[(size_t)st] = 1; work.push_back(st); }
+    // relaxation with a cap: a node on a byte-consuming loop climbs to 255 and stays there (at most 255 rises per node)
+    while (!work.empty()) {
+        const int pc = work.back();
+        work.pop_back();
+        queued[(size_t)pc] = 0;
+        const NfaInst& in = nfa.prog[(size_t)pc];
+        const int targets[2] = {in.op == NfaInst::Match ? -1 : in.x, in.op == NfaInst::Split ? in.y : -1};
+        const int weight = in.op == NfaInst::Byte ? 1 : 0;
+        for (int to : targets) {
+            if (to < 0 || (size_t)to >= n) continue;
+            const int cand = std::min(255, (int)len[(size_t)pc] + weight);
+            if (!reached[(size_t)to] || cand > (int)len[(size_t)to]) {
+                reached[(size_t)to] = 1;
+                len[(size_t)to] = (uint8_t)cand;
+                if (!queued[(size_t)to]) { queued[(size_t)to] = 1; work.push_back(to); }
+            }
+        }
+    }
+    return len;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -512,6 +548,13 @@ static void minimise(Dfa& d, const std::vector<char>& idle) {
     d.stride = stride2;
     d.trans.swap(t2);
     d.accept_of.swap(acc2);
+    if (d.depth.size() == (size_t)n) {
+        std::vector<uint8_t> blk_depth((size_t)nblk, 0);
+        for (int st = 0; st < n; st++) blk_depth[(size_t)blk[st]] = std::max(blk_depth[(size_t)blk[st]], d.depth[(size_t)st]);
+        std::vector<uint8_t> depth2((size_t)nblk, 0);
+        for (int i = 0; i < nblk; i++) depth2[(size_t)i] = blk_depth[(size_t)order[i]];
+        d.depth.swap(depth2);
+    }
     d.num_states = nblk;
     d.first_accept = first_accept;
     if (d.sink_match >= 0) d.sink_match = newid[blk[d.sink_match]];

@@ -55,6 +55,11 @@ struct Dfa {
     // States < idle_end have no partial match in progress (only the implicit ".*" restart): once a walk is idle
     // past a prefilter hit, no match containing that hit can still complete.  State 0 is always idle.
     int idle_end = 1;
+    // depth[s]: no partial match in progress in state s began more than depth[s] bytes ago (255: unbounded - a loop).
+    // Finer than "idle": a local walk that is `k` bytes past the last gram of its chunk can stop as soon as depth < k,
+    // because whatever is still in progress began behind that gram and belongs to a later candidate.  From the longest
+    // path of the NFA to every item of the state's kernel; the maximum over the states that minimisation merges.
+    std::vector<uint8_t> depth;
 };
 
 struct DfaBuildOptions {

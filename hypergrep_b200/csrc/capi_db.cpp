@@ -207,6 +207,13 @@ int gpugrep_db_accept_reports(const gpugrep_db* h, unsigned int group, unsigned 
     return (int)n;
 }
 
+size_t gpugrep_db_copy_depth(const gpugrep_db* h, unsigned int group, uint8_t* depth, size_t cap) {
+    if (!h || group >= h->db->groups.size()) return 0;
+    const auto& d = h->db->groups[group].dfa.depth;
+    if (depth) std::memcpy(depth, d.data(), std::min(cap, d.size()));
+    return d.size();
+}
+
 size_t gpugrep_db_copy_prefilter(const gpugrep_db* h, uint32_t* words, size_t cap_words, uint32_t* hash_mul) {
     if (!h || !h->db->prefilter.enabled) return 0;
     const auto& pf = h->db->prefilter;

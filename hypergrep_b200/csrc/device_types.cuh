@@ -18,6 +18,10 @@ struct GroupDev {
     const uint16_t* ctab;
     const uint8_t* cmap;
     uint32_t crow, cstates;     // bytes per row of ctab, rows
+    // depth[state] (Dfa::depth): how long ago the oldest partial match of the state can have begun, 255 = unbounded; the
+    // copy for shared memory sits behind ctab (cdepth_off: its offset from ctab in 32-bit words)
+    const uint8_t* depth;
+    uint32_t cdepth_off;
     uint32_t stride, eod, first_accept, dead, accept_base, idle_end, mid_other, mid_word;
 };
 

@@ -213,7 +213,10 @@ std::shared_ptr<DeviceDb> engine_upload(const std::shared_ptr<Database>& db, std
         G.trans = (const uint16_t*)upload(t16.data(), t16.size() * sizeof(uint16_t));
         G.cls = (const uint8_t*)upload(d.byte_class, 256);
         G.accept_of = (const uint32_t*)upload(d.accept_of.data(), d.accept_of.size() * sizeof(uint32_t));
-        if (!G.trans || !G.cls || !G.accept_of) { error = "cudaMalloc/cudaMemcpy failed while uploading DFA tables"; return nullptr; }
+        std::vector<uint8_t> depth = d.depth;
+        depth.resize((size_t)d.num_states, 255);   // (a table without depths: never stop early)
+        G.depth = (const uint8_t*)upload(depth.data(), depth.size());
+        if (!G.trans || !G.cls || !G.accept_of || !G.depth) { error = "cudaMalloc/cudaMemcpy failed while uploading DFA tables"; return nullptr; }
         if (db->simple && (size_t)d.num_states * 512 <= ((size_t)256 << 20)) {
             // Byte-indexed table for local verification with the line rules folded in (one load per byte, no special
             // cases in the walk): '\n' and NUL end the scanned block, so their columns hold either the absorbing
@@ -241,7 +244,7 @@ std::shared_ptr<DeviceDb> engine_upload(const std::shared_ptr<Database>& db, std
             // except '\n' and NUL, whose columns carry the line rules: they get classes of their own.
             const int ncls = d.num_classes + 2;
             const size_t ctab_bytes = (size_t)d.num_states * ncls * 2;
-            if (db->groups.size() == 1 && ncls <= 255 && ctab_bytes <= kMaxSharedTableBytes) {
+            if (db->groups.size() == 1 && ncls <= 255 && ctab_bytes + (size_t)d.num_states + 32 <= kMaxSharedTableBytes) {   // (+ the depths)
                 std::vector<uint8_t> cmap2(256);
                 std::vector<int> rep((size_t)ncls, -1);
                 for (int b = 255; b >= 0; b--) {
@@ -249,16 +252,20 @@ std::shared_ptr<DeviceDb> engine_upload(const std::shared_ptr<Database>& db, std
                     cmap2[(size_t)b] = (uint8_t)c;
                     rep[(size_t)c] = b;
                 }
-                std::vector<uint16_t> ctab((size_t)d.num_states * ncls + 8, 0);
+                // the table rounded up to 16 bytes, the depths of the states behind it
+                const size_t ctab_pad = (ctab_bytes + 15) / 16 * 16, depth_pad = ((size_t)d.num_states + 15) / 16 * 16;
+                std::vector<uint16_t> ctab((ctab_pad + depth_pad) / 2, 0);
                 for (int st = 0; st < d.num_states; st++)
                     for (int c = 0; c < ncls; c++)
                         if (rep[(size_t)c] >= 0) ctab[(size_t)st * ncls + c] = flat[(size_t)st * 256 + rep[(size_t)c]];
+                std::memcpy(reinterpret_cast<uint8_t*>(ctab.data()) + ctab_pad, depth.data(), depth.size());
+                G.cdepth_off = (uint32_t)(ctab_pad / 4);
                 G.ctab = (const uint16_t*)upload(ctab.data(), ctab.size() * sizeof(uint16_t));
                 G.cmap = (const uint8_t*)upload(cmap2.data(), 256);
                 if (!G.ctab || !G.cmap) { error = "cudaMalloc/cudaMemcpy failed while uploading DFA tables"; return nullptr; }
                 G.crow = (uint32_t)ncls * 2u;
                 G.cstates = (uint32_t)d.num_states;
-                out->smem_table_bytes = (ctab_bytes + 15) / 16 * 16;
+                out->smem_table_bytes = ctab_pad + depth_pad;
             }
         }
         G.stride = (uint32_t)d.stride;

@@ -45,6 +45,8 @@ __device__ __forceinline__ bool is_word_dev(uint32_t b) {
 // ordinary columns and "matched" is one absorbing state (see engine_upload).
 struct FlatTable {   // [state][256] u16 in global memory
     const uint16_t* __restrict__ flat;
+    const uint8_t* __restrict__ depth;
+    __device__ __forceinline__ uint32_t depth_of(uint32_t s) const { return depth[s]; }
     __device__ __forceinline__ uint32_t cls_of(uint32_t b) const { return b; }   // the table is byte-indexed
     __device__ __forceinline__ uint32_t next(uint32_t s, uint32_t c) const { return flat[(s << 8) | c]; }
     __device__ __forceinline__ uint32_t step(uint32_t s, uint32_t b) const { return flat[(s << 8) | b]; }
@@ -53,6 +55,8 @@ struct SharedTable {   // class-compressed [state][classes] u16 in shared memory
     const uint16_t* tab;
     const uint8_t* cls;
     uint32_t ncls;   // entries per table row
+    const uint8_t* depth;
+    __device__ __forceinline__ uint32_t depth_of(uint32_t s) const { return depth[s]; }
     // the class lookups do not depend on the state: the walk issues the four of a word first, the state chain is then one
     // multiply-add and one load per byte
     __device__ __forceinline__ uint32_t cls_of(uint32_t b) const { return cls[b]; }
@@ -83,7 +87,7 @@ struct GlobalText {
 template <class Table, class Text>
 __device__ __forceinline__ uint32_t walk_words(const Table& T, const Text& X, const GroupDev& G, uint32_t s, uint32_t end, uint32_t cend, uint32_t pos,
                                                uint32_t ifrom, uint32_t line_bit) {
-    const uint32_t first_accept = G.first_accept, idle_end = G.idle_end;
+    const uint32_t first_accept = G.first_accept;
     uint32_t mask = 0;
     if (pos >= end) return G.eod_next[s] >= first_accept ? line_bit : 0u;
     // Whole words.  Every lane of the warp runs the SAME four table steps per word; what a newline adds sits in four
@@ -120,7 +124,10 @@ __device__ __forceinline__ uint32_t walk_words(const Table& T, const Text& X, co
             wpos += 4;
             if (s >= first_accept) {
                 if (wpos >= cend) return mask | line_bit;   // matched, and no further line starts inside the chunk
-            } else if (wpos >= ifrom && s < idle_end) {
+            } else if (wpos >= ifrom && T.depth_of(s) < min(wpos - ifrom + 4u, 255u)) {
+                // whatever is still in progress began behind the last gram of the chunk (Dfa::depth): it belongs to a later
+                // candidate.  (Before: only when NOTHING was in progress - the longest lane of a warp then walked some 60
+                // bytes past its chunk.)
                 return mask;
             }
             if (wpos + 4 > end) break;
@@ -142,7 +149,7 @@ __device__ __forceinline__ uint32_t walk_words(const Table& T, const Text& X, co
         pos++;
         if (s >= first_accept) {
             if (pos >= cend) return mask | line_bit;
-        } else if (pos >= ifrom && s < idle_end) {
+        } else if (pos >= ifrom && T.depth_of(s) < min(pos - ifrom + 4u, 255u)) {
             return mask;
         }
     }
@@ -163,7 +170,7 @@ __device__ uint32_t walk_local(const GroupDev& G, const uint8_t* __restrict__ da
     uint32_t mask = 0;
     const size_t chunk_end = o + 16;
     const uint32_t first_accept = G.first_accept, idle_end = G.idle_end;
-    if (G.flat) return walk_words(FlatTable{G.flat}, GlobalText{data}, G, s, (uint32_t)n, (uint32_t)chunk_end, (uint32_t)t, (uint32_t)idle_from, line_bit);
+    if (G.flat) return walk_words(FlatTable{G.flat, G.depth}, GlobalText{data}, G, s, (uint32_t)n, (uint32_t)chunk_end, (uint32_t)t, (uint32_t)idle_from, line_bit);
     bool done = false;
     ByteCursor c(data, t, n);
     while (c.pos < n) {
@@ -377,14 +384,16 @@ __global__ void __launch_bounds__(kVerifySmemThreads, 2) k_verify_smem(DbView db
                                                                        uint32_t* __restrict__ tile_records) {
     extern __shared__ __align__(16) uint32_t s_verify[];
     const GroupDev G = db.groups[0];
-    const uint32_t table_words = (G.cstates * G.crow + 15u) / 16u * 4u;
+    // class map (256 bytes), table (rounded up to 16 bytes), depths of the states
+    const uint32_t table_words = G.cdepth_off + (G.cstates + 15u) / 16u * 4u;
     {
         const uint32_t* src_cls = reinterpret_cast<const uint32_t*>(G.cmap);
         const uint32_t* src_tab = reinterpret_cast<const uint32_t*>(G.ctab);
         for (uint32_t k = threadIdx.x; k < 64u + table_words; k += blockDim.x) s_verify[k] = k < 64u ? src_cls[k] : src_tab[k - 64u];
         __syncthreads();
     }
-    const SharedTable T{reinterpret_cast<const uint16_t*>(s_verify + 64), reinterpret_cast<const uint8_t*>(s_verify), G.crow / 2u};
+    const SharedTable T{reinterpret_cast<const uint16_t*>(s_verify + 64), reinterpret_cast<const uint8_t*>(s_verify), G.crow / 2u,
+                        reinterpret_cast<const uint8_t*>(s_verify + 64 + G.cdepth_off)};
     const GlobalText X{data};
     const uint32_t end = (uint32_t)n;
     size_t ncand = (size_t)(*meta_total >> 32);

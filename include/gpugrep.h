@@ -203,6 +203,9 @@ GPUGREP_API int gpugrep_db_get_group(const gpugrep_db* db, unsigned int group, g
 /* Copies the tables of one group: byte_class[256], trans[states*stride], accept_of[states]. */
 GPUGREP_API int gpugrep_db_copy_group(const gpugrep_db* db, unsigned int group, uint8_t* byte_class, uint32_t* trans,
                           uint32_t* accept_of);
+/* depth[state] of `group` (no partial match in progress in that state began more than depth bytes ago; 255 = unbounded):
+ * what lets a local verification walk stop early.  Writes up to cap bytes, returns the number of states. */
+GPUGREP_API size_t gpugrep_db_copy_depth(const gpugrep_db* db, unsigned int group, uint8_t* depth, size_t cap);
 /* Reports of accept set `accept` of `group`: writes up to cap (id, singlematch) pairs, returns the count. */
 GPUGREP_API int gpugrep_db_accept_reports(const gpugrep_db* db, unsigned int group, unsigned int accept, unsigned int* ids,
                               unsigned int* singlematch, unsigned int cap);

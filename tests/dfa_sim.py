@@ -52,6 +52,7 @@ class CompiledDb:
         self.rc = rc.value
         self.error = lib.gpugrep_last_error().decode()
         self.groups = []
+        self.depths = []   # per group: depth[state] (see automata.hpp)
         if not self.handle:
             return
         h = ctypes.c_void_p(self.handle)
@@ -72,6 +73,11 @@ class CompiledDb:
                 cnt = lib.gpugrep_db_accept_reports(h, g, k, ids_buf, sm_buf, 4096)
                 reports.append([(ids_buf[i], sm_buf[i]) for i in range(cnt)])
             self.groups.append((gi, cls, trans.reshape(gi.states, gi.stride), acc, reports))
+            lib.gpugrep_db_copy_depth.restype = ctypes.c_size_t
+            lib.gpugrep_db_copy_depth.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_size_t]
+            depth = np.zeros(gi.states, dtype=np.uint8)
+            assert lib.gpugrep_db_copy_depth(h, g, depth.ctypes.data_as(ctypes.c_void_p), gi.states) == gi.states
+            self.depths.append(depth)
         self.prefilter_note = lib.gpugrep_db_prefilter_note(h).decode()
         self._load_grams()
 
@@ -248,7 +254,10 @@ def fast_path_matched_line_starts(db: "CompiledDb", data: bytes) -> set:
                 done_line = False
                 states = [0] * len(db.groups)
                 continue
-            if pos >= o + 19 and (done_line or all(states[k] < g[0].idle_end for k, g in enumerate(db.groups))):
+            # past the last sampled gram of the chunk the walk stops as soon as nothing that is still in progress can have begun at
+            # or before that gram (automata.hpp Dfa::depth; the kernels test this once per word, the model per byte)
+            ifrom = o + (18 if db.odd else 20 - st)
+            if pos >= ifrom and (done_line or all(int(db.depths[k][states[k]]) < min(pos - ifrom + 4, 255) for k in range(len(db.groups)))):
                 break
             if done_line and pos >= o + 16:
                 break
