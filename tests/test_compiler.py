@@ -145,3 +145,38 @@ def test_fast_path_model_anchored_at_every_alignment(patterns, gpu_lib):
         pos += len(pl)
     assert len(truth) >= 64 or patterns[0].startswith(r"\A")
     assert fast_path_matched_line_starts(db, data) == truth
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_state_depth_bounds_the_age_of_partial_matches(seed, gpu_lib):
+    """Dfa::depth (automata.hpp): nothing that is in progress in state s began more than depth[s] bytes ago.  Then a walk
+    that starts only depth[s] bytes earlier - in the mid-line entry state that the byte in front of it selects - must
+    arrive in the very same state.  (This is what lets a verification walk stop early, and what would break it.)"""
+    rng = random.Random(1000 + seed)
+    k = rng.choice([1, 2, 4])
+    patterns = [_factor_pattern(rng) for _ in range(k)]
+    db = CompiledDb(gpu_lib, patterns, [rng.choice([14, 14, 15, 10])] * k, [0] * k)
+    assert db.rc == 0
+    checked = bounded = 0
+    for _ in range(30):
+        text = "".join(rng.choice("abcAB _x1.\t") for _ in range(rng.randint(0, 40)))
+        at = rng.randint(0, len(text))
+        line = (text[:at] + "".join(rng.choice(LITS) for _ in range(rng.randint(1, 3))) + text[at:]).encode("latin1")
+        for (gi, cls, trans, acc, _reports), depth in zip(db.groups, db.depths):
+            s = 0
+            for p, b in enumerate(line):
+                s = int(trans[s, cls[b]])
+                if s >= gi.first_accept or s == gi.dead:
+                    break   # matched (absorbing in simple mode) or dead: nothing to bound
+                d = int(depth[s])
+                checked += 1
+                if d == 255 or d > p + 1:
+                    continue
+                bounded += 1
+                q = p + 1 - d   # the local walk consumes line[q .. p]
+                local = 0 if q == 0 else (gi.entry_mid_word if chr(line[q - 1]).isalnum() or line[q - 1] == 95 else gi.entry_mid_other)
+                for b2 in line[q:p + 1]:
+                    local = int(trans[local, cls[b2]])
+                assert local == s, (patterns, line, p, d)
+    if checked and not bounded:
+        pytest.skip("every state of this set sits behind a loop (depth 255)")
