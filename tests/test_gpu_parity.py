@@ -571,3 +571,38 @@ def test_device_text_reads_stay_inside_the_buffer():
     # longer than the mapping ends with code 7
     control = subprocess.run([sys.executable, script, "--negative"], capture_output=True, text=True, timeout=300, check=False)
     assert control.returncode == 0 and "rc=7" in control.stdout, control.stdout[-1000:] + control.stderr[-1000:]
+
+
+def test_match_ends_from_host_and_device_memory(gpu_lib):
+    """gpugrep_match_ends on the GPU: every (line, id, end) of fixed-width patterns equals what Python's re finds with an
+    overlapping search, for host memory and for a device-resident buffer."""
+    import re
+
+    import torch
+
+    from hypergrep_b200 import utils
+
+    text = synth.syslog_bytes(3 << 20, seed=53, lib=gpu_lib)
+    patterns = ["ERROR", "port [0-9]{5}", r"\d\d:\d\d:\d\d", "ss"]
+    expected = []
+    for number, line in enumerate(text.split(b"\n")[:-1]):
+        row = []
+        for pid, pattern in enumerate(patterns):
+            for m in re.finditer(b"(?=(" + pattern.encode() + b"))", line):
+                row.append((m.end(1), pid))
+        expected += [(number, pid, end) for end, pid in sorted(row)]
+    pa, fa, ia = utils.prepare_patterns(patterns, flags=[0] * len(patterns), ids=list(range(len(patterns))))
+    entry = gpu_lib.gpugrep_match_ends
+    entry.restype = ctypes.c_int
+    entry.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint,
+                      ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), ctypes.c_void_p]
+    host = np.frombuffer(text, dtype=np.uint8)
+    dev = torch.from_numpy(host.copy()).cuda()
+    torch.cuda.synchronize()
+    for pointer, location in ((host.ctypes.data, 0), (dev.data_ptr(), 1)):
+        out = (utils._MatchEnd * (len(expected) + 16))()
+        found = ctypes.c_size_t()
+        assert entry(pointer, len(text), location, pa, fa, ia, len(patterns), 262140, out, len(expected) + 16, ctypes.byref(found), None) == 0
+        assert found.value == len(expected)
+        got = [(out[k].line_number, out[k].id, out[k].end) for k in range(found.value)]
+        assert got == expected, location
